@@ -1,0 +1,257 @@
+"""CPU oracle for the distilled residual 3D U-Net hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a from-scratch, functional restatement (plain torch fp32 ops on CPU or any
+device) of the reference's algorithm for the hot path.  It is the *checker*: only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py` may
+import it.  The product path (`brats2019_b200`) never does.
+
+Parity pin: the reference ships no tests or golden vectors, so this oracle is
+pinned against outputs of the reference itself, generated in the build container by
+`oracle/gen_golden.py` (imports /root/reference/model.py + loss.py + weight_init.py) and
+committed under `tests/golden/`.  `tests/test_oracle.py` checks oracle == golden.
+
+Reference lines followed:
+  model.py:7-14     Trilinear            -> `trilinear_x2`
+  model.py:66-79    conv (k3 p1 no bias) -> `F.conv3d(..., padding=1)`
+  model.py:81-117   Residual             -> `residual_block`
+  model.py:308-433  UNet ctor + forward  -> `param_shapes`, `unet_forward`
+  loss.py:98-122    Dice_loss_joint      -> `dice_loss_joint`
+  loss.py:64-79     BCE_Loss             -> `bce_loss`
+  weight_init.py:22-27                   -> `init_params`
+  test.py:144, metrics.py:108-133        -> `threshold_masks`, `dice_metric`
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+# main.py:56-59 — the only configuration the reference ships.
+DEFAULT_CFG = dict(
+    depth=4,
+    encoder_layers=[1, 2, 2, 4],
+    decoder_layers=[1, 1, 1, 1],
+    number_of_channels=[16, 32, 64, 128],
+    number_of_outputs=3,
+)
+GN_GROUPS = 8          # model.py:95-96, 338
+GN_EPS = 1e-5          # nn.GroupNorm default
+LRELU_SLOPE = 1e-2     # model.py:93-94, 352
+
+
+# ----------------------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------------------
+def _residual_names(prefix, c):
+    # model.py:81-96: conv wrapper adds the `.conv1.conv1.` level (model.py:72)
+    return [
+        (prefix + "conv1.conv1.weight", (c, c, 3, 3, 3)),
+        (prefix + "conv2.conv1.weight", (c, c, 3, 3, 3)),
+        (prefix + "norm1.weight", (c,)),
+        (prefix + "norm1.bias", (c,)),
+        (prefix + "norm2.weight", (c,)),
+        (prefix + "norm2.bias", (c,)),
+    ]
+
+
+def param_shapes(cfg=DEFAULT_CFG):
+    """Ordered (name, shape) list in the reference's `state_dict()` order.
+
+    Order follows module registration order in model.py:309-356: encoder_convs, upsampling,
+    decoder_convs, decoder_convs1x1 lists are registered (empty) first, then conv_input,
+    norm_input, conv_first, conv_output; the lists are filled afterwards, which does not
+    change their position.
+    """
+    ch = cfg["number_of_channels"]
+    depth = cfg["depth"]
+    enc, dec = cfg["encoder_layers"], cfg["decoder_layers"]
+    out = []
+    # encoder_convs (model.py:374-377, 358-372)
+    for i in range(depth - 1):
+        c = ch[i + 1]
+        for j in range(enc[i + 1]):
+            p = "encoder_convs.%d.%d." % (i, j)
+            names = _residual_names(p, c)
+            if j == 0:
+                names = [(p + "downsample.0.weight", (c, ch[i], 2, 2, 2))] + names
+            out += names
+    # upsampling (model.py:397-404)
+    for i in range(depth - 1):
+        out.append(("upsampling.%d.1.weight" % i, (ch[i], ch[i + 1], 1, 1, 1)))
+    # decoder_convs / decoder_convs1x1 (model.py:379-395): `depth` of each, last one dead
+    for i in range(depth):
+        for j in range(dec[i]):
+            out += _residual_names("decoder_convs.%d.%d." % (i, j), ch[i])
+    for i in range(depth):
+        out.append(("decoder_convs1x1.%d.weight" % i, (ch[i], 2 * ch[i], 1, 1, 1)))
+    out.append(("conv_input.weight", (ch[0], 4, 3, 3, 3)))
+    out.append(("norm_input.weight", (ch[0],)))
+    out.append(("norm_input.bias", (ch[0],)))
+    for j in range(enc[0]):
+        out += _residual_names("conv_first.%d." % j, ch[0])
+    out.append(("conv_output.weight", (cfg["number_of_outputs"], ch[0], 3, 3, 3)))
+    out.append(("conv_output.bias", (cfg["number_of_outputs"],)))
+    return out
+
+
+def dead_param_names(cfg=DEFAULT_CFG):
+    """Parameters built but never used by forward (model.py:420 iterates depth-1 only)."""
+    i = cfg["depth"] - 1
+    names = ["decoder_convs1x1.%d.weight" % i]
+    for j in range(cfg["decoder_layers"][i]):
+        names += [n for n, _ in _residual_names("decoder_convs.%d.%d." % (i, j), 0)]
+    return names
+
+
+def init_params(seed, cfg=DEFAULT_CFG):
+    """Deterministic parameters with the *distribution* of weight_init.py:22-27.
+
+    Conv3d weight ~ kaiming_normal_(a=1e-2, 'leaky_relu', fan_in), Conv3d bias ~ N(0,1),
+    GroupNorm weight=1, bias=0.  The draw order is our own (name order of `param_shapes`),
+    so values differ from `model.apply(weight_init)` under the same seed; parity tests load
+    the same state dict into both sides instead of relying on RNG order.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for name, shape in param_shapes(cfg):
+        if len(shape) == 5:
+            fan_in = shape[1] * shape[2] * shape[3] * shape[4]
+            gain = math.sqrt(2.0 / (1 + LRELU_SLOPE ** 2))
+            sd[name] = torch.randn(shape, generator=g) * (gain / math.sqrt(fan_in))
+        elif name.endswith("conv_output.bias"):
+            sd[name] = torch.randn(shape, generator=g)
+        elif name.endswith(".weight"):
+            sd[name] = torch.ones(shape)
+        else:
+            sd[name] = torch.zeros(shape)
+    return sd
+
+
+# ----------------------------------------------------------------------------------------
+# forward
+# ----------------------------------------------------------------------------------------
+def trilinear_x2(x):
+    # model.py:13 — F.interpolate(scale_factor=2, mode='trilinear'), align_corners default False
+    return F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+
+
+def trilinear_x2_explicit(x):
+    """Same op written as the separable fixed-tap stencil:
+    out[2k] = .25 in[k-1] + .75 in[k]; out[2k+1] = .75 in[k] + .25 in[k+1], edge-clamped."""
+    for dim in (2, 3, 4):
+        n = x.shape[dim]
+        idx = torch.arange(n)
+        lo = x.index_select(dim, (idx - 1).clamp(min=0))
+        hi = x.index_select(dim, (idx + 1).clamp(max=n - 1))
+        even = 0.25 * lo + 0.75 * x
+        odd = 0.75 * x + 0.25 * hi
+        x = torch.stack([even, odd], dim=dim + 1).flatten(dim, dim + 1)
+    return x
+
+
+def _gn_lrelu(x, w, b):
+    return F.leaky_relu(F.group_norm(x, GN_GROUPS, w, b, GN_EPS), LRELU_SLOPE)
+
+
+def residual_block(p, prefix, x):
+    # model.py:99-117
+    if prefix + "downsample.0.weight" in p:
+        x = F.conv3d(x, p[prefix + "downsample.0.weight"], stride=2)
+    out = F.conv3d(x, p[prefix + "conv1.conv1.weight"], padding=1)
+    out = _gn_lrelu(out, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"])
+    out = F.conv3d(out, p[prefix + "conv2.conv1.weight"], padding=1)
+    out = _gn_lrelu(out, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])
+    return x + out
+
+
+def unet_logits(p, x, cfg=DEFAULT_CFG):
+    """model.py:407-429 up to (not including) the sigmoid.  x: (B,4,D,H,W) fp32."""
+    depth = cfg["depth"]
+    enc, dec = cfg["encoder_layers"], cfg["decoder_layers"]
+    h = F.conv3d(x, p["conv_input.weight"], padding=1)                       # model.py:412
+    h = F.group_norm(h, GN_GROUPS, p["norm_input.weight"], p["norm_input.bias"], GN_EPS)  # :413, no act
+    for j in range(enc[0]):                                                   # :414
+        h = residual_block(p, "conv_first.%d." % j, h)
+    skips = []
+    for i in range(depth - 1):                                                # :416-418
+        skips.append(h)
+        for j in range(enc[i + 1]):
+            h = residual_block(p, "encoder_convs.%d.%d." % (i, j), h)
+    for i in reversed(range(depth - 1)):                                      # :420-426
+        h = F.conv3d(trilinear_x2(h), p["upsampling.%d.1.weight" % i])        # :421
+        h = F.leaky_relu(h, LRELU_SLOPE)                                      # :422
+        h = torch.cat([skips[i], h], dim=1)                                   # :424
+        h = F.conv3d(h, p["decoder_convs1x1.%d.weight" % i])                  # :425
+        for j in range(dec[i]):                                               # :426
+            h = residual_block(p, "decoder_convs.%d.%d." % (i, j), h)
+    return F.conv3d(h, p["conv_output.weight"], p["conv_output.bias"], padding=1)  # :429
+
+
+def unet_forward(p, x_list, cfg=DEFAULT_CFG):
+    """List-in / list-out like model.py:407-433: returns [sigmoid(logits)]."""
+    return [torch.sigmoid(unet_logits(p, x_list[0], cfg))]
+
+
+# ----------------------------------------------------------------------------------------
+# losses / metrics
+# ----------------------------------------------------------------------------------------
+def dice_loss_joint(x_list, y_list, index=0, priority=1):
+    # loss.py:105-122
+    pred, gt = x_list[index], y_list[index]
+    assert pred.shape == gt.shape
+    n, c = pred.shape[:2]
+    pred = pred.reshape(n, c, -1)
+    gt = gt.reshape(n, c, -1)
+    inter = (pred * gt).sum(dim=(0, 2)) + 1e-6
+    union = (pred ** 2 + gt).sum(dim=(0, 2)) + 2e-6
+    return priority * (1.0 - torch.mean(2.0 * inter / union))
+
+
+def bce_loss(x_list, y_list, index=0, bg_weight=1.0):
+    # loss.py:70-79
+    pred, gt = x_list[index], y_list[index]
+    loss = gt * torch.log(pred + 1e-6) + bg_weight * (1.0 - gt) * torch.log((1.0 + 1e-6) - pred)
+    return -torch.mean(loss)
+
+
+def dice_loss_grad_closed_form(pred, gt):
+    """dL/dpred of dice_loss_joint in closed form, used to check the
+    CUDA backward without autograd: -(2/C) (g U_c - 2 p I_c) / U_c^2."""
+    n, c = pred.shape[:2]
+    dims = [0] + list(range(2, pred.dim()))
+    inter = (pred * gt).sum(dim=dims, keepdim=True) + 1e-6
+    union = (pred ** 2 + gt).sum(dim=dims, keepdim=True) + 2e-6
+    return -(2.0 / c) * (gt * union - 2.0 * pred * inter) / union ** 2
+
+
+def threshold_masks(probs):
+    # test.py:144 — per-channel threshold, no argmax
+    return probs > 0.5
+
+
+def dice_metric(pred_mask, gt_mask):
+    """metrics.py:108-133 (class Dice): per-sample, per-channel thresholded Dice with the
+    both-empty case counted as 1."""
+    n, c = pred_mask.shape[:2]
+    p = pred_mask.reshape(n, c, -1).float()
+    g = gt_mask.reshape(n, c, -1).float()
+    inter = (p * g).sum(-1)
+    denom = p.sum(-1) + g.sum(-1)
+    return torch.where(denom > 0, 2.0 * inter / denom.clamp(min=1.0), torch.ones_like(denom))
+
+
+# ----------------------------------------------------------------------------------------
+# training step (forward + loss + autograd backward) — the oracle for gradients
+# ----------------------------------------------------------------------------------------
+def train_step(p, x, target, with_bce=False, cfg=DEFAULT_CFG):
+    """Returns (loss, probs, {name: grad}) for the live parameters (train.py:201-210)."""
+    dead = set(dead_param_names(cfg))
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items() if k not in dead)
+    probs = unet_forward(leaves, [x], cfg)
+    loss = dice_loss_joint(probs, [target])
+    if with_bce:                                   # main.py:126-128 + train.py:203-205
+        loss = (loss + bce_loss(probs, [target], bg_weight=1e-2)) / 2
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    return loss.detach(), probs[0].detach(), OrderedDict(zip(leaves.keys(), grads))
