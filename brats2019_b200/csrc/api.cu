@@ -1,0 +1,668 @@
+// Host side of libbrats_b200.so: launch planning, TMA tensor maps and the C ABI
+// declared in include/brats_b200.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "../../include/brats_b200.h"
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "wgrad_gemm.cuh"
+
+using namespace b200;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CUDA_OK(x)                                                                        \
+    do {                                                                                  \
+        cudaError_t e_ = (x);                                                             \
+        if (e_ != cudaSuccess) return fail("%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCH_OK(name)                                                                         \
+    do {                                                                                        \
+        cudaError_t e_ = cudaGetLastError();                                                    \
+        if (e_ != cudaSuccess) return fail("launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* b200_last_error(void) { return g_err; }
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;   // B200; used for planning queries on a machine without a GPU
+    }
+    return g_num_sms;
+}
+extern "C" int b200_num_sms(void) { return num_sms(); }
+
+extern "C" int b200_device_check(int dev) {
+    int major = 0, minor = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10) return fail("device %d is sm_%d%d; this library contains sm_100a code only", dev, major, minor);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time: no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::mutex g_mu;
+
+static int get_encode() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available");
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+
+// 2D map over an activation tensor viewed as [rows][C] bf16; box = 8 channels x box_rows rows.
+static int make_act_map(CUtensorMap* m, const void* ptr, int C, long long rows, int box_rows) {
+    if (get_encode()) return 1;
+    if (((uintptr_t)ptr & 15) != 0) return fail("activation pointer not 16-byte aligned");
+    if (box_rows < 1 || box_rows > 256) return fail("TMA box rows %d out of range", box_rows);
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {8, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with %d (C=%d rows=%lld box=%d)", (int)r, C, rows, box_rows);
+    return 0;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline unsigned align_up(unsigned a, unsigned b) { return (a + b - 1) / b * b; }
+static unsigned pow2_cols(unsigned c) {
+    unsigned p = 32;
+    while (p < c) p <<= 1;
+    return p;
+}
+static const unsigned kMaxSmem = 227 * 1024;
+
+// ---------------------------------------------------------------------------------------
+// conv planning
+// ---------------------------------------------------------------------------------------
+static int conv_nmma(const b200_conv_desc* d) { return d->Cout > 256 ? 256 : d->Cout; }
+static int conv_kc(const b200_conv_desc* d) {
+    if (d->mode == MODE_K3) return 16;
+    for (int kc : {64, 32, 16})
+        if (d->Cin_a % kc == 0 && d->Cin_b % kc == 0) return kc;
+    return 0;
+}
+
+static int check_conv_desc(const b200_conv_desc* d) {
+    if (!d) return fail("null conv desc");
+    if (d->mode != MODE_K3 && d->mode != MODE_K1) return fail("conv mode %d unsupported", d->mode);
+    if (d->N < 1 || d->D < 1 || d->H < 1 || d->W < 1) return fail("bad volume %dx%dx%dx%d", d->N, d->D, d->H, d->W);
+    if (d->Cin_a < 16 || d->Cin_a % 16 || d->Cin_b < 0 || d->Cin_b % 16)
+        return fail("Cin_a=%d / Cin_b=%d must be multiples of 16", d->Cin_a, d->Cin_b);
+    const int n = conv_nmma(d);
+    if (!(n == 16 || n == 32 || n == 64 || n == 128 || n == 256) || d->Cout % n)
+        return fail("Cout=%d unsupported (16/32/64/128/256 or a multiple of 256)", d->Cout);
+    if (d->mode == MODE_K3 && (d->Cout > 128 || d->Cin_b != 0)) return fail("k3 conv: Cout<=128 and one source only");
+    if (d->epi == EPI_SIGMOID && (d->mode != MODE_K3 || d->Cout != 16)) return fail("sigmoid epilogue needs k3, Cout=16");
+    if (d->W + 2 > 4000) return fail("W too large");
+    return 0;
+}
+
+static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
+    if (check_conv_desc(d)) return 1;
+    memset(&p, 0, sizeof(p));
+    const int Nm = conv_nmma(d);
+    p.N = d->N; p.D = d->D; p.H = d->H; p.W = d->W;
+    p.Wp = d->W + 2;
+    p.SS = (d->H + 2) * p.Wp;
+    p.sample_rows = (long long)(d->D + 2) * p.SS;
+    p.total_rows = p.sample_rows * d->N;
+    p.mode = d->mode;
+    p.n_jobs = d->Cout / Nm;
+    p.KC = conv_kc(d);
+    if (p.KC == 0) return fail("no K chunk size for Cin_a=%d Cin_b=%d", d->Cin_a, d->Cin_b);
+    p.KGa = d->Cin_a / p.KC;
+    p.KG = p.KGa + d->Cin_b / p.KC;
+    p.Cout_total = d->Cout;
+    const int sms = num_sms();
+    const unsigned bar_bytes = 1024 + 128;
+
+    if (d->mode == MODE_K3) {
+        p.NTG = 3; p.TG = 9;
+        p.w_stage_bytes = (unsigned)(p.TG * p.KC * Nm * 2);
+        double best_cost = 1e300;
+        int bBD = 0, bMB = 0, bWhole = 0;
+        for (int whole = 0; whole < 2; ++whole)
+            for (int BD : {1, 2, 4}) {
+                if (whole && BD != 1) continue;
+                if (BD > d->D) continue;
+                for (int MB : {1, 2, 4}) {
+                    const int R = BD * MB;
+                    if (2 * R * Nm > 512) continue;
+                    const int TR = 128 * MB;
+                    const int SR = TR + 2 * p.Wp + 2;
+                    const int NBX = ceil_div(SR, 256);
+                    const int BR = (ceil_div(SR, NBX) + 7) / 8 * 8;
+                    const int SRp = NBX * BR;
+                    const unsigned xst = 2u * (BD + 2) * SRp * 16;
+                    if (2 * xst + 2 * p.w_stage_bytes + bar_bytes > kMaxSmem) continue;
+                    long long QN, tiles;
+                    if (whole) {
+                        QN = (long long)(d->D - 1) * p.SS + (long long)(d->H - 1) * p.Wp + d->W;
+                        tiles = (long long)d->N * ceil_div(QN, TR);
+                    } else {
+                        QN = (long long)(d->H - 1) * p.Wp + d->W;
+                        tiles = (long long)d->N * ceil_div(d->D, BD) * ceil_div(QN, TR);
+                    }
+                    const long long ctas = std::min<long long>(sms, tiles);
+                    const double amp = (double)(BD + 2) * SRp / ((double)BD * TR);
+                    const double cost = (double)ceil_div(tiles, ctas) * BD * TR * (1.0 + 0.04 * amp);
+                    if (cost < best_cost) { best_cost = cost; bBD = BD; bMB = MB; bWhole = whole; }
+                }
+            }
+        if (bBD == 0) return fail("k3 conv: no tile shape fits (W=%d, Cout=%d)", d->W, d->Cout);
+        p.BD = bBD; p.MB = bMB; p.whole = bWhole;
+        p.TR = 128 * p.MB;
+        const int SR = p.TR + 2 * p.Wp + 2;
+        p.NBX = ceil_div(SR, 256);
+        p.BR = (ceil_div(SR, p.NBX) + 7) / 8 * 8;
+        p.SRp = p.NBX * p.BR;
+        p.nslices = p.BD + 2;
+        p.halo_rows = p.Wp + 1;
+        p.x_plane_bytes = (unsigned)p.nslices * p.SRp * 16;
+        p.x_stage_bytes = (unsigned)(p.KC / 8) * p.x_plane_bytes;
+        if (p.whole) {
+            p.Q0 = p.SS + p.Wp + 1;
+            p.QN = (d->D - 1) * p.SS + (d->H - 1) * p.Wp + d->W;
+            p.tiles_d = 1;
+        } else {
+            p.Q0 = p.Wp + 1;
+            p.QN = (d->H - 1) * p.Wp + d->W;
+            p.tiles_d = ceil_div(d->D, p.BD);
+        }
+        p.tiles_q = ceil_div(p.QN, p.TR);
+        for (int t = 0; t < 27; ++t) p.tap_off[t] = (t / 9) * p.SRp + ((t / 3) % 3) * p.Wp + (t % 3);
+    } else {
+        p.NTG = 1; p.TG = 1;
+        p.w_stage_bytes = (unsigned)(p.KC * Nm * 2);
+        p.MB = (Nm <= 128) ? 2 : 1;
+        p.BD = 1; p.whole = 0;
+        p.TR = 128 * p.MB;
+        p.NBX = p.MB; p.BR = 128; p.SRp = p.TR;
+        p.nslices = 1; p.halo_rows = 0;
+        p.x_plane_bytes = (unsigned)p.TR * 16;
+        p.x_stage_bytes = (unsigned)(p.KC / 8) * p.x_plane_bytes;
+        p.Q0 = 0; p.QN = 0; p.tiles_d = 1;
+        p.tiles_q = ceil_div(p.total_rows, p.TR);
+        p.tap_off[0] = 0;
+    }
+    p.num_tiles = (p.mode == MODE_K3 ? p.N * p.tiles_d : 1) * p.tiles_q;
+    // stages: as many as fit, up to 4
+    unsigned budget = kMaxSmem - bar_bytes;
+    p.x_stages = 2; p.w_stages = 2;
+    auto used = [&]() { return align_up(p.x_stages * p.x_stage_bytes, 128) + p.w_stages * p.w_stage_bytes; };
+    if (used() > budget) return fail("conv: shared memory plan does not fit (%u bytes)", used());
+    for (int round = 0; round < 2; ++round) {
+        ++p.w_stages; if (used() > budget) --p.w_stages;
+        ++p.x_stages; if (used() > budget) --p.x_stages;
+    }
+    p.smem_x_off = 0;
+    p.smem_w_off = align_up(p.x_stages * p.x_stage_bytes, 128);
+    p.smem_bar_off = align_up(p.smem_w_off + p.w_stages * p.w_stage_bytes, 16);
+    p.tmem_cols = pow2_cols(2u * p.BD * p.MB * Nm);
+    if (p.tmem_cols > 512) return fail("conv: TMEM plan does not fit");
+    return 0;
+}
+
+static int conv_grid_ctas(const ConvKParams& p) {
+    int per_job = std::max(1, num_sms() / p.n_jobs);
+    return std::min(per_job, p.num_tiles);
+}
+
+extern "C" size_t b200_conv_packed_weight_bytes(const b200_conv_desc* d) {
+    ConvKParams p;
+    if (plan_conv(d, p)) return 0;
+    return (size_t)p.n_jobs * p.KG * p.NTG * p.w_stage_bytes;
+}
+extern "C" int b200_conv_ctas(const b200_conv_desc* d) {
+    ConvKParams p;
+    if (plan_conv(d, p)) return -1;
+    return conv_grid_ctas(p);
+}
+
+extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const float* w, int Cout_w, int Cin_w,
+                                     int taps_w, int ci_off, int K_real, int N_real, void* packed, void* stream) {
+    ConvKParams p;
+    if (plan_conv(d, p)) return 1;
+    if (kind < 0 || kind > 3) return fail("bad weight kind %d", kind);
+    const int taps_g = (d->mode == MODE_K3) ? 27 : 1;
+    if ((kind == B200_W_FWD || kind == B200_W_DGRAD) && taps_w != taps_g) return fail("taps mismatch %d vs %d", taps_w, taps_g);
+    if ((kind == B200_W_FWD_S2D || kind == B200_W_DGRAD_S2D) && (taps_w != 8 || d->mode != MODE_K1))
+        return fail("s2d weight kinds need a k1 GEMM and a 2x2x2 kernel");
+    if (K_real > d->Cin_a + d->Cin_b || N_real > d->Cout) return fail("K_real/N_real exceed the GEMM extents");
+    PackParams q;
+    q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
+    q.K_real = K_real; q.N_real = N_real;
+    q.n_jobs = p.n_jobs; q.KG = p.KG; q.NTG = p.NTG; q.TG = p.TG; q.KC = p.KC; q.Nmma = conv_nmma(d);
+    const size_t total = (size_t)q.n_jobs * q.KG * q.NTG * q.TG * (q.KC / 8) * q.Nmma;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
+    pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, q);
+    LAUNCH_OK("pack_weight_kernel");
+    return 0;
+}
+
+template <int MODE, int EPI, int NM>
+static int launch_conv(const ConvKParams& p, const CUtensorMap& a, const CUtensorMap& b, unsigned smem, int grid,
+                       cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<MODE, EPI, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kMaxSmem));
+        attr_set = true;
+    }
+    conv_gemm_kernel<MODE, EPI, NM><<<grid, kConvThreads, smem, st>>>(p, a, b);
+    LAUNCH_OK("conv_gemm_kernel");
+    return 0;
+}
+
+extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
+                             void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
+                             float* probs, float* logits, int n_out_real, void* stream) {
+    ConvKParams p;
+    if (plan_conv(d, p)) return 1;
+    if (!src_a || !packed) return fail("conv: null operand");
+    if (d->Cin_b > 0 && !src_b) return fail("conv: second source missing");
+    if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
+    if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
+        return fail("conv: sigmoid epilogue needs bias, probs and 1..4 real outputs");
+    if (stats_partial && (d->mode != MODE_K3 || d->epi != EPI_BF16 || p.n_jobs != 1))
+        return fail("conv: GroupNorm statistics only for the k3 bf16 path");
+    cudaStream_t st = (cudaStream_t)stream;
+    p.wpacked = (const __nv_bfloat16*)packed;
+    p.out = (__nv_bfloat16*)out;
+    p.residual = (const __nv_bfloat16*)residual;
+    p.lrelu_out = lrelu_out;
+    p.stats_partial = stats_partial;
+    p.bias = bias; p.probs = probs; p.logits = logits; p.n_out_real = n_out_real;
+    const int ctas = conv_grid_ctas(p);
+    const int grid = ctas * p.n_jobs;
+    if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)ctas * p.N * 16 * sizeof(float), st));
+    CUtensorMap ma, mb;
+    if (make_act_map(&ma, src_a, d->Cin_a, p.total_rows, p.BR)) return 1;
+    if (d->Cin_b > 0) { if (make_act_map(&mb, src_b, d->Cin_b, p.total_rows, p.BR)) return 1; }
+    else mb = ma;
+    const unsigned smem = p.smem_bar_off + 1024;
+    const int Nm = conv_nmma(d);
+#define CONV_CASE(MODE, EPI, NM) return launch_conv<MODE, EPI, NM>(p, ma, mb, smem, grid, st)
+    if (d->epi == EPI_SIGMOID) CONV_CASE(MODE_K3, EPI_SIGMOID, 16);
+    if (d->mode == MODE_K3) {
+        switch (Nm) {
+            case 16: CONV_CASE(MODE_K3, EPI_BF16, 16);
+            case 32: CONV_CASE(MODE_K3, EPI_BF16, 32);
+            case 64: CONV_CASE(MODE_K3, EPI_BF16, 64);
+            case 128: CONV_CASE(MODE_K3, EPI_BF16, 128);
+        }
+    } else {
+        switch (Nm) {
+            case 16: CONV_CASE(MODE_K1, EPI_BF16, 16);
+            case 32: CONV_CASE(MODE_K1, EPI_BF16, 32);
+            case 64: CONV_CASE(MODE_K1, EPI_BF16, 64);
+            case 128: CONV_CASE(MODE_K1, EPI_BF16, 128);
+            case 256: CONV_CASE(MODE_K1, EPI_BF16, 256);
+        }
+    }
+#undef CONV_CASE
+    return fail("conv: no kernel for mode %d Cout %d", d->mode, d->Cout);
+}
+
+// ---------------------------------------------------------------------------------------
+// wgrad planning
+// ---------------------------------------------------------------------------------------
+struct WgradPlan {
+    WgradKParams k;
+    int banded, folded, accs;
+    unsigned smem;
+    int grid;
+    int BRy;
+};
+
+static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
+    if (!d) return fail("null wgrad desc");
+    if (d->mode != 0 && d->mode != 1) return fail("wgrad mode %d unsupported", d->mode);
+    if (d->Cout < 16 || d->Cout % 16 || d->Cin < 16 || d->Cin % 16) return fail("wgrad: channels must be multiples of 16");
+    memset(&P, 0, sizeof(P));
+    WgradKParams& k = P.k;
+    Vol v{d->N, d->D, d->H, d->W};
+    k.total_rows = v.total_rows();
+    k.Wp = v.Wp();
+    k.SS = (int)v.slice_rows();
+    if (d->mode == 0) {
+        if (d->Cout > 128 || d->Cin > 128) return fail("wgrad k3: channels <= 128");
+        if (d->Cout <= 32) { P.banded = 1; k.M = (d->Cout == 16) ? 64 : 128; }
+        else { P.banded = 0; k.M = (d->Cout == 64) ? 64 : 128; }
+        if (d->Cout == 48 || d->Cout == 80 || d->Cout == 96 || d->Cout == 112) return fail("wgrad k3: Cout %d unsupported", d->Cout);
+        P.folded = (3 * d->Cin <= 256) ? 1 : 0;
+        k.Nmma = P.folded ? 3 * d->Cin : d->Cin;
+        P.accs = (3 * k.Nmma <= 512) ? 1 : 0;
+        k.nfold = P.folded ? 3 : 1;
+        k.nacc = P.accs ? 3 : 1;
+        k.nband_loaded = P.banded ? 3 : 1;
+        int j = 0;
+        for (int kd = 0; kd < (P.banded ? 1 : 3); ++kd)
+            for (int kh = 0; kh < (P.accs ? 1 : 3); ++kh)
+                for (int kw = 0; kw < (P.folded ? 1 : 3); ++kw) {
+                    k.job_kd[j] = P.banded ? 0 : kd - 1;
+                    k.job_kh[j] = P.accs ? 0 : kh - 1;
+                    k.job_kw[j] = P.folded ? 0 : kw - 1;
+                    k.job_xch[j] = 0;
+                    ++j;
+                }
+        k.n_jobs = j;
+    } else {
+        if (d->Cout > 128) return fail("wgrad k1: Cout <= 128");
+        P.banded = 0; P.folded = 0; P.accs = 0;
+        k.M = d->Cout <= 64 ? 64 : 128;
+        k.Nmma = d->Cin > 256 ? 256 : d->Cin;
+        if (d->Cin % k.Nmma) return fail("wgrad k1: Cin %d unsupported", d->Cin);
+        k.nfold = 1; k.nacc = 1; k.nband_loaded = 1;
+        k.n_jobs = d->Cin / k.Nmma;
+        for (int j = 0; j < k.n_jobs; ++j) { k.job_kd[j] = k.job_kh[j] = k.job_kw[j] = 0; k.job_xch[j] = j * k.Nmma; }
+    }
+    if (k.n_jobs > kMaxJobs) return fail("wgrad: too many jobs");
+    k.CoC = d->Cout / 8;
+    k.CiC = (d->mode == 0 ? d->Cin : k.Nmma) / 8;
+    k.y_planes = k.M / 8;
+    k.x_planes = k.Nmma / 8;
+    if (k.nband_loaded * k.CoC > k.y_planes) return fail("wgrad: internal plane count");
+    // stage size: largest KT in {256,128,64} with >= 2 stages
+    const unsigned bar_bytes = 512;
+    k.stages = 0;
+    for (int KT : {256, 128, 64}) {
+        const int XR = KT + (k.nacc > 1 ? 2 * k.Wp : 0);
+        const int NBX = ceil_div(XR, 256);
+        const int BR = (ceil_div(XR, NBX) + 7) / 8 * 8;
+        const unsigned ypl = (unsigned)KT * 16, xpl = (unsigned)NBX * BR * 16;
+        const unsigned stage = k.y_planes * ypl + k.x_planes * xpl;
+        int stages = (int)((kMaxSmem - bar_bytes) / stage);
+        if (stages >= 2) {
+            k.KT = KT; k.XR = XR; k.NBXx = NBX; k.BRx = BR;
+            k.y_plane_bytes = ypl; k.x_plane_bytes = xpl; k.stage_bytes = stage;
+            k.stages = std::min(stages, 4);
+            break;
+        }
+    }
+    if (k.stages == 0) return fail("wgrad: shared memory plan does not fit (Cout=%d Cin=%d W=%d)", d->Cout, d->Cin, d->W);
+    k.stage_tx_bytes = (unsigned)(k.nband_loaded * k.CoC) * k.y_plane_bytes + (unsigned)(k.nfold * k.CiC) * k.x_plane_bytes;
+    k.smem_bar_off = k.stages * k.stage_bytes;
+    P.smem = k.smem_bar_off + bar_bytes;
+    k.tmem_cols = pow2_cols((unsigned)(k.nacc * k.Nmma));
+    if (k.tmem_cols > 512) return fail("wgrad: TMEM plan does not fit");
+    const int total_stages = ceil_div(k.total_rows, k.KT);
+    k.splits = std::max(1, std::min(num_sms() / k.n_jobs, total_stages));
+    k.stages_per_split = ceil_div(total_stages, k.splits);
+    k.splits = ceil_div(total_stages, k.stages_per_split);
+    P.grid = k.splits * k.n_jobs;
+    P.BRy = k.KT;
+    return 0;
+}
+
+extern "C" size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d) {
+    WgradPlan P;
+    if (plan_wgrad(d, P)) return 0;
+    return (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
+}
+
+extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const void* x, void* workspace, float* grad,
+                              int kind, int Cout_w, int Cin_w, int taps_w, int ci_off, int accumulate, void* stream) {
+    WgradPlan P;
+    if (plan_wgrad(d, P)) return 1;
+    if (!dy || !x || !workspace || !grad) return fail("wgrad: null operand");
+    if (kind == B200_G_K3 && (d->mode != 0 || taps_w != 27)) return fail("wgrad: kind/mode mismatch");
+    if (kind == B200_G_K1 && (d->mode != 1 || taps_w != 1)) return fail("wgrad: kind/mode mismatch");
+    if (kind == B200_G_S2D && (d->mode != 1 || taps_w != 8 || d->Cin != 8 * Cin_w)) return fail("wgrad: s2d kind mismatch");
+    if (Cout_w > d->Cout) return fail("wgrad: Cout_w > Cout");
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        attr_set = true;
+    }
+    P.k.partial = (float*)workspace;
+    CUtensorMap my, mx;
+    if (make_act_map(&my, dy, d->Cout, P.k.total_rows, P.BRy)) return 1;
+    if (make_act_map(&mx, x, d->Cin, P.k.total_rows, P.k.BRx)) return 1;
+    wgrad_gemm_kernel<<<P.grid, kWgradThreads, P.smem, st>>>(P.k, my, mx);
+    LAUNCH_OK("wgrad_gemm_kernel");
+    WgradReduceParams q;
+    q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
+    q.Cout_g = d->Cout; q.Cin_g = d->Cin;
+    q.banded = P.banded; q.folded = P.folded; q.accs = P.accs;
+    q.n_jobs = P.k.n_jobs; q.splits = P.k.splits; q.nacc = P.k.nacc; q.M = P.k.M; q.Nmma = P.k.Nmma;
+    q.accumulate = accumulate;
+    const int total = Cout_w * Cin_w * taps_w;
+    wgrad_reduce_kernel<<<std::min((total + 127) / 128, 2048), 128, 0, st>>>(P.k.partial, grad, q);
+    LAUNCH_OK("wgrad_reduce_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// memory-bound ops
+// ---------------------------------------------------------------------------------------
+static int check_act(int N, int D, int H, int W, int C) {
+    if (N < 1 || D < 1 || H < 1 || W < 1) return fail("bad volume %dx%dx%dx%d", N, D, H, W);
+    if (C < 8 || C % 8 || C > 1024) return fail("channel count %d unsupported", C);
+    return 0;
+}
+
+extern "C" int b200_pack_input(const float* x, void* act_out, int N, int D, int H, int W, int Creal, int Cpad,
+                               void* stream) {
+    if (check_act(N, D, H, W, Cpad) || Creal > Cpad) return fail("pack_input: bad channels %d -> %d", Creal, Cpad);
+    Vol v{N, D, H, W};
+    pack_input_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)act_out, v, Creal, Cpad);
+    LAUNCH_OK("pack_input_kernel");
+    return 0;
+}
+
+extern "C" int b200_gn_finalize(const float* stats_partial, int ctas, int N, int C, int D, int H, int W, float eps,
+                                float* mean, float* rstd, void* stream) {
+    if (C % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
+    const double count = (double)(C / 8) * D * H * W;
+    gn_finalize_kernel<<<N, 32, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd);
+    LAUNCH_OK("gn_finalize_kernel");
+    return 0;
+}
+
+extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, const void* residual, void* out, int N, int D, int H, int W, int C,
+                             int do_lrelu, void* stream) {
+    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_apply: C=%d unsupported", C);
+    Vol v{N, D, H, W};
+    gn_apply_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, mean, rstd, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, v, C,
+        do_lrelu);
+    LAUNCH_OK("gn_apply_kernel");
+    return 0;
+}
+
+static int gn_bwd_blocks(int N, int D, int H) {
+    int per = std::max(1, 4 * num_sms() / std::max(1, N));
+    return std::min(per, D * H);
+}
+extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
+    // partial[N][blocks<=4*sms][C][2] + coef[N][C][2]
+    return (size_t)N * (4 * num_sms()) * C * 2 + (size_t)N * C * 2;
+}
+extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd,
+                                const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta,
+                                float* workspace, int N, int D, int H, int W, int C, int do_lrelu, void* stream) {
+    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_backward: C=%d unsupported", C);
+    Vol v{N, D, H, W};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = gn_bwd_blocks(N, D, H);
+    float* partial = workspace;
+    float* coef = workspace + (size_t)N * (4 * num_sms()) * C * 2;
+    gn_bwd_reduce_kernel<<<dim3(blocks, N), kEwThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean,
+                                                                rstd, gamma, beta, partial, v, C, do_lrelu);
+    LAUNCH_OK("gn_bwd_reduce_kernel");
+    const double m = (double)(C / 8) * D * H * W;
+    gn_bwd_finalize_kernel<<<1, 256, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
+    LAUNCH_OK("gn_bwd_finalize_kernel");
+    gn_bwd_apply_kernel<<<N * D * H, kEwThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean, rstd,
+                                                         gamma, beta, coef, (__nv_bfloat16*)dx, v, C, do_lrelu);
+    LAUNCH_OK("gn_bwd_apply_kernel");
+    return 0;
+}
+
+extern "C" int b200_upsample2x(const void* coarse, void* fine, int N, int D, int H, int W, int C, int do_lrelu,
+                               void* stream) {
+    if (check_act(N, D, H, W, C)) return 1;
+    Vol vc{N, D, H, W};
+    upsample2x_lrelu_kernel<<<N * 2 * D * 2 * H, kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)coarse, (__nv_bfloat16*)fine, vc, C, do_lrelu);
+    LAUNCH_OK("upsample2x_lrelu_kernel");
+    return 0;
+}
+extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out, void* dcoarse, int N, int D, int H,
+                                        int W, int C, int do_lrelu, void* stream) {
+    if (check_act(N, D, H, W, C)) return 1;
+    Vol vc{N, D, H, W};
+    upsample2x_lrelu_bwd_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dfine, (const __nv_bfloat16*)fine_out, (__nv_bfloat16*)dcoarse, vc, C, do_lrelu);
+    LAUNCH_OK("upsample2x_lrelu_bwd_kernel");
+    return 0;
+}
+
+extern "C" int b200_space_to_depth(const void* fine, void* coarse, int N, int D, int H, int W, int C, void* stream) {
+    if (check_act(N, D, H, W, C)) return 1;
+    Vol vc{N, D, H, W};
+    s2d_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)fine, (__nv_bfloat16*)coarse,
+                                                                  vc, C);
+    LAUNCH_OK("s2d_kernel");
+    return 0;
+}
+extern "C" int b200_depth_to_space(const void* coarse, const void* residual, void* fine, int N, int D, int H, int W,
+                                   int C, void* stream) {
+    if (check_act(N, D, H, W, C)) return 1;
+    Vol vc{N, D, H, W};
+    d2s_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)coarse,
+                                                                  (const __nv_bfloat16*)residual,
+                                                                  (__nv_bfloat16*)fine, vc, C);
+    LAUNCH_OK("d2s_kernel");
+    return 0;
+}
+extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, int H, int W, int C, void* stream) {
+    if (check_act(N, D, H, W, C)) return 1;
+    Vol v{N, D, H, W};
+    add_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                                  (__nv_bfloat16*)out, v, C);
+    LAUNCH_OK("add_kernel");
+    return 0;
+}
+
+extern "C" size_t b200_sigmoid_backward_workspace_floats(int N, int D, int H) { return (size_t)N * D * H * 4; }
+extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs, void* dlogit_act, float* dbias,
+                                     float* workspace, int N, int D, int H, int W, int Creal, int Cpad, void* stream) {
+    if (check_act(N, D, H, W, Cpad) || Creal > 4) return fail("sigmoid_backward: Creal=%d Cpad=%d unsupported", Creal, Cpad);
+    Vol v{N, D, H, W};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = N * D * H;
+    sigmoid_bwd_pack_kernel<<<blocks, kEwThreads, 0, st>>>(grad_probs, probs, (__nv_bfloat16*)dlogit_act, workspace, v,
+                                                          Creal, Cpad);
+    LAUNCH_OK("sigmoid_bwd_pack_kernel");
+    if (dbias) {
+        reduce_partials_kernel<<<Creal, 256, 0, st>>>(workspace, blocks, 4, Creal, dbias);
+        LAUNCH_OK("reduce_partials_kernel");
+    }
+    return 0;
+}
+
+static int dice_blocks() { return 2 * num_sms(); }
+extern "C" size_t b200_dice_workspace_floats(int B, int C) { return (size_t)B * C * dice_blocks() * 2; }
+extern "C" int b200_dice_sums(const float* probs, const float* target, float* sums, float* workspace, int B, int C,
+                              long long S, void* stream) {
+    if (C < 1 || C > 4) return fail("dice: C=%d unsupported (1..4)", C);
+    if (S % 4) return fail("dice: spatial size must be a multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bx = dice_blocks();
+    dice_partial_kernel<<<dim3(bx, B * C), kEwThreads, 0, st>>>(probs, target, workspace, B, C, S);
+    LAUNCH_OK("dice_partial_kernel");
+    dice_sums_kernel<<<1, 32, 0, st>>>(workspace, B, C, bx, sums);
+    LAUNCH_OK("dice_sums_kernel");
+    return 0;
+}
+extern "C" int b200_dice_loss(const float* sums, int C, float priority, float* loss, void* stream) {
+    dice_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, C, priority, loss);
+    LAUNCH_OK("dice_loss_kernel");
+    return 0;
+}
+extern "C" int b200_dice_backward(const float* probs, const float* target, const float* sums, const float* grad_out,
+                                  float priority, float* grad_probs, int B, int C, long long S, void* stream) {
+    if (C < 1 || C > 4) return fail("dice: C=%d unsupported (1..4)", C);
+    dice_bwd_kernel<<<dim3(dice_blocks(), B * C), kEwThreads, 0, (cudaStream_t)stream>>>(probs, target, sums, grad_out,
+                                                                                        priority, grad_probs, B, C, S);
+    LAUNCH_OK("dice_bwd_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// plan introspection (tests / DESIGN.md): lets a CPU test replay the exact addressing the
+// kernels use.  out[] layout is documented in tests/test_plan_cpu.py.
+// ---------------------------------------------------------------------------------------
+extern "C" int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out) {
+    ConvKParams p;
+    if (plan_conv(d, p)) return 1;
+    const int vals[] = {p.BD, p.MB, p.TR, p.Q0, p.QN, p.tiles_q, p.tiles_d, p.num_tiles, p.whole, p.n_jobs,
+                        p.KG, p.KGa, p.KC, p.NTG, p.TG, p.x_stages, p.w_stages, (int)p.x_stage_bytes,
+                        (int)p.w_stage_bytes, (int)p.x_plane_bytes, p.SRp, p.BR, p.NBX, p.nslices, p.halo_rows,
+                        (int)p.tmem_cols, (int)(p.smem_bar_off + 1024), conv_grid_ctas(p), p.Wp, p.SS};
+    const int nv = (int)(sizeof(vals) / sizeof(int));
+    if (n_out < nv + kMaxTaps) return fail("plan_debug: need %d ints", nv + kMaxTaps);
+    for (int i = 0; i < nv; ++i) out[i] = vals[i];
+    for (int i = 0; i < kMaxTaps; ++i) out[nv + i] = p.tap_off[i];
+    return 0;
+}
+
+extern "C" int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out) {
+    WgradPlan P;
+    if (plan_wgrad(d, P)) return 1;
+    const WgradKParams& k = P.k;
+    const int vals[] = {k.KT, k.XR, k.NBXx, k.BRx, k.nband_loaded, k.CoC, k.CiC, k.nfold, k.nacc, k.M, k.Nmma,
+                        k.n_jobs, k.splits, k.stages_per_split, k.y_planes, k.x_planes, (int)k.y_plane_bytes,
+                        (int)k.x_plane_bytes, (int)k.stage_bytes, (int)k.stage_tx_bytes, k.stages, (int)k.tmem_cols,
+                        (int)P.smem, P.grid, P.banded, P.folded, P.accs, k.Wp, k.SS};
+    const int nv = (int)(sizeof(vals) / sizeof(int));
+    if (n_out < nv + 4 * kMaxJobs) return fail("wgrad_plan_debug: need %d ints", nv + 4 * kMaxJobs);
+    for (int i = 0; i < nv; ++i) out[i] = vals[i];
+    for (int j = 0; j < kMaxJobs; ++j) {
+        out[nv + 4 * j + 0] = k.job_kd[j];
+        out[nv + 4 * j + 1] = k.job_kh[j];
+        out[nv + 4 * j + 2] = k.job_kw[j];
+        out[nv + 4 * j + 3] = k.job_xch[j];
+    }
+    return 0;
+}

@@ -1,0 +1,331 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), bf16 in / fp32 accumulate.
+//
+// Replaces aten::convolution as reached from the reference at model.py:72-73 (k3 p1),
+// model.py:336 (conv_input), model.py:348 (conv_output + sigmoid, model.py:431),
+// model.py:362 (k2 s2, run as a 1x1x1 conv over a space-to-depth tensor), model.py:393/401 (k1),
+// and, with flipped/transposed packed weights, the data-gradient half of its backward
+// (train.py:210).
+//
+// Data layout: zero-halo padded NDHWC (see common.cuh).  Because every activation tensor
+// carries its zero halo in HBM, a 3x3x3 tap is a constant row shift in the linear row
+// index: in[r + (kd-1)*SS + (kh-1)*Wp + (kw-1)].  A tile is a run of 128*MB consecutive rows
+// in each of BD consecutive slices; its input window is loaded ONCE by TMA into shared memory
+// as 16-byte channel-chunk planes ([chunk][slice][row][8 ch]), which is exactly the
+// SWIZZLE_NONE K-major canonical layout of a UMMA operand, so each of the 27 taps is just a
+// different start address in the A descriptor.  Rows that land on halo positions are junk:
+// computed, never stored.
+//
+// Warp roles (256 threads): w0 activation TMA producer, w1 weight bulk-copy producer,
+// w2 MMA issuer (one thread), w3 TMEM allocator, w4-7 epilogue (TMEM -> regs -> HBM).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum { MODE_K3 = 0, MODE_K1 = 1 };
+enum { EPI_BF16 = 0, EPI_SIGMOID = 1 };
+
+constexpr int kMaxTaps = 27;
+constexpr int kConvThreads = 256;
+
+struct ConvKParams {
+    // output volume (interior dims) and padded strides
+    int N, D, H, W, Wp, SS;
+    long long sample_rows, total_rows;
+    int mode;
+    // tiling
+    int BD, MB, TR;        // slices per tile, 128-row blocks per slice-run, rows per run
+    int Q0, QN;            // q-range (rows relative to the slice base) covered by the tiles
+    int tiles_q, tiles_d, num_tiles;
+    int whole;             // 1: q runs over the whole sample (BD == 1), 0: per slice
+    int n_jobs;            // column blocks (each its own packed weights); grid = ctas * n_jobs
+    // K loop
+    int KG, KGa, KC, NTG, TG;
+    // shared-memory plan
+    int x_stages, w_stages;
+    unsigned x_stage_bytes, w_stage_bytes, x_plane_bytes;
+    int SRp, BR, NBX, nslices, halo_rows;
+    int tap_off[kMaxTaps];
+    unsigned smem_x_off, smem_w_off, smem_bar_off;
+    unsigned tmem_cols;
+    // operands
+    const __nv_bfloat16* wpacked;
+    // epilogue
+    int Cout_total;        // channels per row of `out`
+    int lrelu_out;         // apply LeakyReLU(0.01) before storing
+    __nv_bfloat16* out;
+    const __nv_bfloat16* residual;   // optional, same layout as out, added before activation
+    float* stats_partial;            // optional [ctas][N][16] (sum[8], sumsq[8])
+    const float* bias;               // EPI_SIGMOID
+    float* probs;                    // EPI_SIGMOID: fp32 NCDHW (unpadded)
+    float* logits;                   // EPI_SIGMOID: optional fp32 NCDHW
+    int n_out_real;                  // EPI_SIGMOID: real output channels (3)
+};
+
+struct TileCoord {
+    int n, d0, q0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
+    TileCoord c;
+    int tq = t % p.tiles_q;
+    int r = t / p.tiles_q;
+    int td = r % p.tiles_d;
+    c.n = r / p.tiles_d;
+    c.d0 = td * p.BD;
+    c.q0 = p.Q0 + tq * p.TR;
+    return c;
+}
+
+template <int MODE, int EPI, int NMMA>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmB) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int job = blockIdx.x % p.n_jobs;
+    const int cta = blockIdx.x / p.n_jobs;
+    const int ctas = gridDim.x / p.n_jobs;
+
+    uint8_t* smem_x = smem + p.smem_x_off;
+    uint8_t* smem_w = smem + p.smem_w_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = x_full + p.x_stages;
+    uint64_t* w_full = x_empty + p.x_stages;
+    uint64_t* w_empty = w_full + p.w_stages;
+    uint64_t* t_full = w_empty + p.w_stages;
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][16]
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.x_stages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 3) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int R = p.BD * p.MB;  // accumulators (runs) per tile
+
+    if (warp == 0 && lane == 0) {
+        // ================= activation producer (TMA) =================
+        int xs = 0; uint32_t xph = 0;
+        for (int t = cta; t < p.num_tiles; t += ctas) {
+            TileCoord tc = decode_tile(p, t);
+            for (int g = 0; g < p.KG; ++g) {
+                mbar_wait(&x_empty[xs], xph ^ 1);
+                mbar_arrive_expect_tx(&x_full[xs], p.x_stage_bytes);
+                const CUtensorMap* tm = (g < p.KGa) ? &tmA : &tmB;
+                const int ch0 = (g < p.KGa ? g : g - p.KGa) * p.KC;
+                uint8_t* dst = smem_x + (size_t)xs * p.x_stage_bytes;
+                for (int c = 0; c < p.KC / 8; ++c) {
+                    for (int s = 0; s < p.nslices; ++s) {
+                        long long row0;
+                        if (MODE == MODE_K3) {
+                            const int dpi = (p.whole ? 0 : tc.d0 + 1) - 1 + s;
+                            row0 = ((long long)tc.n * (p.D + 2) + dpi) * p.SS + tc.q0 - p.halo_rows;
+                        } else {
+                            row0 = (long long)t * p.TR;
+                        }
+                        for (int b = 0; b < p.NBX; ++b) {
+                            tma_load_2d(dst + (size_t)c * p.x_plane_bytes + ((size_t)s * p.SRp + (size_t)b * p.BR) * 16,
+                                        tm, &x_full[xs], ch0 + c * 8, (int)(row0 + (long long)b * p.BR));
+                        }
+                    }
+                }
+                if (++xs == p.x_stages) { xs = 0; xph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= weight producer (bulk copy) =================
+        int ws = 0; uint32_t wph = 0;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked) +
+                              (size_t)job * p.KG * p.NTG * p.w_stage_bytes;
+        for (int t = cta; t < p.num_tiles; t += ctas) {
+            for (int g = 0; g < p.KG; ++g) {
+                for (int tg = 0; tg < p.NTG; ++tg) {
+                    mbar_wait(&w_empty[ws], wph ^ 1);
+                    mbar_arrive_expect_tx(&w_full[ws], p.w_stage_bytes);
+                    bulk_load_1d(smem_w + (size_t)ws * p.w_stage_bytes,
+                                 wsrc + (size_t)(g * p.NTG + tg) * p.w_stage_bytes, p.w_stage_bytes, &w_full[ws]);
+                    if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc(128, NMMA, 0, 0);
+        const uint32_t xbase = smem_u32(smem_x), wbase = smem_u32(smem_w);
+        const int ksteps = p.KC / 16;
+        int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
+        int it = 0;
+        for (int t = cta; t < p.num_tiles; t += ctas, ++it) {
+            const int as = it & 1;
+            mbar_wait(&t_empty[as], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            for (int g = 0; g < p.KG; ++g) {
+                mbar_wait(&x_full[xs], xph);
+                tc_fence_after();
+                const uint32_t xst = xbase + xs * p.x_stage_bytes;
+                for (int tg = 0; tg < p.NTG; ++tg) {
+                    mbar_wait(&w_full[ws], wph);
+                    tc_fence_after();
+                    const uint32_t wst = wbase + ws * p.w_stage_bytes;
+                    for (int r = 0; r < R; ++r) {
+                        const int dz = r / p.MB, mb = r - dz * p.MB;
+                        const uint32_t dtm = tmem_base + (uint32_t)((as * R + r) * NMMA);
+                        const uint32_t run_row = (uint32_t)(dz * p.SRp + mb * 128);
+                        for (int tl = 0; tl < p.TG; ++tl) {
+                            const uint32_t arow = run_row + (uint32_t)p.tap_off[tg * p.TG + tl];
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                const uint64_t adesc =
+                                    make_smem_desc(xst + (2 * ks) * p.x_plane_bytes + arow * 16, p.x_plane_bytes, 128);
+                                const uint64_t bdesc = make_smem_desc(
+                                    wst + (uint32_t)((tl * (p.KC / 8) + 2 * ks) * NMMA * 16), NMMA * 16, 128);
+                                const uint32_t acc = (g | tg | tl | ks) != 0;
+                                umma_bf16(dtm, adesc, bdesc, idesc, acc);
+                            }
+                        }
+                    }
+                    umma_commit(&w_empty[ws]);
+                    if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
+                }
+                umma_commit(&x_empty[xs]);
+                if (++xs == p.x_stages) { xs = 0; xph ^= 1; }
+            }
+            umma_commit(&t_full[as]);
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew+32)
+        const int m = ew * 32 + lane;       // row within a 128-row block
+        constexpr int GS = (NMMA >= 16 ? NMMA / 8 : 1);   // channels per GroupNorm group
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        int cur_n = -1;
+        const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr);
+
+        auto flush_stats = [&](int n) {
+            // all 128 epilogue threads participate
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ssum[i] = warp_sum(ssum[i]); ssq[i] = warp_sum(ssq[i]); }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { stat_smem[ew * 16 + i] = ssum[i]; stat_smem[ew * 16 + 8 + i] = ssq[i]; }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (m < 16) {
+                float v = stat_smem[m] + stat_smem[16 + m] + stat_smem[32 + m] + stat_smem[48 + m];
+                p.stats_partial[((size_t)cta * p.N + n) * 16 + m] = v;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        };
+
+        int it = 0;
+        for (int t = cta; t < p.num_tiles; t += ctas, ++it) {
+            const int as = it & 1;
+            TileCoord tc = decode_tile(p, t);
+            if (do_stats && tc.n != cur_n) {
+                if (cur_n >= 0) flush_stats(cur_n);
+                cur_n = tc.n;
+            }
+            mbar_wait(&t_full[as], (it >> 1) & 1);
+            tc_fence_after();
+            for (int r = 0; r < R; ++r) {
+                const int dz = r / p.MB, mb = r - dz * p.MB;
+                // ---- which voxel is this row? ----
+                bool valid;
+                long long orow;      // output row in the padded tensor
+                int vd = 0, vh = 0, vw = 0;
+                if (MODE == MODE_K3) {
+                    const int q = tc.q0 + mb * 128 + m;
+                    const int dpo = (p.whole ? 0 : tc.d0 + 1) + dz;
+                    const int dq = q / p.SS;
+                    const int r2 = q - dq * p.SS;
+                    const int hp = r2 / p.Wp;
+                    const int wp = r2 - hp * p.Wp;
+                    const int dp = dpo + dq;
+                    valid = (q < p.Q0 + p.QN) && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
+                    orow = ((long long)tc.n * (p.D + 2) + dpo) * p.SS + q;
+                    vd = dp - 1; vh = hp - 1; vw = wp - 1;
+                } else {
+                    orow = (long long)t * p.TR + mb * 128 + m;
+                    valid = orow < p.total_rows;
+                }
+                const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((as * R + r) * NMMA);
+#pragma unroll
+                for (int c0 = 0; c0 < NMMA; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + c0, v);
+                    if (EPI == EPI_BF16) {
+                        if (valid) {
+                            if (do_stats) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const int gi = (c0 + i) / GS;
+                                    ssum[gi] += v[i];
+                                    ssq[gi] += v[i] * v[i];
+                                }
+                            }
+                            const size_t off = (size_t)orow * p.Cout_total + (size_t)job * NMMA + c0;
+                            if (p.residual) {
+                                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+                                float f[8];
+                                uint4 q0 = rp[0], q1 = rp[1];
+                                unpack_bf16x8(q0, f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] += f[i];
+                                unpack_bf16x8(q1, f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+                            }
+                            if (p.lrelu_out) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i]);
+                            }
+                            uint4* op = reinterpret_cast<uint4*>(p.out + off);
+                            op[0] = pack_bf16x8(v);
+                            op[1] = pack_bf16x8(v + 8);
+                        }
+                    } else {  // EPI_SIGMOID: first n_out_real columns are real
+                        if (valid && c0 == 0) {
+                            const size_t plane = (size_t)p.D * p.H * p.W;
+                            const size_t vox = ((size_t)vd * p.H + vh) * p.W + vw;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                if (c < p.n_out_real) {
+                                    const float z = v[c] + p.bias[c];
+                                    const size_t o = ((size_t)tc.n * p.n_out_real + c) * plane + vox;
+                                    if (p.logits) p.logits[o] = z;
+                                    p.probs[o] = 1.f / (1.f + __expf(-z));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&t_empty[as]);
+        }
+        if (do_stats && cur_n >= 0) flush_stats(cur_n);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace b200

@@ -1,0 +1,656 @@
+// Memory-bound kernels of the ResUNet hot path: layout conversion, GroupNorm apply/backward,
+// LeakyReLU, residual add, trilinear x2 up-sampling (forward + adjoint), space-to-depth,
+// sigmoid/Dice, weight packing and the deterministic partial reductions.
+//
+// All activation tensors are zero-halo padded NDHWC bf16 (common.cuh).  Kernels that walk a
+// tensor use one CTA per (n, d, h) line: W*C contiguous elements, 16-byte vectors of 8
+// channels per thread, so every global access is a fully coalesced 128-bit transaction and
+// halo elements are never touched (they stay zero).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kEwThreads = 256;
+
+__device__ __forceinline__ void line_coords(const Vol& v, int line, int& n, int& d, int& h) {
+    h = line % v.H;
+    int t = line / v.H;
+    d = t % v.D;
+    n = t / v.D;
+}
+
+// ---------------------------------------------------------------------------------------
+// (B,Creal,D,H,W) fp32 NCDHW  ->  zero-halo NDHWC bf16 with Cpad channels (extra channels 0).
+// Entry layout conversion for model.py:407-412 (`input = x[0]`).
+// ---------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, Vol v, int Creal,
+                                  int Cpad) {
+    int n, d, h;
+    line_coords(v, blockIdx.x, n, d, h);
+    const size_t plane = (size_t)v.D * v.H * v.W;
+    const size_t src0 = (size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W;
+    const long long row0 = v.row(n, d + 1, h + 1, 1);
+    for (int w = threadIdx.x; w < v.W; w += blockDim.x) {
+        for (int c0 = 0; c0 < Cpad; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = (c0 + i < Creal) ? x[src0 + (size_t)(c0 + i) * plane + w] : 0.f;
+            *reinterpret_cast<uint4*>(out + (size_t)(row0 + w) * Cpad + c0) = pack_bf16x8(f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm statistics: conv epilogue partials [ctas][N][16] -> mean/rstd [N][8]
+// (aten::native_group_norm statistics, model.py:95-96/338; eps 1e-5, biased variance)
+// ---------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, int N, double count, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+    const int n = blockIdx.x, g = threadIdx.x;
+    if (g >= 8) return;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < ctas; ++c) {
+        s += (double)partial[((size_t)c * N + n) * 16 + g];
+        q += (double)partial[((size_t)c * N + n) * 16 + 8 + g];
+    }
+    const double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[n * 8 + g] = (float)m;
+    rstd[n * 8 + g] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------------------------------
+// y = act( (x - mean) * rstd * gamma + beta ) [+ residual]      (model.py:105-115, 413)
+//   residual is added AFTER the activation (out = x + lrelu(gn(conv))), model.py:115.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, Vol v, int C,
+                int do_lrelu) {
+    __shared__ float s_scale[256], s_shift[256];
+    int n, d, h;
+    line_coords(v, blockIdx.x, n, d, h);
+    const int gs = C / 8;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        const float sc = rstd[n * 8 + g] * gamma[c];
+        s_scale[c] = sc;
+        s_shift[c] = beta[c] - mean[n * 8 + g] * sc;
+    }
+    __syncthreads();
+    const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
+    const int nvec = v.W * C / 8;
+    const int cvec = C / 8;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int cb = (i % cvec) * 8;
+        float f[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(x + base + (size_t)i * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float z = f[k] * s_scale[cb + k] + s_shift[cb + k];
+            f[k] = do_lrelu ? lrelu(z) : z;
+        }
+        if (residual) {
+            float r[8];
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(residual + base + (size_t)i * 8), r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += r[k];
+        }
+        *reinterpret_cast<uint4*>(out + base + (size_t)i * 8) = pack_bf16x8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm (+LeakyReLU) backward, pass 1: per (n, c) sums  S1 = sum dz, S2 = sum dz * xhat
+//   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
+// grid = (blocks_per_sample, N); each CTA walks lines blockIdx.x, +gridDim.x, ... of sample n and
+// writes partial[n][blockIdx.x][C][2].  Fixed summation order -> deterministic.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
+                     Vol v, int C, int do_lrelu) {
+    __shared__ float s_a[256], s_b[256], s_g[256], s_be[256];
+    __shared__ float s_red[kEwThreads * 16];
+    const int n = blockIdx.y;
+    const int gs = C / 8;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        s_a[c] = rstd[n * 8 + g];
+        s_b[c] = -mean[n * 8 + g] * rstd[n * 8 + g];
+        s_g[c] = gamma[c];
+        s_be[c] = beta[c];
+    }
+    __syncthreads();
+    const int cvec = C / 8;            // divides blockDim, so a thread always sees the same 8 channels
+    const int cb = (threadIdx.x % cvec) * 8;
+    const int nvec = v.W * cvec;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    for (int line = blockIdx.x; line < v.D * v.H; line += gridDim.x) {
+        const int d = line / v.H, h = line % v.H;
+        const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+            float fx[8], fd[8];
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(x + base + (size_t)i * 8), fx);
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(dy + base + (size_t)i * 8), fd);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
+                float dz = fd[k];
+                if (do_lrelu) {
+                    const float z = xh * s_g[cb + k] + s_be[cb + k];
+                    dz = z > 0.f ? dz : 0.01f * dz;
+                }
+                s1[k] += dz;
+                s2[k] += dz * xh;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_red[threadIdx.x * 16 + k] = s1[k]; s_red[threadIdx.x * 16 + 8 + k] = s2[k]; }
+    __syncthreads();
+    // output o = (channel c, which): sum over the threads that own chunk c/8, fixed order
+    for (int o = threadIdx.x; o < C * 2; o += blockDim.x) {
+        const int c = o >> 1, which = o & 1;
+        const int chunk = c / 8, k = c % 8;
+        float acc = 0.f;
+        for (int t = chunk; t < blockDim.x; t += cvec) acc += s_red[t * 16 + which * 8 + k];
+        partial[(((size_t)n * gridDim.x + blockIdx.x) * C + c) * 2 + which] = acc;
+    }
+}
+
+// pass 2: partial[n][blocks][C][2] -> coef[n][C][2] = (A_g, B_g) per channel's group, and
+//         dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.      grid = 1, block = C threads (C <= 256)
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
+                                       const float* __restrict__ gamma, float* __restrict__ coef,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ double sh1[256], sh2[256];
+    const int c = threadIdx.x;
+    const int gs = C / 8;
+    double tg = 0.0, tb = 0.0;
+    for (int n = 0; n < N; ++n) {
+        double a = 0.0, b = 0.0;
+        if (c < C) {
+            for (int k = 0; k < blocks; ++k) {
+                a += (double)partial[(((size_t)n * blocks + k) * C + c) * 2 + 0];
+                b += (double)partial[(((size_t)n * blocks + k) * C + c) * 2 + 1];
+            }
+            tb += a;
+            tg += b;
+            sh1[c] = a * (double)gamma[c];
+            sh2[c] = b * (double)gamma[c];
+        }
+        __syncthreads();
+        if (c < C) {
+            const int g0 = (c / gs) * gs;
+            double A = 0.0, B = 0.0;
+            for (int k = 0; k < gs; ++k) { A += sh1[g0 + k]; B += sh2[g0 + k]; }
+            coef[((size_t)n * C + c) * 2 + 0] = (float)(A / m);
+            coef[((size_t)n * C + c) * 2 + 1] = (float)(B / m);
+        }
+        __syncthreads();
+    }
+    if (c < C) {
+        dgamma[c] = (float)tg;
+        dbeta[c] = (float)tb;
+    }
+}
+
+// pass 3: dx = rstd * (dz*gamma - A_g - xhat*B_g)
+__global__ void __launch_bounds__(kEwThreads)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx, Vol v, int C, int do_lrelu) {
+    __shared__ float s_a[256], s_b[256], s_g[256], s_be[256], s_A[256], s_B[256];
+    int n, d, h;
+    line_coords(v, blockIdx.x, n, d, h);
+    const int gs = C / 8;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        s_a[c] = rstd[n * 8 + g];
+        s_b[c] = -mean[n * 8 + g] * rstd[n * 8 + g];
+        s_g[c] = gamma[c];
+        s_be[c] = beta[c];
+        s_A[c] = coef[((size_t)n * C + c) * 2 + 0];
+        s_B[c] = coef[((size_t)n * C + c) * 2 + 1];
+    }
+    __syncthreads();
+    const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
+    const int cvec = C / 8;
+    const int nvec = v.W * cvec;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int cb = (i % cvec) * 8;
+        float fx[8], fd[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(x + base + (size_t)i * 8), fx);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(dy + base + (size_t)i * 8), fd);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
+            float dz = fd[k];
+            if (do_lrelu) {
+                const float z = xh * s_g[cb + k] + s_be[cb + k];
+                dz = z > 0.f ? dz : 0.01f * dz;
+            }
+            fx[k] = s_a[cb + k] * (dz * s_g[cb + k] - s_A[cb + k] - xh * s_B[cb + k]);
+        }
+        *reinterpret_cast<uint4*>(dx + base + (size_t)i * 8) = pack_bf16x8(fx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Trilinear x2, align_corners=False (model.py:7-14; aten::upsample_trilinear3d) + LeakyReLU
+// (model.py:422).  out[2k] = .25 in[k-1] + .75 in[k], out[2k+1] = .75 in[k] + .25 in[k+1],
+// indices clamped.  `vc` = coarse volume, output volume is 2x in each dim.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void up_taps(int i, int K, int& i0, int& i1, float& w0, float& w1) {
+    const int k = i >> 1;
+    if (i & 1) { i0 = k; i1 = min(k + 1, K - 1); w0 = 0.75f; w1 = 0.25f; }
+    else       { i0 = max(k - 1, 0); i1 = k; w0 = 0.25f; w1 = 0.75f; }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+upsample2x_lrelu_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, Vol vc, int C,
+                        int do_lrelu) {
+    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
+    int n, d, h;
+    line_coords(vf, blockIdx.x, n, d, h);
+    int d0, d1, h0, h1;
+    float wd0, wd1, wh0, wh1;
+    up_taps(d, vc.D, d0, d1, wd0, wd1);
+    up_taps(h, vc.H, h0, h1, wh0, wh1);
+    const size_t r00 = (size_t)vc.row(n, d0 + 1, h0 + 1, 1) * C, r01 = (size_t)vc.row(n, d0 + 1, h1 + 1, 1) * C;
+    const size_t r10 = (size_t)vc.row(n, d1 + 1, h0 + 1, 1) * C, r11 = (size_t)vc.row(n, d1 + 1, h1 + 1, 1) * C;
+    const float c00 = wd0 * wh0, c01 = wd0 * wh1, c10 = wd1 * wh0, c11 = wd1 * wh1;
+    const size_t obase = (size_t)vf.row(n, d + 1, h + 1, 1) * C;
+    const int cvec = C / 8;
+    const int nvec = vf.W * cvec;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int w = i / cvec, cv = i % cvec;
+        int w0, w1;
+        float ww0, ww1;
+        up_taps(w, vc.W, w0, w1, ww0, ww1);
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        const size_t rows[4] = {r00, r01, r10, r11};
+        const float cw[4] = {c00, c01, c10, c11};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float a[8], b[8];
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(in + rows[t] + (size_t)w0 * C + cv * 8), a);
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(in + rows[t] + (size_t)w1 * C + cv * 8), b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += cw[t] * (ww0 * a[k] + ww1 * b[k]);
+        }
+        if (do_lrelu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = lrelu(acc[k]);
+        }
+        *reinterpret_cast<uint4*>(out + obase + (size_t)i * 8) = pack_bf16x8(acc);
+    }
+}
+
+// Adjoint of the above (aten::upsample_trilinear3d_backward fused with leaky_relu_backward):
+// dcoarse[k] = sum_i wt(i -> k) * dy[i] * lrelu'(y[i]); `y` is the forward output (its sign
+// equals the sign of the pre-activation).  One CTA per coarse line.
+__device__ __forceinline__ int down_taps(int k, int K, int* idx, float* wt) {
+    int n = 0;
+    if (k > 0) { idx[n] = 2 * k - 1; wt[n] = 0.25f; ++n; }
+    idx[n] = 2 * k;     wt[n] = 0.75f + (k == 0 ? 0.25f : 0.f);     ++n;
+    idx[n] = 2 * k + 1; wt[n] = 0.75f + (k == K - 1 ? 0.25f : 0.f); ++n;
+    if (k < K - 1) { idx[n] = 2 * k + 2; wt[n] = 0.25f; ++n; }
+    return n;
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+upsample2x_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                            __nv_bfloat16* __restrict__ dcoarse, Vol vc, int C, int do_lrelu) {
+    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
+    int n, d, h;
+    line_coords(vc, blockIdx.x, n, d, h);
+    int di[4], hi[4];
+    float dw[4], hw[4];
+    const int nd = down_taps(d, vc.D, di, dw), nh = down_taps(h, vc.H, hi, hw);
+    const size_t obase = (size_t)vc.row(n, d + 1, h + 1, 1) * C;
+    const int cvec = C / 8;
+    const int nvec = vc.W * cvec;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int w = i / cvec, cv = i % cvec;
+        int wi[4];
+        float ww[4];
+        const int nw = down_taps(w, vc.W, wi, ww);
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int a = 0; a < nd; ++a)
+            for (int b = 0; b < nh; ++b) {
+                const size_t rb = (size_t)vf.row(n, di[a] + 1, hi[b] + 1, 1) * C + cv * 8;
+                const float wab = dw[a] * hw[b];
+                for (int c = 0; c < nw; ++c) {
+                    float g[8], yy[8];
+                    unpack_bf16x8(*reinterpret_cast<const uint4*>(dy + rb + (size_t)wi[c] * C), g);
+                    const float wt = wab * ww[c];
+                    if (do_lrelu) {
+                        unpack_bf16x8(*reinterpret_cast<const uint4*>(y + rb + (size_t)wi[c] * C), yy);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] += wt * (yy[k] > 0.f ? g[k] : 0.01f * g[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] += wt * g[k];
+                    }
+                }
+            }
+        *reinterpret_cast<uint4*>(dcoarse + obase + (size_t)i * 8) = pack_bf16x8(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// space-to-depth / depth-to-space for the k2 s2 conv (model.py:360-363):
+//   s2d[n][d][h][w][((kd*2+kh)*2+kw)*C + c] = fine[n][2d+kd][2h+kh][2w+kw][c]
+// `vc` = coarse volume.  d2s optionally adds a residual (fine layout) - the skip-gradient add.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+s2d_kernel(const __nv_bfloat16* __restrict__ fine, __nv_bfloat16* __restrict__ coarse, Vol vc, int C) {
+    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
+    int n, d, h;
+    line_coords(vc, blockIdx.x, n, d, h);
+    const int cvec2 = 2 * C / 8;                 // vectors per (kw, c) pair run
+    const int nvec = vc.W * 4 * cvec2;
+    const size_t obase = (size_t)vc.row(n, d + 1, h + 1, 1) * (8 * C);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int j = i % cvec2;          // vector inside the 2C-element (kw,c) run
+        int t = i / cvec2;
+        const int dh = t % 4;             // kd*2+kh
+        const int w = t / 4;
+        const size_t src = (size_t)vf.row(n, 2 * d + (dh >> 1) + 1, 2 * h + (dh & 1) + 1, 2 * w + 1) * C + j * 8;
+        const size_t dst = obase + (size_t)w * 8 * C + (size_t)dh * 2 * C + j * 8;
+        *reinterpret_cast<uint4*>(coarse + dst) = *reinterpret_cast<const uint4*>(fine + src);
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+d2s_kernel(const __nv_bfloat16* __restrict__ coarse, const __nv_bfloat16* __restrict__ residual,
+           __nv_bfloat16* __restrict__ fine, Vol vc, int C) {
+    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
+    int n, d, h;
+    line_coords(vc, blockIdx.x, n, d, h);
+    const int cvec2 = 2 * C / 8;
+    const int nvec = vc.W * 4 * cvec2;
+    const size_t ibase = (size_t)vc.row(n, d + 1, h + 1, 1) * (8 * C);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int j = i % cvec2;
+        int t = i / cvec2;
+        const int dh = t % 4;
+        const int w = t / 4;
+        const size_t dst = (size_t)vf.row(n, 2 * d + (dh >> 1) + 1, 2 * h + (dh & 1) + 1, 2 * w + 1) * C + j * 8;
+        const size_t src = ibase + (size_t)w * 8 * C + (size_t)dh * 2 * C + j * 8;
+        uint4 q = *reinterpret_cast<const uint4*>(coarse + src);
+        if (residual) {
+            float a[8], b[8];
+            unpack_bf16x8(q, a);
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(residual + dst), b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += b[k];
+            q = pack_bf16x8(a);
+        }
+        *reinterpret_cast<uint4*>(fine + dst) = q;
+    }
+}
+
+// out = a + b over the interior (gradient accumulation where two paths meet)
+__global__ void __launch_bounds__(kEwThreads)
+add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out,
+           Vol v, int C) {
+    int n, d, h;
+    line_coords(v, blockIdx.x, n, d, h);
+    const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
+    const int nvec = v.W * C / 8;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float fa[8], fb[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(a + base + (size_t)i * 8), fa);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(b + base + (size_t)i * 8), fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+        *reinterpret_cast<uint4*>(out + base + (size_t)i * 8) = pack_bf16x8(fa);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// sigmoid backward + layout: gp (grad wrt probs, fp32 NCDHW, Creal channels), probs ->
+// dlogit = gp * p * (1-p) as zero-halo NDHWC bf16 (Cpad channels) + per-CTA bias-grad partials
+// (model.py:431 backward; conv_output.bias grad).  partial[blocks][4]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+sigmoid_bwd_pack_kernel(const float* __restrict__ gp, const float* __restrict__ probs,
+                        __nv_bfloat16* __restrict__ dlogit, float* __restrict__ bias_partial, Vol v, int Creal,
+                        int Cpad) {
+    __shared__ float s_red[kEwThreads / 32][4];
+    int n, d, h;
+    line_coords(v, blockIdx.x, n, d, h);
+    const size_t plane = (size_t)v.D * v.H * v.W;
+    const size_t src0 = (size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W;
+    const long long row0 = v.row(n, d + 1, h + 1, 1);
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = threadIdx.x; w < v.W; w += blockDim.x) {
+        for (int c0 = 0; c0 < Cpad; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                f[i] = 0.f;
+                if (c0 + i < Creal) {
+                    const size_t o = src0 + (size_t)(c0 + i) * plane + w;
+                    const float p = probs[o];
+                    f[i] = gp[o] * p * (1.f - p);
+                    if (c0 + i < 4) bsum[c0 + i] += f[i];
+                }
+            }
+            *reinterpret_cast<uint4*>(dlogit + (size_t)(row0 + w) * Cpad + c0) = pack_bf16x8(f);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bsum[c] = warp_sum(bsum[c]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int c = 0; c < 4; ++c) s_red[warp][c] = bsum[c];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float a = 0.f;
+        for (int k = 0; k < kEwThreads / 32; ++k) a += s_red[k][threadIdx.x];
+        bias_partial[(size_t)blockIdx.x * 4 + threadIdx.x] = a;
+    }
+}
+
+// out[j] = sum_i partial[i*stride + j], j < n_out, in double, fixed order.
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int count, int stride, int n_out,
+                                       float* __restrict__ out) {
+    const int j = blockIdx.x;
+    __shared__ double sh[256];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) a += (double)partial[(size_t)i * stride + j];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && j < n_out) out[j] = (float)sh[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// Dice_loss_joint (loss.py:98-122).  probs/target fp32 (B,C,S) contiguous, C <= 4.
+//   sums[c] = sum p*g, sums[4+c] = sum (p^2 + g)          (per-CTA partials [blocks][8])
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+dice_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ partial, int B,
+                    int C, long long S) {
+    // grid = (blocks_x, B*C)
+    const int bc = blockIdx.y;
+    const int c = bc % C;
+    const float* pp = p + (size_t)bc * S;
+    const float* gg = g + (size_t)bc * S;
+    float si = 0.f, su = 0.f;
+    const long long nv = (S % 4 == 0) ? S / 4 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(pp)[i];
+        const float4 b = reinterpret_cast<const float4*>(gg)[i];
+        si += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        su += (a.x * a.x + b.x) + (a.y * a.y + b.y) + (a.z * a.z + b.z) + (a.w * a.w + b.w);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nv * 4 + threadIdx.x; i < S; i += blockDim.x) {
+            si += pp[i] * gg[i];
+            su += pp[i] * pp[i] + gg[i];
+        }
+    __shared__ float s_i[kEwThreads / 32], s_u[kEwThreads / 32];
+    si = warp_sum(si);
+    su = warp_sum(su);
+    if ((threadIdx.x & 31) == 0) { s_i[threadIdx.x >> 5] = si; s_u[threadIdx.x >> 5] = su; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < kEwThreads / 32; ++k) { a += s_i[k]; b += s_u[k]; }
+        float* o = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+        o[0] = a;
+        o[1] = b;
+        (void)c;
+    }
+}
+
+// partial[B*C][blocks][2] -> sums[8] (I_c at [c], U_c at [4+c]), no epsilons yet (so that a
+// data-parallel all-reduce can be applied to `sums` before the loss is formed).
+__global__ void dice_sums_kernel(const float* __restrict__ partial, int B, int C, int blocks, float* __restrict__ sums) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    double si = 0.0, su = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < blocks; ++k) {
+            si += (double)partial[((size_t)(b * C + c) * blocks + k) * 2 + 0];
+            su += (double)partial[((size_t)(b * C + c) * blocks + k) * 2 + 1];
+        }
+    sums[c] = (float)si;
+    sums[4 + c] = (float)su;
+}
+
+// loss = priority * (1 - mean_c 2 (I_c + 1e-6) / (U_c + 2e-6))
+__global__ void dice_loss_kernel(const float* __restrict__ sums, int C, float priority, float* __restrict__ loss) {
+    if (threadIdx.x == 0) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc += 2.f * (sums[c] + 1e-6f) / (sums[4 + c] + 2e-6f);
+        loss[0] = priority * (1.f - acc / C);
+    }
+}
+
+// dL/dp = gout * priority * -(2/C) (g U_c - 2 p I_c) / U_c^2     
+__global__ void __launch_bounds__(kEwThreads)
+dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ sums,
+                const float* __restrict__ gout, float priority, float* __restrict__ dp, int B, int C, long long S) {
+    const int bc = blockIdx.y;
+    const int c = bc % C;
+    const float I = sums[c] + 1e-6f, U = sums[4 + c] + 2e-6f;
+    const float k = -gout[0] * priority * (2.f / C) / (U * U);
+    const float* pp = p + (size_t)bc * S;
+    const float* gg = g + (size_t)bc * S;
+    float* dd = dp + (size_t)bc * S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x)
+        dd[i] = k * (gg[i] * U - 2.f * pp[i] * I);
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight packing: PyTorch fp32 (Cout, Cin, kd, kh, kw) -> bf16 UMMA B-operand stage images
+//   packed[job][g][tg][tl][kchunk][n][8]  (one contiguous w_stage per (job, g, tg))
+// GEMM view: Wg[tap][k][n].  `kind` selects how (tap,k,n) map into the PyTorch tensor:
+//   0 forward          k = ci, n = co, tap as is
+//   1 data-gradient k3 k = co, n = ci, tap mirrored (26 - tap); k1: tap 0
+//   2 forward k2s2 over space-to-depth: k = tap8*Cin + ci, n = co
+//   3 data-gradient k2s2 (to space-to-depth layout): k = co, n = tap8*Cin + ci
+// ci_off: first input channel of the PyTorch tensor this GEMM's k (kind 0) or n (kind 1) refers to.
+// ---------------------------------------------------------------------------------------
+struct PackParams {
+    int kind, Cout_w, Cin_w, taps_w;   // PyTorch tensor dims (taps_w = kd*kh*kw)
+    int ci_off;
+    int K_real, N_real;                // logical GEMM extents before padding
+    int n_jobs, KG, NTG, TG, KC, Nmma;
+};
+
+__device__ __forceinline__ float fetch_weight(const float* w, const PackParams& q, int tap, int k, int n) {
+    if (k >= q.K_real || n >= q.N_real) return 0.f;
+    int co, ci, tp;
+    switch (q.kind) {
+        case 0: co = n; ci = k + q.ci_off; tp = tap; break;
+        case 1: co = k; ci = n + q.ci_off; tp = q.taps_w - 1 - tap; break;
+        case 2: co = n; ci = k % q.Cin_w; tp = k / q.Cin_w; break;
+        default: co = k; ci = n % q.Cin_w; tp = n / q.Cin_w; break;
+    }
+    return w[((size_t)co * q.Cin_w + ci) * q.taps_w + tp];
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, PackParams q) {
+    const size_t total = (size_t)q.n_jobs * q.KG * q.NTG * q.TG * (q.KC / 8) * q.Nmma;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t t = i;
+        const int nrow = t % q.Nmma; t /= q.Nmma;
+        const int kch = t % (q.KC / 8); t /= (q.KC / 8);
+        const int tl = t % q.TG; t /= q.TG;
+        const int tg = t % q.NTG; t /= q.NTG;
+        const int g = t % q.KG; t /= q.KG;
+        const int job = (int)t;
+        const int tap = tg * q.TG + tl;
+        const int n = job * q.Nmma + nrow;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fetch_weight(w, q, tap, g * q.KC + kch * 8 + e, n);
+        *reinterpret_cast<uint4*>(packed + i * 8) = pack_bf16x8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// wgrad partial reduction: partial[job][split][nacc][M][Nmma] -> fp32 grad, PyTorch layout.
+//   kind 0: k3 conv  dW[co][ci][kd][kh][kw]           (banded / folded / multi-acc per flags)
+//   kind 1: k1 conv  dW[co][ci_off + ci]
+//   kind 2: k2s2 via s2d: X channel k = tap8*Cin + ci -> dW[co][ci][tap8]
+// ---------------------------------------------------------------------------------------
+struct WgradReduceParams {
+    int kind, Cout_w, Cin_w, taps_w, ci_off;
+    int Cout_g, Cin_g;       // channel extents of dY / X as seen by the GEMM (padded)
+    int banded, folded, accs;
+    int n_jobs, splits, nacc, M, Nmma;
+    int accumulate;          // add into grad instead of overwriting
+};
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q) {
+    const int total = q.Cout_w * q.Cin_w * q.taps_w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tp = i % q.taps_w;
+        const int ci_w = (i / q.taps_w) % q.Cin_w;
+        const int co = i / (q.taps_w * q.Cin_w);
+        int job, t, row, col;
+        if (q.kind == 0) {
+            const int kd = tp / 9, kh = (tp / 3) % 3, kw = tp % 3;
+            job = ((q.banded ? 0 : kd) * (q.accs ? 1 : 3) + (q.accs ? 0 : kh)) * (q.folded ? 1 : 3) + (q.folded ? 0 : kw);
+            row = (q.banded ? kd * q.Cout_g : 0) + co;
+            col = (q.folded ? kw * q.Cin_g : 0) + ci_w;
+            t = q.accs ? kh : 0;
+        } else if (q.kind == 1) {
+            const int ci = ci_w - q.ci_off;
+            if (ci < 0 || ci >= q.Cin_g) continue;
+            job = ci / q.Nmma; col = ci % q.Nmma; row = co; t = 0;
+        } else {
+            const int k = tp * q.Cin_w + ci_w;
+            job = k / q.Nmma; col = k % q.Nmma; row = co; t = 0;
+        }
+        double a = 0.0;
+        for (int s = 0; s < q.splits; ++s)
+            a += (double)partial[((((size_t)job * q.splits + s) * q.nacc + t) * q.M + row) * q.Nmma + col];
+        if (q.accumulate) grad[i] += (float)a;
+        else grad[i] = (float)a;
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,168 @@
+// Weight-gradient GEMM on tcgen05 (sm_100a): dW[tap][co][ci] = sum_rows dY[row][co] * X[row + shift(tap)][ci].
+//
+// Replaces the weight half of aten::convolution_backward reached from train.py:210 for every
+// conv of model.py (k3: model.py:72-73, 336, 348; k1: 393, 401; k2s2 via space-to-depth: 362).
+//
+// The contraction index is the voxel row, so both operands are read MN-major straight out of
+// the same [chunk][row][8 ch] shared-memory planes the forward kernel uses (SWIZZLE_NONE
+// MN-major canonical layout: 8 rows x 16 B core matrices).  Because HBM tensors carry zero
+// halos, dY is zero on every junk row and the sum may run over the plain linear row range.
+//
+// To fill the 64/128-row M dimension with small channel counts, M stacks `nband` copies of dY
+// shifted by whole slices (one per kd tap) and N stacks `nfold` copies of X shifted by one row
+// (one per kw tap); the three kh taps go to separate TMEM accumulators.  Each CTA owns a
+// (job, K-split) pair, accumulates in TMEM over its row range and writes one fp32 partial;
+// `wgrad_reduce_kernel` sums the partials in a fixed order (deterministic) into the fp32
+// gradient in PyTorch (Cout, Cin, kd, kh, kw) layout.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kWgradThreads = 256;
+constexpr int kMaxJobs = 32;
+
+struct WgradKParams {
+    long long total_rows;
+    int Wp, SS;
+    int KT;             // rows per pipeline stage (multiple of 16, <= 256)
+    int XR;             // rows per X plane (KT + 2*Wp when nacc == 3, else KT), multiple of 8
+    int NBXx, BRx;      // TMA boxes per X plane and rows per box
+    int nband_loaded;   // dY bands actually loaded (3 when banded, else 1)
+    int CoC, CiC;       // 8-channel chunks of dY / X per band / fold
+    int nfold, nacc;
+    int M, Nmma;
+    int n_jobs, splits;
+    int stages_per_split;       // pipeline stages each split walks
+    int job_kd[kMaxJobs], job_kh[kMaxJobs], job_kw[kMaxJobs];   // fixed tap offsets in {-1,0,1}
+    int job_xch[kMaxJobs];      // first X channel of this job (N-chunk jobs of wide 1x1 convs)
+    int y_planes, x_planes;     // planes reserved in smem (>= loaded; M/8 and Nmma/8)
+    unsigned y_plane_bytes, x_plane_bytes, stage_bytes, stage_tx_bytes;
+    int stages;
+    unsigned smem_bar_off;
+    unsigned tmem_cols;
+    float* partial;             // [job][split][nacc][M][Nmma]
+};
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ WgradKParams p, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ CUtensorMap tmX) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int job = blockIdx.x % p.n_jobs;
+    const int split = blockIdx.x / p.n_jobs;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* done = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 3) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long first_row = (long long)split * p.stages_per_split * p.KT;
+    int nst = p.stages_per_split;
+    {
+        long long remaining = p.total_rows - first_row;
+        long long need = remaining <= 0 ? 0 : (remaining + p.KT - 1) / p.KT;
+        if (need < nst) nst = (int)need;
+    }
+    const unsigned y_bytes = (unsigned)p.y_planes * p.y_plane_bytes;
+
+    if (warp == 0 && lane == 0) {
+        // ================= producer =================
+        int s = 0; uint32_t ph = 0;
+        for (int i = 0; i < nst; ++i) {
+            const long long r0 = first_row + (long long)i * p.KT;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
+            uint8_t* ybase = smem + (size_t)s * p.stage_bytes;
+            uint8_t* xbase = ybase + y_bytes;
+            for (int b = 0; b < p.nband_loaded; ++b) {
+                const int kd = (p.nband_loaded > 1) ? (b - 1) : p.job_kd[job];
+                const long long yr = r0 - (long long)kd * p.SS;
+                for (int c = 0; c < p.CoC; ++c)
+                    tma_load_2d(ybase + (size_t)(b * p.CoC + c) * p.y_plane_bytes, &tmY, &full[s], c * 8, (int)yr);
+            }
+            for (int f = 0; f < p.nfold; ++f) {
+                const int kw = (p.nfold > 1) ? (f - 1) : p.job_kw[job];
+                const long long xr = r0 + kw + (p.nacc > 1 ? -(long long)p.Wp : (long long)p.job_kh[job] * p.Wp);
+                for (int c = 0; c < p.CiC; ++c)
+                    for (int b = 0; b < p.NBXx; ++b)
+                        tma_load_2d(xbase + (size_t)(f * p.CiC + c) * p.x_plane_bytes + (size_t)b * p.BRx * 16, &tmX,
+                                    &full[s], p.job_xch[job] + c * 8, (int)(xr + (long long)b * p.BRx));
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 2 && lane == 0) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc(p.M, p.Nmma, 1, 1);
+        const uint32_t sbase = smem_u32(smem);
+        int s = 0; uint32_t ph = 0;
+        for (int i = 0; i < nst; ++i) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t ya = sbase + s * p.stage_bytes;
+            const uint32_t xa = ya + y_bytes;
+            for (int t = 0; t < p.nacc; ++t) {
+                const uint32_t xrow = (p.nacc > 1) ? (uint32_t)(t * p.Wp) : 0u;
+                for (int ks = 0; ks < p.KT / 16; ++ks) {
+                    const uint64_t adesc = make_smem_desc(ya + (uint32_t)(ks * 16) * 16, 128, p.y_plane_bytes);
+                    const uint64_t bdesc = make_smem_desc(xa + (xrow + (uint32_t)(ks * 16)) * 16, 128, p.x_plane_bytes);
+                    umma_bf16(tmem_base + (uint32_t)(t * p.Nmma), adesc, bdesc, idesc, (i | ks) != 0);
+                }
+            }
+            umma_commit(&empty[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(done);
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> fp32 partial =================
+        const int ew = warp - 4;
+        float* dst = p.partial + ((size_t)job * p.splits + split) * p.nacc * p.M * p.Nmma;
+        int row; bool row_ok;
+        if (p.M == 128) { row = ew * 32 + lane; row_ok = true; }
+        else            { row = ew * 16 + lane; row_ok = lane < 16; }   // M=64: lanes 0-15 of each quadrant
+        if (nst > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+        }
+        for (int t = 0; t < p.nacc; ++t) {
+            for (int c0 = 0; c0 < p.Nmma; c0 += 16) {
+                float v[16];
+                if (nst > 0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * p.Nmma + c0), v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+                if (row_ok) {
+                    float4* o = reinterpret_cast<float4*>(dst + ((size_t)t * p.M + row) * p.Nmma + c0);
+                    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace b200

@@ -1,0 +1,253 @@
+"""Thin Python wrappers over the C ABI: torch tensors in, raw device pointers out.
+
+PyTorch is used here for device memory and streams only.  Every function launches
+hand-written sm_100a kernels from libbrats_b200.so on `torch.cuda.current_stream()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, WgradDesc, check
+
+MODE_K3, MODE_K1 = 0, 1
+EPI_BF16, EPI_SIGMOID = 0, 1
+W_FWD, W_DGRAD, W_FWD_S2D, W_DGRAD_S2D = 0, 1, 2, 3
+G_K3, G_K1, G_S2D = 0, 1, 2
+GN_EPS = 1e-5
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+# ------------------------------------------------------------------------------------------
+# activation buffers: zero-halo padded NDHWC bf16, shape (N, D+2, H+2, W+2, C)
+# ------------------------------------------------------------------------------------------
+def act_zeros(N, D, H, W, Cc, device):
+    return torch.zeros((N, D + 2, H + 2, W + 2, Cc), dtype=torch.bfloat16, device=device)
+
+
+def act_dims(t):
+    N, Dp, Hp, Wp, Cc = t.shape
+    return N, Dp - 2, Hp - 2, Wp - 2, Cc
+
+
+def act_from_ncdhw(x, Cpad=None):
+    """Reference-side helper (tests): fp32 NCDHW -> act, done with torch ops."""
+    N, Cc, D, H, W = x.shape
+    Cpad = Cpad or pad16(Cc)
+    a = act_zeros(N, D, H, W, Cpad, x.device)
+    a[:, 1:-1, 1:-1, 1:-1, :Cc] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    return a
+
+
+def act_to_ncdhw(a, Cc=None):
+    """Reference-side helper (tests): act interior -> fp32 NCDHW."""
+    Cc = Cc or a.shape[-1]
+    return a[:, 1:-1, 1:-1, 1:-1, :Cc].permute(0, 4, 1, 2, 3).float().contiguous()
+
+
+def pack_input(x, Cpad=16, out=None):
+    N, Cc, D, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+    if out is None:
+        out = act_zeros(N, D, H, W, Cpad, x.device)
+    check(_lib.lib().b200_pack_input(_p(x), _p(out), N, D, H, W, Cc, Cpad, _stream()), "b200_pack_input")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------
+def conv_desc(mode, N, D, H, W, Cin_a, Cout, Cin_b=0, epi=EPI_BF16):
+    return ConvDesc(mode, epi, N, D, H, W, Cin_a, Cin_b, Cout)
+
+
+def conv_ctas(desc):
+    n = _lib.lib().b200_conv_ctas(C.byref(desc))
+    if n < 0:
+        check(1, "b200_conv_ctas")
+    return n
+
+
+def conv_pack_weight(desc, kind, w, ci_off=0, K_real=None, N_real=None, out=None):
+    """w: fp32 (Cout_w, Cin_w, *kernel) cuda tensor -> packed bf16 operand images (uint8 buffer)."""
+    L = _lib.lib()
+    nbytes = L.b200_conv_packed_weight_bytes(C.byref(desc))
+    if nbytes == 0:
+        check(1, "b200_conv_packed_weight_bytes")
+    w = w.detach()
+    assert w.dtype == torch.float32 and w.is_cuda
+    w = w.contiguous()
+    Cout_w, Cin_w = w.shape[0], w.shape[1]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    if K_real is None or N_real is None:
+        if kind == W_FWD:
+            k, n = Cin_w - ci_off, Cout_w
+        elif kind == W_DGRAD:
+            k, n = Cout_w, Cin_w - ci_off
+        elif kind == W_FWD_S2D:
+            k, n = 8 * Cin_w, Cout_w
+        else:
+            k, n = Cout_w, 8 * Cin_w
+        K_real = k if K_real is None else K_real
+        N_real = n if N_real is None else N_real
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    assert out.numel() >= nbytes
+    check(L.b200_conv_pack_weight(C.byref(desc), kind, _p(w), Cout_w, Cin_w, taps, ci_off, K_real, N_real, _p(out),
+                                  _stream()), "b200_conv_pack_weight")
+    return out
+
+
+def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=False, stats=None, bias=None,
+             probs=None, logits=None, n_out_real=0):
+    check(_lib.lib().b200_conv_run(C.byref(desc), _p(src_a), _p(src_b), _p(packed), _p(out), _p(residual),
+                                   1 if lrelu else 0, _p(stats), _p(bias), _p(probs), _p(logits), n_out_real,
+                                   _stream()), "b200_conv_run")
+    return out
+
+
+def wgrad_desc(mode, N, D, H, W, Cout, Cin):
+    return WgradDesc(mode, N, D, H, W, Cout, Cin)
+
+
+def wgrad_workspace(desc, device):
+    nbytes = _lib.lib().b200_wgrad_workspace_bytes(C.byref(desc))
+    if nbytes == 0:
+        check(1, "b200_wgrad_workspace_bytes")
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+
+def wgrad_run(desc, dy, x, grad, kind, ci_off=0, accumulate=False, workspace=None):
+    """grad: fp32 (Cout_w, Cin_w, *kernel) contiguous; written (or accumulated) in place."""
+    if workspace is None:
+        workspace = wgrad_workspace(desc, dy.device)
+    assert grad.dtype == torch.float32 and grad.is_contiguous()
+    taps = 1
+    for s in grad.shape[2:]:
+        taps *= s
+    check(_lib.lib().b200_wgrad_run(C.byref(desc), _p(dy), _p(x), _p(workspace), _p(grad), kind, grad.shape[0],
+                                    grad.shape[1], taps, ci_off, 1 if accumulate else 0, _stream()),
+          "b200_wgrad_run")
+    return grad
+
+
+# ------------------------------------------------------------------------------------------
+# GroupNorm / activation / residual
+# ------------------------------------------------------------------------------------------
+def gn_finalize(stats, ctas, N, Cc, D, H, W, mean, rstd):
+    check(_lib.lib().b200_gn_finalize(_p(stats), ctas, N, Cc, D, H, W, GN_EPS, _p(mean), _p(rstd), _stream()),
+          "b200_gn_finalize")
+
+
+def gn_apply(x, mean, rstd, gamma, beta, out, residual=None, lrelu=True):
+    N, D, H, W, Cc = act_dims(x)
+    check(_lib.lib().b200_gn_apply(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), N, D, H, W,
+                                   Cc, 1 if lrelu else 0, _stream()), "b200_gn_apply")
+    return out
+
+
+def gn_backward_workspace(N, Cc, device):
+    n = _lib.lib().b200_gn_backward_workspace_floats(N, Cc)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
+def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lrelu=True):
+    N, D, H, W, Cc = act_dims(x)
+    check(_lib.lib().b200_gn_backward(_p(x), _p(dy), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma),
+                                      _p(dbeta), _p(workspace), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
+          "b200_gn_backward")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------
+# resampling / layout
+# ------------------------------------------------------------------------------------------
+def upsample2x(coarse, fine, lrelu=True):
+    N, D, H, W, Cc = act_dims(coarse)
+    check(_lib.lib().b200_upsample2x(_p(coarse), _p(fine), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
+          "b200_upsample2x")
+    return fine
+
+
+def upsample2x_backward(dfine, fine_out, dcoarse, lrelu=True):
+    N, D, H, W, Cc = act_dims(dcoarse)
+    check(_lib.lib().b200_upsample2x_backward(_p(dfine), _p(fine_out), _p(dcoarse), N, D, H, W, Cc,
+                                              1 if lrelu else 0, _stream()), "b200_upsample2x_backward")
+    return dcoarse
+
+
+def space_to_depth(fine, coarse):
+    N, D, H, W, C8 = act_dims(coarse)
+    check(_lib.lib().b200_space_to_depth(_p(fine), _p(coarse), N, D, H, W, C8 // 8, _stream()), "b200_space_to_depth")
+    return coarse
+
+
+def depth_to_space(coarse, fine, residual=None):
+    N, D, H, W, C8 = act_dims(coarse)
+    check(_lib.lib().b200_depth_to_space(_p(coarse), _p(residual), _p(fine), N, D, H, W, C8 // 8, _stream()),
+          "b200_depth_to_space")
+    return fine
+
+
+def add(a, b, out):
+    N, D, H, W, Cc = act_dims(a)
+    check(_lib.lib().b200_add(_p(a), _p(b), _p(out), N, D, H, W, Cc, _stream()), "b200_add")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# sigmoid backward / Dice
+# ------------------------------------------------------------------------------------------
+def sigmoid_backward(grad_probs, probs, dlogit_act, dbias, workspace=None):
+    N, Cr, D, H, W = probs.shape
+    Cpad = dlogit_act.shape[-1]
+    if workspace is None:
+        workspace = torch.empty(_lib.lib().b200_sigmoid_backward_workspace_floats(N, D, H), dtype=torch.float32,
+                                device=probs.device)
+    check(_lib.lib().b200_sigmoid_backward(_p(grad_probs), _p(probs), _p(dlogit_act), _p(dbias), _p(workspace), N, D,
+                                           H, W, Cr, Cpad, _stream()), "b200_sigmoid_backward")
+    return dlogit_act
+
+
+def dice_sums(probs, target, sums=None, workspace=None):
+    B, Cc = probs.shape[:2]
+    S = probs[0, 0].numel()
+    if sums is None:
+        sums = torch.zeros(8, dtype=torch.float32, device=probs.device)
+    if workspace is None:
+        workspace = torch.empty(_lib.lib().b200_dice_workspace_floats(B, Cc), dtype=torch.float32, device=probs.device)
+    check(_lib.lib().b200_dice_sums(_p(probs), _p(target), _p(sums), _p(workspace), B, Cc, S, _stream()),
+          "b200_dice_sums")
+    return sums
+
+
+def dice_loss(sums, Cc, priority, loss=None):
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=sums.device)
+    check(_lib.lib().b200_dice_loss(_p(sums), Cc, float(priority), _p(loss), _stream()), "b200_dice_loss")
+    return loss
+
+
+def dice_backward(probs, target, sums, grad_out, priority, grad_probs=None):
+    B, Cc = probs.shape[:2]
+    S = probs[0, 0].numel()
+    if grad_probs is None:
+        grad_probs = torch.empty_like(probs)
+    check(_lib.lib().b200_dice_backward(_p(probs), _p(target), _p(sums), _p(grad_out), float(priority),
+                                        _p(grad_probs), B, Cc, S, _stream()), "b200_dice_backward")
+    return grad_probs

@@ -1,0 +1,126 @@
+/* C ABI of libbrats_b200.so — the B200-native (sm_100a) kernels behind the reference's
+ * `model.UNet` / `loss.Dice_loss_joint` hot path (lachinov/brats2019).
+ *
+ * The reference has no FFI of its own: its hot path is `torch.nn` calls made from Python
+ * (model.py, loss.py).  Each entry point below therefore replaces one ATen operator family the
+ * reference reaches, cited as reference file:line.  The Python mirror of the reference's
+ * `nn.Module` interface (brats2019_b200/model.py, loss.py) binds these with ctypes; see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller; the library owns nothing persistent.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and never synchronise.
+ *  - Return value 0 = ok; non-zero = error, text available from b200_last_error().
+ *  - No CPU fallback, no cuDNN fallback: unsupported shapes or a non-sm_100 device are errors.
+ *  - Activation tensors ("act") are bf16, zero-halo padded NDHWC:
+ *        act[n][dp][hp][wp][c],  dp < D+2, hp < H+2, wp < W+2, interior at index >= 1,
+ *    every halo element must be 0 when a buffer is first handed to the library (allocate
+ *    zero-filled); kernels never write halos.  Channel counts are multiples of 16.
+ */
+#ifndef BRATS_B200_H
+#define BRATS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200_last_error(void);
+/* 0 if device `dev` is compute capability 10.x with tcgen05/TMA available. */
+int b200_device_check(int dev);
+int b200_num_sms(void);
+
+/* ---- layout (model.py:410-412 `input = x[0]`) -------------------------------------------- */
+/* x: fp32 (N,Creal,D,H,W) contiguous  ->  act with Cpad channels (channels >= Creal are 0). */
+int b200_pack_input(const float* x, void* act_out, int N, int D, int H, int W, int Creal, int Cpad, void* stream);
+
+/* ---- convolution, forward and data-gradient (aten::convolution, model.py:72-73, 336, 348,
+ *      362, 393, 401; data half of convolution_backward, train.py:210) ------------------- */
+typedef struct b200_conv_desc {
+    int mode;          /* 0: 3x3x3 stride 1 pad 1;  1: 1x1x1 */
+    int epi;           /* 0: store bf16 act;  1: + bias, sigmoid, store fp32 NCDHW (conv_output) */
+    int N, D, H, W;    /* output volume (== input volume) */
+    int Cin_a, Cin_b;  /* channels of the two K sources (Cin_b = 0 if unused): cat([a,b]) fused */
+    int Cout;          /* GEMM N: stored channels per output row (multiple of 16) */
+} b200_conv_desc;
+
+/* weight "kind" for b200_conv_pack_weight (how the GEMM reads the PyTorch tensor) */
+enum { B200_W_FWD = 0, B200_W_DGRAD = 1, B200_W_FWD_S2D = 2, B200_W_DGRAD_S2D = 3 };
+
+size_t b200_conv_packed_weight_bytes(const b200_conv_desc* d);
+/* CTAs the conv will launch per column job == leading extent of stats_partial. */
+int b200_conv_ctas(const b200_conv_desc* d);
+/* w: fp32 PyTorch layout (Cout_w, Cin_w, taps_w) -> bf16 UMMA operand images in `packed`.
+ * K_real/N_real: logical GEMM extents; rows/cols beyond them are zero padding.
+ * ci_off: first PyTorch input channel addressed (halves of the cat conv). */
+int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const float* w, int Cout_w, int Cin_w, int taps_w,
+                          int ci_off, int K_real, int N_real, void* packed, void* stream);
+/* out = conv(cat[src_a, src_b]) (+ residual) (lrelu optional).
+ * stats_partial (optional, epi 0, mode 0): fp32 [b200_conv_ctas][N][16] per-CTA GroupNorm
+ *   partial sums (8 group sums, 8 group sums of squares) of the fp32 accumulators.
+ * epi 1: bias[n_out_real], probs/logits fp32 (N,n_out_real,D,H,W); logits may be NULL. */
+int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed, void* out,
+                  const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
+                  float* logits, int n_out_real, void* stream);
+
+/* ---- convolution weight gradient (weight half of convolution_backward, train.py:210) ---- */
+typedef struct b200_wgrad_desc {
+    int mode;          /* 0: 3x3x3;  1: 1x1x1 */
+    int N, D, H, W;
+    int Cout;          /* channels of dy (padded, multiple of 16) */
+    int Cin;           /* channels of x  (padded, multiple of 16) */
+} b200_wgrad_desc;
+enum { B200_G_K3 = 0, B200_G_K1 = 1, B200_G_S2D = 2 };
+size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d);
+/* grad: fp32 PyTorch layout (Cout_w, Cin_w, taps_w).  kind: B200_G_*.  accumulate != 0 adds. */
+int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const void* x, void* workspace, float* grad, int kind,
+                   int Cout_w, int Cin_w, int taps_w, int ci_off, int accumulate, void* stream);
+
+/* ---- GroupNorm(8) + LeakyReLU(0.01) + residual add (aten::native_group_norm, leaky_relu_,
+ *      add; model.py:95-96, 105-115, 338, 413) ------------------------------------------- */
+int b200_gn_finalize(const float* stats_partial, int ctas, int N, int C, int D, int H, int W, float eps, float* mean,
+                     float* rstd, void* stream);
+int b200_gn_apply(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  const void* residual, void* out, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
+size_t b200_gn_backward_workspace_floats(int N, int C);
+/* dx, dgamma, dbeta of y = lrelu?(GN(x)); dy is the gradient w.r.t. y. */
+int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, void* dx, float* dgamma, float* dbeta, float* workspace, int N, int D, int H,
+                     int W, int C, int do_lrelu, void* stream);
+
+/* ---- trilinear x2 (aten::upsample_trilinear3d, model.py:7-14) fused with LeakyReLU
+ *      (model.py:422); (N,D,H,W) is the COARSE volume -------------------------------------- */
+int b200_upsample2x(const void* coarse, void* fine, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
+int b200_upsample2x_backward(const void* dfine, const void* fine_out, void* dcoarse, int N, int D, int H, int W, int C,
+                             int do_lrelu, void* stream);
+
+/* ---- space-to-depth helpers for the 2x2x2 stride-2 conv (model.py:360-363) ---------------
+ * (N,D,H,W) is the COARSE volume; coarse has 8*C channels, fine has C. */
+int b200_space_to_depth(const void* fine, void* coarse, int N, int D, int H, int W, int C, void* stream);
+int b200_depth_to_space(const void* coarse, const void* residual, void* fine, int N, int D, int H, int W, int C,
+                        void* stream);
+int b200_add(const void* a, const void* b, void* out, int N, int D, int H, int W, int C, void* stream);
+
+/* ---- sigmoid backward (model.py:431) -> act gradient + conv_output.bias gradient -------- */
+size_t b200_sigmoid_backward_workspace_floats(int N, int D, int H);
+int b200_sigmoid_backward(const float* grad_probs, const float* probs, void* dlogit_act, float* dbias,
+                          float* workspace, int N, int D, int H, int W, int Creal, int Cpad, void* stream);
+
+/* ---- Dice_loss_joint (loss.py:98-122) ---------------------------------------------------- */
+size_t b200_dice_workspace_floats(int B, int C);
+/* sums[8]: I_c = sum p*g at [c], U_c = sum (p^2+g) at [4+c] (no epsilons; all-reducible). */
+int b200_dice_sums(const float* probs, const float* target, float* sums, float* workspace, int B, int C, long long S,
+                   void* stream);
+int b200_dice_loss(const float* sums, int C, float priority, float* loss, void* stream);
+int b200_dice_backward(const float* probs, const float* target, const float* sums, const float* grad_out,
+                       float priority, float* grad_probs, int B, int C, long long S, void* stream);
+
+/* ---- plan introspection (tests): integer dump of the launch plan ---------------- */
+int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);
+int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRATS_B200_H */

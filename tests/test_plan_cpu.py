@@ -1,0 +1,184 @@
+"""CPU: replay the launch plans of the CUDA kernels in numpy/torch and check the ADDRESSING
+(tile decode, halo window, tap row shifts, band/fold stacking, job split) against
+torch.nn.functional on small volumes.  No GPU and no compute call into the library: only the
+host-side planners (b200_*_plan_debug) run.  What the hardware does with the descriptors is
+covered by the `-m gpu` tests; this pins the index arithmetic they are fed.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from brats2019_b200 import _lib
+from brats2019_b200._lib import ConvDesc, WgradDesc
+
+CONV_FIELDS = ("BD MB TR Q0 QN tiles_q tiles_d num_tiles whole n_jobs KG KGa KC NTG TG x_stages w_stages "
+               "x_stage_bytes w_stage_bytes x_plane_bytes SRp BR NBX nslices halo_rows tmem_cols smem ctas Wp SS").split()
+WGRAD_FIELDS = ("KT XR NBXx BRx nband_loaded CoC CiC nfold nacc M Nmma n_jobs splits stages_per_split y_planes "
+                "x_planes y_plane_bytes x_plane_bytes stage_bytes stage_tx_bytes stages tmem_cols smem grid banded "
+                "folded accs Wp SS").split()
+
+
+def conv_plan(mode, N, D, H, W, Cin_a, Cout, Cin_b=0, epi=0):
+    d = ConvDesc(mode, epi, N, D, H, W, Cin_a, Cin_b, Cout)
+    out = (C.c_int * 96)()
+    assert _lib.lib().b200_conv_plan_debug(C.byref(d), out, 96) == 0, _lib.lib().b200_last_error()
+    p = {k: out[i] for i, k in enumerate(CONV_FIELDS)}
+    p["tap_off"] = [out[len(CONV_FIELDS) + i] for i in range(27)]
+    return p
+
+
+def wgrad_plan(mode, N, D, H, W, Cout, Cin):
+    d = WgradDesc(mode, N, D, H, W, Cout, Cin)
+    out = (C.c_int * 256)()
+    assert _lib.lib().b200_wgrad_plan_debug(C.byref(d), out, 256) == 0, _lib.lib().b200_last_error()
+    p = {k: out[i] for i, k in enumerate(WGRAD_FIELDS)}
+    nv = len(WGRAD_FIELDS)
+    p["jobs"] = [tuple(out[nv + 4 * j + i] for i in range(4)) for j in range(p["n_jobs"])]
+    return p
+
+
+def padded_rows(x):
+    """(N,C,D,H,W) -> [rows][C] zero-halo padded, linear row order of common.cuh::Vol::row."""
+    N, Cc, D, H, W = x.shape
+    a = torch.zeros(N, D + 2, H + 2, W + 2, Cc)
+    a[:, 1:-1, 1:-1, 1:-1] = x.permute(0, 2, 3, 4, 1)
+    return a.reshape(-1, Cc)
+
+
+def fetch_rows(rows, start, count):
+    """TMA semantics: rows outside [0, total) read as zero."""
+    total = rows.shape[0]
+    out = torch.zeros(count, rows.shape[1])
+    lo, hi = max(start, 0), min(start + count, total)
+    if hi > lo:
+        out[lo - start:hi - start] = rows[lo:hi]
+    return out
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 4, 4), (2, 5, 6, 9), (1, 8, 8, 8), (1, 3, 16, 40), (2, 16, 16, 16)])
+@pytest.mark.parametrize("cout", [16, 128])
+def test_conv3_addressing(shape, cout):
+    N, D, H, W = shape
+    Cin = 16
+    p = conv_plan(0, N, D, H, W, Cin, cout)
+    torch.manual_seed(0)
+    x = torch.randn(N, Cin, D, H, W)
+    w = torch.randn(4, Cin, 3, 3, 3)              # 4 real output channels are enough to pin addressing
+    ref = F.conv3d(x, w, padding=1)
+    rows = padded_rows(x)
+    Wp, SS, Dp = p["Wp"], p["SS"], D + 2
+    out = torch.zeros(N, 4, D, H, W)
+    written = torch.zeros(N, D, H, W, dtype=torch.int32)
+    wt = w.reshape(4, Cin, 27)
+    assert p["num_tiles"] == (N * p["tiles_d"]) * p["tiles_q"]
+    for t in range(p["num_tiles"]):
+        tq, r = t % p["tiles_q"], t // p["tiles_q"]
+        td, n = r % p["tiles_d"], r // p["tiles_d"]
+        d0, q0 = td * p["BD"], p["Q0"] + tq * p["TR"]
+        # stage image: nslices x SRp rows
+        plane = torch.zeros(p["nslices"] * p["SRp"], Cin)
+        for s in range(p["nslices"]):
+            dpi = (0 if p["whole"] else d0 + 1) - 1 + s
+            row0 = (n * Dp + dpi) * SS + q0 - p["halo_rows"]
+            for b in range(p["NBX"]):
+                plane[s * p["SRp"] + b * p["BR"]: s * p["SRp"] + (b + 1) * p["BR"]] = fetch_rows(rows, row0 + b * p["BR"], p["BR"])
+        for run in range(p["BD"] * p["MB"]):
+            dz, mb = run // p["MB"], run % p["MB"]
+            acc = torch.zeros(128, 4)
+            for tap in range(27):
+                a0 = dz * p["SRp"] + mb * 128 + p["tap_off"][tap]
+                assert a0 + 128 <= plane.shape[0], "A operand would read past the stage plane"
+                acc += plane[a0:a0 + 128] @ wt[:, :, tap].T
+            for m in range(128):
+                q = q0 + mb * 128 + m
+                dpo = (0 if p["whole"] else d0 + 1) + dz
+                dq, r2 = divmod(q, SS)
+                hp, wp = divmod(r2, Wp)
+                dp = dpo + dq
+                valid = q < p["Q0"] + p["QN"] and 1 <= dp <= D and 1 <= hp <= H and 1 <= wp <= W
+                if valid:
+                    orow = (n * Dp + dpo) * SS + q
+                    assert orow == ((n * Dp + dp) * (H + 2) + hp) * Wp + wp
+                    out[n, :, dp - 1, hp - 1, wp - 1] = acc[m]
+                    written[n, dp - 1, hp - 1, wp - 1] += 1
+    assert (written == 1).all(), "every interior voxel must be produced exactly once"
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), atol=1e-4)
+    assert p["smem"] <= 227 * 1024 and p["tmem_cols"] <= 512
+    assert 2 * p["BD"] * p["MB"] * min(cout, 256) <= p["tmem_cols"]
+
+
+def test_conv1_plan_covers_all_rows():
+    p = conv_plan(1, 2, 6, 8, 12, 32, 16, Cin_b=32)
+    total = 2 * 8 * 10 * 14
+    assert p["num_tiles"] * p["TR"] >= total and (p["num_tiles"] - 1) * p["TR"] < total
+    assert p["KG"] == 2 * p["KGa"] and p["KC"] * p["KGa"] == 32 and p["NBX"] * p["BR"] == p["TR"]
+    p = conv_plan(1, 1, 4, 4, 4, 64, 512)
+    assert p["n_jobs"] == 2 and p["tmem_cols"] == 512
+
+
+@pytest.mark.parametrize("cfg", [(16, 16), (32, 32), (64, 64), (128, 128)])
+def test_wgrad3_addressing(cfg):
+    Cout, Cin = cfg
+    N, D, H, W = 2, 3, 4, 5
+    p = wgrad_plan(0, N, D, H, W, Cout, Cin)
+    torch.manual_seed(1)
+    co_r, ci_r = 3, 2          # real channels used for the check (others zero) keeps it fast
+    x = torch.zeros(N, Cin, D, H, W); x[:, :ci_r] = torch.randn(N, ci_r, D, H, W)
+    dy = torch.zeros(N, Cout, D, H, W); dy[:, :co_r] = torch.randn(N, co_r, D, H, W)
+    w = torch.zeros(Cout, Cin, 3, 3, 3, requires_grad=True)
+    F.conv3d(x, w, padding=1).backward(dy)
+    ref = w.grad[:co_r, :ci_r]
+    X, Y = padded_rows(x), padded_rows(dy)
+    total = X.shape[0]
+    Wp, SS, KT = p["Wp"], p["SS"], p["KT"]
+    M, Nm, nacc = p["M"], p["Nmma"], p["nacc"]
+    partial = torch.zeros(p["n_jobs"], p["splits"], nacc, M, Nm)
+    for job, (jkd, jkh, jkw, jx) in enumerate(p["jobs"]):
+        for split in range(p["splits"]):
+            first = split * p["stages_per_split"] * KT
+            nst = min(p["stages_per_split"], max(0, -(-(total - first) // KT)))
+            for i in range(nst):
+                r0 = first + i * KT
+                A = torch.zeros(KT, M)        # [k][m]; unloaded bands stay zero here (garbage on HW)
+                for b in range(p["nband_loaded"]):
+                    kd = (b - 1) if p["nband_loaded"] > 1 else jkd
+                    A[:, b * Cout:(b + 1) * Cout] = fetch_rows(Y, r0 - kd * SS, KT)
+                XR = p["NBXx"] * p["BRx"]
+                Bm = torch.zeros(XR, Nm)
+                for f in range(p["nfold"]):
+                    kw = (f - 1) if p["nfold"] > 1 else jkw
+                    xr = r0 + kw + (-Wp if nacc > 1 else jkh * Wp)
+                    Bm[:, f * Cin:(f + 1) * Cin] = fetch_rows(X, xr, XR)[:, jx:jx + Cin]
+                for t in range(nacc):
+                    xrow = t * Wp if nacc > 1 else 0
+                    assert xrow + KT <= XR
+                    partial[job, split, t] += A.T @ Bm[xrow:xrow + KT]
+    red = partial.sum(1)
+    got = torch.zeros(co_r, ci_r, 3, 3, 3)
+    for co in range(co_r):
+        for ci in range(ci_r):
+            for tp in range(27):
+                kd, kh, kw = tp // 9, (tp // 3) % 3, tp % 3
+                job = ((0 if p["banded"] else kd) * (1 if p["accs"] else 3) + (0 if p["accs"] else kh)) * \
+                      (1 if p["folded"] else 3) + (0 if p["folded"] else kw)
+                row = (kd * Cout if p["banded"] else 0) + co
+                col = (kw * Cin if p["folded"] else 0) + ci
+                t = kh if p["accs"] else 0
+                got[co, ci, kd, kh, kw] = red[job, t, row, col]
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-3)
+    assert p["smem"] <= 227 * 1024 and p["tmem_cols"] <= 512 and p["nacc"] * p["Nmma"] <= p["tmem_cols"]
+    assert p["grid"] == p["splits"] * p["n_jobs"]
+
+
+def test_library_exports_every_declared_symbol():
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "brats_b200.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
