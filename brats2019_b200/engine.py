@@ -1,0 +1,362 @@
+"""Kernel sequencing for the residual 3D U-Net: forward and backward of model.py:407-433 as a
+fixed list of launches into libbrats_b200.so.
+
+The engine owns, per input shape, a set of named zero-halo activation buffers (allocated
+once, reused every step; halos stay zero because no kernel writes them) and the packed bf16
+weight images (re-packed only when a parameter's version counter changes).  All launches go
+to `torch.cuda.current_stream()`; nothing here synchronises the device.
+
+Algebraic restructurings relative to the reference (all exact in real arithmetic):
+  * `Conv1x1(trilinear_x2(x))` (model.py:399-402, 421) runs as `trilinear_x2(Conv1x1(x))`: the
+    1x1x1 conv commutes with the interpolation, and runs on 8x fewer voxels.
+  * `Conv1x1(cat([skip, up]))` (model.py:424-425) runs as one GEMM whose K loop walks the two
+    source tensors; the concatenated tensor is never materialised.
+  * `Conv3d(k=2, s=2)` (model.py:360-363) runs as space-to-depth followed by a 1x1x1 GEMM.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+LEAK = 0.01
+
+
+class _Plan:
+    """Buffers for one (N, D, H, W) input shape."""
+
+    def __init__(self, N, D, H, W, depth, device):
+        self.N, self.device = N, device
+        self.dims = [(D >> l, H >> l, W >> l) for l in range(depth)]
+        self.acts = {}
+        self.misc = {}
+        self.generation = 0
+
+    def act(self, name, level, Cc):
+        key = (name, level, Cc)
+        t = self.acts.get(key)
+        if t is None:
+            D, H, W = self.dims[level]
+            t = ops.act_zeros(self.N, D, H, W, Cc, self.device)
+            self.acts[key] = t
+        return t
+
+    def f32(self, name, n):
+        t = self.misc.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=torch.float32, device=self.device)
+            self.misc[name] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in list(self.acts.values()) + list(self.misc.values()))
+
+
+class Engine:
+    def __init__(self, module):
+        self.m = module
+        self.depth = module.depth
+        self.ch = list(module.number_of_channels)
+        self.enc = list(module.encoder_layers)
+        self.dec = list(module.decoder_layers)
+        self.n_out = module.number_of_outputs
+        if any(c % 16 or c > 128 for c in self.ch):
+            raise RuntimeError("brats2019_b200: channel counts must be multiples of 16 and <= 128, got %s" % self.ch)
+        if self.n_out > 4:
+            raise RuntimeError("brats2019_b200: at most 4 output channels supported")
+        self.plans = {}
+        self.packed = {}
+        self.last = None          # (plan, generation) of the most recent training forward
+
+    # ---------------------------------------------------------------------------------
+    def plan_for(self, x):
+        N, Cc, D, H, W = x.shape
+        q = 1 << (self.depth - 1)
+        if Cc != 4 or D % q or H % q or W % q:
+            raise RuntimeError("brats2019_b200: input must be (N,4,D,H,W) with D,H,W divisible by %d, got %s"
+                               % (q, tuple(x.shape)))
+        key = (N, D, H, W, x.device.index)
+        p = self.plans.get(key)
+        if p is None:
+            p = _Plan(N, D, H, W, self.depth, x.device)
+            self.plans[key] = p
+        return p
+
+    def _params(self):
+        return dict(self.m.named_parameters())
+
+    def _pack(self, desc, kind, name, w, ci_off=0, K_real=None, N_real=None):
+        key = (name, kind, ci_off, desc.mode, desc.Cin_a, desc.Cin_b, desc.Cout)
+        ent = self.packed.get(key)
+        ver = (w._version, w.data_ptr())
+        if ent is None or ent[0] != ver:
+            buf = ops.conv_pack_weight(desc, kind, w, ci_off=ci_off, K_real=K_real, N_real=N_real,
+                                       out=None if ent is None else ent[1])
+            ent = (ver, buf)
+            self.packed[key] = ent
+        return ent[1]
+
+    # ---------------------------------------------------------------------------------
+    # building blocks
+    # ---------------------------------------------------------------------------------
+    def _conv3_gn(self, P, lvl, wname, w, src, cname, Cin_real=None):
+        """c = conv3(src) with fused GroupNorm statistics; returns (c, mean, rstd)."""
+        D, H, W = P.dims[lvl]
+        Cout = w.shape[0]
+        Cin = src.shape[-1]
+        desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, Cin, Cout)
+        pk = self._pack(desc, ops.W_FWD, wname, w, K_real=w.shape[1], N_real=Cout)
+        c = P.act(cname, lvl, Cout)
+        ctas = ops.conv_ctas(desc)
+        stats = P.f32("stats:" + cname, ctas * P.N * 16)
+        ops.conv_run(desc, src, pk, c, stats=stats)
+        mean = P.f32("mean:" + cname, P.N * 8)
+        rstd = P.f32("rstd:" + cname, P.N * 8)
+        ops.gn_finalize(stats, ctas, P.N, Cout, D, H, W, mean, rstd)
+        return c, mean, rstd
+
+    def _residual_fwd(self, P, lvl, prefix, x_in, prm):
+        """model.py:99-117 (after the optional downsample): x + lrelu(gn2(conv2(lrelu(gn1(conv1(x))))))."""
+        Cc = x_in.shape[-1]
+        c1, m1, r1 = self._conv3_gn(P, lvl, prefix + "conv1.conv1.weight", prm[prefix + "conv1.conv1.weight"], x_in,
+                                    prefix + "c1")
+        a1 = ops.gn_apply(c1, m1, r1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
+                          P.act(prefix + "a1", lvl, Cc), lrelu=True)
+        c2, m2, r2 = self._conv3_gn(P, lvl, prefix + "conv2.conv1.weight", prm[prefix + "conv2.conv1.weight"], a1,
+                                    prefix + "c2")
+        out = ops.gn_apply(c2, m2, r2, prm[prefix + "norm2.weight"], prm[prefix + "norm2.bias"],
+                           P.act(prefix + "out", lvl, Cc), residual=x_in, lrelu=True)
+        return out
+
+    def _conv1(self, P, lvl, wname, w, kind, src_a, out, src_b=None, ci_off=0, residual=None):
+        D, H, W = P.dims[lvl]
+        Cout = out.shape[-1]
+        desc = ops.conv_desc(ops.MODE_K1, P.N, D, H, W, src_a.shape[-1], Cout,
+                             Cin_b=0 if src_b is None else src_b.shape[-1])
+        pk = self._pack(desc, kind, wname, w, ci_off=ci_off,
+                        K_real=src_a.shape[-1] + (0 if src_b is None else src_b.shape[-1]), N_real=Cout)
+        return ops.conv_run(desc, src_a, pk, out, src_b=src_b, residual=residual)
+
+    # ---------------------------------------------------------------------------------
+    # forward
+    # ---------------------------------------------------------------------------------
+    def forward(self, x, want_logits=False, training=False):
+        P = self.plan_for(x)
+        P.generation += 1
+        prm = self._params()
+        ch = self.ch
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
+        c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c")
+        h = ops.gn_apply(c, m, r, prm["norm_input.weight"], prm["norm_input.bias"], P.act("in.a", 0, ch[0]),
+                         lrelu=False)                                                     # model.py:412-413
+        for j in range(self.enc[0]):                                                      # model.py:414
+            h = self._residual_fwd(P, 0, "conv_first.%d." % j, h, prm)
+        skips = []
+        for i in range(self.depth - 1):                                                   # model.py:416-418
+            skips.append(h)
+            D, H, W = P.dims[i + 1]
+            s2d = ops.space_to_depth(h, P.act("enc%d.s2d" % i, i + 1, 8 * ch[i]))
+            wname = "encoder_convs.%d.0.downsample.0.weight" % i
+            h = self._conv1(P, i + 1, wname, prm[wname], ops.W_FWD_S2D, s2d, P.act("enc%d.down" % i, i + 1, ch[i + 1]))
+            for j in range(self.enc[i + 1]):
+                h = self._residual_fwd(P, i + 1, "encoder_convs.%d.%d." % (i, j), h, prm)
+        for i in reversed(range(self.depth - 1)):                                         # model.py:420-426
+            wname = "upsampling.%d.1.weight" % i
+            ulo = self._conv1(P, i + 1, wname, prm[wname], ops.W_FWD, h, P.act("dec%d.ulo" % i, i + 1, ch[i]))
+            up = ops.upsample2x(ulo, P.act("dec%d.up" % i, i, ch[i]), lrelu=True)         # model.py:421-422
+            wname = "decoder_convs1x1.%d.weight" % i
+            h = self._conv1(P, i, wname, prm[wname], ops.W_FWD, skips[i], P.act("dec%d.cc" % i, i, ch[i]), src_b=up)
+            for j in range(self.dec[i]):
+                h = self._residual_fwd(P, i, "decoder_convs.%d.%d." % (i, j), h, prm)
+        D, H, W = P.dims[0]
+        desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, ch[0], 16, epi=ops.EPI_SIGMOID)
+        w = prm["conv_output.weight"]
+        pk = self._pack(desc, ops.W_FWD, "conv_output.weight", w, K_real=ch[0], N_real=self.n_out)
+        probs = torch.empty((P.N, self.n_out, D, H, W), dtype=torch.float32, device=x.device)
+        logits = torch.empty_like(probs) if want_logits else None
+        ops.conv_run(desc, h, pk, None, bias=prm["conv_output.bias"].detach(), probs=probs, logits=logits,
+                     n_out_real=self.n_out)                                               # model.py:429-431
+        P.misc["final_h"] = h
+        if training:
+            self.last = (P, P.generation, probs)
+        return (probs, logits) if want_logits else probs
+
+    # ---------------------------------------------------------------------------------
+    # backward
+    # ---------------------------------------------------------------------------------
+    def _wgrad(self, P, lvl, mode, dy, x, grad, kind, ci_off=0, accumulate=False):
+        D, H, W = P.dims[lvl]
+        desc = ops.wgrad_desc(mode, P.N, D, H, W, dy.shape[-1], x.shape[-1])
+        ws = P.misc.get("wgrad_ws")
+        need = ops._lib.lib().b200_wgrad_workspace_bytes(desc) // 4
+        if need == 0:
+            ops.check(1, "b200_wgrad_workspace_bytes")
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.float32, device=P.device)
+            P.misc["wgrad_ws"] = ws
+        ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=ws)
+
+    def _dgrad3(self, P, lvl, wname, w, dy, out, residual=None):
+        D, H, W = P.dims[lvl]
+        desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, dy.shape[-1], out.shape[-1])
+        pk = self._pack(desc, ops.W_DGRAD, wname, w, K_real=w.shape[0], N_real=w.shape[1])
+        return ops.conv_run(desc, dy, pk, out, residual=residual)
+
+    def _gn_bwd(self, P, lvl, cname, x, dy, gamma, beta, dx, grads, gname, bname, lrelu=True):
+        Cc = x.shape[-1]
+        ws = P.misc.get("gn_ws")
+        need = ops._lib.lib().b200_gn_backward_workspace_floats(P.N, Cc)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.float32, device=P.device)
+            P.misc["gn_ws"] = ws
+        dg = torch.empty(Cc, dtype=torch.float32, device=P.device)
+        db = torch.empty(Cc, dtype=torch.float32, device=P.device)
+        ops.gn_backward(x, dy, P.misc["mean:" + cname], P.misc["rstd:" + cname], gamma, beta, dx, dg, db, ws,
+                        lrelu=lrelu)
+        grads[gname] = dg
+        grads[bname] = db
+        return dx
+
+    def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads):
+        """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns grad w.r.t. x_in
+        (written into d_in_buf), which includes the identity path (model.py:115)."""
+        Cc = x_in.shape[-1]
+        c1 = P.act(prefix + "c1", lvl, Cc)
+        a1 = P.act(prefix + "a1", lvl, Cc)
+        c2 = P.act(prefix + "c2", lvl, Cc)
+        t0 = P.act("tmp.g0", lvl, Cc)
+        t1 = P.act("tmp.g1", lvl, Cc)
+        w1n, w2n = prefix + "conv1.conv1.weight", prefix + "conv2.conv1.weight"
+        dc2 = self._gn_bwd(P, lvl, prefix + "c2", c2, d_out, prm[prefix + "norm2.weight"], prm[prefix + "norm2.bias"],
+                           t0, grads, prefix + "norm2.weight", prefix + "norm2.bias")
+        g2 = torch.empty_like(prm[w2n])
+        self._wgrad(P, lvl, 0, dc2, a1, g2, ops.G_K3)
+        grads[w2n] = g2
+        da1 = self._dgrad3(P, lvl, w2n, prm[w2n], dc2, t1)
+        dc1 = self._gn_bwd(P, lvl, prefix + "c1", c1, da1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
+                           t0, grads, prefix + "norm1.weight", prefix + "norm1.bias")
+        g1 = torch.empty_like(prm[w1n])
+        self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3)
+        grads[w1n] = g1
+        return self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out)
+
+    def backward(self, gprobs):
+        """gprobs: fp32 (N, n_out, D, H, W) gradient w.r.t. the returned probabilities.
+        Returns {parameter name: fp32 gradient} for the live parameters."""
+        if self.last is None:
+            raise RuntimeError("brats2019_b200: backward without a training forward")
+        P, gen, probs = self.last
+        if gen != P.generation:
+            raise RuntimeError("brats2019_b200: activations were overwritten by a later forward of the same shape; "
+                               "run backward before the next forward")
+        prm = {k: v.detach() for k, v in self._params().items()}
+        ch = self.ch
+        grads = {}
+        gprobs = gprobs.contiguous().float()
+        D, H, W = P.dims[0]
+        # conv_output + sigmoid (model.py:429-431)
+        dlog = P.act("g.dlogit", 0, 16)
+        dbias = torch.empty(self.n_out, dtype=torch.float32, device=P.device)
+        ops.sigmoid_backward(gprobs, probs, dlog, dbias,
+                             workspace=P.f32("sig_ws", ops._lib.lib().b200_sigmoid_backward_workspace_floats(P.N, D, H)))
+        grads["conv_output.bias"] = dbias
+        h_last = P.misc["final_h"]
+        gw = torch.empty_like(prm["conv_output.weight"])
+        self._wgrad(P, 0, 0, dlog, h_last, gw, ops.G_K3)
+        grads["conv_output.weight"] = gw
+        # ping-pong gradient buffers per level: "g.A"/"g.B"
+        def gbuf(name, lvl, Cc):
+            return P.act("g." + name, lvl, Cc)
+
+        cur = self._dgrad3(P, 0, "conv_output.weight", prm["conv_output.weight"], dlog, gbuf("A", 0, ch[0]))
+        cur_name = "A"
+
+        def other(n):
+            return "B" if n == "A" else "A"
+
+        dskip = [None] * (self.depth - 1)
+        # ---- decoder, levels 0 .. depth-2 (reverse of the forward order) ----
+        for i in range(self.depth - 1):
+            for j in reversed(range(self.dec[i])):
+                prefix = "decoder_convs.%d.%d." % (i, j)
+                x_in = P.act("dec%d.cc" % i, i, ch[i]) if j == 0 else P.act("decoder_convs.%d.%d.out" % (i, j - 1), i, ch[i])
+                nxt = other(cur_name)
+                cur = self._residual_bwd(P, i, prefix, x_in, cur, gbuf(nxt, i, ch[i]), prm, grads)
+                cur_name = nxt
+            # cat conv (model.py:424-425): cc = W[:, :C] skip + W[:, C:] up
+            wname = "decoder_convs1x1.%d.weight" % i
+            w = prm[wname]
+            skip = self._skip_tensor(P, i)
+            up = P.act("dec%d.up" % i, i, ch[i])
+            gcat = torch.empty_like(w)
+            self._wgrad(P, i, 1, cur, skip, gcat, ops.G_K1, ci_off=0)
+            self._wgrad(P, i, 1, cur, up, gcat, ops.G_K1, ci_off=ch[i])
+            grads[wname] = gcat
+            dskip[i] = self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf("skip", i, ch[i]), ci_off=0)
+            dup = self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf(other(cur_name), i, ch[i]), ci_off=ch[i])
+            # lrelu + trilinear adjoint (model.py:421-422)
+            dulo = ops.upsample2x_backward(dup, up, gbuf("ulo", i + 1, ch[i]), lrelu=True)
+            wname = "upsampling.%d.1.weight" % i
+            w = prm[wname]
+            h_lo = self._level_output(P, i + 1)
+            gup = torch.empty_like(w)
+            self._wgrad(P, i + 1, 1, dulo, h_lo, gup, ops.G_K1)
+            grads[wname] = gup
+            cur = self._conv1(P, i + 1, wname, w, ops.W_DGRAD, dulo, gbuf("A", i + 1, ch[i + 1]))
+            cur_name = "A"
+        # At this point `cur` is the gradient w.r.t. the bottleneck output (encoder level depth-1).
+        # ---- encoder, levels depth-1 .. 1 ----
+        for i in reversed(range(self.depth - 1)):
+            lvl = i + 1
+            for j in reversed(range(self.enc[lvl])):
+                prefix = "encoder_convs.%d.%d." % (i, j)
+                x_in = P.act("enc%d.down" % i, lvl, ch[lvl]) if j == 0 else P.act("encoder_convs.%d.%d.out" % (i, j - 1), lvl, ch[lvl])
+                nxt = other(cur_name)
+                cur = self._residual_bwd(P, lvl, prefix, x_in, cur, gbuf(nxt, lvl, ch[lvl]), prm, grads)
+                cur_name = nxt
+            wname = "encoder_convs.%d.0.downsample.0.weight" % i
+            w = prm[wname]
+            s2d = P.act("enc%d.s2d" % i, lvl, 8 * ch[i])
+            gd = torch.empty_like(w)
+            self._wgrad(P, lvl, 1, cur, s2d, gd, ops.G_S2D)
+            grads[wname] = gd
+            ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
+            # back to the fine grid, adding the skip-connection gradient from the decoder
+            cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
+            cur_name = "A"
+        # ---- level 0 head ----
+        for j in reversed(range(self.enc[0])):
+            prefix = "conv_first.%d." % j
+            x_in = P.act("in.a", 0, ch[0]) if j == 0 else P.act("conv_first.%d.out" % (j - 1), 0, ch[0])
+            nxt = other(cur_name)
+            cur = self._residual_bwd(P, 0, prefix, x_in, cur, gbuf(nxt, 0, ch[0]), prm, grads)
+            cur_name = nxt
+        dcin = self._gn_bwd(P, 0, "in.c", P.act("in.c", 0, ch[0]), cur, prm["norm_input.weight"], prm["norm_input.bias"],
+                            gbuf(other(cur_name), 0, ch[0]), grads, "norm_input.weight", "norm_input.bias", lrelu=False)
+        gin = torch.empty_like(prm["conv_input.weight"])
+        self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), gin, ops.G_K3)
+        grads["conv_input.weight"] = gin
+        return grads
+
+    # forward-activation lookups used by backward ---------------------------------------
+    def _level_output(self, P, lvl):
+        """Feature map at encoder/decoder level `lvl` that was fed to upsampling[lvl-1] in forward."""
+        ch = self.ch
+        if lvl == self.depth - 1:
+            i = lvl - 1
+            return P.act("encoder_convs.%d.%d.out" % (i, self.enc[lvl] - 1), lvl, ch[lvl])
+        if self.dec[lvl] > 0:
+            return P.act("decoder_convs.%d.%d.out" % (lvl, self.dec[lvl] - 1), lvl, ch[lvl])
+        return P.act("dec%d.cc" % lvl, lvl, ch[lvl])
+
+    def _skip_tensor(self, P, i):
+        """skip_connections[i] of model.py:417: the level-i encoder output."""
+        ch = self.ch
+        if i == 0:
+            if self.enc[0] > 0:
+                return P.act("conv_first.%d.out" % (self.enc[0] - 1), 0, ch[0])
+            return P.act("in.a", 0, ch[0])
+        return P.act("encoder_convs.%d.%d.out" % (i - 1, self.enc[i] - 1), i, ch[i])
