@@ -52,6 +52,24 @@ class _Plan:
         return sum(t.numel() * t.element_size() for t in list(self.acts.values()) + list(self.misc.values()))
 
 
+class GradStore:
+    """Where backward puts parameter gradients.  Default: one fresh fp32 tensor per parameter."""
+
+    def __init__(self):
+        self.grads = {}
+
+    def new(self, name, like):
+        t = torch.empty(like.shape, dtype=torch.float32, device=like.device)
+        self.grads[name] = t
+        return t
+
+    def mark(self):
+        """Called by Engine.backward at level boundaries: everything allocated so far is final."""
+
+    def finish(self):
+        """Called once at the end of backward."""
+
+
 class Engine:
     def __init__(self, module):
         self.m = module
@@ -212,12 +230,10 @@ class Engine:
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.float32, device=P.device)
             P.misc["gn_ws"] = ws
-        dg = torch.empty(Cc, dtype=torch.float32, device=P.device)
-        db = torch.empty(Cc, dtype=torch.float32, device=P.device)
+        dg = grads.new(gname, gamma)
+        db = grads.new(bname, beta)
         ops.gn_backward(x, dy, P.misc["mean:" + cname], P.misc["rstd:" + cname], gamma, beta, dx, dg, db, ws,
                         lrelu=lrelu)
-        grads[gname] = dg
-        grads[bname] = db
         return dx
 
     def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads):
@@ -232,20 +248,18 @@ class Engine:
         w1n, w2n = prefix + "conv1.conv1.weight", prefix + "conv2.conv1.weight"
         dc2 = self._gn_bwd(P, lvl, prefix + "c2", c2, d_out, prm[prefix + "norm2.weight"], prm[prefix + "norm2.bias"],
                            t0, grads, prefix + "norm2.weight", prefix + "norm2.bias")
-        g2 = torch.empty_like(prm[w2n])
-        self._wgrad(P, lvl, 0, dc2, a1, g2, ops.G_K3)
-        grads[w2n] = g2
+        self._wgrad(P, lvl, 0, dc2, a1, grads.new(w2n, prm[w2n]), ops.G_K3)
         da1 = self._dgrad3(P, lvl, w2n, prm[w2n], dc2, t1)
         dc1 = self._gn_bwd(P, lvl, prefix + "c1", c1, da1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
                            t0, grads, prefix + "norm1.weight", prefix + "norm1.bias")
-        g1 = torch.empty_like(prm[w1n])
-        self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3)
-        grads[w1n] = g1
+        self._wgrad(P, lvl, 0, dc1, x_in, grads.new(w1n, prm[w1n]), ops.G_K3)
         return self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out)
 
-    def backward(self, gprobs):
+    def backward(self, gprobs, store=None):
         """gprobs: fp32 (N, n_out, D, H, W) gradient w.r.t. the returned probabilities.
-        Returns {parameter name: fp32 gradient} for the live parameters."""
+        Returns {parameter name: fp32 gradient} for the live parameters.  `store` decides where
+        gradients live (GradStore: fresh tensors; parallel.BucketedAllReduce: views of one flat
+        buffer, all-reduced bucket by bucket while the rest of backward still runs)."""
         if self.last is None:
             raise RuntimeError("brats2019_b200: backward without a training forward")
         P, gen, probs = self.last
@@ -254,19 +268,16 @@ class Engine:
                                "run backward before the next forward")
         prm = {k: v.detach() for k, v in self._params().items()}
         ch = self.ch
-        grads = {}
+        grads = store if store is not None else GradStore()
         gprobs = gprobs.contiguous().float()
         D, H, W = P.dims[0]
         # conv_output + sigmoid (model.py:429-431)
         dlog = P.act("g.dlogit", 0, 16)
-        dbias = torch.empty(self.n_out, dtype=torch.float32, device=P.device)
+        dbias = grads.new("conv_output.bias", prm["conv_output.bias"])
         ops.sigmoid_backward(gprobs, probs, dlog, dbias,
                              workspace=P.f32("sig_ws", ops._lib.lib().b200_sigmoid_backward_workspace_floats(P.N, D, H)))
-        grads["conv_output.bias"] = dbias
         h_last = P.misc["final_h"]
-        gw = torch.empty_like(prm["conv_output.weight"])
-        self._wgrad(P, 0, 0, dlog, h_last, gw, ops.G_K3)
-        grads["conv_output.weight"] = gw
+        self._wgrad(P, 0, 0, dlog, h_last, grads.new("conv_output.weight", prm["conv_output.weight"]), ops.G_K3)
         # ping-pong gradient buffers per level: "g.A"/"g.B"
         def gbuf(name, lvl, Cc):
             return P.act("g." + name, lvl, Cc)
@@ -291,10 +302,9 @@ class Engine:
             w = prm[wname]
             skip = self._skip_tensor(P, i)
             up = P.act("dec%d.up" % i, i, ch[i])
-            gcat = torch.empty_like(w)
+            gcat = grads.new(wname, w)
             self._wgrad(P, i, 1, cur, skip, gcat, ops.G_K1, ci_off=0)
             self._wgrad(P, i, 1, cur, up, gcat, ops.G_K1, ci_off=ch[i])
-            grads[wname] = gcat
             dskip[i] = self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf("skip", i, ch[i]), ci_off=0)
             dup = self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf(other(cur_name), i, ch[i]), ci_off=ch[i])
             # lrelu + trilinear adjoint (model.py:421-422)
@@ -302,9 +312,8 @@ class Engine:
             wname = "upsampling.%d.1.weight" % i
             w = prm[wname]
             h_lo = self._level_output(P, i + 1)
-            gup = torch.empty_like(w)
-            self._wgrad(P, i + 1, 1, dulo, h_lo, gup, ops.G_K1)
-            grads[wname] = gup
+            self._wgrad(P, i + 1, 1, dulo, h_lo, grads.new(wname, w), ops.G_K1)
+            grads.mark()
             cur = self._conv1(P, i + 1, wname, w, ops.W_DGRAD, dulo, gbuf("A", i + 1, ch[i + 1]))
             cur_name = "A"
         # At this point `cur` is the gradient w.r.t. the bottleneck output (encoder level depth-1).
@@ -320,9 +329,8 @@ class Engine:
             wname = "encoder_convs.%d.0.downsample.0.weight" % i
             w = prm[wname]
             s2d = P.act("enc%d.s2d" % i, lvl, 8 * ch[i])
-            gd = torch.empty_like(w)
-            self._wgrad(P, lvl, 1, cur, s2d, gd, ops.G_S2D)
-            grads[wname] = gd
+            self._wgrad(P, lvl, 1, cur, s2d, grads.new(wname, w), ops.G_S2D)
+            grads.mark()
             ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
             # back to the fine grid, adding the skip-connection gradient from the decoder
             cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
@@ -336,10 +344,10 @@ class Engine:
             cur_name = nxt
         dcin = self._gn_bwd(P, 0, "in.c", P.act("in.c", 0, ch[0]), cur, prm["norm_input.weight"], prm["norm_input.bias"],
                             gbuf(other(cur_name), 0, ch[0]), grads, "norm_input.weight", "norm_input.bias", lrelu=False)
-        gin = torch.empty_like(prm["conv_input.weight"])
-        self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), gin, ops.G_K3)
-        grads["conv_input.weight"] = gin
-        return grads
+        self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), grads.new("conv_input.weight", prm["conv_input.weight"]),
+                    ops.G_K3)
+        grads.finish()
+        return grads.grads
 
     # forward-activation lookups used by backward ---------------------------------------
     def _level_output(self, P, lvl):

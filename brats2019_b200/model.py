@@ -79,15 +79,9 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gprobs):
         eng = ctx.module._engine()
-        grads = eng.backward(gprobs)
-        hook = ctx.module._grad_ready_hook
-        out = []
-        for n in ctx.names:
-            g = grads.get(n)
-            out.append(g)
-        if hook is not None:
-            hook(ctx.names, out)
-        return (None, None, None) + tuple(out)
+        factory = ctx.module._grad_store_factory
+        grads = eng.backward(gprobs, factory() if factory is not None else None)
+        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
 class UNet(nn.Module):
@@ -131,7 +125,7 @@ class UNet(nn.Module):
         self.construct_encoder_convs(depth=depth, number_of_channels=number_of_channels)
         self.construct_upsampling_convs(depth=depth, number_of_channels=number_of_channels)
 
-        self._grad_ready_hook = None     # set by the data-parallel wrapper
+        self._grad_store_factory = None     # set by parallel.DistributedUNet (bucketed all-reduce)
 
     # -- construction helpers, same structure as model.py:358-404 --------------------------
     def _make_encoder_layer(self, in_channels, channels, blocks, stride=1, block=Residual):
@@ -177,7 +171,7 @@ class UNet(nn.Module):
     def __getstate__(self):
         d = self.__dict__.copy()
         d.pop("_eng", None)                  # buffers/plans are rebuilt lazily after unpickling
-        d["_grad_ready_hook"] = None
+        d["_grad_store_factory"] = None
         return d
 
     def dead_parameter_names(self):

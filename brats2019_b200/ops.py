@@ -18,6 +18,13 @@ W_FWD, W_DGRAD, W_FWD_S2D, W_DGRAD_S2D = 0, 1, 2, 3
 G_K3, G_K1, G_S2D = 0, 1, 2
 GN_EPS = 1e-5
 
+# kernels of ours enqueued so far (bench.py reports the count inside its timed region)
+LAUNCHES = [0]
+
+
+def _count(n):
+    LAUNCHES[0] += n
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -64,6 +71,7 @@ def pack_input(x, Cpad=16, out=None):
     if out is None:
         out = act_zeros(N, D, H, W, Cpad, x.device)
     check(_lib.lib().b200_pack_input(_p(x), _p(out), N, D, H, W, Cc, Cpad, _stream()), "b200_pack_input")
+    _count(1)
     return out
 
 
@@ -110,6 +118,7 @@ def conv_pack_weight(desc, kind, w, ci_off=0, K_real=None, N_real=None, out=None
     assert out.numel() >= nbytes
     check(L.b200_conv_pack_weight(C.byref(desc), kind, _p(w), Cout_w, Cin_w, taps, ci_off, K_real, N_real, _p(out),
                                   _stream()), "b200_conv_pack_weight")
+    _count(1)
     return out
 
 
@@ -118,6 +127,7 @@ def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=Fal
     check(_lib.lib().b200_conv_run(C.byref(desc), _p(src_a), _p(src_b), _p(packed), _p(out), _p(residual),
                                    1 if lrelu else 0, _p(stats), _p(bias), _p(probs), _p(logits), n_out_real,
                                    _stream()), "b200_conv_run")
+    _count(1)
     return out
 
 
@@ -143,6 +153,7 @@ def wgrad_run(desc, dy, x, grad, kind, ci_off=0, accumulate=False, workspace=Non
     check(_lib.lib().b200_wgrad_run(C.byref(desc), _p(dy), _p(x), _p(workspace), _p(grad), kind, grad.shape[0],
                                     grad.shape[1], taps, ci_off, 1 if accumulate else 0, _stream()),
           "b200_wgrad_run")
+    _count(2)
     return grad
 
 
@@ -152,12 +163,14 @@ def wgrad_run(desc, dy, x, grad, kind, ci_off=0, accumulate=False, workspace=Non
 def gn_finalize(stats, ctas, N, Cc, D, H, W, mean, rstd):
     check(_lib.lib().b200_gn_finalize(_p(stats), ctas, N, Cc, D, H, W, GN_EPS, _p(mean), _p(rstd), _stream()),
           "b200_gn_finalize")
+    _count(1)
 
 
 def gn_apply(x, mean, rstd, gamma, beta, out, residual=None, lrelu=True):
     N, D, H, W, Cc = act_dims(x)
     check(_lib.lib().b200_gn_apply(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), N, D, H, W,
                                    Cc, 1 if lrelu else 0, _stream()), "b200_gn_apply")
+    _count(1)
     return out
 
 
@@ -171,6 +184,7 @@ def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lr
     check(_lib.lib().b200_gn_backward(_p(x), _p(dy), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma),
                                       _p(dbeta), _p(workspace), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
           "b200_gn_backward")
+    _count(3)
     return dx
 
 
@@ -181,6 +195,7 @@ def upsample2x(coarse, fine, lrelu=True):
     N, D, H, W, Cc = act_dims(coarse)
     check(_lib.lib().b200_upsample2x(_p(coarse), _p(fine), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
           "b200_upsample2x")
+    _count(1)
     return fine
 
 
@@ -188,12 +203,14 @@ def upsample2x_backward(dfine, fine_out, dcoarse, lrelu=True):
     N, D, H, W, Cc = act_dims(dcoarse)
     check(_lib.lib().b200_upsample2x_backward(_p(dfine), _p(fine_out), _p(dcoarse), N, D, H, W, Cc,
                                               1 if lrelu else 0, _stream()), "b200_upsample2x_backward")
+    _count(1)
     return dcoarse
 
 
 def space_to_depth(fine, coarse):
     N, D, H, W, C8 = act_dims(coarse)
     check(_lib.lib().b200_space_to_depth(_p(fine), _p(coarse), N, D, H, W, C8 // 8, _stream()), "b200_space_to_depth")
+    _count(1)
     return coarse
 
 
@@ -201,12 +218,14 @@ def depth_to_space(coarse, fine, residual=None):
     N, D, H, W, C8 = act_dims(coarse)
     check(_lib.lib().b200_depth_to_space(_p(coarse), _p(residual), _p(fine), N, D, H, W, C8 // 8, _stream()),
           "b200_depth_to_space")
+    _count(1)
     return fine
 
 
 def add(a, b, out):
     N, D, H, W, Cc = act_dims(a)
     check(_lib.lib().b200_add(_p(a), _p(b), _p(out), N, D, H, W, Cc, _stream()), "b200_add")
+    _count(1)
     return out
 
 
@@ -221,6 +240,7 @@ def sigmoid_backward(grad_probs, probs, dlogit_act, dbias, workspace=None):
                                 device=probs.device)
     check(_lib.lib().b200_sigmoid_backward(_p(grad_probs), _p(probs), _p(dlogit_act), _p(dbias), _p(workspace), N, D,
                                            H, W, Cr, Cpad, _stream()), "b200_sigmoid_backward")
+    _count(2)
     return dlogit_act
 
 
@@ -233,6 +253,7 @@ def dice_sums(probs, target, sums=None, workspace=None):
         workspace = torch.empty(_lib.lib().b200_dice_workspace_floats(B, Cc), dtype=torch.float32, device=probs.device)
     check(_lib.lib().b200_dice_sums(_p(probs), _p(target), _p(sums), _p(workspace), B, Cc, S, _stream()),
           "b200_dice_sums")
+    _count(2)
     return sums
 
 
@@ -240,6 +261,7 @@ def dice_loss(sums, Cc, priority, loss=None):
     if loss is None:
         loss = torch.empty(1, dtype=torch.float32, device=sums.device)
     check(_lib.lib().b200_dice_loss(_p(sums), Cc, float(priority), _p(loss), _stream()), "b200_dice_loss")
+    _count(1)
     return loss
 
 
@@ -250,4 +272,5 @@ def dice_backward(probs, target, sums, grad_out, priority, grad_probs=None):
         grad_probs = torch.empty_like(probs)
     check(_lib.lib().b200_dice_backward(_p(probs), _p(target), _p(sums), _p(grad_out), float(priority),
                                         _p(grad_probs), B, Cc, S, _stream()), "b200_dice_backward")
+    _count(1)
     return grad_probs
