@@ -33,6 +33,8 @@ _PROTOS = {
     "b200_last_error": (C.c_char_p, []),
     "b200_device_check": (c_int, [c_int]),
     "b200_num_sms": (c_int, []),
+    "b200_act_guard_rows": (c_ll, [c_int, c_int, c_int]),
+    "b200_act_plane_rows": (c_ll, [c_int, c_int, c_int, c_int]),
     "b200_pack_input": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_conv_packed_weight_bytes": (c_size_t, [C.POINTER(ConvDesc)]),
     "b200_conv_ctas": (c_int, [C.POINTER(ConvDesc)]),

@@ -4,10 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
-#include <mutex>
 
 #include "../../include/brats_b200.h"
 #include "conv_gemm.cuh"
@@ -63,38 +63,18 @@ extern "C" int b200_device_check(int dev) {
 }
 
 // ---------------------------------------------------------------------------------------
-// TMA tensor maps (driver entry point fetched at run time: no link-time libcuda dependency)
+// activation geometry (chunk-planar zero-halo layout, common.cuh)
 // ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-static std::mutex g_mu;
-
-static int get_encode() {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_encode) return 0;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available");
-    g_encode = (EncodeTiledFn)fn;
-    return 0;
+extern "C" long long b200_act_guard_rows(int D, int H, int W) {
+    Vol v{1, D, H, W};
+    return v.guard_rows();
 }
-
-// 2D map over an activation tensor viewed as [rows][C] bf16; box = 8 channels x box_rows rows.
-static int make_act_map(CUtensorMap* m, const void* ptr, int C, long long rows, int box_rows) {
-    if (get_encode()) return 1;
-    if (((uintptr_t)ptr & 15) != 0) return fail("activation pointer not 16-byte aligned");
-    if (box_rows < 1 || box_rows > 256) return fail("TMA box rows %d out of range", box_rows);
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {8, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with %d (C=%d rows=%lld box=%d)", (int)r, C, rows, box_rows);
+extern "C" long long b200_act_plane_rows(int N, int D, int H, int W) {
+    Vol v{N, D, H, W};
+    return v.plane_rows();
+}
+static int check_ptr16(const void* p, const char* what) {
+    if (((uintptr_t)p & 15) != 0) return fail("%s pointer not 16-byte aligned", what);
     return 0;
 }
 
@@ -160,15 +140,13 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
         for (int whole = 0; whole < 2; ++whole)
             for (int BD : {1, 2, 4}) {
                 if (whole && BD != 1) continue;
-                if (BD > d->D) continue;
+                if (BD > d->D || d->D % BD) continue;     // no ragged slice groups
                 for (int MB : {1, 2, 4}) {
                     const int R = BD * MB;
                     if (2 * R * Nm > 512) continue;
                     const int TR = 128 * MB;
                     const int SR = TR + 2 * p.Wp + 2;
-                    const int NBX = ceil_div(SR, 256);
-                    const int BR = (ceil_div(SR, NBX) + 7) / 8 * 8;
-                    const int SRp = NBX * BR;
+                    const int SRp = (SR + 7) / 8 * 8;
                     const unsigned xst = 2u * (BD + 2) * SRp * 16;
                     if (2 * xst + 2 * p.w_stage_bytes + bar_bytes > kMaxSmem) continue;
                     long long QN, tiles;
@@ -189,9 +167,7 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
         p.BD = bBD; p.MB = bMB; p.whole = bWhole;
         p.TR = 128 * p.MB;
         const int SR = p.TR + 2 * p.Wp + 2;
-        p.NBX = ceil_div(SR, 256);
-        p.BR = (ceil_div(SR, p.NBX) + 7) / 8 * 8;
-        p.SRp = p.NBX * p.BR;
+        p.SRp = (SR + 7) / 8 * 8;
         p.nslices = p.BD + 2;
         p.halo_rows = p.Wp + 1;
         p.x_plane_bytes = (unsigned)p.nslices * p.SRp * 16;
@@ -213,7 +189,7 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
         p.MB = (Nm <= 128) ? 2 : 1;
         p.BD = 1; p.whole = 0;
         p.TR = 128 * p.MB;
-        p.NBX = p.MB; p.BR = 128; p.SRp = p.TR;
+        p.SRp = p.TR;
         p.nslices = 1; p.halo_rows = 0;
         p.x_plane_bytes = (unsigned)p.TR * 16;
         p.x_stage_bytes = (unsigned)(p.KC / 8) * p.x_plane_bytes;
@@ -277,15 +253,14 @@ extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const fl
 }
 
 template <int MODE, int EPI, int NM>
-static int launch_conv(const ConvKParams& p, const CUtensorMap& a, const CUtensorMap& b, unsigned smem, int grid,
-                       cudaStream_t st) {
+static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<MODE, EPI, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kMaxSmem));
         attr_set = true;
     }
-    conv_gemm_kernel<MODE, EPI, NM><<<grid, kConvThreads, smem, st>>>(p, a, b);
+    conv_gemm_kernel<MODE, EPI, NM><<<grid, kConvThreads, smem, st>>>(p);
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
 }
@@ -304,21 +279,28 @@ extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const v
         return fail("conv: GroupNorm statistics only for the k3 bf16 path");
     cudaStream_t st = (cudaStream_t)stream;
     p.wpacked = (const __nv_bfloat16*)packed;
-    p.out = (__nv_bfloat16*)out;
-    p.residual = (const __nv_bfloat16*)residual;
     p.lrelu_out = lrelu_out;
     p.stats_partial = stats_partial;
     p.bias = bias; p.probs = probs; p.logits = logits; p.n_out_real = n_out_real;
+    {
+        const char* dbg = getenv("B200_CONV_DEBUG");     // perf probes only (tests/perf_probe.py)
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
     const int ctas = conv_grid_ctas(p);
     const int grid = ctas * p.n_jobs;
     if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)ctas * p.N * 16 * sizeof(float), st));
-    CUtensorMap ma, mb;
-    if (make_act_map(&ma, src_a, d->Cin_a, p.total_rows, p.BR)) return 1;
-    if (d->Cin_b > 0) { if (make_act_map(&mb, src_b, d->Cin_b, p.total_rows, p.BR)) return 1; }
-    else mb = ma;
+    if (check_ptr16(src_a, "src_a") || check_ptr16(src_b, "src_b") || check_ptr16(out, "out") ||
+        check_ptr16(residual, "residual") || check_ptr16(packed, "packed weights"))
+        return 1;
+    Vol vol{d->N, d->D, d->H, d->W};
+    p.src_a = make_act(src_a, vol);
+    p.src_b = make_act(d->Cin_b > 0 ? src_b : src_a, vol);
+    p.out = make_act(out, vol);
+    p.residual = make_act(residual, vol);
+    if (p.x_stage_bytes >= (1u << 20) || p.w_stage_bytes >= (1u << 20)) return fail("conv: stage exceeds the mbarrier tx-count range");
     const unsigned smem = p.smem_bar_off + 1024;
     const int Nm = conv_nmma(d);
-#define CONV_CASE(MODE, EPI, NM) return launch_conv<MODE, EPI, NM>(p, ma, mb, smem, grid, st)
+#define CONV_CASE(MODE, EPI, NM) return launch_conv<MODE, EPI, NM>(p, smem, grid, st)
     if (d->epi == EPI_SIGMOID) CONV_CASE(MODE_K3, EPI_SIGMOID, 16);
     if (d->mode == MODE_K3) {
         switch (Nm) {
@@ -348,7 +330,6 @@ struct WgradPlan {
     int banded, folded, accs;
     unsigned smem;
     int grid;
-    int BRy;
 };
 
 static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
@@ -403,14 +384,12 @@ static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
     const unsigned bar_bytes = 512;
     k.stages = 0;
     for (int KT : {256, 128, 64}) {
-        const int XR = KT + (k.nacc > 1 ? 2 * k.Wp : 0);
-        const int NBX = ceil_div(XR, 256);
-        const int BR = (ceil_div(XR, NBX) + 7) / 8 * 8;
-        const unsigned ypl = (unsigned)KT * 16, xpl = (unsigned)NBX * BR * 16;
+        const int XR = (KT + (k.nacc > 1 ? 2 * k.Wp : 0) + 7) / 8 * 8;
+        const unsigned ypl = (unsigned)KT * 16, xpl = (unsigned)XR * 16;
         const unsigned stage = k.y_planes * ypl + k.x_planes * xpl;
         int stages = (int)((kMaxSmem - bar_bytes) / stage);
         if (stages >= 2) {
-            k.KT = KT; k.XR = XR; k.NBXx = NBX; k.BRx = BR;
+            k.KT = KT; k.XR = XR;
             k.y_plane_bytes = ypl; k.x_plane_bytes = xpl; k.stage_bytes = stage;
             k.stages = std::min(stages, 4);
             break;
@@ -427,7 +406,6 @@ static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
     k.stages_per_split = ceil_div(total_stages, k.splits);
     k.splits = ceil_div(total_stages, k.stages_per_split);
     P.grid = k.splits * k.n_jobs;
-    P.BRy = k.KT;
     return 0;
 }
 
@@ -453,10 +431,12 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
         attr_set = true;
     }
     P.k.partial = (float*)workspace;
-    CUtensorMap my, mx;
-    if (make_act_map(&my, dy, d->Cout, P.k.total_rows, P.BRy)) return 1;
-    if (make_act_map(&mx, x, d->Cin, P.k.total_rows, P.k.BRx)) return 1;
-    wgrad_gemm_kernel<<<P.grid, kWgradThreads, P.smem, st>>>(P.k, my, mx);
+    if (check_ptr16(dy, "dy") || check_ptr16(x, "x")) return 1;
+    Vol vol{d->N, d->D, d->H, d->W};
+    P.k.dy = make_act(dy, vol);
+    P.k.x = make_act(x, vol);
+    if (P.k.stage_tx_bytes >= (1u << 20)) return fail("wgrad: stage exceeds the mbarrier tx-count range");
+    wgrad_gemm_kernel<<<P.grid, kWgradThreads, P.smem, st>>>(P.k);
     LAUNCH_OK("wgrad_gemm_kernel");
     WgradReduceParams q;
     q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
@@ -483,7 +463,8 @@ extern "C" int b200_pack_input(const float* x, void* act_out, int N, int D, int 
                                void* stream) {
     if (check_act(N, D, H, W, Cpad) || Creal > Cpad) return fail("pack_input: bad channels %d -> %d", Creal, Cpad);
     Vol v{N, D, H, W};
-    pack_input_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)act_out, v, Creal, Cpad);
+    if (Creal > 8) return fail("pack_input: at most 8 real channels");
+    pack_input_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(x, make_act(act_out, v), v, Creal);
     LAUNCH_OK("pack_input_kernel");
     return 0;
 }
@@ -502,9 +483,9 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
                              int do_lrelu, void* stream) {
     if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_apply: C=%d unsupported", C);
     Vol v{N, D, H, W};
-    gn_apply_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, mean, rstd, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, v, C,
-        do_lrelu);
+    gn_apply_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(x, v), mean, rstd, gamma, beta,
+                                                                        make_act(residual, v), make_act(out, v), v, C,
+                                                                        do_lrelu);
     LAUNCH_OK("gn_apply_kernel");
     return 0;
 }
@@ -526,14 +507,14 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     const int blocks = gn_bwd_blocks(N, D, H);
     float* partial = workspace;
     float* coef = workspace + (size_t)N * (4 * num_sms()) * C * 2;
-    gn_bwd_reduce_kernel<<<dim3(blocks, N), kEwThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean,
-                                                                rstd, gamma, beta, partial, v, C, do_lrelu);
+    gn_bwd_reduce_kernel<<<dim3(blocks, N), kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                                partial, v, C, do_lrelu);
     LAUNCH_OK("gn_bwd_reduce_kernel");
     const double m = (double)(C / 8) * D * H * W;
     gn_bwd_finalize_kernel<<<1, 256, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
     LAUNCH_OK("gn_bwd_finalize_kernel");
-    gn_bwd_apply_kernel<<<N * D * H, kEwThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, mean, rstd,
-                                                         gamma, beta, coef, (__nv_bfloat16*)dx, v, C, do_lrelu);
+    gn_bwd_apply_kernel<<<N * D * H, kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
+                                                         make_act(dx, v), v, C, do_lrelu);
     LAUNCH_OK("gn_bwd_apply_kernel");
     return 0;
 }
@@ -542,8 +523,9 @@ extern "C" int b200_upsample2x(const void* coarse, void* fine, int N, int D, int
                                void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
-    upsample2x_lrelu_kernel<<<N * 2 * D * 2 * H, kEwThreads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)coarse, (__nv_bfloat16*)fine, vc, C, do_lrelu);
+    Vol vf{N, 2 * D, 2 * H, 2 * W};
+    upsample2x_lrelu_kernel<<<N * 2 * D * 2 * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(coarse, vc),
+                                                                                       make_act(fine, vf), vc, C, do_lrelu);
     LAUNCH_OK("upsample2x_lrelu_kernel");
     return 0;
 }
@@ -551,8 +533,9 @@ extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out,
                                         int W, int C, int do_lrelu, void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
+    Vol vf{N, 2 * D, 2 * H, 2 * W};
     upsample2x_lrelu_bwd_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dfine, (const __nv_bfloat16*)fine_out, (__nv_bfloat16*)dcoarse, vc, C, do_lrelu);
+        make_act(dfine, vf), make_act(fine_out, vf), make_act(dcoarse, vc), vc, C, do_lrelu);
     LAUNCH_OK("upsample2x_lrelu_bwd_kernel");
     return 0;
 }
@@ -560,8 +543,8 @@ extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out,
 extern "C" int b200_space_to_depth(const void* fine, void* coarse, int N, int D, int H, int W, int C, void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
-    s2d_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)fine, (__nv_bfloat16*)coarse,
-                                                                  vc, C);
+    Vol vf{N, 2 * D, 2 * H, 2 * W};
+    s2d_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(fine, vf), make_act(coarse, vc), vc, C);
     LAUNCH_OK("s2d_kernel");
     return 0;
 }
@@ -569,17 +552,16 @@ extern "C" int b200_depth_to_space(const void* coarse, const void* residual, voi
                                    int C, void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
-    d2s_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)coarse,
-                                                                  (const __nv_bfloat16*)residual,
-                                                                  (__nv_bfloat16*)fine, vc, C);
+    Vol vf{N, 2 * D, 2 * H, 2 * W};
+    d2s_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(coarse, vc), make_act(residual, vf),
+                                                                  make_act(fine, vf), vc, C);
     LAUNCH_OK("d2s_kernel");
     return 0;
 }
 extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, int H, int W, int C, void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
     Vol v{N, D, H, W};
-    add_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
-                                                                  (__nv_bfloat16*)out, v, C);
+    add_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(a, v), make_act(b, v), make_act(out, v), v, C);
     LAUNCH_OK("add_kernel");
     return 0;
 }
@@ -588,11 +570,11 @@ extern "C" size_t b200_sigmoid_backward_workspace_floats(int N, int D, int H) { 
 extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs, void* dlogit_act, float* dbias,
                                      float* workspace, int N, int D, int H, int W, int Creal, int Cpad, void* stream) {
     if (check_act(N, D, H, W, Cpad) || Creal > 4) return fail("sigmoid_backward: Creal=%d Cpad=%d unsupported", Creal, Cpad);
+    (void)Cpad;     // only chunk 0 is written; the other chunks of the destination stay zero
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = N * D * H;
-    sigmoid_bwd_pack_kernel<<<blocks, kEwThreads, 0, st>>>(grad_probs, probs, (__nv_bfloat16*)dlogit_act, workspace, v,
-                                                          Creal, Cpad);
+    sigmoid_bwd_pack_kernel<<<blocks, kEwThreads, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal);
     LAUNCH_OK("sigmoid_bwd_pack_kernel");
     if (dbias) {
         reduce_partials_kernel<<<Creal, 256, 0, st>>>(workspace, blocks, 4, Creal, dbias);
@@ -638,7 +620,7 @@ extern "C" int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out
     if (plan_conv(d, p)) return 1;
     const int vals[] = {p.BD, p.MB, p.TR, p.Q0, p.QN, p.tiles_q, p.tiles_d, p.num_tiles, p.whole, p.n_jobs,
                         p.KG, p.KGa, p.KC, p.NTG, p.TG, p.x_stages, p.w_stages, (int)p.x_stage_bytes,
-                        (int)p.w_stage_bytes, (int)p.x_plane_bytes, p.SRp, p.BR, p.NBX, p.nslices, p.halo_rows,
+                        (int)p.w_stage_bytes, (int)p.x_plane_bytes, p.SRp, p.nslices, p.halo_rows,
                         (int)p.tmem_cols, (int)(p.smem_bar_off + 1024), conv_grid_ctas(p), p.Wp, p.SS};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv + kMaxTaps) return fail("plan_debug: need %d ints", nv + kMaxTaps);
@@ -651,7 +633,7 @@ extern "C" int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_o
     WgradPlan P;
     if (plan_wgrad(d, P)) return 1;
     const WgradKParams& k = P.k;
-    const int vals[] = {k.KT, k.XR, k.NBXx, k.BRx, k.nband_loaded, k.CoC, k.CiC, k.nfold, k.nacc, k.M, k.Nmma,
+    const int vals[] = {k.KT, k.XR, k.nband_loaded, k.CoC, k.CiC, k.nfold, k.nacc, k.M, k.Nmma,
                         k.n_jobs, k.splits, k.stages_per_split, k.y_planes, k.x_planes, (int)k.y_plane_bytes,
                         (int)k.x_plane_bytes, (int)k.stage_bytes, (int)k.stage_tx_bytes, k.stages, (int)k.tmem_cols,
                         (int)P.smem, P.grid, P.banded, P.folded, P.accs, k.Wp, k.SS};

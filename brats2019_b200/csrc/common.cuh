@@ -9,10 +9,19 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------
-// Activation layout in HBM ("zero-halo padded NDHWC")
-//   tensor[n][dp][hp][wp][c]   dp in [0,D+2), hp in [0,H+2), wp in [0,W+2), bf16
-//   interior voxels are dp,hp,wp >= 1; every halo element is 0 and is never written.
-//   A "row" is one voxel (C channels); rows are numbered linearly over the padded volume.
+// Activation layout in HBM: chunk-planar, zero-halo ("NC/8 DHW 8c" with halos and guards)
+//
+//   act[chunk][guard + row + guard][8]     bf16, chunk = channel / 8
+//   row = ((n*(D+2) + dp)*(H+2) + hp)*(W+2) + wp    linear index over the zero-padded volume
+//
+//   * interior voxels are dp,hp,wp >= 1; every halo voxel is 0 and is never written, so a
+//     3x3x3 tap is a constant row shift and needs no boundary handling;
+//   * `guard` zero rows before and after each plane let tiles run past either end of the
+//     tensor (ragged last tile, halo of the first/last slice, wgrad K tails) without any
+//     out-of-bounds logic;
+//   * the 8 channels x R rows a tensor-core operand needs are ONE contiguous range of a plane,
+//     fetched by a single cp.async.bulk, and land in shared memory already in the SWIZZLE_NONE
+//     canonical UMMA layout (8 rows x 16 B core matrices).
 // ---------------------------------------------------------------------------------------
 struct Vol {
     int N, D, H, W;
@@ -25,7 +34,26 @@ struct Vol {
     __host__ __device__ long long row(int n, int dp, int hp, int wp) const {
         return (((long long)n * Dp() + dp) * Hp() + hp) * Wp() + wp;
     }
+    // zero rows kept before and after every chunk plane
+    __host__ __device__ long long guard_rows() const { return (slice_rows() + 2LL * Wp() + 1024 + 7) / 8 * 8; }
+    __host__ __device__ long long plane_rows() const { return total_rows() + 2 * guard_rows(); }
 };
+
+// A view of one activation tensor: base pointer of the allocation + plane geometry.
+struct ActRef {
+    __nv_bfloat16* base;
+    long long plane_rows, guard;
+    __host__ __device__ __nv_bfloat16* at(int chunk, long long row) const {
+        return base + ((size_t)chunk * plane_rows + guard + row) * 8;
+    }
+};
+__host__ __device__ inline ActRef make_act(const void* p, const Vol& v) {
+    ActRef a;
+    a.base = (__nv_bfloat16*)p;
+    a.plane_rows = v.plane_rows();
+    a.guard = v.guard_rows();
+    return a;
+}
 
 // ---------------------------------------------------------------------------------------
 // small utilities
@@ -145,8 +173,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+    // no "memory" clobber: ordering against the mbarrier waits is provided by tc_fence_after(); a
+    // clobber here makes the compiler re-load every kernel parameter between two MMA issues.
 }
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

@@ -6,16 +6,17 @@
 // and, with flipped/transposed packed weights, the data-gradient half of its backward
 // (train.py:210).
 //
-// Data layout: zero-halo padded NDHWC (see common.cuh).  Because every activation tensor
-// carries its zero halo in HBM, a 3x3x3 tap is a constant row shift in the linear row
+// Data layout: chunk-planar zero-halo activations (see common.cuh).  Because every activation
+// tensor carries its zero halo in HBM, a 3x3x3 tap is a constant row shift in the linear row
 // index: in[r + (kd-1)*SS + (kh-1)*Wp + (kw-1)].  A tile is a run of 128*MB consecutive rows
-// in each of BD consecutive slices; its input window is loaded ONCE by TMA into shared memory
-// as 16-byte channel-chunk planes ([chunk][slice][row][8 ch]), which is exactly the
-// SWIZZLE_NONE K-major canonical layout of a UMMA operand, so each of the 27 taps is just a
-// different start address in the A descriptor.  Rows that land on halo positions are junk:
-// computed, never stored.
+// in each of BD consecutive slices; its input window is loaded ONCE per 16-channel K group:
+// each (8-channel chunk, slice) is one contiguous range of a chunk plane in HBM, fetched by a
+// single cp.async.bulk (TMA bulk engine) straight into its [chunk][slice][row][8 ch] shared
+// memory plane - exactly the SWIZZLE_NONE K-major canonical layout of a UMMA operand - so each
+// of the 27 taps is just a different start address in the A descriptor.  Rows that land on
+// halo positions are junk: computed, never stored.
 //
-// Warp roles (256 threads): w0 activation TMA producer, w1 weight bulk-copy producer,
+// Warp roles (256 threads): w0 activation bulk-copy producer, w1 weight bulk-copy producer,
 // w2 MMA issuer (one thread), w3 TMEM allocator, w4-7 epilogue (TMEM -> regs -> HBM).
 #pragma once
 #include "common.cuh"
@@ -44,22 +45,24 @@ struct ConvKParams {
     // shared-memory plan
     int x_stages, w_stages;
     unsigned x_stage_bytes, w_stage_bytes, x_plane_bytes;
-    int SRp, BR, NBX, nslices, halo_rows;
+    int SRp, nslices, halo_rows;
     int tap_off[kMaxTaps];
     unsigned smem_x_off, smem_w_off, smem_bar_off;
     unsigned tmem_cols;
     // operands
+    ActRef src_a, src_b;   // chunk-planar activations (src_b only when KG > KGa)
     const __nv_bfloat16* wpacked;
     // epilogue
-    int Cout_total;        // channels per row of `out`
+    int Cout_total;        // channels of `out`
     int lrelu_out;         // apply LeakyReLU(0.01) before storing
-    __nv_bfloat16* out;
-    const __nv_bfloat16* residual;   // optional, same layout as out, added before activation
+    ActRef out;
+    ActRef residual;       // optional (base == nullptr if unused), same layout as out, added before activation
     float* stats_partial;            // optional [ctas][N][16] (sum[8], sumsq[8])
     const float* bias;               // EPI_SIGMOID
     float* probs;                    // EPI_SIGMOID: fp32 NCDHW (unpadded)
     float* logits;                   // EPI_SIGMOID: optional fp32 NCDHW
     int n_out_real;                  // EPI_SIGMOID: real output channels (3)
+    int debug;                       // perf probes only: 1 = skip activation loads, 2 = skip MMAs
 };
 
 struct TileCoord {
@@ -79,10 +82,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
 
 template <int MODE, int EPI, int NMMA>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ CUtensorMap tmA,
-                 const __grid_constant__ CUtensorMap tmB) {
+conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int job = blockIdx.x % p.n_jobs;
     const int cta = blockIdx.x / p.n_jobs;
@@ -100,10 +102,6 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][16]
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.x_stages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -117,36 +115,45 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
     const int R = p.BD * p.MB;  // accumulators (runs) per tile
 
-    if (warp == 0 && lane == 0) {
+    // Role code is executed by the WHOLE warp with warp-uniform values; only the instruction
+    // issue is predicated on elect_one().  (Putting the role under `lane == 0` makes ptxas wrap
+    // every UTCHMMA/UTMALDG in an ELECT + R2UR waterfall: ~5x slower MMA issue, measured.)
+    if (warp == 0) {
         // ================= activation producer (TMA) =================
         int xs = 0; uint32_t xph = 0;
         for (int t = cta; t < p.num_tiles; t += ctas) {
             TileCoord tc = decode_tile(p, t);
             for (int g = 0; g < p.KG; ++g) {
                 mbar_wait(&x_empty[xs], xph ^ 1);
-                mbar_arrive_expect_tx(&x_full[xs], p.x_stage_bytes);
-                const CUtensorMap* tm = (g < p.KGa) ? &tmA : &tmB;
-                const int ch0 = (g < p.KGa ? g : g - p.KGa) * p.KC;
-                uint8_t* dst = smem_x + (size_t)xs * p.x_stage_bytes;
-                for (int c = 0; c < p.KC / 8; ++c) {
-                    for (int s = 0; s < p.nslices; ++s) {
-                        long long row0;
-                        if (MODE == MODE_K3) {
-                            const int dpi = (p.whole ? 0 : tc.d0 + 1) - 1 + s;
-                            row0 = ((long long)tc.n * (p.D + 2) + dpi) * p.SS + tc.q0 - p.halo_rows;
-                        } else {
-                            row0 = (long long)t * p.TR;
-                        }
-                        for (int b = 0; b < p.NBX; ++b) {
-                            tma_load_2d(dst + (size_t)c * p.x_plane_bytes + ((size_t)s * p.SRp + (size_t)b * p.BR) * 16,
-                                        tm, &x_full[xs], ch0 + c * 8, (int)(row0 + (long long)b * p.BR));
+                if (elect_one()) {
+                    if (p.debug & 1) {
+                        mbar_arrive(&x_full[xs]);
+                    } else {
+                        mbar_arrive_expect_tx(&x_full[xs], p.x_stage_bytes);
+                        const ActRef& src = (g < p.KGa) ? p.src_a : p.src_b;
+                        const int chunk0 = (g < p.KGa ? g : g - p.KGa) * (p.KC / 8);
+                        uint8_t* dst = smem_x + (size_t)xs * p.x_stage_bytes;
+                        const uint32_t bytes = (uint32_t)p.SRp * 16;
+                        for (int c = 0; c < p.KC / 8; ++c) {
+                            for (int s = 0; s < p.nslices; ++s) {
+                                long long row0;
+                                if (MODE == MODE_K3) {
+                                    const int dpi = (p.whole ? 0 : tc.d0 + 1) - 1 + s;
+                                    row0 = ((long long)tc.n * (p.D + 2) + dpi) * p.SS + tc.q0 - p.halo_rows;
+                                } else {
+                                    row0 = (long long)t * p.TR;
+                                }
+                                bulk_load_1d(dst + (size_t)c * p.x_plane_bytes + (size_t)s * p.SRp * 16,
+                                             src.at(chunk0 + c, row0), bytes, &x_full[xs]);
+                            }
                         }
                     }
                 }
+                __syncwarp();
                 if (++xs == p.x_stages) { xs = 0; xph ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ================= weight producer (bulk copy) =================
         int ws = 0; uint32_t wph = 0;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked) +
@@ -155,18 +162,29 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ 
             for (int g = 0; g < p.KG; ++g) {
                 for (int tg = 0; tg < p.NTG; ++tg) {
                     mbar_wait(&w_empty[ws], wph ^ 1);
-                    mbar_arrive_expect_tx(&w_full[ws], p.w_stage_bytes);
-                    bulk_load_1d(smem_w + (size_t)ws * p.w_stage_bytes,
-                                 wsrc + (size_t)(g * p.NTG + tg) * p.w_stage_bytes, p.w_stage_bytes, &w_full[ws]);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&w_full[ws], p.w_stage_bytes);
+                        bulk_load_1d(smem_w + (size_t)ws * p.w_stage_bytes,
+                                     wsrc + (size_t)(g * p.NTG + tg) * p.w_stage_bytes, p.w_stage_bytes, &w_full[ws]);
+                    }
+                    __syncwarp();
                     if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
                 }
             }
         }
-    } else if (warp == 2 && lane == 0) {
+    } else if (warp == 2) {
         // ================= MMA issuer =================
+        // Descriptor high words are loop invariant (LBO, SBO, version); only the 14-bit start
+        // address field changes per MMA, so each issue costs a couple of integer adds.
         constexpr uint32_t idesc = make_idesc(128, NMMA, 0, 0);
-        const uint32_t xbase = smem_u32(smem_x), wbase = smem_u32(smem_w);
+        const uint32_t plane16 = p.x_plane_bytes >> 4;
+        const uint64_t a_hi = ((uint64_t)(plane16 & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+        const uint64_t b_hi = ((uint64_t)((NMMA * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+        const uint32_t xbase16 = smem_u32(smem_x) >> 4, wbase16 = smem_u32(smem_w) >> 4;
+        const uint32_t xstage16 = p.x_stage_bytes >> 4, wstage16 = p.w_stage_bytes >> 4;
         const int ksteps = p.KC / 16;
+        const uint32_t wtap16 = (uint32_t)(p.KC / 8) * NMMA;     // 16B units per tap in a weight stage
+        const bool skip_mma = (p.debug & 2) != 0;
         int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
         int it = 0;
         for (int t = cta; t < p.num_tiles; t += ctas, ++it) {
@@ -176,34 +194,64 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ 
             for (int g = 0; g < p.KG; ++g) {
                 mbar_wait(&x_full[xs], xph);
                 tc_fence_after();
-                const uint32_t xst = xbase + xs * p.x_stage_bytes;
+                const uint32_t xst16 = xbase16 + xs * xstage16;
                 for (int tg = 0; tg < p.NTG; ++tg) {
                     mbar_wait(&w_full[ws], wph);
                     tc_fence_after();
-                    const uint32_t wst = wbase + ws * p.w_stage_bytes;
-                    for (int r = 0; r < R; ++r) {
-                        const int dz = r / p.MB, mb = r - dz * p.MB;
-                        const uint32_t dtm = tmem_base + (uint32_t)((as * R + r) * NMMA);
-                        const uint32_t run_row = (uint32_t)(dz * p.SRp + mb * 128);
-                        for (int tl = 0; tl < p.TG; ++tl) {
-                            const uint32_t arow = run_row + (uint32_t)p.tap_off[tg * p.TG + tl];
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint64_t adesc =
-                                    make_smem_desc(xst + (2 * ks) * p.x_plane_bytes + arow * 16, p.x_plane_bytes, 128);
-                                const uint64_t bdesc = make_smem_desc(
-                                    wst + (uint32_t)((tl * (p.KC / 8) + 2 * ks) * NMMA * 16), NMMA * 16, 128);
-                                const uint32_t acc = (g | tg | tl | ks) != 0;
-                                umma_bf16(dtm, adesc, bdesc, idesc, acc);
+                    const uint32_t wst16 = wbase16 + ws * wstage16;
+                    const int* toff = &p.tap_off[tg * p.TG];
+                    uint32_t dtm = tmem_base + (uint32_t)(as * R * NMMA);
+                    uint32_t first = (g | tg) == 0 ? 0u : 1u;
+                    if (MODE == MODE_K3) {
+                        // compile-time shape: KC = 16 (one K=16 MMA per tap), 9 taps per weight stage
+                        uint32_t t9[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) t9[i] = (uint32_t)toff[i];
+                        const int BD = p.BD, MB = p.MB, SRp = p.SRp;
+                        if (!skip_mma && elect_one()) {
+                            for (int dz = 0; dz < BD; ++dz) {
+                                for (int mb = 0; mb < MB; ++mb, dtm += NMMA) {
+                                    const uint32_t a_run16 = xst16 + (uint32_t)(dz * SRp + mb * 128);
+#pragma unroll
+                                    for (int tl = 0; tl < 9; ++tl) {
+                                        umma_bf16(dtm, a_hi | (uint64_t)(a_run16 + t9[tl]),
+                                                  b_hi | (uint64_t)(wst16 + (uint32_t)(tl * 2 * NMMA)), idesc,
+                                                  tl == 0 ? first : 1u);
+                                    }
+                                }
+                            }
+                        }
+                    } else if (!skip_mma && elect_one()) {
+                        for (int dz = 0; dz < p.BD; ++dz) {
+                            for (int mb = 0; mb < p.MB; ++mb, dtm += NMMA) {
+                                const uint32_t a_run16 = xst16 + (uint32_t)(dz * p.SRp + mb * 128);
+                                uint32_t b16 = wst16;
+                                uint32_t acc = first;
+                                for (int tl = 0; tl < p.TG; ++tl) {
+                                    uint32_t a16 = a_run16 + (uint32_t)toff[tl];
+                                    for (int ks = 0; ks < ksteps; ++ks) {
+                                        umma_bf16(dtm, a_hi | (uint64_t)(a16 & 0x3FFF), b_hi | (uint64_t)(b16 & 0x3FFF),
+                                                  idesc, acc);
+                                        acc = 1u;
+                                        a16 += 2 * plane16;
+                                        b16 += 2 * NMMA;
+                                    }
+                                    b16 += wtap16 - (uint32_t)ksteps * 2 * NMMA;
+                                }
                             }
                         }
                     }
-                    umma_commit(&w_empty[ws]);
+                    __syncwarp();
+                    if (elect_one()) umma_commit(&w_empty[ws]);
+                    __syncwarp();
                     if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
                 }
-                umma_commit(&x_empty[xs]);
+                if (elect_one()) umma_commit(&x_empty[xs]);
+                __syncwarp();
                 if (++xs == p.x_stages) { xs = 0; xph ^= 1; }
             }
-            umma_commit(&t_full[as]);
+            if (elect_one()) umma_commit(&t_full[as]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
@@ -280,15 +328,13 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ 
                                     ssq[gi] += v[i] * v[i];
                                 }
                             }
-                            const size_t off = (size_t)orow * p.Cout_total + (size_t)job * NMMA + c0;
-                            if (p.residual) {
-                                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+                            const int ch = (job * NMMA + c0) >> 3;      // first of the two 8-channel chunks
+                            if (p.residual.base) {
                                 float f[8];
-                                uint4 q0 = rp[0], q1 = rp[1];
-                                unpack_bf16x8(q0, f);
+                                unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch, orow)), f);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] += f[i];
-                                unpack_bf16x8(q1, f);
+                                unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch + 1, orow)), f);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
                             }
@@ -296,9 +342,8 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p, const __grid_constant__ 
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i]);
                             }
-                            uint4* op = reinterpret_cast<uint4*>(p.out + off);
-                            op[0] = pack_bf16x8(v);
-                            op[1] = pack_bf16x8(v + 8);
+                            *reinterpret_cast<uint4*>(p.out.at(ch, orow)) = pack_bf16x8(v);
+                            *reinterpret_cast<uint4*>(p.out.at(ch + 1, orow)) = pack_bf16x8(v + 8);
                         }
                     } else {  // EPI_SIGMOID: first n_out_real columns are real
                         if (valid && c0 == 0) {

@@ -2,10 +2,10 @@
 // LeakyReLU, residual add, trilinear x2 up-sampling (forward + adjoint), space-to-depth,
 // sigmoid/Dice, weight packing and the deterministic partial reductions.
 //
-// All activation tensors are zero-halo padded NDHWC bf16 (common.cuh).  Kernels that walk a
-// tensor use one CTA per (n, d, h) line: W*C contiguous elements, 16-byte vectors of 8
-// channels per thread, so every global access is a fully coalesced 128-bit transaction and
-// halo elements are never touched (they stay zero).
+// All activation tensors are chunk-planar zero-halo bf16 (common.cuh).  Kernels that walk a
+// tensor use one CTA per (n, d, h) line; a thread handles 16-byte vectors (8 channels of one
+// voxel) with the voxel index fastest across threads, so a warp touches 512 contiguous bytes of
+// one chunk plane per access.  Halo and guard rows are never touched (they stay zero).
 #pragma once
 #include "common.cuh"
 
@@ -19,25 +19,24 @@ __device__ __forceinline__ void line_coords(const Vol& v, int line, int& n, int&
     d = t % v.D;
     n = t / v.D;
 }
+__device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& q) { *reinterpret_cast<uint4*>(p) = q; }
 
 // ---------------------------------------------------------------------------------------
-// (B,Creal,D,H,W) fp32 NCDHW  ->  zero-halo NDHWC bf16 with Cpad channels (extra channels 0).
-// Entry layout conversion for model.py:407-412 (`input = x[0]`).
+// (B,Creal,D,H,W) fp32 NCDHW  ->  act; only chunk 0 is written (Creal <= 8), higher chunks of the
+// destination stay zero.  Entry layout conversion for model.py:407-412 (`input = x[0]`).
 // ---------------------------------------------------------------------------------------
-__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, Vol v, int Creal,
-                                  int Cpad) {
+__global__ void pack_input_kernel(const float* __restrict__ x, ActRef out, Vol v, int Creal) {
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
     const size_t plane = (size_t)v.D * v.H * v.W;
     const size_t src0 = (size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W;
     const long long row0 = v.row(n, d + 1, h + 1, 1);
     for (int w = threadIdx.x; w < v.W; w += blockDim.x) {
-        for (int c0 = 0; c0 < Cpad; c0 += 8) {
-            float f[8];
+        float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = (c0 + i < Creal) ? x[src0 + (size_t)(c0 + i) * plane + w] : 0.f;
-            *reinterpret_cast<uint4*>(out + (size_t)(row0 + w) * Cpad + c0) = pack_bf16x8(f);
-        }
+        for (int i = 0; i < 8; ++i) f[i] = (i < Creal) ? x[src0 + (size_t)i * plane + w] : 0.f;
+        st16(out.at(0, row0 + w), pack_bf16x8(f));
     }
 }
 
@@ -66,10 +65,9 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, 
 //   residual is added AFTER the activation (out = x + lrelu(gn(conv))), model.py:115.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                const float* __restrict__ gamma, const float* __restrict__ beta,
-                const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, Vol v, int C,
-                int do_lrelu) {
+gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, ActRef residual, ActRef out, Vol v,
+                int C, int do_lrelu) {
     __shared__ float s_scale[256], s_shift[256];
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
@@ -81,41 +79,41 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ m
         s_shift[c] = beta[c] - mean[n * 8 + g] * sc;
     }
     __syncthreads();
-    const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
-    const int nvec = v.W * C / 8;
-    const int cvec = C / 8;
+    const long long row0 = v.row(n, d + 1, h + 1, 1);
+    const int nvec = v.W * (C / 8);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cb = (i % cvec) * 8;
+        const int cv = i / v.W, w = i - cv * v.W;
+        const int cb = cv * 8;
         float f[8];
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(x + base + (size_t)i * 8), f);
+        unpack_bf16x8(ld16(x.at(cv, row0 + w)), f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float z = f[k] * s_scale[cb + k] + s_shift[cb + k];
             f[k] = do_lrelu ? lrelu(z) : z;
         }
-        if (residual) {
+        if (residual.base) {
             float r[8];
-            unpack_bf16x8(*reinterpret_cast<const uint4*>(residual + base + (size_t)i * 8), r);
+            unpack_bf16x8(ld16(residual.at(cv, row0 + w)), r);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] += r[k];
         }
-        *reinterpret_cast<uint4*>(out + base + (size_t)i * 8) = pack_bf16x8(f);
+        st16(out.at(cv, row0 + w), pack_bf16x8(f));
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // GroupNorm (+LeakyReLU) backward, pass 1: per (n, c) sums  S1 = sum dz, S2 = sum dz * xhat
 //   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
-// grid = (blocks_per_sample, N); each CTA walks lines blockIdx.x, +gridDim.x, ... of sample n and
-// writes partial[n][blockIdx.x][C][2].  Fixed summation order -> deterministic.
+// grid = (blocks_per_sample, N); each CTA walks lines blockIdx.x, +gridDim.x, ... of sample n,
+// one 8-channel chunk plane at a time, and writes partial[n][blockIdx.x][C][2].
+// Fixed summation order -> deterministic.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
-gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                     const float* __restrict__ mean, const float* __restrict__ rstd,
+gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
                      Vol v, int C, int do_lrelu) {
     __shared__ float s_a[256], s_b[256], s_g[256], s_be[256];
-    __shared__ float s_red[kEwThreads * 16];
+    __shared__ float s_red[kEwThreads / 32][16];
     const int n = blockIdx.y;
     const int gs = C / 8;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -126,19 +124,23 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
         s_be[c] = beta[c];
     }
     __syncthreads();
-    const int cvec = C / 8;            // divides blockDim, so a thread always sees the same 8 channels
-    const int cb = (threadIdx.x % cvec) * 8;
-    const int nvec = v.W * cvec;
-    float s1[8], s2[8];
+    const int nlines = v.D * v.H;
+    const int my_lines = (nlines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int items = my_lines * v.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int cv = 0; cv < C / 8; ++cv) {
+        const int cb = cv * 8;
+        float s1[8], s2[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    for (int line = blockIdx.x; line < v.D * v.H; line += gridDim.x) {
-        const int d = line / v.H, h = line % v.H;
-        const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+        for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+            const int li = idx / v.W, w = idx - li * v.W;
+            const int line = blockIdx.x + li * gridDim.x;
+            const int d = line / v.H, h = line - d * v.H;
+            const long long r = v.row(n, d + 1, h + 1, 1 + w);
             float fx[8], fd[8];
-            unpack_bf16x8(*reinterpret_cast<const uint4*>(x + base + (size_t)i * 8), fx);
-            unpack_bf16x8(*reinterpret_cast<const uint4*>(dy + base + (size_t)i * 8), fd);
+            unpack_bf16x8(ld16(x.at(cv, r)), fx);
+            unpack_bf16x8(ld16(dy.at(cv, r)), fd);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
@@ -151,22 +153,25 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                 s2[k] += dz * xh;
             }
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s_red[threadIdx.x * 16 + k] = s1[k]; s_red[threadIdx.x * 16 + 8 + k] = s2[k]; }
-    __syncthreads();
-    // output o = (channel c, which): sum over the threads that own chunk c/8, fixed order
-    for (int o = threadIdx.x; o < C * 2; o += blockDim.x) {
-        const int c = o >> 1, which = o & 1;
-        const int chunk = c / 8, k = c % 8;
-        float acc = 0.f;
-        for (int t = chunk; t < blockDim.x; t += cvec) acc += s_red[t * 16 + which * 8 + k];
-        partial[(((size_t)n * gridDim.x + blockIdx.x) * C + c) * 2 + which] = acc;
+        for (int k = 0; k < 8; ++k) { s1[k] = warp_sum(s1[k]); s2[k] = warp_sum(s2[k]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s_red[warp][k] = s1[k]; s_red[warp][8 + k] = s2[k]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            float acc = 0.f;
+            for (int q = 0; q < kEwThreads / 32; ++q) acc += s_red[q][threadIdx.x];
+            const int k = threadIdx.x & 7, which = threadIdx.x >> 3;
+            partial[(((size_t)n * gridDim.x + blockIdx.x) * C + cb + k) * 2 + which] = acc;
+        }
+        __syncthreads();
     }
 }
 
 // pass 2: partial[n][blocks][C][2] -> coef[n][C][2] = (A_g, B_g) per channel's group, and
-//         dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.      grid = 1, block = C threads (C <= 256)
+//         dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.      grid = 1, block = 256 threads (C <= 256)
 __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
                                        const float* __restrict__ gamma, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -204,10 +209,9 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, int bl
 
 // pass 3: dx = rstd * (dz*gamma - A_g - xhat*B_g)
 __global__ void __launch_bounds__(kEwThreads)
-gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx, Vol v, int C, int do_lrelu) {
+gn_bwd_apply_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
+                    ActRef dx, Vol v, int C, int do_lrelu) {
     __shared__ float s_a[256], s_b[256], s_g[256], s_be[256], s_A[256], s_B[256];
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
@@ -222,14 +226,14 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
         s_B[c] = coef[((size_t)n * C + c) * 2 + 1];
     }
     __syncthreads();
-    const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
-    const int cvec = C / 8;
-    const int nvec = v.W * cvec;
+    const long long row0 = v.row(n, d + 1, h + 1, 1);
+    const int nvec = v.W * (C / 8);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cb = (i % cvec) * 8;
+        const int cv = i / v.W, w = i - cv * v.W;
+        const int cb = cv * 8;
         float fx[8], fd[8];
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(x + base + (size_t)i * 8), fx);
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(dy + base + (size_t)i * 8), fd);
+        unpack_bf16x8(ld16(x.at(cv, row0 + w)), fx);
+        unpack_bf16x8(ld16(dy.at(cv, row0 + w)), fd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
@@ -240,7 +244,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
             }
             fx[k] = s_a[cb + k] * (dz * s_g[cb + k] - s_A[cb + k] - xh * s_B[cb + k]);
         }
-        *reinterpret_cast<uint4*>(dx + base + (size_t)i * 8) = pack_bf16x8(fx);
+        st16(dx.at(cv, row0 + w), pack_bf16x8(fx));
     }
 }
 
@@ -256,8 +260,7 @@ __device__ __forceinline__ void up_taps(int i, int K, int& i0, int& i1, float& w
 }
 
 __global__ void __launch_bounds__(kEwThreads)
-upsample2x_lrelu_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, Vol vc, int C,
-                        int do_lrelu) {
+upsample2x_lrelu_kernel(ActRef in, ActRef out, Vol vc, int C, int do_lrelu) {
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vf, blockIdx.x, n, d, h);
@@ -265,27 +268,24 @@ upsample2x_lrelu_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __r
     float wd0, wd1, wh0, wh1;
     up_taps(d, vc.D, d0, d1, wd0, wd1);
     up_taps(h, vc.H, h0, h1, wh0, wh1);
-    const size_t r00 = (size_t)vc.row(n, d0 + 1, h0 + 1, 1) * C, r01 = (size_t)vc.row(n, d0 + 1, h1 + 1, 1) * C;
-    const size_t r10 = (size_t)vc.row(n, d1 + 1, h0 + 1, 1) * C, r11 = (size_t)vc.row(n, d1 + 1, h1 + 1, 1) * C;
-    const float c00 = wd0 * wh0, c01 = wd0 * wh1, c10 = wd1 * wh0, c11 = wd1 * wh1;
-    const size_t obase = (size_t)vf.row(n, d + 1, h + 1, 1) * C;
-    const int cvec = C / 8;
-    const int nvec = vf.W * cvec;
+    const long long rows[4] = {vc.row(n, d0 + 1, h0 + 1, 1), vc.row(n, d0 + 1, h1 + 1, 1), vc.row(n, d1 + 1, h0 + 1, 1),
+                               vc.row(n, d1 + 1, h1 + 1, 1)};
+    const float cw[4] = {wd0 * wh0, wd0 * wh1, wd1 * wh0, wd1 * wh1};
+    const long long orow0 = vf.row(n, d + 1, h + 1, 1);
+    const int nvec = vf.W * (C / 8);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int w = i / cvec, cv = i % cvec;
+        const int cv = i / vf.W, w = i - cv * vf.W;
         int w0, w1;
         float ww0, ww1;
         up_taps(w, vc.W, w0, w1, ww0, ww1);
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        const size_t rows[4] = {r00, r01, r10, r11};
-        const float cw[4] = {c00, c01, c10, c11};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             float a[8], b[8];
-            unpack_bf16x8(*reinterpret_cast<const uint4*>(in + rows[t] + (size_t)w0 * C + cv * 8), a);
-            unpack_bf16x8(*reinterpret_cast<const uint4*>(in + rows[t] + (size_t)w1 * C + cv * 8), b);
+            unpack_bf16x8(ld16(in.at(cv, rows[t] + w0)), a);
+            unpack_bf16x8(ld16(in.at(cv, rows[t] + w1)), b);
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] += cw[t] * (ww0 * a[k] + ww1 * b[k]);
         }
@@ -293,7 +293,7 @@ upsample2x_lrelu_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __r
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = lrelu(acc[k]);
         }
-        *reinterpret_cast<uint4*>(out + obase + (size_t)i * 8) = pack_bf16x8(acc);
+        st16(out.at(cv, orow0 + w), pack_bf16x8(acc));
     }
 }
 
@@ -310,19 +310,17 @@ __device__ __forceinline__ int down_taps(int k, int K, int* idx, float* wt) {
 }
 
 __global__ void __launch_bounds__(kEwThreads)
-upsample2x_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                            __nv_bfloat16* __restrict__ dcoarse, Vol vc, int C, int do_lrelu) {
+upsample2x_lrelu_bwd_kernel(ActRef dy, ActRef y, ActRef dcoarse, Vol vc, int C, int do_lrelu) {
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vc, blockIdx.x, n, d, h);
     int di[4], hi[4];
     float dw[4], hw[4];
     const int nd = down_taps(d, vc.D, di, dw), nh = down_taps(h, vc.H, hi, hw);
-    const size_t obase = (size_t)vc.row(n, d + 1, h + 1, 1) * C;
-    const int cvec = C / 8;
-    const int nvec = vc.W * cvec;
+    const long long orow0 = vc.row(n, d + 1, h + 1, 1);
+    const int nvec = vc.W * (C / 8);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int w = i / cvec, cv = i % cvec;
+        const int cv = i / vc.W, w = i - cv * vc.W;
         int wi[4];
         float ww[4];
         const int nw = down_taps(w, vc.W, wi, ww);
@@ -331,14 +329,14 @@ upsample2x_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfl
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
         for (int a = 0; a < nd; ++a)
             for (int b = 0; b < nh; ++b) {
-                const size_t rb = (size_t)vf.row(n, di[a] + 1, hi[b] + 1, 1) * C + cv * 8;
+                const long long rb = vf.row(n, di[a] + 1, hi[b] + 1, 1);
                 const float wab = dw[a] * hw[b];
                 for (int c = 0; c < nw; ++c) {
                     float g[8], yy[8];
-                    unpack_bf16x8(*reinterpret_cast<const uint4*>(dy + rb + (size_t)wi[c] * C), g);
+                    unpack_bf16x8(ld16(dy.at(cv, rb + wi[c])), g);
                     const float wt = wab * ww[c];
                     if (do_lrelu) {
-                        unpack_bf16x8(*reinterpret_cast<const uint4*>(y + rb + (size_t)wi[c] * C), yy);
+                        unpack_bf16x8(ld16(y.at(cv, rb + wi[c])), yy);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) acc[k] += wt * (yy[k] > 0.f ? g[k] : 0.01f * g[k]);
                     } else {
@@ -347,90 +345,91 @@ upsample2x_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfl
                     }
                 }
             }
-        *reinterpret_cast<uint4*>(dcoarse + obase + (size_t)i * 8) = pack_bf16x8(acc);
+        st16(dcoarse.at(cv, orow0 + w), pack_bf16x8(acc));
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // space-to-depth / depth-to-space for the k2 s2 conv (model.py:360-363):
-//   s2d[n][d][h][w][((kd*2+kh)*2+kw)*C + c] = fine[n][2d+kd][2h+kh][2w+kw][c]
-// `vc` = coarse volume.  d2s optionally adds a residual (fine layout) - the skip-gradient add.
+//   s2d channel ((kd*2+kh)*2+kw)*C + c of coarse voxel (d,h,w) = fine[2d+kd][2h+kh][2w+kw][c]
+// i.e. coarse chunk (tap8 * C/8 + cf) <- fine chunk cf.  A thread moves the two kw neighbours
+// (32 contiguous bytes of a fine plane).  `vc` = coarse volume; C = fine channels.
+// d2s optionally adds a residual (fine layout) - the skip-gradient add.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
-s2d_kernel(const __nv_bfloat16* __restrict__ fine, __nv_bfloat16* __restrict__ coarse, Vol vc, int C) {
+s2d_kernel(ActRef fine, ActRef coarse, Vol vc, int C) {
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vc, blockIdx.x, n, d, h);
-    const int cvec2 = 2 * C / 8;                 // vectors per (kw, c) pair run
-    const int nvec = vc.W * 4 * cvec2;
-    const size_t obase = (size_t)vc.row(n, d + 1, h + 1, 1) * (8 * C);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int j = i % cvec2;          // vector inside the 2C-element (kw,c) run
-        int t = i / cvec2;
-        const int dh = t % 4;             // kd*2+kh
-        const int w = t / 4;
-        const size_t src = (size_t)vf.row(n, 2 * d + (dh >> 1) + 1, 2 * h + (dh & 1) + 1, 2 * w + 1) * C + j * 8;
-        const size_t dst = obase + (size_t)w * 8 * C + (size_t)dh * 2 * C + j * 8;
-        *reinterpret_cast<uint4*>(coarse + dst) = *reinterpret_cast<const uint4*>(fine + src);
+    const int ccf = C / 8;
+    const int items = ccf * 4 * vc.W;
+    const long long orow0 = vc.row(n, d + 1, h + 1, 1);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int w = i % vc.W;
+        const int t = i / vc.W;
+        const int dh = t & 3, cf = t >> 2;
+        const long long fr = vf.row(n, 2 * d + (dh >> 1) + 1, 2 * h + (dh & 1) + 1, 2 * w + 1);
+        const __nv_bfloat16* src = fine.at(cf, fr);
+        st16(coarse.at((dh * 2 + 0) * ccf + cf, orow0 + w), ld16(src));
+        st16(coarse.at((dh * 2 + 1) * ccf + cf, orow0 + w), ld16(src + 8));
     }
 }
 
 __global__ void __launch_bounds__(kEwThreads)
-d2s_kernel(const __nv_bfloat16* __restrict__ coarse, const __nv_bfloat16* __restrict__ residual,
-           __nv_bfloat16* __restrict__ fine, Vol vc, int C) {
+d2s_kernel(ActRef coarse, ActRef residual, ActRef fine, Vol vc, int C) {
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vc, blockIdx.x, n, d, h);
-    const int cvec2 = 2 * C / 8;
-    const int nvec = vc.W * 4 * cvec2;
-    const size_t ibase = (size_t)vc.row(n, d + 1, h + 1, 1) * (8 * C);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int j = i % cvec2;
-        int t = i / cvec2;
-        const int dh = t % 4;
-        const int w = t / 4;
-        const size_t dst = (size_t)vf.row(n, 2 * d + (dh >> 1) + 1, 2 * h + (dh & 1) + 1, 2 * w + 1) * C + j * 8;
-        const size_t src = ibase + (size_t)w * 8 * C + (size_t)dh * 2 * C + j * 8;
-        uint4 q = *reinterpret_cast<const uint4*>(coarse + src);
-        if (residual) {
-            float a[8], b[8];
-            unpack_bf16x8(q, a);
-            unpack_bf16x8(*reinterpret_cast<const uint4*>(residual + dst), b);
+    const int ccf = C / 8;
+    const int items = ccf * 4 * vc.W;
+    const long long irow0 = vc.row(n, d + 1, h + 1, 1);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int w = i % vc.W;
+        const int t = i / vc.W;
+        const int dh = t & 3, cf = t >> 2;
+        const long long fr = vf.row(n, 2 * d + (dh >> 1) + 1, 2 * h + (dh & 1) + 1, 2 * w + 1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += b[k];
-            q = pack_bf16x8(a);
+        for (int kw = 0; kw < 2; ++kw) {
+            uint4 q = ld16(coarse.at((dh * 2 + kw) * ccf + cf, irow0 + w));
+            if (residual.base) {
+                float a[8], b[8];
+                unpack_bf16x8(q, a);
+                unpack_bf16x8(ld16(residual.at(cf, fr + kw)), b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += b[k];
+                q = pack_bf16x8(a);
+            }
+            st16(fine.at(cf, fr + kw), q);
         }
-        *reinterpret_cast<uint4*>(fine + dst) = q;
     }
 }
 
 // out = a + b over the interior (gradient accumulation where two paths meet)
 __global__ void __launch_bounds__(kEwThreads)
-add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out,
-           Vol v, int C) {
+add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C) {
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
-    const size_t base = (size_t)v.row(n, d + 1, h + 1, 1) * C;
-    const int nvec = v.W * C / 8;
+    const long long row0 = v.row(n, d + 1, h + 1, 1);
+    const int nvec = v.W * (C / 8);
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int cv = i / v.W, w = i - cv * v.W;
         float fa[8], fb[8];
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(a + base + (size_t)i * 8), fa);
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(b + base + (size_t)i * 8), fb);
+        unpack_bf16x8(ld16(a.at(cv, row0 + w)), fa);
+        unpack_bf16x8(ld16(b.at(cv, row0 + w)), fb);
 #pragma unroll
         for (int k = 0; k < 8; ++k) fa[k] += fb[k];
-        *reinterpret_cast<uint4*>(out + base + (size_t)i * 8) = pack_bf16x8(fa);
+        st16(out.at(cv, row0 + w), pack_bf16x8(fa));
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// sigmoid backward + layout: gp (grad wrt probs, fp32 NCDHW, Creal channels), probs ->
-// dlogit = gp * p * (1-p) as zero-halo NDHWC bf16 (Cpad channels) + per-CTA bias-grad partials
-// (model.py:431 backward; conv_output.bias grad).  partial[blocks][4]
+// sigmoid backward + layout: gp (grad wrt probs, fp32 NCDHW, Creal <= 4 channels), probs ->
+// dlogit = gp * p * (1-p) into chunk 0 of an act tensor (other chunks stay zero) + per-CTA
+// bias-grad partials (model.py:431 backward; conv_output.bias grad).  partial[blocks][4]
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
-sigmoid_bwd_pack_kernel(const float* __restrict__ gp, const float* __restrict__ probs,
-                        __nv_bfloat16* __restrict__ dlogit, float* __restrict__ bias_partial, Vol v, int Creal,
-                        int Cpad) {
+sigmoid_bwd_pack_kernel(const float* __restrict__ gp, const float* __restrict__ probs, ActRef dlogit,
+                        float* __restrict__ bias_partial, Vol v, int Creal) {
     __shared__ float s_red[kEwThreads / 32][4];
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
@@ -439,20 +438,18 @@ sigmoid_bwd_pack_kernel(const float* __restrict__ gp, const float* __restrict__ 
     const long long row0 = v.row(n, d + 1, h + 1, 1);
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     for (int w = threadIdx.x; w < v.W; w += blockDim.x) {
-        for (int c0 = 0; c0 < Cpad; c0 += 8) {
-            float f[8];
+        float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                f[i] = 0.f;
-                if (c0 + i < Creal) {
-                    const size_t o = src0 + (size_t)(c0 + i) * plane + w;
-                    const float p = probs[o];
-                    f[i] = gp[o] * p * (1.f - p);
-                    if (c0 + i < 4) bsum[c0 + i] += f[i];
-                }
+        for (int i = 0; i < 8; ++i) {
+            f[i] = 0.f;
+            if (i < Creal) {
+                const size_t o = src0 + (size_t)i * plane + w;
+                const float p = probs[o];
+                f[i] = gp[o] * p * (1.f - p);
+                if (i < 4) bsum[i] += f[i];
             }
-            *reinterpret_cast<uint4*>(dlogit + (size_t)(row0 + w) * Cpad + c0) = pack_bf16x8(f);
         }
+        st16(dlogit.at(0, row0 + w), pack_bf16x8(f));
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) bsum[c] = warp_sum(bsum[c]);

@@ -5,8 +5,10 @@
 //
 // The contraction index is the voxel row, so both operands are read MN-major straight out of
 // the same [chunk][row][8 ch] shared-memory planes the forward kernel uses (SWIZZLE_NONE
-// MN-major canonical layout: 8 rows x 16 B core matrices).  Because HBM tensors carry zero
-// halos, dY is zero on every junk row and the sum may run over the plain linear row range.
+// MN-major canonical layout: 8 rows x 16 B core matrices); each plane of a stage is one
+// contiguous range of a chunk plane in HBM, fetched by a single cp.async.bulk.  Because HBM
+// tensors carry zero halos and zero guard rows, dY is zero on every junk row and the sum may run
+// over the plain linear row range, including past either end of the tensor.
 //
 // To fill the 64/128-row M dimension with small channel counts, M stacks `nband` copies of dY
 // shifted by whole slices (one per kd tap) and N stacks `nfold` copies of X shifted by one row
@@ -27,7 +29,6 @@ struct WgradKParams {
     int Wp, SS;
     int KT;             // rows per pipeline stage (multiple of 16, <= 256)
     int XR;             // rows per X plane (KT + 2*Wp when nacc == 3, else KT), multiple of 8
-    int NBXx, BRx;      // TMA boxes per X plane and rows per box
     int nband_loaded;   // dY bands actually loaded (3 when banded, else 1)
     int CoC, CiC;       // 8-channel chunks of dY / X per band / fold
     int nfold, nacc;
@@ -41,14 +42,14 @@ struct WgradKParams {
     int stages;
     unsigned smem_bar_off;
     unsigned tmem_cols;
+    ActRef dy, x;               // chunk-planar activations
     float* partial;             // [job][split][nacc][M][Nmma]
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
-wgrad_gemm_kernel(const __grid_constant__ WgradKParams p, const __grid_constant__ CUtensorMap tmY,
-                  const __grid_constant__ CUtensorMap tmX) {
+wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int job = blockIdx.x % p.n_jobs;
     const int split = blockIdx.x / p.n_jobs;
@@ -59,10 +60,6 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p, const __grid_constant_
     uint64_t* done = empty + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmY);
-        tma_prefetch_desc(&tmX);
-    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(done, 1);
@@ -83,53 +80,72 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p, const __grid_constant_
     }
     const unsigned y_bytes = (unsigned)p.y_planes * p.y_plane_bytes;
 
-    if (warp == 0 && lane == 0) {
+    // Whole-warp role code with elect_one() around the issue (see conv_gemm.cuh for why).
+    if (warp == 0) {
         // ================= producer =================
         int s = 0; uint32_t ph = 0;
         for (int i = 0; i < nst; ++i) {
             const long long r0 = first_row + (long long)i * p.KT;
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
-            uint8_t* ybase = smem + (size_t)s * p.stage_bytes;
-            uint8_t* xbase = ybase + y_bytes;
-            for (int b = 0; b < p.nband_loaded; ++b) {
-                const int kd = (p.nband_loaded > 1) ? (b - 1) : p.job_kd[job];
-                const long long yr = r0 - (long long)kd * p.SS;
-                for (int c = 0; c < p.CoC; ++c)
-                    tma_load_2d(ybase + (size_t)(b * p.CoC + c) * p.y_plane_bytes, &tmY, &full[s], c * 8, (int)yr);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
+                uint8_t* ybase = smem + (size_t)s * p.stage_bytes;
+                uint8_t* xbase = ybase + y_bytes;
+                for (int b = 0; b < p.nband_loaded; ++b) {
+                    const int kd = (p.nband_loaded > 1) ? (b - 1) : p.job_kd[job];
+                    const long long yr = r0 - (long long)kd * p.SS;
+                    for (int c = 0; c < p.CoC; ++c)
+                        bulk_load_1d(ybase + (size_t)(b * p.CoC + c) * p.y_plane_bytes, p.dy.at(c, yr), p.y_plane_bytes,
+                                     &full[s]);
+                }
+                for (int f = 0; f < p.nfold; ++f) {
+                    const int kw = (p.nfold > 1) ? (f - 1) : p.job_kw[job];
+                    const long long xr = r0 + kw + (p.nacc > 1 ? -(long long)p.Wp : (long long)p.job_kh[job] * p.Wp);
+                    for (int c = 0; c < p.CiC; ++c)
+                        bulk_load_1d(xbase + (size_t)(f * p.CiC + c) * p.x_plane_bytes, p.x.at(p.job_xch[job] / 8 + c, xr),
+                                     p.x_plane_bytes, &full[s]);
+                }
             }
-            for (int f = 0; f < p.nfold; ++f) {
-                const int kw = (p.nfold > 1) ? (f - 1) : p.job_kw[job];
-                const long long xr = r0 + kw + (p.nacc > 1 ? -(long long)p.Wp : (long long)p.job_kh[job] * p.Wp);
-                for (int c = 0; c < p.CiC; ++c)
-                    for (int b = 0; b < p.NBXx; ++b)
-                        tma_load_2d(xbase + (size_t)(f * p.CiC + c) * p.x_plane_bytes + (size_t)b * p.BRx * 16, &tmX,
-                                    &full[s], p.job_xch[job] + c * 8, (int)(xr + (long long)b * p.BRx));
-            }
+            __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 2 && lane == 0) {
+    } else if (warp == 2) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc(p.M, p.Nmma, 1, 1);
-        const uint32_t sbase = smem_u32(smem);
+        const uint32_t sbase16 = smem_u32(smem) >> 4;
+        const uint32_t stage16 = p.stage_bytes >> 4, ybytes16 = y_bytes >> 4;
+        // MN-major SWIZZLE_NONE: LBO = 128 B between 8-row K groups, SBO = plane stride between 8-channel blocks
+        const uint64_t a_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((p.y_plane_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+        const uint64_t b_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((p.x_plane_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+        const int ksteps = p.KT / 16;
         int s = 0; uint32_t ph = 0;
         for (int i = 0; i < nst; ++i) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            const uint32_t ya = sbase + s * p.stage_bytes;
-            const uint32_t xa = ya + y_bytes;
-            for (int t = 0; t < p.nacc; ++t) {
-                const uint32_t xrow = (p.nacc > 1) ? (uint32_t)(t * p.Wp) : 0u;
-                for (int ks = 0; ks < p.KT / 16; ++ks) {
-                    const uint64_t adesc = make_smem_desc(ya + (uint32_t)(ks * 16) * 16, 128, p.y_plane_bytes);
-                    const uint64_t bdesc = make_smem_desc(xa + (xrow + (uint32_t)(ks * 16)) * 16, 128, p.x_plane_bytes);
-                    umma_bf16(tmem_base + (uint32_t)(t * p.Nmma), adesc, bdesc, idesc, (i | ks) != 0);
+            if (elect_one()) {
+                const uint32_t ya16 = sbase16 + s * stage16;
+                const uint32_t xa16 = ya16 + ybytes16;
+                uint32_t acc = i != 0;
+                for (int t = 0; t < p.nacc; ++t) {
+                    uint32_t a16 = ya16;
+                    uint32_t b16 = xa16 + ((p.nacc > 1) ? (uint32_t)(t * p.Wp) : 0u);
+                    const uint32_t dtm = tmem_base + (uint32_t)(t * p.Nmma);
+                    uint32_t acc_t = acc;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        umma_bf16(dtm, a_hi | (uint64_t)(a16 & 0x3FFF), b_hi | (uint64_t)(b16 & 0x3FFF), idesc, acc_t);
+                        acc_t = 1u;
+                        a16 += 16;      // 16 rows * 16 B, in 16-byte units
+                        b16 += 16;
+                    }
                 }
             }
-            umma_commit(&empty[s]);
+            __syncwarp();
+            if (elect_one()) umma_commit(&empty[s]);
+            __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(done);
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> fp32 partial =================
         const int ew = warp - 4;

@@ -49,7 +49,8 @@ class _Plan:
         return t
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in list(self.acts.values()) + list(self.misc.values()))
+        return sum(a.nbytes() for a in self.acts.values()) + sum(
+            t.numel() * t.element_size() for t in self.misc.values() if torch.is_tensor(t))
 
 
 class GradStore:
@@ -121,7 +122,7 @@ class Engine:
         """c = conv3(src) with fused GroupNorm statistics; returns (c, mean, rstd)."""
         D, H, W = P.dims[lvl]
         Cout = w.shape[0]
-        Cin = src.shape[-1]
+        Cin = src.C
         desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, Cin, Cout)
         pk = self._pack(desc, ops.W_FWD, wname, w, K_real=w.shape[1], N_real=Cout)
         c = P.act(cname, lvl, Cout)
@@ -135,7 +136,7 @@ class Engine:
 
     def _residual_fwd(self, P, lvl, prefix, x_in, prm):
         """model.py:99-117 (after the optional downsample): x + lrelu(gn2(conv2(lrelu(gn1(conv1(x))))))."""
-        Cc = x_in.shape[-1]
+        Cc = x_in.C
         c1, m1, r1 = self._conv3_gn(P, lvl, prefix + "conv1.conv1.weight", prm[prefix + "conv1.conv1.weight"], x_in,
                                     prefix + "c1")
         a1 = ops.gn_apply(c1, m1, r1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
@@ -148,11 +149,11 @@ class Engine:
 
     def _conv1(self, P, lvl, wname, w, kind, src_a, out, src_b=None, ci_off=0, residual=None):
         D, H, W = P.dims[lvl]
-        Cout = out.shape[-1]
-        desc = ops.conv_desc(ops.MODE_K1, P.N, D, H, W, src_a.shape[-1], Cout,
-                             Cin_b=0 if src_b is None else src_b.shape[-1])
+        Cout = out.C
+        desc = ops.conv_desc(ops.MODE_K1, P.N, D, H, W, src_a.C, Cout,
+                             Cin_b=0 if src_b is None else src_b.C)
         pk = self._pack(desc, kind, wname, w, ci_off=ci_off,
-                        K_real=src_a.shape[-1] + (0 if src_b is None else src_b.shape[-1]), N_real=Cout)
+                        K_real=src_a.C + (0 if src_b is None else src_b.C), N_real=Cout)
         return ops.conv_run(desc, src_a, pk, out, src_b=src_b, residual=residual)
 
     # ---------------------------------------------------------------------------------
@@ -207,7 +208,7 @@ class Engine:
     # ---------------------------------------------------------------------------------
     def _wgrad(self, P, lvl, mode, dy, x, grad, kind, ci_off=0, accumulate=False):
         D, H, W = P.dims[lvl]
-        desc = ops.wgrad_desc(mode, P.N, D, H, W, dy.shape[-1], x.shape[-1])
+        desc = ops.wgrad_desc(mode, P.N, D, H, W, dy.C, x.C)
         ws = P.misc.get("wgrad_ws")
         need = ops._lib.lib().b200_wgrad_workspace_bytes(desc) // 4
         if need == 0:
@@ -219,12 +220,12 @@ class Engine:
 
     def _dgrad3(self, P, lvl, wname, w, dy, out, residual=None):
         D, H, W = P.dims[lvl]
-        desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, dy.shape[-1], out.shape[-1])
+        desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, dy.C, out.C)
         pk = self._pack(desc, ops.W_DGRAD, wname, w, K_real=w.shape[0], N_real=w.shape[1])
         return ops.conv_run(desc, dy, pk, out, residual=residual)
 
     def _gn_bwd(self, P, lvl, cname, x, dy, gamma, beta, dx, grads, gname, bname, lrelu=True):
-        Cc = x.shape[-1]
+        Cc = x.C
         ws = P.misc.get("gn_ws")
         need = ops._lib.lib().b200_gn_backward_workspace_floats(P.N, Cc)
         if ws is None or ws.numel() < need:
@@ -239,7 +240,7 @@ class Engine:
     def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads):
         """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns grad w.r.t. x_in
         (written into d_in_buf), which includes the identity path (model.py:115)."""
-        Cc = x_in.shape[-1]
+        Cc = x_in.C
         c1 = P.act(prefix + "c1", lvl, Cc)
         a1 = P.act(prefix + "a1", lvl, Cc)
         c2 = P.act(prefix + "c2", lvl, Cc)

@@ -39,30 +39,72 @@ def pad16(c):
 
 
 # ------------------------------------------------------------------------------------------
-# activation buffers: zero-halo padded NDHWC bf16, shape (N, D+2, H+2, W+2, C)
+# activation buffers: chunk-planar, zero halos, zero guard rows (csrc/common.cuh):
+#   t[C/8][guard + N*(D+2)*(H+2)*(W+2) + guard][8]  bf16
 # ------------------------------------------------------------------------------------------
+class Act:
+    """One activation tensor in the library's HBM layout (a torch buffer + its geometry)."""
+    __slots__ = ("t", "N", "D", "H", "W", "C", "G", "PR")
+
+    def __init__(self, N, D, H, W, Cc, device):
+        assert Cc % 8 == 0
+        L = _lib.lib()
+        self.N, self.D, self.H, self.W, self.C = N, D, H, W, Cc
+        self.G = L.b200_act_guard_rows(D, H, W)
+        self.PR = L.b200_act_plane_rows(N, D, H, W)
+        self.t = torch.zeros((Cc // 8, self.PR, 8), dtype=torch.bfloat16, device=device)
+
+    def data_ptr(self):
+        return self.t.data_ptr()
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def padded(self):
+        """View (C/8, N, D+2, H+2, W+2, 8) of the rows between the guards."""
+        rows = self.N * (self.D + 2) * (self.H + 2) * (self.W + 2)
+        return self.t[:, self.G:self.G + rows].view(self.C // 8, self.N, self.D + 2, self.H + 2, self.W + 2, 8)
+
+    def interior(self):
+        return self.padded()[:, :, 1:-1, 1:-1, 1:-1, :]
+
+    def nbytes(self):
+        return self.t.numel() * 2
+
+
 def act_zeros(N, D, H, W, Cc, device):
-    return torch.zeros((N, D + 2, H + 2, W + 2, Cc), dtype=torch.bfloat16, device=device)
+    return Act(N, D, H, W, Cc, device)
 
 
-def act_dims(t):
-    N, Dp, Hp, Wp, Cc = t.shape
-    return N, Dp - 2, Hp - 2, Wp - 2, Cc
+def act_dims(a):
+    return a.N, a.D, a.H, a.W, a.C
 
 
 def act_from_ncdhw(x, Cpad=None):
     """Reference-side helper (tests): fp32 NCDHW -> act, done with torch ops."""
     N, Cc, D, H, W = x.shape
     Cpad = Cpad or pad16(Cc)
-    a = act_zeros(N, D, H, W, Cpad, x.device)
-    a[:, 1:-1, 1:-1, 1:-1, :Cc] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    a = Act(N, D, H, W, Cpad, x.device)
+    xp = torch.zeros((N, Cpad, D, H, W), dtype=torch.bfloat16, device=x.device)
+    xp[:, :Cc] = x.to(torch.bfloat16)
+    a.interior().copy_(xp.view(N, Cpad // 8, 8, D, H, W).permute(1, 0, 3, 4, 5, 2))
     return a
 
 
 def act_to_ncdhw(a, Cc=None):
     """Reference-side helper (tests): act interior -> fp32 NCDHW."""
-    Cc = Cc or a.shape[-1]
-    return a[:, 1:-1, 1:-1, 1:-1, :Cc].permute(0, 4, 1, 2, 3).float().contiguous()
+    Cc = Cc or a.C
+    x = a.interior().permute(1, 0, 5, 2, 3, 4).reshape(a.N, a.C, a.D, a.H, a.W)
+    return x[:, :Cc].float().contiguous()
+
+
+def act_outside_absmax(a):
+    """Reference-side helper (tests): max |value| over halo and guard elements (must stay 0)."""
+    c = a.t.clone()
+    rows = a.N * (a.D + 2) * (a.H + 2) * (a.W + 2)
+    c[:, a.G:a.G + rows].view(a.C // 8, a.N, a.D + 2, a.H + 2, a.W + 2, 8)[:, :, 1:-1, 1:-1, 1:-1, :] = 0
+    return c.float().abs().max()
 
 
 def pack_input(x, Cpad=16, out=None):
@@ -70,6 +112,7 @@ def pack_input(x, Cpad=16, out=None):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
     if out is None:
         out = act_zeros(N, D, H, W, Cpad, x.device)
+    assert Cc <= 8 and out.C == Cpad
     check(_lib.lib().b200_pack_input(_p(x), _p(out), N, D, H, W, Cc, Cpad, _stream()), "b200_pack_input")
     _count(1)
     return out
@@ -234,7 +277,7 @@ def add(a, b, out):
 # ------------------------------------------------------------------------------------------
 def sigmoid_backward(grad_probs, probs, dlogit_act, dbias, workspace=None):
     N, Cr, D, H, W = probs.shape
-    Cpad = dlogit_act.shape[-1]
+    Cpad = dlogit_act.C
     if workspace is None:
         workspace = torch.empty(_lib.lib().b200_sigmoid_backward_workspace_floats(N, D, H), dtype=torch.float32,
                                 device=probs.device)

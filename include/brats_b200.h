@@ -12,10 +12,12 @@
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and never synchronise.
  *  - Return value 0 = ok; non-zero = error, text available from b200_last_error().
  *  - No CPU fallback, no cuDNN fallback: unsupported shapes or a non-sm_100 device are errors.
- *  - Activation tensors ("act") are bf16, zero-halo padded NDHWC:
- *        act[n][dp][hp][wp][c],  dp < D+2, hp < H+2, wp < W+2, interior at index >= 1,
- *    every halo element must be 0 when a buffer is first handed to the library (allocate
- *    zero-filled); kernels never write halos.  Channel counts are multiples of 16.
+ *  - Activation tensors ("act") are bf16, chunk-planar with zero halos and zero guard rows:
+ *        act[C/8][guard + rows + guard][8],   rows = N*(D+2)*(H+2)*(W+2),
+ *        row(n,dp,hp,wp) = ((n*(D+2)+dp)*(H+2)+hp)*(W+2)+wp, interior at dp,hp,wp >= 1,
+ *        guard = b200_act_guard_rows(D,H,W); the pointer passed is the start of the allocation.
+ *    Every halo and guard element must be 0 when a buffer is first handed to the library
+ *    (allocate zero-filled); kernels never write them.  Channel counts are multiples of 16.
  */
 #ifndef BRATS_B200_H
 #define BRATS_B200_H
@@ -30,6 +32,10 @@ const char* b200_last_error(void);
 /* 0 if device `dev` is compute capability 10.x with tcgen05/TMA available. */
 int b200_device_check(int dev);
 int b200_num_sms(void);
+
+/* ---- activation geometry ----------------------------------------------------------------- */
+long long b200_act_guard_rows(int D, int H, int W);
+long long b200_act_plane_rows(int N, int D, int H, int W);   /* rows per chunk plane incl. both guards */
 
 /* ---- layout (model.py:410-412 `input = x[0]`) -------------------------------------------- */
 /* x: fp32 (N,Creal,D,H,W) contiguous  ->  act with Cpad channels (channels >= Creal are 0). */

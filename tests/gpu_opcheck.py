@@ -56,9 +56,8 @@ def group_ew():
     x = torch.randn(N, 4, D, H, W, device=dev)
     a = ops.pack_input(x, 16)
     report("pack_input interior", ops.act_to_ncdhw(a, 4), bf(x), tol_abs=0)
-    halo = a.clone(); halo[:, 1:-1, 1:-1, 1:-1] = 0
-    report("pack_input halo zero / pad channels", torch.cat([halo.float().flatten(), a[..., 4:].float().flatten()]),
-           torch.zeros(halo.numel() + a[..., 4:].numel(), device=dev), tol_abs=0)
+    report("pack_input halo+guard zero", ops.act_outside_absmax(a).view(1), torch.zeros(1, device=dev), tol_abs=0)
+    report("pack_input pad channels zero", ops.act_to_ncdhw(a)[:, 4:], torch.zeros(N, 12, D, H, W, device=dev), tol_abs=0)
 
     for Cc in (16, 32, 64, 128):
         xc = bf(torch.randn(N, Cc, D, H, W, device=dev) * 2 + 0.5)
@@ -109,8 +108,7 @@ def group_ew():
         dco = ops.act_zeros(N, D, H, W, Cc, dev)
         ops.upsample2x_backward(ops.act_from_ncdhw(dy), fine, dco, lrelu=True)
         report("upsample2x backward C=%d" % Cc, ops.act_to_ncdhw(dco), xr.grad, tol_rel=1e-2)
-        halo = fine.clone(); halo[:, 1:-1, 1:-1, 1:-1] = 0
-        report("upsample2x halo untouched C=%d" % Cc, halo.float(), torch.zeros_like(halo).float(), tol_abs=0)
+        report("upsample2x halo+guard untouched C=%d" % Cc, ops.act_outside_absmax(fine).view(1), torch.zeros(1, device=dev), tol_abs=0)
     # s2d / d2s / add
     Cc = 16
     xf = bf(torch.randn(N, Cc, 2 * D, 2 * H, 2 * W, device=dev))
@@ -146,7 +144,7 @@ def group_ew():
     ops.sigmoid_backward(gp, probs, dl, dbias)
     refdl = pr.grad * probs * (1 - probs)
     report("sigmoid backward", ops.act_to_ncdhw(dl, 3), bf(refdl), tol_rel=1e-2)
-    report("sigmoid backward pad channels zero", dl[..., 3:].float(), torch.zeros_like(dl[..., 3:]).float(), tol_abs=0)
+    report("sigmoid backward pad channels zero", ops.act_to_ncdhw(dl)[:, 3:], torch.zeros(N, 13, D2, H2, W2, device=dev), tol_abs=0)
     report("bias grad", dbias, refdl.sum(dim=(0, 2, 3, 4)), tol_rel=2e-3)
 
 
@@ -176,8 +174,7 @@ def _conv3_case(name, N, D, H, W, Cin, Cout, residual=False, lrelu=False, stats=
     ops.conv_run(desc, xa, packed, out, residual=ra, lrelu=lrelu, stats=st)
     torch.cuda.synchronize()
     ok = report("conv3 %s" % name, ops.act_to_ncdhw(out, Cout), ref, tol_rel=1.5e-2, extra="ctas=%d" % ctas)
-    halo = out.clone(); halo[:, 1:-1, 1:-1, 1:-1] = 0
-    report("conv3 %s halo stays zero" % name, halo.float(), torch.zeros_like(halo).float(), tol_abs=0)
+    report("conv3 %s halo+guard stay zero" % name, ops.act_outside_absmax(out).view(1), torch.zeros(1, device=dev), tol_abs=0)
     if stats and not residual and not lrelu and Cout % 8 == 0:
         g = F.conv3d(x, w, padding=1).view(N, 8, -1)
         s = st.sum(0)
@@ -232,6 +229,7 @@ def group_conv1():
         out = ops.act_zeros(N, D, H, W, Cout, dev)
         ops.conv_run(desc, ops.act_from_ncdhw(x), packed, out)
         report("conv1 %d->%d" % (Cin, Cout), ops.act_to_ncdhw(out), F.conv3d(x, w), tol_rel=1.5e-2)
+        report("conv1 %d->%d halo+guard stay zero" % (Cin, Cout), ops.act_outside_absmax(out).view(1), torch.zeros(1, device=dev), tol_abs=0)
     # cat conv: two sources
     for Cc in (16, 64):
         a = bf(torch.randn(N, Cc, D, H, W, device=dev)); b = bf(torch.randn(N, Cc, D, H, W, device=dev))

@@ -15,8 +15,8 @@ from brats2019_b200 import _lib
 from brats2019_b200._lib import ConvDesc, WgradDesc
 
 CONV_FIELDS = ("BD MB TR Q0 QN tiles_q tiles_d num_tiles whole n_jobs KG KGa KC NTG TG x_stages w_stages "
-               "x_stage_bytes w_stage_bytes x_plane_bytes SRp BR NBX nslices halo_rows tmem_cols smem ctas Wp SS").split()
-WGRAD_FIELDS = ("KT XR NBXx BRx nband_loaded CoC CiC nfold nacc M Nmma n_jobs splits stages_per_split y_planes "
+               "x_stage_bytes w_stage_bytes x_plane_bytes SRp nslices halo_rows tmem_cols smem ctas Wp SS").split()
+WGRAD_FIELDS = ("KT XR nband_loaded CoC CiC nfold nacc M Nmma n_jobs splits stages_per_split y_planes "
                 "x_planes y_plane_bytes x_plane_bytes stage_bytes stage_tx_bytes stages tmem_cols smem grid banded "
                 "folded accs Wp SS").split()
 
@@ -48,9 +48,12 @@ def padded_rows(x):
     return a.reshape(-1, Cc)
 
 
-def fetch_rows(rows, start, count):
-    """TMA semantics: rows outside [0, total) read as zero."""
+def fetch_rows(rows, start, count, guard=None):
+    """Bulk-copy semantics with zero guard rows: rows outside [0, total) read as zero, and must lie
+    inside the guard the layout reserves (b200_act_guard_rows)."""
     total = rows.shape[0]
+    if guard is not None:
+        assert start >= -guard and start + count <= total + guard, (start, count, total, guard)
     out = torch.zeros(count, rows.shape[1])
     lo, hi = max(start, 0), min(start + count, total)
     if hi > lo:
@@ -70,6 +73,8 @@ def test_conv3_addressing(shape, cout):
     ref = F.conv3d(x, w, padding=1)
     rows = padded_rows(x)
     Wp, SS, Dp = p["Wp"], p["SS"], D + 2
+    guard = _lib.lib().b200_act_guard_rows(D, H, W)
+    assert _lib.lib().b200_act_plane_rows(N, D, H, W) == rows.shape[0] + 2 * guard
     out = torch.zeros(N, 4, D, H, W)
     written = torch.zeros(N, D, H, W, dtype=torch.int32)
     wt = w.reshape(4, Cin, 27)
@@ -83,8 +88,7 @@ def test_conv3_addressing(shape, cout):
         for s in range(p["nslices"]):
             dpi = (0 if p["whole"] else d0 + 1) - 1 + s
             row0 = (n * Dp + dpi) * SS + q0 - p["halo_rows"]
-            for b in range(p["NBX"]):
-                plane[s * p["SRp"] + b * p["BR"]: s * p["SRp"] + (b + 1) * p["BR"]] = fetch_rows(rows, row0 + b * p["BR"], p["BR"])
+            plane[s * p["SRp"]:(s + 1) * p["SRp"]] = fetch_rows(rows, row0, p["SRp"], guard)
         for run in range(p["BD"] * p["MB"]):
             dz, mb = run // p["MB"], run % p["MB"]
             acc = torch.zeros(128, 4)
@@ -114,7 +118,7 @@ def test_conv1_plan_covers_all_rows():
     p = conv_plan(1, 2, 6, 8, 12, 32, 16, Cin_b=32)
     total = 2 * 8 * 10 * 14
     assert p["num_tiles"] * p["TR"] >= total and (p["num_tiles"] - 1) * p["TR"] < total
-    assert p["KG"] == 2 * p["KGa"] and p["KC"] * p["KGa"] == 32 and p["NBX"] * p["BR"] == p["TR"]
+    assert p["KG"] == 2 * p["KGa"] and p["KC"] * p["KGa"] == 32 and p["SRp"] == p["TR"]
     p = conv_plan(1, 1, 4, 4, 4, 64, 512)
     assert p["n_jobs"] == 2 and p["tmem_cols"] == 512
 
@@ -134,6 +138,7 @@ def test_wgrad3_addressing(cfg):
     X, Y = padded_rows(x), padded_rows(dy)
     total = X.shape[0]
     Wp, SS, KT = p["Wp"], p["SS"], p["KT"]
+    guard = _lib.lib().b200_act_guard_rows(D, H, W)
     M, Nm, nacc = p["M"], p["Nmma"], p["nacc"]
     partial = torch.zeros(p["n_jobs"], p["splits"], nacc, M, Nm)
     for job, (jkd, jkh, jkw, jx) in enumerate(p["jobs"]):
@@ -145,13 +150,13 @@ def test_wgrad3_addressing(cfg):
                 A = torch.zeros(KT, M)        # [k][m]; unloaded bands stay zero here (garbage on HW)
                 for b in range(p["nband_loaded"]):
                     kd = (b - 1) if p["nband_loaded"] > 1 else jkd
-                    A[:, b * Cout:(b + 1) * Cout] = fetch_rows(Y, r0 - kd * SS, KT)
-                XR = p["NBXx"] * p["BRx"]
+                    A[:, b * Cout:(b + 1) * Cout] = fetch_rows(Y, r0 - kd * SS, KT, guard)
+                XR = p["XR"]
                 Bm = torch.zeros(XR, Nm)
                 for f in range(p["nfold"]):
                     kw = (f - 1) if p["nfold"] > 1 else jkw
                     xr = r0 + kw + (-Wp if nacc > 1 else jkh * Wp)
-                    Bm[:, f * Cin:(f + 1) * Cin] = fetch_rows(X, xr, XR)[:, jx:jx + Cin]
+                    Bm[:, f * Cin:(f + 1) * Cin] = fetch_rows(X, xr, XR, guard)[:, jx:jx + Cin]
                 for t in range(nacc):
                     xrow = t * Wp if nacc > 1 else 0
                     assert xrow + KT <= XR
