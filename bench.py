@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--batch", type=int, default=2, help="volumes per GPU per step (config 3: 2)")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-multi", action="store_true", help="also capture the step as a CUDA graph when N > 1")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of one CUDA graph per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +198,9 @@ def main():
     if world > 1:
         net = DistributedUNet(model)
         crit.process_group = net.process_group
-    opt = torch.optim.Adam(model.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True)   # main.py:133-140
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True,
+                           capturable=use_graph)                                            # main.py:133-140
 
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(Bsz, 4, S, S, S, generator=g).pin_memory()
@@ -240,11 +244,30 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    if use_graph:
+        # the whole step as ONE CUDA-graph launch (brats2019_b200.graphs): same kernels, same work,
+        # no per-launch Python/driver overhead.  Static input buffers are refreshed by copy_.
+        from brats2019_b200.graphs import GraphedForward, GraphedTrainStep
+        gstep = GraphedTrainStep(net, crit, opt, x_dev, t_dev, warmup=1)
+        launches_per_step = None
+
+        def step_resident():          # noqa: F811
+            return gstep()
+
+        def step_e2e():               # noqa: F811
+            return gstep(x_host, t_host).item()      # H2D copies + graph + D2H loss read
+        l0 = ops.LAUNCHES[0]
+        GraphedTrainStep._eager(gstep)                # count kernels of one eager step (same as the graph's)
+        launches_per_step = ops.LAUNCHES[0] - l0
+        for _ in range(2):
+            step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if use_graph:
+        launches = launches_per_step * args.steps
     ms_step = ms_total / args.steps
     vox_step = Bsz * S ** 3 * world
     value = vox_step / (ms_step * 1e-3)
@@ -259,7 +282,11 @@ def main():
     with torch.no_grad():
         for _ in range(3):
             net([x_dev])
-        ms_fwd, _ = timed(lambda: net([x_dev]), args.steps)
+        if use_graph:
+            gf = GraphedForward(net, x_dev)
+            ms_fwd, _ = timed(lambda: gf(), args.steps)
+        else:
+            ms_fwd, _ = timed(lambda: net([x_dev]), args.steps)
     model.train()
     fwd_value = vox_step / (ms_fwd / args.steps * 1e-3)
 
@@ -315,7 +342,7 @@ def main():
                                    "(BASELINE config 3%s)" % (" + NCCL grad all-reduce" if world > 1 else "", Bsz, S,
                                                               "/4" if world > 1 else ""),
                        "per_gpu_batch": Bsz, "global_batch": Bsz * world, "volume": [4, S, S, S],
-                       "parallelism": "dp%d" % world,
+                       "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
                        "l2": "no flush needed: per-step working set (>2 GB of activations) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

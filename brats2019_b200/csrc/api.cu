@@ -501,7 +501,7 @@ extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
 extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta,
                                 float* workspace, int N, int D, int H, int W, int C, int do_lrelu, void* stream) {
-    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_backward: C=%d unsupported", C);
+    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8) || 1024 % (2 * C)) return fail("gn_backward: C=%d unsupported", C);
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = gn_bwd_blocks(N, D, H);
@@ -511,7 +511,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
                                                                 partial, v, C, do_lrelu);
     LAUNCH_OK("gn_bwd_reduce_kernel");
     const double m = (double)(C / 8) * D * H * W;
-    gn_bwd_finalize_kernel<<<1, 256, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
+    gn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
     LAUNCH_OK("gn_bwd_finalize_kernel");
     gn_bwd_apply_kernel<<<N * D * H, kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
                                                          make_act(dx, v), v, C, do_lrelu);

@@ -171,39 +171,52 @@ gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
 }
 
 // pass 2: partial[n][blocks][C][2] -> coef[n][C][2] = (A_g, B_g) per channel's group, and
-//         dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.      grid = 1, block = 256 threads (C <= 256)
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
-                                       const float* __restrict__ gamma, float* __restrict__ coef,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ double sh1[256], sh2[256];
-    const int c = threadIdx.x;
+//         dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.   grid = 1, block = 1024 threads, C <= 256.
+// Each of the 2C per-sample sums is split over T = 1024/(2C) threads (strided, fixed order) and
+// combined in a fixed order, so the result is deterministic and the latency is ~blocks/T loads.
+__global__ void __launch_bounds__(1024)
+gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
+                       const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+    __shared__ double s_part[1024];
+    __shared__ double s_sum[512];      // [c][which]
+    __shared__ double s_tot[512];      // running sum over n
+    const int t = threadIdx.x;
+    const int nout = 2 * C;
+    const int T = 1024 / nout;         // threads per output (C in {16..256} -> T in {32..2})
+    const int o = t / T, j = t - o * T;
     const int gs = C / 8;
-    double tg = 0.0, tb = 0.0;
+    if (t < nout) s_tot[t] = 0.0;
     for (int n = 0; n < N; ++n) {
-        double a = 0.0, b = 0.0;
-        if (c < C) {
-            for (int k = 0; k < blocks; ++k) {
-                a += (double)partial[(((size_t)n * blocks + k) * C + c) * 2 + 0];
-                b += (double)partial[(((size_t)n * blocks + k) * C + c) * 2 + 1];
-            }
-            tb += a;
-            tg += b;
-            sh1[c] = a * (double)gamma[c];
-            sh2[c] = b * (double)gamma[c];
+        double a = 0.0;
+        if (o < nout) {
+            const float* src = partial + ((size_t)n * blocks * C) * 2 + o;      // o = c*2 + which
+            for (int k = j; k < blocks; k += T) a += (double)src[(size_t)k * C * 2];
+        }
+        s_part[t] = a;
+        __syncthreads();
+        if (t < nout) {
+            double acc = 0.0;
+            for (int q = 0; q < T; ++q) acc += s_part[t * T + q];
+            s_sum[t] = acc;
+            s_tot[t] += acc;
         }
         __syncthreads();
-        if (c < C) {
-            const int g0 = (c / gs) * gs;
+        if (t < C) {
+            const int g0 = (t / gs) * gs;
             double A = 0.0, B = 0.0;
-            for (int k = 0; k < gs; ++k) { A += sh1[g0 + k]; B += sh2[g0 + k]; }
-            coef[((size_t)n * C + c) * 2 + 0] = (float)(A / m);
-            coef[((size_t)n * C + c) * 2 + 1] = (float)(B / m);
+            for (int k = 0; k < gs; ++k) {
+                A += s_sum[(g0 + k) * 2 + 0] * (double)gamma[g0 + k];
+                B += s_sum[(g0 + k) * 2 + 1] * (double)gamma[g0 + k];
+            }
+            coef[((size_t)n * C + t) * 2 + 0] = (float)(A / m);
+            coef[((size_t)n * C + t) * 2 + 1] = (float)(B / m);
         }
         __syncthreads();
     }
-    if (c < C) {
-        dgamma[c] = (float)tg;
-        dbeta[c] = (float)tb;
+    if (t < C) {
+        dbeta[t] = (float)s_tot[t * 2 + 0];
+        dgamma[t] = (float)s_tot[t * 2 + 1];
     }
 }
 

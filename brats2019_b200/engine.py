@@ -108,7 +108,9 @@ class Engine:
         key = (name, kind, ci_off, desc.mode, desc.Cin_a, desc.Cin_b, desc.Cout)
         ent = self.packed.get(key)
         ver = (w._version, w.data_ptr())
-        if ent is None or ent[0] != ver:
+        # while a CUDA graph is being captured the pack kernels must be part of it (the weights
+        # change between replays), so the version cache is bypassed
+        if ent is None or ent[0] != ver or torch.cuda.is_current_stream_capturing():
             buf = ops.conv_pack_weight(desc, kind, w, ci_off=ci_off, K_real=K_real, N_real=N_real,
                                        out=None if ent is None else ent[1])
             ent = (ver, buf)
