@@ -188,6 +188,21 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # Everything below runs on a non-default stream: work queued on the legacy default stream
+    # implicitly synchronises with every blocking stream and breaks CUDA-graph capture.
+    main_stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(main_stream):
+        run(args, rank, world, local_rank, dev)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run(args, rank, world, local_rank, dev):
+    import torch
+    import torch.distributed as dist
+    import brats2019_b200 as B
+    from brats2019_b200 import ops
+    from brats2019_b200.parallel import DistributedUNet
     peaks = read_peaks()
     Bsz, S = args.batch, args.size
     model = B.UNet(**B.DEFAULT_CFG)
@@ -354,8 +369,6 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -444,8 +444,8 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     q.banded = P.banded; q.folded = P.folded; q.accs = P.accs;
     q.n_jobs = P.k.n_jobs; q.splits = P.k.splits; q.nacc = P.k.nacc; q.M = P.k.M; q.Nmma = P.k.Nmma;
     q.accumulate = accumulate;
-    const int total = Cout_w * Cin_w * taps_w;
-    wgrad_reduce_kernel<<<std::min((total + 127) / 128, 2048), 128, 0, st>>>(P.k.partial, grad, q);
+    const int total = q.n_jobs * q.nacc * q.M * q.Nmma;
+    wgrad_reduce_kernel<<<std::min((total + 127) / 128, 4096), 128, 0, st>>>(P.k.partial, grad, q);
     LAUNCH_OK("wgrad_reduce_kernel");
     return 0;
 }
@@ -473,7 +473,7 @@ extern "C" int b200_gn_finalize(const float* stats_partial, int ctas, int N, int
                                 float* mean, float* rstd, void* stream) {
     if (C % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
     const double count = (double)(C / 8) * D * H * W;
-    gn_finalize_kernel<<<N, 32, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd);
+    gn_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd);
     LAUNCH_OK("gn_finalize_kernel");
     return 0;
 }

@@ -44,20 +44,31 @@ __global__ void pack_input_kernel(const float* __restrict__ x, ActRef out, Vol v
 // GroupNorm statistics: conv epilogue partials [ctas][N][16] -> mean/rstd [N][8]
 // (aten::native_group_norm statistics, model.py:95-96/338; eps 1e-5, biased variance)
 // ---------------------------------------------------------------------------------------
+// grid = N, block = 256: each of the 16 sums is split over 16 threads (strided over CTAs, fixed
+// order) and combined in a fixed order -> deterministic, ~ctas/16 dependent loads of latency.
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, int N, double count, float eps,
                                    float* __restrict__ mean, float* __restrict__ rstd) {
-    const int n = blockIdx.x, g = threadIdx.x;
-    if (g >= 8) return;
-    double s = 0.0, q = 0.0;
-    for (int c = 0; c < ctas; ++c) {
-        s += (double)partial[((size_t)c * N + n) * 16 + g];
-        q += (double)partial[((size_t)c * N + n) * 16 + 8 + g];
+    __shared__ double s_part[256];
+    __shared__ double s_sum[16];
+    const int n = blockIdx.x, t = threadIdx.x;
+    const int o = t >> 4, j = t & 15;
+    double a = 0.0;
+    for (int c = j; c < ctas; c += 16) a += (double)partial[((size_t)c * N + n) * 16 + o];
+    s_part[t] = a;
+    __syncthreads();
+    if (t < 16) {
+        double acc = 0.0;
+        for (int q = 0; q < 16; ++q) acc += s_part[t * 16 + q];
+        s_sum[t] = acc;
     }
-    const double m = s / count;
-    double var = q / count - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[n * 8 + g] = (float)m;
-    rstd[n * 8 + g] = (float)(1.0 / sqrt(var + (double)eps));
+    __syncthreads();
+    if (t < 8) {
+        const double m = s_sum[t] / count;
+        double var = s_sum[8 + t] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[n * 8 + t] = (float)m;
+        rstd[n * 8 + t] = (float)(1.0 / sqrt(var + (double)eps));
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -634,32 +645,45 @@ struct WgradReduceParams {
     int accumulate;          // add into grad instead of overwriting
 };
 
+// One thread per accumulator element (job, acc, row, col): coalesced reads of the partials over
+// `col`, fixed-order sum over the K splits, one scattered write into the PyTorch-layout gradient.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q) {
-    const int total = q.Cout_w * q.Cin_w * q.taps_w;
+    const int per_job = q.nacc * q.M * q.Nmma;
+    const int total = q.n_jobs * per_job;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int tp = i % q.taps_w;
-        const int ci_w = (i / q.taps_w) % q.Cin_w;
-        const int co = i / (q.taps_w * q.Cin_w);
-        int job, t, row, col;
+        const int col = i % q.Nmma;
+        int r = i / q.Nmma;
+        const int row = r % q.M;
+        r /= q.M;
+        const int t = r % q.nacc;
+        const int job = r / q.nacc;
+        int co, ci_w, tp;
         if (q.kind == 0) {
-            const int kd = tp / 9, kh = (tp / 3) % 3, kw = tp % 3;
-            job = ((q.banded ? 0 : kd) * (q.accs ? 1 : 3) + (q.accs ? 0 : kh)) * (q.folded ? 1 : 3) + (q.folded ? 0 : kw);
-            row = (q.banded ? kd * q.Cout_g : 0) + co;
-            col = (q.folded ? kw * q.Cin_g : 0) + ci_w;
-            t = q.accs ? kh : 0;
+            int jj = job;
+            const int jkw = q.folded ? 0 : jj % 3; if (!q.folded) jj /= 3;
+            const int jkh = q.accs ? 0 : jj % 3;   if (!q.accs) jj /= 3;
+            const int jkd = q.banded ? 0 : jj;
+            const int kd = q.banded ? row / q.Cout_g : jkd;
+            co = q.banded ? row % q.Cout_g : row;
+            const int kw = q.folded ? col / q.Cin_g : jkw;
+            ci_w = q.folded ? col % q.Cin_g : col;
+            const int kh = q.accs ? t : jkh;
+            if (kd > 2 || kw > 2) continue;      // unused band / padding of the M or N extent
+            tp = (kd * 3 + kh) * 3 + kw;
         } else if (q.kind == 1) {
-            const int ci = ci_w - q.ci_off;
-            if (ci < 0 || ci >= q.Cin_g) continue;
-            job = ci / q.Nmma; col = ci % q.Nmma; row = co; t = 0;
+            co = row; ci_w = q.ci_off + job * q.Nmma + col; tp = 0;
         } else {
-            const int k = tp * q.Cin_w + ci_w;
-            job = k / q.Nmma; col = k % q.Nmma; row = co; t = 0;
+            const int k = job * q.Nmma + col;
+            co = row; tp = k / q.Cin_w; ci_w = k % q.Cin_w;
         }
+        if (co >= q.Cout_w || ci_w >= q.Cin_w || tp >= q.taps_w) continue;
+        if (q.kind == 1 && (job * q.Nmma + col) >= q.Cin_g) continue;
+        const float* src = partial + (size_t)job * q.splits * per_job + (size_t)(i - job * per_job);
         double a = 0.0;
-        for (int s = 0; s < q.splits; ++s)
-            a += (double)partial[((((size_t)job * q.splits + s) * q.nacc + t) * q.M + row) * q.Nmma + col];
-        if (q.accumulate) grad[i] += (float)a;
-        else grad[i] = (float)a;
+        for (int s = 0; s < q.splits; ++s) a += (double)src[(size_t)s * per_job];
+        const size_t o = ((size_t)co * q.Cin_w + ci_w) * q.taps_w + tp;
+        if (q.accumulate) grad[o] += (float)a;
+        else grad[o] = (float)a;
     }
 }
 
