@@ -453,6 +453,15 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
 // ---------------------------------------------------------------------------------------
 // memory-bound ops
 // ---------------------------------------------------------------------------------------
+// lines per CTA for the line-walking kernels: a power of two <= 16 that divides D*H (so a CTA
+// never straddles two samples) and still leaves >= ~8 CTAs per SM
+static int lines_per_block(int N, int D, int H) {
+    const long long lines = (long long)N * D * H;
+    int lpb = 1;
+    while (lpb < 16 && (D * H) % (lpb * 2) == 0 && lines / (lpb * 2) >= 8LL * num_sms()) lpb *= 2;
+    return lpb;
+}
+
 static int check_act(int N, int D, int H, int W, int C) {
     if (N < 1 || D < 1 || H < 1 || W < 1) return fail("bad volume %dx%dx%dx%d", N, D, H, W);
     if (C < 8 || C % 8 || C > 1024) return fail("channel count %d unsupported", C);
@@ -483,16 +492,17 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
                              int do_lrelu, void* stream) {
     if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_apply: C=%d unsupported", C);
     Vol v{N, D, H, W};
-    gn_apply_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(x, v), mean, rstd, gamma, beta,
-                                                                        make_act(residual, v), make_act(out, v), v, C,
-                                                                        do_lrelu);
+    const int lpb = lines_per_block(N, D, H);
+    gn_apply_kernel<<<N * D * H / lpb, kEwThreads, 0, (cudaStream_t)stream>>>(
+        make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu, lpb);
     LAUNCH_OK("gn_apply_kernel");
     return 0;
 }
 
 static int gn_bwd_blocks(int N, int D, int H) {
+    // CTAs per sample for the reduction: ~4 per SM over the batch, each with >= 4 lines of work
     int per = std::max(1, 4 * num_sms() / std::max(1, N));
-    return std::min(per, D * H);
+    return std::max(1, std::min(per, D * H / 4));
 }
 extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
     // partial[N][blocks<=4*sms][C][2] + coef[N][C][2]
@@ -513,8 +523,9 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     const double m = (double)(C / 8) * D * H * W;
     gn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
     LAUNCH_OK("gn_bwd_finalize_kernel");
-    gn_bwd_apply_kernel<<<N * D * H, kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
-                                                         make_act(dx, v), v, C, do_lrelu);
+    const int lpb = lines_per_block(N, D, H);
+    gn_bwd_apply_kernel<<<N * D * H / lpb, kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                               coef, make_act(dx, v), v, C, do_lrelu, lpb);
     LAUNCH_OK("gn_bwd_apply_kernel");
     return 0;
 }
@@ -561,7 +572,9 @@ extern "C" int b200_depth_to_space(const void* coarse, const void* residual, voi
 extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, int H, int W, int C, void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
     Vol v{N, D, H, W};
-    add_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(a, v), make_act(b, v), make_act(out, v), v, C);
+    const int lpb = lines_per_block(N, D, H);
+    add_kernel<<<N * D * H / lpb, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(a, v), make_act(b, v), make_act(out, v),
+                                                                        v, C, lpb);
     LAUNCH_OK("add_kernel");
     return 0;
 }

@@ -19,6 +19,30 @@ __device__ __forceinline__ void line_coords(const Vol& v, int line, int& n, int&
     d = t % v.D;
     n = t / v.D;
 }
+// A CTA owns `lpb` consecutive lines (all of one sample: lpb divides D*H).  Vector j of the CTA
+// -> (line, 8-channel chunk cv, voxel w); voxel index fastest so a warp reads 512 contiguous bytes.
+struct LineVec {
+    int n, cv, w;
+    long long row;      // row of the voxel in the padded volume
+    bool ok;
+};
+__device__ __forceinline__ LineVec line_vec(const Vol& v, int line0, int lpb, int nvec, int j) {
+    LineVec r;
+    const int ll = j / nvec;
+    const int i = j - ll * nvec;
+    r.ok = ll < lpb;
+    r.cv = i / v.W;
+    r.w = i - r.cv * v.W;
+    const int line = line0 + (r.ok ? ll : 0);
+    const int h = line % v.H;
+    const int t = line / v.H;
+    const int d = t % v.D;
+    r.n = t / v.D;
+    r.row = v.row(r.n, d + 1, h + 1, 1 + r.w);
+    return r;
+}
+constexpr int kUnroll = 4;
+
 __device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& q) { *reinterpret_cast<uint4*>(p) = q; }
 
@@ -78,10 +102,10 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, 
 __global__ void __launch_bounds__(kEwThreads)
 gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, ActRef residual, ActRef out, Vol v,
-                int C, int do_lrelu) {
+                int C, int do_lrelu, int lpb) {
     __shared__ float s_scale[256], s_shift[256];
-    int n, d, h;
-    line_coords(v, blockIdx.x, n, d, h);
+    const int line0 = blockIdx.x * lpb;
+    const int n = line0 / (v.D * v.H);
     const int gs = C / 8;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / gs;
@@ -90,25 +114,38 @@ gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restric
         s_shift[c] = beta[c] - mean[n * 8 + g] * sc;
     }
     __syncthreads();
-    const long long row0 = v.row(n, d + 1, h + 1, 1);
     const int nvec = v.W * (C / 8);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = i / v.W, w = i - cv * v.W;
-        const int cb = cv * 8;
-        float f[8];
-        unpack_bf16x8(ld16(x.at(cv, row0 + w)), f);
+    const int total = lpb * nvec;
+    for (int j0 = threadIdx.x; j0 < total; j0 += blockDim.x * kUnroll) {
+        LineVec lv[kUnroll];
+        uint4 qx[kUnroll], qr[kUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float z = f[k] * s_scale[cb + k] + s_shift[cb + k];
-            f[k] = do_lrelu ? lrelu(z) : z;
+        for (int u = 0; u < kUnroll; ++u) {
+            lv[u] = line_vec(v, line0, lpb, nvec, j0 + u * blockDim.x);
+            if (lv[u].ok) {
+                qx[u] = ld16(x.at(lv[u].cv, lv[u].row));
+                if (residual.base) qr[u] = ld16(residual.at(lv[u].cv, lv[u].row));
+            }
         }
-        if (residual.base) {
-            float r[8];
-            unpack_bf16x8(ld16(residual.at(cv, row0 + w)), r);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] += r[k];
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!lv[u].ok) continue;
+            const int cb = lv[u].cv * 8;
+            float f[8];
+            unpack_bf16x8(qx[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float z = f[k] * s_scale[cb + k] + s_shift[cb + k];
+                f[k] = do_lrelu ? lrelu(z) : z;
+            }
+            if (residual.base) {
+                float r[8];
+                unpack_bf16x8(qr[u], r);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] += r[k];
+            }
+            st16(out.at(lv[u].cv, lv[u].row), pack_bf16x8(f));
         }
-        st16(out.at(cv, row0 + w), pack_bf16x8(f));
     }
 }
 
@@ -144,24 +181,39 @@ gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
         float s1[8], s2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-        for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
-            const int li = idx / v.W, w = idx - li * v.W;
-            const int line = blockIdx.x + li * gridDim.x;
-            const int d = line / v.H, h = line - d * v.H;
-            const long long r = v.row(n, d + 1, h + 1, 1 + w);
-            float fx[8], fd[8];
-            unpack_bf16x8(ld16(x.at(cv, r)), fx);
-            unpack_bf16x8(ld16(dy.at(cv, r)), fd);
+        for (int idx0 = threadIdx.x; idx0 < items; idx0 += blockDim.x * kUnroll) {
+            uint4 qx[kUnroll], qd[kUnroll];
+            bool ok[kUnroll];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
-                float dz = fd[k];
-                if (do_lrelu) {
-                    const float z = xh * s_g[cb + k] + s_be[cb + k];
-                    dz = z > 0.f ? dz : 0.01f * dz;
+            for (int u = 0; u < kUnroll; ++u) {
+                const int idx = idx0 + u * blockDim.x;
+                ok[u] = idx < items;
+                if (ok[u]) {
+                    const int li = idx / v.W, w = idx - li * v.W;
+                    const int line = blockIdx.x + li * gridDim.x;
+                    const int d = line / v.H, h = line - d * v.H;
+                    const long long r = v.row(n, d + 1, h + 1, 1 + w);
+                    qx[u] = ld16(x.at(cv, r));
+                    qd[u] = ld16(dy.at(cv, r));
                 }
-                s1[k] += dz;
-                s2[k] += dz * xh;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (!ok[u]) continue;
+                float fx[8], fd[8];
+                unpack_bf16x8(qx[u], fx);
+                unpack_bf16x8(qd[u], fd);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
+                    float dz = fd[k];
+                    if (do_lrelu) {
+                        const float z = xh * s_g[cb + k] + s_be[cb + k];
+                        dz = z > 0.f ? dz : 0.01f * dz;
+                    }
+                    s1[k] += dz;
+                    s2[k] += dz * xh;
+                }
             }
         }
 #pragma unroll
@@ -235,10 +287,10 @@ gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int
 __global__ void __launch_bounds__(kEwThreads)
 gn_bwd_apply_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
-                    ActRef dx, Vol v, int C, int do_lrelu) {
+                    ActRef dx, Vol v, int C, int do_lrelu, int lpb) {
     __shared__ float s_a[256], s_b[256], s_g[256], s_be[256], s_A[256], s_B[256];
-    int n, d, h;
-    line_coords(v, blockIdx.x, n, d, h);
+    const int line0 = blockIdx.x * lpb;
+    const int n = line0 / (v.D * v.H);
     const int gs = C / 8;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / gs;
@@ -250,25 +302,38 @@ gn_bwd_apply_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const f
         s_B[c] = coef[((size_t)n * C + c) * 2 + 1];
     }
     __syncthreads();
-    const long long row0 = v.row(n, d + 1, h + 1, 1);
     const int nvec = v.W * (C / 8);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = i / v.W, w = i - cv * v.W;
-        const int cb = cv * 8;
-        float fx[8], fd[8];
-        unpack_bf16x8(ld16(x.at(cv, row0 + w)), fx);
-        unpack_bf16x8(ld16(dy.at(cv, row0 + w)), fd);
+    const int total = lpb * nvec;
+    for (int j0 = threadIdx.x; j0 < total; j0 += blockDim.x * kUnroll) {
+        LineVec lv[kUnroll];
+        uint4 qx[kUnroll], qd[kUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
-            float dz = fd[k];
-            if (do_lrelu) {
-                const float z = xh * s_g[cb + k] + s_be[cb + k];
-                dz = z > 0.f ? dz : 0.01f * dz;
+        for (int u = 0; u < kUnroll; ++u) {
+            lv[u] = line_vec(v, line0, lpb, nvec, j0 + u * blockDim.x);
+            if (lv[u].ok) {
+                qx[u] = ld16(x.at(lv[u].cv, lv[u].row));
+                qd[u] = ld16(dy.at(lv[u].cv, lv[u].row));
             }
-            fx[k] = s_a[cb + k] * (dz * s_g[cb + k] - s_A[cb + k] - xh * s_B[cb + k]);
         }
-        st16(dx.at(cv, row0 + w), pack_bf16x8(fx));
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!lv[u].ok) continue;
+            const int cb = lv[u].cv * 8;
+            float fx[8], fd[8];
+            unpack_bf16x8(qx[u], fx);
+            unpack_bf16x8(qd[u], fd);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
+                float dz = fd[k];
+                if (do_lrelu) {
+                    const float z = xh * s_g[cb + k] + s_be[cb + k];
+                    dz = z > 0.f ? dz : 0.01f * dz;
+                }
+                fx[k] = s_a[cb + k] * (dz * s_g[cb + k] - s_A[cb + k] - xh * s_B[cb + k]);
+            }
+            st16(dx.at(lv[u].cv, lv[u].row), pack_bf16x8(fx));
+        }
     }
 }
 
@@ -430,19 +495,31 @@ d2s_kernel(ActRef coarse, ActRef residual, ActRef fine, Vol vc, int C) {
 
 // out = a + b over the interior (gradient accumulation where two paths meet)
 __global__ void __launch_bounds__(kEwThreads)
-add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C) {
-    int n, d, h;
-    line_coords(v, blockIdx.x, n, d, h);
-    const long long row0 = v.row(n, d + 1, h + 1, 1);
+add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, int lpb) {
+    const int line0 = blockIdx.x * lpb;
     const int nvec = v.W * (C / 8);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = i / v.W, w = i - cv * v.W;
-        float fa[8], fb[8];
-        unpack_bf16x8(ld16(a.at(cv, row0 + w)), fa);
-        unpack_bf16x8(ld16(b.at(cv, row0 + w)), fb);
+    const int total = lpb * nvec;
+    for (int j0 = threadIdx.x; j0 < total; j0 += blockDim.x * kUnroll) {
+        LineVec lv[kUnroll];
+        uint4 qa[kUnroll], qb[kUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
-        st16(out.at(cv, row0 + w), pack_bf16x8(fa));
+        for (int u = 0; u < kUnroll; ++u) {
+            lv[u] = line_vec(v, line0, lpb, nvec, j0 + u * blockDim.x);
+            if (lv[u].ok) {
+                qa[u] = ld16(a.at(lv[u].cv, lv[u].row));
+                qb[u] = ld16(b.at(lv[u].cv, lv[u].row));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!lv[u].ok) continue;
+            float fa[8], fb[8];
+            unpack_bf16x8(qa[u], fa);
+            unpack_bf16x8(qb[u], fb);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+            st16(out.at(lv[u].cv, lv[u].row), pack_bf16x8(fa));
+        }
     }
 }
 
