@@ -205,7 +205,9 @@ def run(args, rank, world, local_rank, dev):
     from brats2019_b200.parallel import DistributedUNet
     peaks = read_peaks()
     Bsz, S = args.batch, args.size
-    model = B.UNet(**B.DEFAULT_CFG)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the reference-compatible ctor prints 'UNet [...]' (model.py:311)
+        model = B.UNet(**B.DEFAULT_CFG)
     init_weights(model, 1337)
     model = model.to(dev).train()
     crit = B.Dice_loss_joint(index=0, priority=1)
