@@ -90,7 +90,16 @@ static const unsigned kMaxSmem = 227 * 1024;
 // ---------------------------------------------------------------------------------------
 // conv planning
 // ---------------------------------------------------------------------------------------
-static int conv_nmma(const b200_conv_desc* d) { return d->Cout > 256 ? 256 : d->Cout; }
+// kw-fold (conv_gemm.cuh): 3x3x3, bf16 epilogue, Cout 16 or 32 -> GEMM N = 3*Cout
+static bool conv_fold(const b200_conv_desc* d) {
+    static int no_fold = -1;
+    if (no_fold < 0) { const char* e = getenv("B200_NO_FOLD"); no_fold = (e && atoi(e)) ? 1 : 0; }
+    return !no_fold && d->mode == MODE_K3 && d->epi == EPI_BF16 && (d->Cout == 16 || d->Cout == 32);
+}
+static int conv_nmma(const b200_conv_desc* d) {
+    if (conv_fold(d)) return 3 * d->Cout;
+    return d->Cout > 256 ? 256 : d->Cout;
+}
 static int conv_kc(const b200_conv_desc* d) {
     if (d->mode == MODE_K3) return 16;
     for (int kc : {64, 32, 16})
@@ -104,7 +113,7 @@ static int check_conv_desc(const b200_conv_desc* d) {
     if (d->N < 1 || d->D < 1 || d->H < 1 || d->W < 1) return fail("bad volume %dx%dx%dx%d", d->N, d->D, d->H, d->W);
     if (d->Cin_a < 16 || d->Cin_a % 16 || d->Cin_b < 0 || d->Cin_b % 16)
         return fail("Cin_a=%d / Cin_b=%d must be multiples of 16", d->Cin_a, d->Cin_b);
-    const int n = conv_nmma(d);
+    const int n = d->Cout > 256 ? 256 : d->Cout;
     if (!(n == 16 || n == 32 || n == 64 || n == 128 || n == 256) || d->Cout % n)
         return fail("Cout=%d unsupported (16/32/64/128/256 or a multiple of 256)", d->Cout);
     if (d->mode == MODE_K3 && (d->Cout > 128 || d->Cin_b != 0)) return fail("k3 conv: Cout<=128 and one source only");
@@ -123,17 +132,19 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     p.sample_rows = (long long)(d->D + 2) * p.SS;
     p.total_rows = p.sample_rows * d->N;
     p.mode = d->mode;
-    p.n_jobs = d->Cout / Nm;
+    const bool fold = conv_fold(d);
+    const int RB = fold ? 126 : 128;
+    p.n_jobs = fold ? 1 : d->Cout / Nm;
     p.KC = conv_kc(d);
     if (p.KC == 0) return fail("no K chunk size for Cin_a=%d Cin_b=%d", d->Cin_a, d->Cin_b);
     p.KGa = d->Cin_a / p.KC;
     p.KG = p.KGa + d->Cin_b / p.KC;
     p.Cout_total = d->Cout;
     const int sms = num_sms();
-    const unsigned bar_bytes = 1024 + 128;
+    const unsigned bar_bytes = kConvTailBytes + 128;
 
     if (d->mode == MODE_K3) {
-        p.NTG = 3; p.TG = 9;
+        p.NTG = 3; p.TG = fold ? 3 : 9;
         p.w_stage_bytes = (unsigned)(p.TG * p.KC * Nm * 2);
         double best_cost = 1e300;
         int bBD = 0, bMB = 0, bWhole = 0;
@@ -144,8 +155,8 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
                 for (int MB : {1, 2, 4}) {
                     const int R = BD * MB;
                     if (2 * R * Nm > 512) continue;
-                    const int TR = 128 * MB;
-                    const int SR = TR + 2 * p.Wp + 2;
+                    const int TR = RB * MB;
+                    const int SR = (MB - 1) * RB + 128 + 2 * p.Wp + (fold ? 0 : 2);
                     const int SRp = (SR + 7) / 8 * 8;
                     const unsigned xst = 2u * (BD + 2) * SRp * 16;
                     if (2 * xst + 2 * p.w_stage_bytes + bar_bytes > kMaxSmem) continue;
@@ -165,8 +176,8 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
             }
         if (bBD == 0) return fail("k3 conv: no tile shape fits (W=%d, Cout=%d)", d->W, d->Cout);
         p.BD = bBD; p.MB = bMB; p.whole = bWhole;
-        p.TR = 128 * p.MB;
-        const int SR = p.TR + 2 * p.Wp + 2;
+        p.TR = RB * p.MB;
+        const int SR = (p.MB - 1) * RB + 128 + 2 * p.Wp + (fold ? 0 : 2);
         p.SRp = (SR + 7) / 8 * 8;
         p.nslices = p.BD + 2;
         p.halo_rows = p.Wp + 1;
@@ -182,7 +193,11 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
             p.tiles_d = ceil_div(d->D, p.BD);
         }
         p.tiles_q = ceil_div(p.QN, p.TR);
-        for (int t = 0; t < 27; ++t) p.tap_off[t] = (t / 9) * p.SRp + ((t / 3) % 3) * p.Wp + (t % 3);
+        if (fold) {
+            for (int t = 0; t < 9; ++t) p.tap_off[t] = (t / 3) * p.SRp + (t % 3) * p.Wp;     // (kd, kh); kw lives in N
+        } else {
+            for (int t = 0; t < 27; ++t) p.tap_off[t] = (t / 9) * p.SRp + ((t / 3) % 3) * p.Wp + (t % 3);
+        }
     } else {
         p.NTG = 1; p.TG = 1;
         p.w_stage_bytes = (unsigned)(p.KC * Nm * 2);
@@ -245,6 +260,8 @@ extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const fl
     q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
     q.K_real = K_real; q.N_real = N_real;
     q.n_jobs = p.n_jobs; q.KG = p.KG; q.NTG = p.NTG; q.TG = p.TG; q.KC = p.KC; q.Nmma = conv_nmma(d);
+    q.fold = conv_fold(d) ? 1 : 0;
+    if (q.fold && kind > B200_W_DGRAD) return fail("fold applies to 3x3x3 weights only");
     const size_t total = (size_t)q.n_jobs * q.KG * q.NTG * q.TG * (q.KC / 8) * q.Nmma;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
     pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, q);
@@ -252,15 +269,15 @@ extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const fl
     return 0;
 }
 
-template <int MODE, int EPI, int NM>
+template <int MODE, int EPI, int NM, int FOLD>
 static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<MODE, EPI, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<MODE, EPI, NM, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kMaxSmem));
         attr_set = true;
     }
-    conv_gemm_kernel<MODE, EPI, NM><<<grid, kConvThreads, smem, st>>>(p);
+    conv_gemm_kernel<MODE, EPI, NM, FOLD><<<grid, kConvThreads, smem, st>>>(p);
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
 }
@@ -298,24 +315,28 @@ extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const v
     p.out = make_act(out, vol);
     p.residual = make_act(residual, vol);
     if (p.x_stage_bytes >= (1u << 20) || p.w_stage_bytes >= (1u << 20)) return fail("conv: stage exceeds the mbarrier tx-count range");
-    const unsigned smem = p.smem_bar_off + 1024;
+    const unsigned smem = p.smem_bar_off + kConvTailBytes;
     const int Nm = conv_nmma(d);
-#define CONV_CASE(MODE, EPI, NM) return launch_conv<MODE, EPI, NM>(p, smem, grid, st)
-    if (d->epi == EPI_SIGMOID) CONV_CASE(MODE_K3, EPI_SIGMOID, 16);
+#define CONV_CASE(MODE, EPI, NM, FOLD) return launch_conv<MODE, EPI, NM, FOLD>(p, smem, grid, st)
+    if (d->epi == EPI_SIGMOID) CONV_CASE(MODE_K3, EPI_SIGMOID, 16, 0);
     if (d->mode == MODE_K3) {
+        if (conv_fold(d)) {
+            if (Nm == 48) CONV_CASE(MODE_K3, EPI_BF16, 48, 1);
+            if (Nm == 96) CONV_CASE(MODE_K3, EPI_BF16, 96, 1);
+        }
         switch (Nm) {
-            case 16: CONV_CASE(MODE_K3, EPI_BF16, 16);
-            case 32: CONV_CASE(MODE_K3, EPI_BF16, 32);
-            case 64: CONV_CASE(MODE_K3, EPI_BF16, 64);
-            case 128: CONV_CASE(MODE_K3, EPI_BF16, 128);
+            case 16: CONV_CASE(MODE_K3, EPI_BF16, 16, 0);
+            case 32: CONV_CASE(MODE_K3, EPI_BF16, 32, 0);
+            case 64: CONV_CASE(MODE_K3, EPI_BF16, 64, 0);
+            case 128: CONV_CASE(MODE_K3, EPI_BF16, 128, 0);
         }
     } else {
         switch (Nm) {
-            case 16: CONV_CASE(MODE_K1, EPI_BF16, 16);
-            case 32: CONV_CASE(MODE_K1, EPI_BF16, 32);
-            case 64: CONV_CASE(MODE_K1, EPI_BF16, 64);
-            case 128: CONV_CASE(MODE_K1, EPI_BF16, 128);
-            case 256: CONV_CASE(MODE_K1, EPI_BF16, 256);
+            case 16: CONV_CASE(MODE_K1, EPI_BF16, 16, 0);
+            case 32: CONV_CASE(MODE_K1, EPI_BF16, 32, 0);
+            case 64: CONV_CASE(MODE_K1, EPI_BF16, 64, 0);
+            case 128: CONV_CASE(MODE_K1, EPI_BF16, 128, 0);
+            case 256: CONV_CASE(MODE_K1, EPI_BF16, 256, 0);
         }
     }
 #undef CONV_CASE
@@ -631,10 +652,11 @@ extern "C" int b200_dice_backward(const float* probs, const float* target, const
 extern "C" int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out) {
     ConvKParams p;
     if (plan_conv(d, p)) return 1;
+    const int fold_flag = conv_fold(d) ? 1 : 0, RBv = fold_flag ? 126 : 128;
     const int vals[] = {p.BD, p.MB, p.TR, p.Q0, p.QN, p.tiles_q, p.tiles_d, p.num_tiles, p.whole, p.n_jobs,
                         p.KG, p.KGa, p.KC, p.NTG, p.TG, p.x_stages, p.w_stages, (int)p.x_stage_bytes,
                         (int)p.w_stage_bytes, (int)p.x_plane_bytes, p.SRp, p.nslices, p.halo_rows,
-                        (int)p.tmem_cols, (int)(p.smem_bar_off + 1024), conv_grid_ctas(p), p.Wp, p.SS};
+                        (int)p.tmem_cols, (int)(p.smem_bar_off + kConvTailBytes), conv_grid_ctas(p), p.Wp, p.SS, fold_flag, RBv};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv + kMaxTaps) return fail("plan_debug: need %d ints", nv + kMaxTaps);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];

@@ -16,8 +16,16 @@
 // of the 27 taps is just a different start address in the A descriptor.  Rows that land on
 // halo positions are junk: computed, never stored.
 //
-// Warp roles (256 threads): w0 activation bulk-copy producer, w1 weight bulk-copy producer,
-// w2 MMA issuer (one thread), w3 TMEM allocator, w4-7 epilogue (TMEM -> regs -> HBM).
+// kw-fold (FOLD = 1, Cout <= 32): a K=16 MMA costs max(46, N/2) cycles regardless of N <= 92
+// (measured, tools/umma_probe.cu), so with N = Cout = 16 the tensor pipe idles 5/6 of the time.
+// The fold makes N = 3*Cout: column block kw holds  P_kw[r] = sum_{kd,kh,ci} X[r+(kd-1)SS+(kh-1)Wp] W[kd,kh,kw]
+// (9 MMAs per run instead of 27) and the epilogue forms  out[r] = P_0[r-1] + P_1[r] + P_2[r+1]
+// with warp shuffles (+ a 2-row exchange through shared memory at warp boundaries).  Blocks then
+// advance by 126 rows: P rows 0 and 127 of a 128-row block only feed their neighbours.
+//
+// Warp roles (384 threads): w0 activation bulk-copy producer, w1 weight bulk-copy producer,
+// w2 MMA issuer (one elected lane), w3 TMEM allocator, w4-7 and w8-11 two epilogue groups
+// (TMEM -> regs -> HBM) that take alternate runs of a tile.
 #pragma once
 #include "common.cuh"
 
@@ -27,7 +35,8 @@ enum { MODE_K3 = 0, MODE_K1 = 1 };
 enum { EPI_BF16 = 0, EPI_SIGMOID = 1 };
 
 constexpr int kMaxTaps = 27;
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;
+constexpr unsigned kConvTailBytes = 3072;   // barriers + TMEM slot + stats + fold exchange buffers
 
 struct ConvKParams {
     // output volume (interior dims) and padded strides
@@ -80,9 +89,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int t) {
     return c;
 }
 
-template <int MODE, int EPI, int NMMA>
+template <int MODE, int EPI, int NMMA, int FOLD>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+    constexpr int RB = FOLD ? 126 : 128;            // output rows per 128-row MMA block
+    constexpr int CO = FOLD ? NMMA / 3 : NMMA;      // output channels handled by this CTA job
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -100,12 +111,13 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
     uint64_t* t_full = w_empty + p.w_stages;
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][16]
+    float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [8 warps][16]
+    float* xch_smem = stat_smem + 8 * 16;                        // [2 groups][2 bufs][4 warps][2][16]
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.x_stages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 256); }
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -203,18 +215,19 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                     uint32_t dtm = tmem_base + (uint32_t)(as * R * NMMA);
                     uint32_t first = (g | tg) == 0 ? 0u : 1u;
                     if (MODE == MODE_K3) {
-                        // compile-time shape: KC = 16 (one K=16 MMA per tap), 9 taps per weight stage
-                        uint32_t t9[9];
+                        // compile-time shape: KC = 16 (one K=16 MMA per tap), TGc taps per weight stage
+                        constexpr int TGc = FOLD ? 3 : 9;
+                        uint32_t tof[TGc];
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) t9[i] = (uint32_t)toff[i];
+                        for (int i = 0; i < TGc; ++i) tof[i] = (uint32_t)toff[i];
                         const int BD = p.BD, MB = p.MB, SRp = p.SRp;
                         if (!skip_mma && elect_one()) {
                             for (int dz = 0; dz < BD; ++dz) {
                                 for (int mb = 0; mb < MB; ++mb, dtm += NMMA) {
-                                    const uint32_t a_run16 = xst16 + (uint32_t)(dz * SRp + mb * 128);
+                                    const uint32_t a_run16 = xst16 + (uint32_t)(dz * SRp + mb * RB);
 #pragma unroll
-                                    for (int tl = 0; tl < 9; ++tl) {
-                                        umma_bf16(dtm, a_hi | (uint64_t)(a_run16 + t9[tl]),
+                                    for (int tl = 0; tl < TGc; ++tl) {
+                                        umma_bf16(dtm, a_hi | (uint64_t)(a_run16 + tof[tl]),
                                                   b_hi | (uint64_t)(wst16 + (uint32_t)(tl * 2 * NMMA)), idesc,
                                                   tl == 0 ? first : 1u);
                                     }
@@ -254,30 +267,36 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew+32)
+        // ================= epilogue (two groups of 4 warps, alternate runs) =================
+        const int grp = (warp - 4) >> 2;
+        const int ew = (warp - 4) & 3;      // TMEM lanes [32*ew, 32*ew+32)
         const int m = ew * 32 + lane;       // row within a 128-row block
-        constexpr int GS = (NMMA >= 16 ? NMMA / 8 : 1);   // channels per GroupNorm group
+        constexpr int GS = (CO >= 16 ? CO / 8 : 1);   // channels per GroupNorm group
         float ssum[8], ssq[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         int cur_n = -1;
         const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr);
+        float* xch = xch_smem + grp * (2 * 4 * 2 * 16);
+        int xbuf = 0;
 
         auto flush_stats = [&](int n) {
-            // all 128 epilogue threads participate
+            // all 256 epilogue threads participate
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ssum[i] = warp_sum(ssum[i]); ssq[i] = warp_sum(ssq[i]); }
+            const int w8 = warp - 4;
             if (lane == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { stat_smem[ew * 16 + i] = ssum[i]; stat_smem[ew * 16 + 8 + i] = ssq[i]; }
+                for (int i = 0; i < 8; ++i) { stat_smem[w8 * 16 + i] = ssum[i]; stat_smem[w8 * 16 + 8 + i] = ssq[i]; }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (m < 16) {
-                float v = stat_smem[m] + stat_smem[16 + m] + stat_smem[32 + m] + stat_smem[48 + m];
-                p.stats_partial[((size_t)cta * p.N + n) * 16 + m] = v;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (w8 == 0 && lane < 16) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v += stat_smem[k * 16 + lane];
+                p.stats_partial[((size_t)cta * p.N + n) * 16 + lane] = v;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         };
@@ -292,14 +311,14 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             }
             mbar_wait(&t_full[as], (it >> 1) & 1);
             tc_fence_after();
-            for (int r = 0; r < R; ++r) {
+            for (int r = grp; r < R; r += 2) {
                 const int dz = r / p.MB, mb = r - dz * p.MB;
                 // ---- which voxel is this row? ----
                 bool valid;
                 long long orow;      // output row in the padded tensor
                 int vd = 0, vh = 0, vw = 0;
                 if (MODE == MODE_K3) {
-                    const int q = tc.q0 + mb * 128 + m;
+                    const int q = tc.q0 + mb * RB + m - (FOLD ? 1 : 0);
                     const int dpo = (p.whole ? 0 : tc.d0 + 1) + dz;
                     const int dq = q / p.SS;
                     const int r2 = q - dq * p.SS;
@@ -307,6 +326,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                     const int wp = r2 - hp * p.Wp;
                     const int dp = dpo + dq;
                     valid = (q < p.Q0 + p.QN) && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
+                    if (FOLD) valid = valid && m >= 1 && m <= RB;
                     orow = ((long long)tc.n * (p.D + 2) + dpo) * p.SS + q;
                     vd = dp - 1; vh = hp - 1; vw = wp - 1;
                 } else {
@@ -315,9 +335,36 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 }
                 const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((as * R + r) * NMMA);
 #pragma unroll
-                for (int c0 = 0; c0 < NMMA; c0 += 16) {
+                for (int c0 = 0; c0 < CO; c0 += 16) {
                     float v[16];
-                    tmem_ld16(trow + c0, v);
+                    if (FOLD) {
+                        float a0[16], a2[16];
+                        tmem_ld16(trow + c0, a0);
+                        tmem_ld16(trow + CO + c0, v);
+                        tmem_ld16(trow + 2 * CO + c0, a2);
+                        float* xb = xch + xbuf * (4 * 2 * 16);
+                        if (lane == 31) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) xb[(ew * 2 + 0) * 16 + i] = a0[i];
+                        }
+                        if (lane == 0) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) xb[(ew * 2 + 1) * 16 + i] = a2[i];
+                        }
+                        if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                        else          asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float lo = __shfl_up_sync(0xffffffffu, a0[i], 1);
+                            float hi = __shfl_down_sync(0xffffffffu, a2[i], 1);
+                            if (lane == 0) lo = ew > 0 ? xb[((ew - 1) * 2 + 0) * 16 + i] : 0.f;
+                            if (lane == 31) hi = ew < 3 ? xb[((ew + 1) * 2 + 1) * 16 + i] : 0.f;
+                            v[i] += lo + hi;
+                        }
+                        xbuf ^= 1;
+                    } else {
+                        tmem_ld16(trow + c0, v);
+                    }
                     if (EPI == EPI_BF16) {
                         if (valid) {
                             if (do_stats) {
@@ -328,7 +375,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                                     ssq[gi] += v[i] * v[i];
                                 }
                             }
-                            const int ch = (job * NMMA + c0) >> 3;      // first of the two 8-channel chunks
+                            const int ch = (job * CO + c0) >> 3;      // first of the two 8-channel chunks
                             if (p.residual.base) {
                                 float f[8];
                                 unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch, orow)), f);
@@ -355,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                                     const float z = v[c] + p.bias[c];
                                     const size_t o = ((size_t)tc.n * p.n_out_real + c) * plane + vox;
                                     if (p.logits) p.logits[o] = z;
-                                    p.probs[o] = 1.f / (1.f + __expf(-z));
+                                    p.probs[o] = 1.f / (1.f + expf(-z));
                                 }
                             }
                         }

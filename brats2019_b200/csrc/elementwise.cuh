@@ -675,9 +675,18 @@ struct PackParams {
     int ci_off;
     int K_real, N_real;                // logical GEMM extents before padding
     int n_jobs, KG, NTG, TG, KC, Nmma;
+    int fold;                          // kw-fold: GEMM tap = kd*3+kh (9 taps), n = kw*(Nmma/3) + channel
 };
 
 __device__ __forceinline__ float fetch_weight(const float* w, const PackParams& q, int tap, int k, int n) {
+    if (q.fold) {
+        const int cg = q.Nmma / 3;
+        const int kw = n / cg, c = n - kw * cg;
+        if (k >= q.K_real || c >= q.N_real) return 0.f;
+        const int tp = tap * 3 + kw;
+        if (q.kind == 0) return w[((size_t)c * q.Cin_w + (k + q.ci_off)) * q.taps_w + tp];
+        return w[((size_t)k * q.Cin_w + (c + q.ci_off)) * q.taps_w + (q.taps_w - 1 - tp)];
+    }
     if (k >= q.K_real || n >= q.N_real) return 0.f;
     int co, ci, tp;
     switch (q.kind) {

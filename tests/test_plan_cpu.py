@@ -15,7 +15,7 @@ from brats2019_b200 import _lib
 from brats2019_b200._lib import ConvDesc, WgradDesc
 
 CONV_FIELDS = ("BD MB TR Q0 QN tiles_q tiles_d num_tiles whole n_jobs KG KGa KC NTG TG x_stages w_stages "
-               "x_stage_bytes w_stage_bytes x_plane_bytes SRp nslices halo_rows tmem_cols smem ctas Wp SS").split()
+               "x_stage_bytes w_stage_bytes x_plane_bytes SRp nslices halo_rows tmem_cols smem ctas Wp SS fold RB").split()
 WGRAD_FIELDS = ("KT XR nband_loaded CoC CiC nfold nacc M Nmma n_jobs splits stages_per_split y_planes "
                 "x_planes y_plane_bytes x_plane_bytes stage_bytes stage_tx_bytes stages tmem_cols smem grid banded "
                 "folded accs Wp SS").split()
@@ -62,7 +62,7 @@ def fetch_rows(rows, start, count, guard=None):
 
 
 @pytest.mark.parametrize("shape", [(1, 4, 4, 4), (2, 5, 6, 9), (1, 8, 8, 8), (1, 3, 16, 40), (2, 16, 16, 16)])
-@pytest.mark.parametrize("cout", [16, 128])
+@pytest.mark.parametrize("cout", [16, 32, 128])
 def test_conv3_addressing(shape, cout):
     N, D, H, W = shape
     Cin = 16
@@ -89,15 +89,29 @@ def test_conv3_addressing(shape, cout):
             dpi = (0 if p["whole"] else d0 + 1) - 1 + s
             row0 = (n * Dp + dpi) * SS + q0 - p["halo_rows"]
             plane[s * p["SRp"]:(s + 1) * p["SRp"]] = fetch_rows(rows, row0, p["SRp"], guard)
+        fold, RB = p["fold"], p["RB"]
         for run in range(p["BD"] * p["MB"]):
             dz, mb = run // p["MB"], run % p["MB"]
-            acc = torch.zeros(128, 4)
-            for tap in range(27):
-                a0 = dz * p["SRp"] + mb * 128 + p["tap_off"][tap]
-                assert a0 + 128 <= plane.shape[0], "A operand would read past the stage plane"
-                acc += plane[a0:a0 + 128] @ wt[:, :, tap].T
+            if fold:
+                # N = (kw, co): 9 (kd,kh) MMAs, then out[m] = P[m-1][kw0] + P[m][kw1] + P[m+1][kw2]
+                P = torch.zeros(128, 3, 4)
+                for t9 in range(9):
+                    a0 = dz * p["SRp"] + mb * RB + p["tap_off"][t9]
+                    assert a0 + 128 <= plane.shape[0], "A operand would read past the stage plane"
+                    for kw in range(3):
+                        P[:, kw] += plane[a0:a0 + 128] @ wt[:, :, t9 * 3 + kw].T
+                acc = torch.zeros(128, 4)
+                acc[1:127] = P[0:126, 0] + P[1:127, 1] + P[2:128, 2]
+            else:
+                acc = torch.zeros(128, 4)
+                for tap in range(27):
+                    a0 = dz * p["SRp"] + mb * 128 + p["tap_off"][tap]
+                    assert a0 + 128 <= plane.shape[0], "A operand would read past the stage plane"
+                    acc += plane[a0:a0 + 128] @ wt[:, :, tap].T
             for m in range(128):
-                q = q0 + mb * 128 + m
+                if fold and not (1 <= m <= RB):
+                    continue
+                q = q0 + mb * RB + m - (1 if fold else 0)
                 dpo = (0 if p["whole"] else d0 + 1) + dz
                 dq, r2 = divmod(q, SS)
                 hp, wp = divmod(r2, Wp)
@@ -111,7 +125,8 @@ def test_conv3_addressing(shape, cout):
     assert (written == 1).all(), "every interior voxel must be produced exactly once"
     np.testing.assert_allclose(out.numpy(), ref.numpy(), atol=1e-4)
     assert p["smem"] <= 227 * 1024 and p["tmem_cols"] <= 512
-    assert 2 * p["BD"] * p["MB"] * min(cout, 256) <= p["tmem_cols"]
+    assert 2 * p["BD"] * p["MB"] * (3 * cout if p["fold"] else min(cout, 256)) <= p["tmem_cols"]
+    assert p["fold"] == (1 if cout in (16, 32) else 0)
 
 
 def test_conv1_plan_covers_all_rows():
