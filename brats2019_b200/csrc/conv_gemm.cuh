@@ -35,8 +35,9 @@ enum { MODE_K3 = 0, MODE_K1 = 1 };
 enum { EPI_BF16 = 0, EPI_SIGMOID = 1 };
 
 constexpr int kMaxTaps = 27;
-constexpr int kConvThreads = 384;
-constexpr unsigned kConvTailBytes = 3072;   // barriers + TMEM slot + stats + fold exchange buffers
+constexpr int kEpiGroups = 3;                       // epilogue warp groups (4 warps each)
+constexpr int kConvThreads = 128 + 128 * kEpiGroups;
+constexpr unsigned kConvTailBytes = 4096;   // barriers + TMEM slot + stats + fold exchange buffers
 
 struct ConvKParams {
     // output volume (interior dims) and padded strides
@@ -111,13 +112,13 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
     uint64_t* t_full = w_empty + p.w_stages;
     uint64_t* t_empty = t_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [8 warps][16]
-    float* xch_smem = stat_smem + 8 * 16;                        // [2 groups][2 bufs][4 warps][2][16]
+    float* stat_smem = reinterpret_cast<float*>(tmem_slot + 4);  // [4*kEpiGroups warps][16]
+    float* xch_smem = stat_smem + 4 * kEpiGroups * 16;           // [groups][2 bufs][4 warps][2][16]
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.x_stages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 256); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128 * kEpiGroups); }
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -267,7 +268,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ================= epilogue (two groups of 4 warps, alternate runs) =================
+        // ================= epilogue (kEpiGroups groups of 4 warps take runs round-robin) =================
         const int grp = (warp - 4) >> 2;
         const int ew = (warp - 4) & 3;      // TMEM lanes [32*ew, 32*ew+32)
         const int m = ew * 32 + lane;       // row within a 128-row block
@@ -281,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
         int xbuf = 0;
 
         auto flush_stats = [&](int n) {
-            // all 256 epilogue threads participate
+            // all epilogue threads participate
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ssum[i] = warp_sum(ssum[i]); ssq[i] = warp_sum(ssq[i]); }
             const int w8 = warp - 4;
@@ -289,14 +290,14 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { stat_smem[w8 * 16 + i] = ssum[i]; stat_smem[w8 * 16 + 8 + i] = ssq[i]; }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiGroups) : "memory");
             if (w8 == 0 && lane < 16) {
                 float v = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v += stat_smem[k * 16 + lane];
+                for (int k = 0; k < 4 * kEpiGroups; ++k) v += stat_smem[k * 16 + lane];
                 p.stats_partial[((size_t)cta * p.N + n) * 16 + lane] = v;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiGroups) : "memory");
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         };
@@ -311,7 +312,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             }
             mbar_wait(&t_full[as], (it >> 1) & 1);
             tc_fence_after();
-            for (int r = grp; r < R; r += 2) {
+            for (int r = grp; r < R; r += kEpiGroups) {
                 const int dz = r / p.MB, mb = r - dz * p.MB;
                 // ---- which voxel is this row? ----
                 bool valid;
@@ -339,27 +340,53 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                     float v[16];
                     if (FOLD) {
                         float a0[16], a2[16];
-                        tmem_ld16(trow + c0, a0);
-                        tmem_ld16(trow + CO + c0, v);
-                        tmem_ld16(trow + 2 * CO + c0, a2);
+                        {
+                            uint32_t r0[16], r1[16], r2[16];
+                            tmem_ld16_nowait(trow + c0, r0);
+                            tmem_ld16_nowait(trow + CO + c0, r1);
+                            tmem_ld16_nowait(trow + 2 * CO + c0, r2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                a0[i] = __uint_as_float(r0[i]);
+                                v[i] = __uint_as_float(r1[i]);
+                                a2[i] = __uint_as_float(r2[i]);
+                            }
+                        }
+                        // rows m-1 / m+1 live in the neighbouring lanes; across a warp boundary they
+                        // come through shared memory (lane 31's P_0 row and lane 0's P_2 row per warp).
                         float* xb = xch + xbuf * (4 * 2 * 16);
-                        if (lane == 31) {
+                        float bnd[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) xb[(ew * 2 + 0) * 16 + i] = a0[i];
+                        for (int i = 0; i < 16; ++i) bnd[i] = 0.f;
+                        if (!(p.debug & 4)) {
+                            if (lane == 31) {
+                                float4* d4 = reinterpret_cast<float4*>(xb + (ew * 2 + 0) * 16);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) d4[i] = make_float4(a0[4 * i], a0[4 * i + 1], a0[4 * i + 2], a0[4 * i + 3]);
+                            } else if (lane == 0) {
+                                float4* d4 = reinterpret_cast<float4*>(xb + (ew * 2 + 1) * 16);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) d4[i] = make_float4(a2[4 * i], a2[4 * i + 1], a2[4 * i + 2], a2[4 * i + 3]);
+                            }
+                            asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                            if ((lane == 0 && ew > 0) || (lane == 31 && ew < 3)) {
+                                const float4* s4 = reinterpret_cast<const float4*>(
+                                    lane == 0 ? xb + ((ew - 1) * 2 + 0) * 16 : xb + ((ew + 1) * 2 + 1) * 16);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 t4 = s4[i];
+                                    bnd[4 * i] = t4.x; bnd[4 * i + 1] = t4.y; bnd[4 * i + 2] = t4.z; bnd[4 * i + 3] = t4.w;
+                                }
+                            }
                         }
-                        if (lane == 0) {
+                        if (!(p.debug & 8)) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) xb[(ew * 2 + 1) * 16 + i] = a2[i];
-                        }
-                        if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-                        else          asm volatile("bar.sync 3, 128;" ::: "memory");
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float lo = __shfl_up_sync(0xffffffffu, a0[i], 1);
-                            float hi = __shfl_down_sync(0xffffffffu, a2[i], 1);
-                            if (lane == 0) lo = ew > 0 ? xb[((ew - 1) * 2 + 0) * 16 + i] : 0.f;
-                            if (lane == 31) hi = ew < 3 ? xb[((ew + 1) * 2 + 1) * 16 + i] : 0.f;
-                            v[i] += lo + hi;
+                            for (int i = 0; i < 16; ++i) {
+                                const float up = __shfl_up_sync(0xffffffffu, a0[i], 1);
+                                const float dn = __shfl_down_sync(0xffffffffu, a2[i], 1);
+                                v[i] += (lane == 0 ? bnd[i] : up) + (lane == 31 ? bnd[i] : dn);
+                            }
                         }
                         xbuf ^= 1;
                     } else {
