@@ -466,7 +466,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     q.n_jobs = P.k.n_jobs; q.splits = P.k.splits; q.nacc = P.k.nacc; q.M = P.k.M; q.Nmma = P.k.Nmma;
     q.accumulate = accumulate;
     const int total = q.n_jobs * q.nacc * q.M * q.Nmma;
-    wgrad_reduce_kernel<<<std::min((total + 127) / 128, 4096), 128, 0, st>>>(P.k.partial, grad, q);
+    wgrad_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(P.k.partial, grad, q);
     LAUNCH_OK("wgrad_reduce_kernel");
     return 0;
 }
@@ -481,6 +481,29 @@ static int lines_per_block(int N, int D, int H) {
     int lpb = 1;
     while (lpb < 16 && (D * H) % (lpb * 2) == 0 && lines / (lpb * 2) >= 8LL * num_sms()) lpb *= 2;
     return lpb;
+}
+
+static FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) { f.mul = 0; f.sh = 0; return f; }
+    unsigned sh = 0;
+    while ((1ull << sh) < d) ++sh;                       // ceil(log2 d)
+    // n/d = umulhi(n, m) >> (sh-1) with m = ceil(2^(31+sh)/d): exact for n < 2^24 (checked for every
+    // divisor the planners produce in tests/test_plan_cpu.py::test_fastdiv)
+    unsigned long long m = ((1ull << (31 + sh)) + d - 1) / d;      // fits 32 bits for n < 2^31
+    f.mul = (unsigned)m;
+    f.sh = sh - 1;
+    return f;
+}
+static LineGeom make_line_geom(int W, int C, int lpb) {
+    LineGeom g;
+    g.nvec = W * (C / 8);
+    g.W = W;
+    g.lpb = lpb;
+    g.by_nvec = make_fastdiv((unsigned)g.nvec);
+    g.by_W = make_fastdiv((unsigned)W);
+    return g;
 }
 
 static int check_act(int N, int D, int H, int W, int C) {
@@ -515,7 +538,8 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
     Vol v{N, D, H, W};
     const int lpb = lines_per_block(N, D, H);
     gn_apply_kernel<<<N * D * H / lpb, kEwThreads, 0, (cudaStream_t)stream>>>(
-        make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu, lpb);
+        make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu,
+        make_line_geom(W, C, lpb));
     LAUNCH_OK("gn_apply_kernel");
     return 0;
 }
@@ -546,7 +570,8 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     LAUNCH_OK("gn_bwd_finalize_kernel");
     const int lpb = lines_per_block(N, D, H);
     gn_bwd_apply_kernel<<<N * D * H / lpb, kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                               coef, make_act(dx, v), v, C, do_lrelu, lpb);
+                                                               coef, make_act(dx, v), v, C, do_lrelu,
+                                                               make_line_geom(W, C, lpb));
     LAUNCH_OK("gn_bwd_apply_kernel");
     return 0;
 }
@@ -595,7 +620,7 @@ extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, i
     Vol v{N, D, H, W};
     const int lpb = lines_per_block(N, D, H);
     add_kernel<<<N * D * H / lpb, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(a, v), make_act(b, v), make_act(out, v),
-                                                                        v, C, lpb);
+                                                                        v, C, make_line_geom(W, C, lpb));
     LAUNCH_OK("add_kernel");
     return 0;
 }

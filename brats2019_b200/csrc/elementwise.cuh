@@ -19,26 +19,40 @@ __device__ __forceinline__ void line_coords(const Vol& v, int line, int& n, int&
     d = t % v.D;
     n = t / v.D;
 }
+// Division by a runtime constant without the ~25-instruction integer divide: q = (n * mul) >> 32 >> sh
+// (exact for 0 <= n < 2^31 with the host-computed round-up multiplier).
+struct FastDiv {
+    unsigned mul, sh, d;
+    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> sh); }
+};
+
 // A CTA owns `lpb` consecutive lines (all of one sample: lpb divides D*H).  Vector j of the CTA
 // -> (line, 8-channel chunk cv, voxel w); voxel index fastest so a warp reads 512 contiguous bytes.
+// The first row of each line is computed once per CTA into shared memory (line_rows).
+struct LineGeom {
+    FastDiv by_nvec, by_W;
+    int nvec, W, lpb;
+};
 struct LineVec {
-    int n, cv, w;
+    int cv;
     long long row;      // row of the voxel in the padded volume
     bool ok;
 };
-__device__ __forceinline__ LineVec line_vec(const Vol& v, int line0, int lpb, int nvec, int j) {
+__device__ __forceinline__ void fill_line_rows(const Vol& v, int line0, int lpb, long long* s_rows) {
+    for (int ll = threadIdx.x; ll < lpb; ll += blockDim.x) {
+        const int line = line0 + ll;
+        const int h = line % v.H;
+        const int t = line / v.H;
+        s_rows[ll] = v.row(t / v.D, (t % v.D) + 1, h + 1, 1);
+    }
+}
+__device__ __forceinline__ LineVec line_vec(const LineGeom& g, const long long* s_rows, int j) {
     LineVec r;
-    const int ll = j / nvec;
-    const int i = j - ll * nvec;
-    r.ok = ll < lpb;
-    r.cv = i / v.W;
-    r.w = i - r.cv * v.W;
-    const int line = line0 + (r.ok ? ll : 0);
-    const int h = line % v.H;
-    const int t = line / v.H;
-    const int d = t % v.D;
-    r.n = t / v.D;
-    r.row = v.row(r.n, d + 1, h + 1, 1 + r.w);
+    const int ll = g.by_nvec.div(j);
+    const int i = j - ll * g.nvec;
+    r.ok = ll < g.lpb;
+    r.cv = g.by_W.div(i);
+    r.row = s_rows[r.ok ? ll : 0] + (i - r.cv * g.W);
     return r;
 }
 constexpr int kUnroll = 4;
@@ -102,9 +116,12 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, 
 __global__ void __launch_bounds__(kEwThreads)
 gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, ActRef residual, ActRef out, Vol v,
-                int C, int do_lrelu, int lpb) {
+                int C, int do_lrelu, LineGeom lg) {
     __shared__ float s_scale[256], s_shift[256];
+    __shared__ long long s_rows[16];
+    const int lpb = lg.lpb;
     const int line0 = blockIdx.x * lpb;
+    fill_line_rows(v, line0, lpb, s_rows);
     const int n = line0 / (v.D * v.H);
     const int gs = C / 8;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -121,7 +138,7 @@ gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restric
         uint4 qx[kUnroll], qr[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            lv[u] = line_vec(v, line0, lpb, nvec, j0 + u * blockDim.x);
+            lv[u] = line_vec(lg, s_rows, j0 + u * blockDim.x);
             if (lv[u].ok) {
                 qx[u] = ld16(x.at(lv[u].cv, lv[u].row));
                 if (residual.base) qr[u] = ld16(residual.at(lv[u].cv, lv[u].row));
@@ -287,9 +304,12 @@ gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int
 __global__ void __launch_bounds__(kEwThreads)
 gn_bwd_apply_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
-                    ActRef dx, Vol v, int C, int do_lrelu, int lpb) {
+                    ActRef dx, Vol v, int C, int do_lrelu, LineGeom lg) {
     __shared__ float s_a[256], s_b[256], s_g[256], s_be[256], s_A[256], s_B[256];
+    __shared__ long long s_rows[16];
+    const int lpb = lg.lpb;
     const int line0 = blockIdx.x * lpb;
+    fill_line_rows(v, line0, lpb, s_rows);
     const int n = line0 / (v.D * v.H);
     const int gs = C / 8;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -309,7 +329,7 @@ gn_bwd_apply_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const f
         uint4 qx[kUnroll], qd[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            lv[u] = line_vec(v, line0, lpb, nvec, j0 + u * blockDim.x);
+            lv[u] = line_vec(lg, s_rows, j0 + u * blockDim.x);
             if (lv[u].ok) {
                 qx[u] = ld16(x.at(lv[u].cv, lv[u].row));
                 qd[u] = ld16(dy.at(lv[u].cv, lv[u].row));
@@ -495,8 +515,12 @@ d2s_kernel(ActRef coarse, ActRef residual, ActRef fine, Vol vc, int C) {
 
 // out = a + b over the interior (gradient accumulation where two paths meet)
 __global__ void __launch_bounds__(kEwThreads)
-add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, int lpb) {
+add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, LineGeom lg) {
+    __shared__ long long s_rows[16];
+    const int lpb = lg.lpb;
     const int line0 = blockIdx.x * lpb;
+    fill_line_rows(v, line0, lpb, s_rows);
+    __syncthreads();
     const int nvec = v.W * (C / 8);
     const int total = lpb * nvec;
     for (int j0 = threadIdx.x; j0 < total; j0 += blockDim.x * kUnroll) {
@@ -504,7 +528,7 @@ add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, int lpb) {
         uint4 qa[kUnroll], qb[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            lv[u] = line_vec(v, line0, lpb, nvec, j0 + u * blockDim.x);
+            lv[u] = line_vec(lg, s_rows, j0 + u * blockDim.x);
             if (lv[u].ok) {
                 qa[u] = ld16(a.at(lv[u].cv, lv[u].row));
                 qb[u] = ld16(b.at(lv[u].cv, lv[u].row));
@@ -731,46 +755,59 @@ struct WgradReduceParams {
     int accumulate;          // add into grad instead of overwriting
 };
 
-// One thread per accumulator element (job, acc, row, col): coalesced reads of the partials over
-// `col`, fixed-order sum over the K splits, one scattered write into the PyTorch-layout gradient.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q) {
+// A 256-thread CTA owns 32 consecutive accumulator elements (job, acc, row, col): warp w sums the
+// K splits s = w, w+8, ... (128-byte coalesced reads of the partials), the 8 warp sums are combined
+// in a fixed order through shared memory (deterministic), and one scattered write goes into the
+// PyTorch-layout gradient.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q) {
+    __shared__ double s_acc[8][32];
     const int per_job = q.nacc * q.M * q.Nmma;
     const int total = q.n_jobs * per_job;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int col = i % q.Nmma;
-        int r = i / q.Nmma;
-        const int row = r % q.M;
-        r /= q.M;
-        const int t = r % q.nacc;
-        const int job = r / q.nacc;
-        int co, ci_w, tp;
-        if (q.kind == 0) {
-            int jj = job;
-            const int jkw = q.folded ? 0 : jj % 3; if (!q.folded) jj /= 3;
-            const int jkh = q.accs ? 0 : jj % 3;   if (!q.accs) jj /= 3;
-            const int jkd = q.banded ? 0 : jj;
-            const int kd = q.banded ? row / q.Cout_g : jkd;
-            co = q.banded ? row % q.Cout_g : row;
-            const int kw = q.folded ? col / q.Cin_g : jkw;
-            ci_w = q.folded ? col % q.Cin_g : col;
-            const int kh = q.accs ? t : jkh;
-            if (kd > 2 || kw > 2) continue;      // unused band / padding of the M or N extent
-            tp = (kd * 3 + kh) * 3 + kw;
-        } else if (q.kind == 1) {
-            co = row; ci_w = q.ci_off + job * q.Nmma + col; tp = 0;
-        } else {
-            const int k = job * q.Nmma + col;
-            co = row; tp = k / q.Cin_w; ci_w = k % q.Cin_w;
-        }
-        if (co >= q.Cout_w || ci_w >= q.Cin_w || tp >= q.taps_w) continue;
-        if (q.kind == 1 && (job * q.Nmma + col) >= q.Cin_g) continue;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int i = blockIdx.x * 32 + l;
+    double a = 0.0;
+    int job = 0;
+    if (i < total) {
+        job = i / per_job;
         const float* src = partial + (size_t)job * q.splits * per_job + (size_t)(i - job * per_job);
-        double a = 0.0;
-        for (int s = 0; s < q.splits; ++s) a += (double)src[(size_t)s * per_job];
-        const size_t o = ((size_t)co * q.Cin_w + ci_w) * q.taps_w + tp;
-        if (q.accumulate) grad[o] += (float)a;
-        else grad[o] = (float)a;
+        for (int s = w; s < q.splits; s += 8) a += (double)src[(size_t)s * per_job];
     }
+    s_acc[w][l] = a;
+    __syncthreads();
+    if (w != 0 || i >= total) return;
+    a = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += s_acc[k][l];
+    const int col = i % q.Nmma;
+    int r = i / q.Nmma;
+    const int row = r % q.M;
+    r /= q.M;
+    const int t = r % q.nacc;
+    int co, ci_w, tp;
+    if (q.kind == 0) {
+        int jj = job;
+        const int jkw = q.folded ? 0 : jj % 3; if (!q.folded) jj /= 3;
+        const int jkh = q.accs ? 0 : jj % 3;   if (!q.accs) jj /= 3;
+        const int jkd = q.banded ? 0 : jj;
+        const int kd = q.banded ? row / q.Cout_g : jkd;
+        co = q.banded ? row % q.Cout_g : row;
+        const int kw = q.folded ? col / q.Cin_g : jkw;
+        ci_w = q.folded ? col % q.Cin_g : col;
+        const int kh = q.accs ? t : jkh;
+        if (kd > 2 || kw > 2) return;      // unused band / padding of the M or N extent
+        tp = (kd * 3 + kh) * 3 + kw;
+    } else if (q.kind == 1) {
+        if (job * q.Nmma + col >= q.Cin_g) return;
+        co = row; ci_w = q.ci_off + job * q.Nmma + col; tp = 0;
+    } else {
+        const int k = job * q.Nmma + col;
+        co = row; tp = k / q.Cin_w; ci_w = k % q.Cin_w;
+    }
+    if (co >= q.Cout_w || ci_w >= q.Cin_w || tp >= q.taps_w) return;
+    const size_t o = ((size_t)co * q.Cin_w + ci_w) * q.taps_w + tp;
+    if (q.accumulate) grad[o] += (float)a;
+    else grad[o] = (float)a;
 }
 
 }  // namespace b200

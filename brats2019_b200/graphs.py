@@ -47,6 +47,37 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.loss
 
+    # -- host-input pipeline: the H2D copy of step i+1 overlaps the compute of step i -------------
+    def prefetch(self, x_host, t_host):
+        """Start copying the NEXT step's (pinned) host batch on a copy stream into a staging slot."""
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.t)) for _ in range(2)]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot_in, self._slot_out = 0, 0
+            for e in self._free:
+                e.record()
+        k = self._slot_in
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._free[k])          # the step that read this slot has consumed it
+            self._stage[k][0].copy_(x_host, non_blocking=True)
+            self._stage[k][1].copy_(t_host, non_blocking=True)
+            self._ready[k].record()
+        self._slot_in = k ^ 1
+
+    def step_prefetched(self):
+        """Run one step on the oldest prefetched batch; returns the static loss tensor."""
+        k = self._slot_out
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[k])
+        self.x.copy_(self._stage[k][0], non_blocking=True)       # device-to-device, ~40 us
+        self.t.copy_(self._stage[k][1], non_blocking=True)
+        self._free[k].record()
+        self._slot_out = k ^ 1
+        self.graph.replay()
+        return self.loss
+
 
 class GraphedForward:
     """probs = model([x])[0] under no_grad (Trainer.predict, train.py:129-143) as one graph launch."""

@@ -202,3 +202,17 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_fastdiv_formula_is_exact_for_planner_divisors():
+    """The memory-bound kernels divide by W and W*C/8 with umulhi(n, ceil(2^(31+s)/d)) >> (s-1)."""
+    for d in [2, 3, 5, 6, 7, 10, 12, 16, 20, 24, 30, 32, 40, 48, 60, 64, 80, 96, 120, 128, 160, 192, 240, 256, 320,
+              480, 512, 640, 960, 1280, 1920, 2560, 3840]:
+        sh = 0
+        while (1 << sh) < d:
+            sh += 1
+        m = ((1 << (31 + sh)) + d - 1) // d
+        assert m < 2 ** 32
+        n = np.arange(0, 1 << 20, dtype=np.uint64)
+        q = ((n * np.uint64(m)) >> np.uint64(32)) >> np.uint64(sh - 1)
+        assert (q == n // np.uint64(d)).all(), d
