@@ -129,6 +129,8 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     p.N = d->N; p.D = d->D; p.H = d->H; p.W = d->W;
     p.Wp = d->W + 2;
     p.SS = (d->H + 2) * p.Wp;
+    p.by_SS = make_fastdiv((unsigned)p.SS);
+    p.by_Wp = make_fastdiv((unsigned)p.Wp);
     p.sample_rows = (long long)(d->D + 2) * p.SS;
     p.total_rows = p.sample_rows * d->N;
     p.mode = d->mode;
@@ -213,13 +215,19 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
         p.tap_off[0] = 0;
     }
     p.num_tiles = (p.mode == MODE_K3 ? p.N * p.tiles_d : 1) * p.tiles_q;
-    // stages: as many as fit, up to 4
+    // stages: as many as fit, up to 4; small filters stay resident (a weight stage round trip is
+    // ~1.3 us, longer than the MMAs that consume it when Cout <= 32)
     unsigned budget = kMaxSmem - bar_bytes;
     p.x_stages = 2; p.w_stages = 2;
+    const unsigned w_total = (unsigned)(p.KG * p.NTG) * p.w_stage_bytes;
+    if (d->mode == MODE_K3 && p.KG * p.NTG <= 8 && w_total <= 64 * 1024 && align_up(2 * p.x_stage_bytes, 128) + w_total <= budget) {
+        p.w_resident = 1;
+        p.w_stages = p.KG * p.NTG;
+    }
     auto used = [&]() { return align_up(p.x_stages * p.x_stage_bytes, 128) + p.w_stages * p.w_stage_bytes; };
     if (used() > budget) return fail("conv: shared memory plan does not fit (%u bytes)", used());
     for (int round = 0; round < 2; ++round) {
-        ++p.w_stages; if (used() > budget) --p.w_stages;
+        if (!p.w_resident) { ++p.w_stages; if (used() > budget) --p.w_stages; }
         ++p.x_stages; if (used() > budget) --p.x_stages;
     }
     p.smem_x_off = 0;
@@ -483,19 +491,6 @@ static int lines_per_block(int N, int D, int H) {
     return lpb;
 }
 
-static FastDiv make_fastdiv(unsigned d) {
-    FastDiv f;
-    f.d = d;
-    if (d <= 1) { f.mul = 0; f.sh = 0; return f; }
-    unsigned sh = 0;
-    while ((1ull << sh) < d) ++sh;                       // ceil(log2 d)
-    // n/d = umulhi(n, m) >> (sh-1) with m = ceil(2^(31+sh)/d): exact for n < 2^24 (checked for every
-    // divisor the planners produce in tests/test_plan_cpu.py::test_fastdiv)
-    unsigned long long m = ((1ull << (31 + sh)) + d - 1) / d;      // fits 32 bits for n < 2^31
-    f.mul = (unsigned)m;
-    f.sh = sh - 1;
-    return f;
-}
 static LineGeom make_line_geom(int W, int C, int lpb) {
     LineGeom g;
     g.nvec = W * (C / 8);
@@ -547,11 +542,14 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
 static int gn_bwd_blocks(int N, int D, int H) {
     // CTAs per sample for the reduction: ~4 per SM over the batch, each with >= 4 lines of work
     int per = std::max(1, 4 * num_sms() / std::max(1, N));
-    return std::max(1, std::min(per, D * H / 4));
+    per = std::max(1, std::min(per, D * H / 4));
+    per = std::max(per, (D * H + kMaxRedLines - 1) / kMaxRedLines);     // row table of the kernel
+    return std::min(per, D * H);
 }
+static int gn_bwd_max_blocks() { return 4 * num_sms() + 2048; }      // >= gn_bwd_blocks() for any volume up to 1M lines
 extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
-    // partial[N][blocks<=4*sms][C][2] + coef[N][C][2]
-    return (size_t)N * (4 * num_sms()) * C * 2 + (size_t)N * C * 2;
+    // partial[N][blocks][C][2] + coef[N][C][2]
+    return (size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2;
 }
 extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta,
@@ -561,9 +559,10 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = gn_bwd_blocks(N, D, H);
     float* partial = workspace;
-    float* coef = workspace + (size_t)N * (4 * num_sms()) * C * 2;
+    if (blocks > gn_bwd_max_blocks()) return fail("gn_backward: volume too large");
+    float* coef = workspace + (size_t)N * gn_bwd_max_blocks() * C * 2;
     gn_bwd_reduce_kernel<<<dim3(blocks, N), kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                                partial, v, C, do_lrelu);
+                                                                partial, v, C, do_lrelu, make_fastdiv((unsigned)W));
     LAUNCH_OK("gn_bwd_reduce_kernel");
     const double m = (double)(C / 8) * D * H * W;
     gn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);

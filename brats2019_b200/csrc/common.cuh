@@ -39,6 +39,26 @@ struct Vol {
     __host__ __device__ long long plane_rows() const { return total_rows() + 2 * guard_rows(); }
 };
 
+// Division by a runtime constant without the ~25-instruction integer divide:
+//   n / d == umulhi(n, mul) >> sh   with mul = ceil(2^(31+s)/d), sh = s-1, s = ceil(log2 d)
+// exact for 0 <= n < 2^24 (tests/test_plan_cpu.py checks the formula for every divisor in use).
+struct FastDiv {
+    unsigned mul, sh, d;
+    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> sh); }
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    f.mul = 0;
+    f.sh = 0;
+    if (d <= 1) return f;
+    unsigned s = 0;
+    while ((1ull << s) < d) ++s;
+    f.mul = (unsigned)(((1ull << (31 + s)) + d - 1) / d);
+    f.sh = s - 1;
+    return f;
+}
+
 // A view of one activation tensor: base pointer of the allocation + plane geometry.
 struct ActRef {
     __nv_bfloat16* base;

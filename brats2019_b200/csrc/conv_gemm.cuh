@@ -42,6 +42,7 @@ constexpr unsigned kConvTailBytes = 4096;   // barriers + TMEM slot + stats + fo
 struct ConvKParams {
     // output volume (interior dims) and padded strides
     int N, D, H, W, Wp, SS;
+    FastDiv by_SS, by_Wp;
     long long sample_rows, total_rows;
     int mode;
     // tiling
@@ -54,6 +55,7 @@ struct ConvKParams {
     int KG, KGa, KC, NTG, TG;
     // shared-memory plan
     int x_stages, w_stages;
+    int w_resident;        // 1: all KG*NTG weight stages stay in shared memory for the whole kernel
     unsigned x_stage_bytes, w_stage_bytes, x_plane_bytes;
     int SRp, nslices, halo_rows;
     int tap_off[kMaxTaps];
@@ -174,7 +176,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
         for (int t = cta; t < p.num_tiles; t += ctas) {
             for (int g = 0; g < p.KG; ++g) {
                 for (int tg = 0; tg < p.NTG; ++tg) {
-                    mbar_wait(&w_empty[ws], wph ^ 1);
+                    if (!p.w_resident) mbar_wait(&w_empty[ws], wph ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&w_full[ws], p.w_stage_bytes);
                         bulk_load_1d(smem_w + (size_t)ws * p.w_stage_bytes,
@@ -184,6 +186,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                     if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
                 }
             }
+            if (p.w_resident) break;      // one pass fills every slot; they are never released
         }
     } else if (warp == 2) {
         // ================= MMA issuer =================
@@ -209,8 +212,10 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 tc_fence_after();
                 const uint32_t xst16 = xbase16 + xs * xstage16;
                 for (int tg = 0; tg < p.NTG; ++tg) {
-                    mbar_wait(&w_full[ws], wph);
-                    tc_fence_after();
+                    if (!p.w_resident || it == 0) {
+                        mbar_wait(&w_full[ws], wph);
+                        tc_fence_after();
+                    }
                     const uint32_t wst16 = wbase16 + ws * wstage16;
                     const int* toff = &p.tap_off[tg * p.TG];
                     uint32_t dtm = tmem_base + (uint32_t)(as * R * NMMA);
@@ -256,8 +261,10 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                         }
                     }
                     __syncwarp();
-                    if (elect_one()) umma_commit(&w_empty[ws]);
-                    __syncwarp();
+                    if (!p.w_resident) {
+                        if (elect_one()) umma_commit(&w_empty[ws]);
+                        __syncwarp();
+                    }
                     if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&x_empty[xs]);
@@ -321,9 +328,9 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 if (MODE == MODE_K3) {
                     const int q = tc.q0 + mb * RB + m - (FOLD ? 1 : 0);
                     const int dpo = (p.whole ? 0 : tc.d0 + 1) + dz;
-                    const int dq = q / p.SS;
+                    const int dq = p.by_SS.div(q);
                     const int r2 = q - dq * p.SS;
-                    const int hp = r2 / p.Wp;
+                    const int hp = p.by_Wp.div(r2);
                     const int wp = r2 - hp * p.Wp;
                     const int dp = dpo + dq;
                     valid = (q < p.Q0 + p.QN) && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
@@ -356,9 +363,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                         // rows m-1 / m+1 live in the neighbouring lanes; across a warp boundary they
                         // come through shared memory (lane 31's P_0 row and lane 0's P_2 row per warp).
                         float* xb = xch + xbuf * (4 * 2 * 16);
-                        float bnd[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) bnd[i] = 0.f;
+                        float bnd[16];      // read only by lanes 0/31; rows 0 and 127 of a block are never stored
                         if (!(p.debug & 4)) {
                             if (lane == 31) {
                                 float4* d4 = reinterpret_cast<float4*>(xb + (ew * 2 + 0) * 16);
@@ -370,9 +375,11 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                                 for (int i = 0; i < 4; ++i) d4[i] = make_float4(a2[4 * i], a2[4 * i + 1], a2[4 * i + 2], a2[4 * i + 3]);
                             }
                             asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-                            if ((lane == 0 && ew > 0) || (lane == 31 && ew < 3)) {
+                            if (lane == 0 || lane == 31) {
+                                // (warp 0 / lane 0 and warp 3 / lane 31 read a neighbour slot that holds
+                                // finite junk: their rows m = 0 and m = 127 are never stored)
                                 const float4* s4 = reinterpret_cast<const float4*>(
-                                    lane == 0 ? xb + ((ew - 1) * 2 + 0) * 16 : xb + ((ew + 1) * 2 + 1) * 16);
+                                    lane == 0 ? xb + (((ew + 3) & 3) * 2 + 0) * 16 : xb + (((ew + 1) & 3) * 2 + 1) * 16);
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     const float4 t4 = s4[i];

@@ -12,6 +12,7 @@
 namespace b200 {
 
 constexpr int kEwThreads = 256;
+constexpr int kMaxRedLines = 512;    // lines one gn_bwd_reduce CTA may own
 
 __device__ __forceinline__ void line_coords(const Vol& v, int line, int& n, int& d, int& h) {
     h = line % v.H;
@@ -19,13 +20,6 @@ __device__ __forceinline__ void line_coords(const Vol& v, int line, int& n, int&
     d = t % v.D;
     n = t / v.D;
 }
-// Division by a runtime constant without the ~25-instruction integer divide: q = (n * mul) >> 32 >> sh
-// (exact for 0 <= n < 2^31 with the host-computed round-up multiplier).
-struct FastDiv {
-    unsigned mul, sh, d;
-    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> sh); }
-};
-
 // A CTA owns `lpb` consecutive lines (all of one sample: lpb divides D*H).  Vector j of the CTA
 // -> (line, 8-channel chunk cv, voxel w); voxel index fastest so a warp reads 512 contiguous bytes.
 // The first row of each line is computed once per CTA into shared memory (line_rows).
@@ -176,7 +170,7 @@ gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restric
 __global__ void __launch_bounds__(kEwThreads)
 gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
-                     Vol v, int C, int do_lrelu) {
+                     Vol v, int C, int do_lrelu, FastDiv by_W) {
     __shared__ float s_a[256], s_b[256], s_g[256], s_be[256];
     __shared__ float s_red[kEwThreads / 32][16];
     const int n = blockIdx.y;
@@ -192,6 +186,15 @@ gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
     const int nlines = v.D * v.H;
     const int my_lines = (nlines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int items = my_lines * v.W;
+    // first row of each of this CTA's lines, computed once (kMaxRedLines bounds the table; the
+    // host sizes the grid so that my_lines never exceeds it)
+    __shared__ long long s_rows[kMaxRedLines];
+    for (int li = threadIdx.x; li < my_lines; li += blockDim.x) {
+        const int line = blockIdx.x + li * gridDim.x;
+        const int d = line / v.H, h = line - d * v.H;
+        s_rows[li] = v.row(n, d + 1, h + 1, 1);
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int cv = 0; cv < C / 8; ++cv) {
         const int cb = cv * 8;
@@ -206,10 +209,8 @@ gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
                 const int idx = idx0 + u * blockDim.x;
                 ok[u] = idx < items;
                 if (ok[u]) {
-                    const int li = idx / v.W, w = idx - li * v.W;
-                    const int line = blockIdx.x + li * gridDim.x;
-                    const int d = line / v.H, h = line - d * v.H;
-                    const long long r = v.row(n, d + 1, h + 1, 1 + w);
+                    const int li = by_W.div(idx);
+                    const long long r = s_rows[li] + (idx - li * v.W);
                     qx[u] = ld16(x.at(cv, r));
                     qd[u] = ld16(dy.at(cv, r));
                 }

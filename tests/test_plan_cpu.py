@@ -205,14 +205,25 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_fastdiv_formula_is_exact_for_planner_divisors():
-    """The memory-bound kernels divide by W and W*C/8 with umulhi(n, ceil(2^(31+s)/d)) >> (s-1)."""
-    for d in [2, 3, 5, 6, 7, 10, 12, 16, 20, 24, 30, 32, 40, 48, 60, 64, 80, 96, 120, 128, 160, 192, 240, 256, 320,
-              480, 512, 640, 960, 1280, 1920, 2560, 3840]:
+    """Kernels divide by W, W*C/8, Wp and SS = Hp*Wp with umulhi(n, ceil(2^(31+s)/d)) >> (s-1);
+    operands stay below 2^24 (rows of one padded sample, vectors of one CTA)."""
+    divs = {2, 3, 5, 6, 7, 10, 12, 16, 20, 24, 30, 32, 40, 48, 60, 64, 80, 96, 120, 128, 160, 192, 240, 256, 320, 480,
+            512, 640, 960, 1280, 1920, 2560, 3840}
+    for side in (16, 24, 32, 48, 64, 96, 128, 144, 160, 192, 240, 20, 40, 80, 30, 60, 120, 18, 36, 72):
+        divs.add(side + 2)
+        for other in (16, 32, 64, 128, 144, 160, 192, 240, 20, 40, 80, 30, 60, 120):
+            divs.add((side + 2) * (other + 2))
+    rng = np.random.default_rng(0)
+    for d in sorted(divs):
         sh = 0
         while (1 << sh) < d:
             sh += 1
         m = ((1 << (31 + sh)) + d - 1) // d
         assert m < 2 ** 32
-        n = np.arange(0, 1 << 20, dtype=np.uint64)
+        # the quotient can only be wrong next to a multiple of d: test every k*d-1, k*d, k*d+1 below 2^24
+        k = np.arange(0, (1 << 24) // d + 1, dtype=np.uint64) * np.uint64(d)
+        n = np.concatenate([k, k + np.uint64(1), np.maximum(k, np.uint64(1)) - np.uint64(1),
+                            rng.integers(0, 1 << 24, 4096).astype(np.uint64)])
+        n = n[n < (1 << 24)]
         q = ((n * np.uint64(m)) >> np.uint64(32)) >> np.uint64(sh - 1)
         assert (q == n // np.uint64(d)).all(), d
