@@ -192,3 +192,54 @@ def test_rejects_bad_inputs():
         m([torch.zeros(1, 4, 12, 16, 16, device="cuda")])      # 12 not divisible by 8
     with pytest.raises(RuntimeError):
         m([torch.zeros(1, 4, 16, 16, 16)])                     # CPU tensor: no fallback
+
+
+def _oracle_gpu_fp32(sd, x):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        return O.unet_logits(sdc, x)
+
+
+def test_full_brats_volume_inference_config2():
+    """BASELINE config 2: one 4x240x240x155 volume zero-padded to 4x240x240x160 (test.py:93,
+    loader_helper.py:99-103), eval / no_grad.  Checker: the oracle in fp32 on the same GPU."""
+    sd = O.init_params(1337)
+    g = torch.Generator().manual_seed(21)
+    x = torch.zeros(1, 4, 240, 240, 160)
+    x[..., :155] = torch.randn(1, 4, 240, 240, 155, generator=g)
+    x = x.cuda()
+    m = _model(sd).eval()
+    (probs,), logits = m([x], return_logits=True)
+    ref = _oracle_gpu_fp32(sd, x)
+    st = _fwd_stats(logits, ref)
+    print("config2 240x240x160", {k: round(v, 5) for k, v in st.items()})
+    assert torch.isfinite(logits).all()
+    assert st["logit_max"] <= CAP["logit_max"] and st["logit_mean"] <= CAP["logit_mean"]
+    assert st["prob"] <= CAP["prob"] and st["mask_dice"] >= CAP["mask_dice"]
+    del m, probs, logits, ref
+    torch.cuda.empty_cache()
+
+
+def test_reference_training_patch_shape_144x144x128():
+    """main.py:111: SimpleReader patch 144x144x128, batch 1 (main.py:22 default): fwd + Dice + bwd."""
+    import brats2019_b200 as B
+    sd = O.init_params(1337)
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(1, 4, 144, 144, 128, generator=g).cuda()
+    t = (torch.rand(1, 3, 144, 144, 128, generator=g) > 0.7).float().cuda()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    loss_ref, _, grads_ref = O.train_step(sdc, x, t)
+    m = _model(sd).train()
+    loss = B.Dice_loss_joint()(m([x]), [t])
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= CAP["loss"]
+    rels = torch.tensor([((p.grad - grads_ref[n]).norm() / grads_ref[n].norm().clamp_min(1e-20)).item()
+                         for n, p in m.named_parameters() if p.grad is not None])
+    print("patch 144x144x128 grad rel-L2 max %.4f median %.4f" % (rels.max().item(), rels.median().item()))
+    assert rels.max().item() <= CAP["grad_max"] and rels.median().item() <= CAP["grad_median"]
+    del m
+    torch.cuda.empty_cache()
