@@ -57,6 +57,10 @@ _PROTOS = {
     "b200_dice_sums": (c_int, [P, P, P, P, c_int, c_int, c_ll, P]),
     "b200_dice_loss": (c_int, [P, c_int, c_float, P, P]),
     "b200_dice_backward": (c_int, [P, P, P, P, c_float, P, c_int, c_int, c_ll, P]),
+    "b200_bce_workspace_floats": (c_size_t, []),
+    "b200_bce_sum": (c_int, [P, P, c_float, P, P, c_ll, P]),
+    "b200_bce_loss": (c_int, [P, C.c_double, P, P]),
+    "b200_bce_backward": (c_int, [P, P, P, c_float, C.c_double, P, c_ll, P]),
     "b200_conv_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
 }

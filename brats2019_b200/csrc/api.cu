@@ -669,6 +669,31 @@ extern "C" int b200_dice_backward(const float* probs, const float* target, const
     return 0;
 }
 
+// BCE_Loss (loss.py:64-79) -------------------------------------------------------------------
+extern "C" size_t b200_bce_workspace_floats(void) { return (size_t)dice_blocks(); }
+extern "C" int b200_bce_sum(const float* probs, const float* target, float bg_weight, float* sum, float* workspace,
+                            long long numel, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bx = dice_blocks();
+    bce_partial_kernel<<<bx, kEwThreads, 0, st>>>(probs, target, bg_weight, workspace, numel);
+    LAUNCH_OK("bce_partial_kernel");
+    reduce_partials_kernel<<<1, 256, 0, st>>>(workspace, bx, 1, 1, sum);
+    LAUNCH_OK("reduce_partials_kernel");
+    return 0;
+}
+extern "C" int b200_bce_loss(const float* sum, double global_numel, float* loss, void* stream) {
+    bce_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sum, global_numel, loss);
+    LAUNCH_OK("bce_loss_kernel");
+    return 0;
+}
+extern "C" int b200_bce_backward(const float* probs, const float* target, const float* grad_out, float bg_weight,
+                                 double global_numel, float* grad_probs, long long numel, void* stream) {
+    bce_bwd_kernel<<<dice_blocks() * 2, kEwThreads, 0, (cudaStream_t)stream>>>(probs, target, grad_out, bg_weight,
+                                                                              (float)(1.0 / global_numel), grad_probs, numel);
+    LAUNCH_OK("bce_bwd_kernel");
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // plan introspection (tests / DESIGN.md): lets a CPU test replay the exact addressing the
 // kernels use.  out[] layout is documented in tests/test_plan_cpu.py.

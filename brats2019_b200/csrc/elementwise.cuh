@@ -686,6 +686,48 @@ dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const 
 }
 
 // ---------------------------------------------------------------------------------------
+// BCE_Loss (loss.py:64-79): -mean( g log(p+1e-6) + w (1-g) log((1+1e-6) - p) ), w = bg_weight.
+//   forward: per-CTA partial sums of the bracket  (partial[blocks])
+//   backward: dL/dp = -gout/numel * ( g/(p+1e-6) - w (1-g)/((1+1e-6) - p) )
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+bce_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, float w, float* __restrict__ partial,
+                   long long n) {
+    float acc = 0.f;
+    const long long nv = ((n & 3) == 0) ? n / 4 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(p)[i];
+        const float4 b = reinterpret_cast<const float4*>(g)[i];
+        acc += b.x * logf(a.x + 1e-6f) + w * (1.f - b.x) * logf((1.f + 1e-6f) - a.x);
+        acc += b.y * logf(a.y + 1e-6f) + w * (1.f - b.y) * logf((1.f + 1e-6f) - a.y);
+        acc += b.z * logf(a.z + 1e-6f) + w * (1.f - b.z) * logf((1.f + 1e-6f) - a.z);
+        acc += b.w * logf(a.w + 1e-6f) + w * (1.f - b.w) * logf((1.f + 1e-6f) - a.w);
+    }
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc += g[i] * logf(p[i] + 1e-6f) + w * (1.f - g[i]) * logf((1.f + 1e-6f) - p[i]);
+    __shared__ float s_red[kEwThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int k = 0; k < kEwThreads / 32; ++k) a += s_red[k];
+        partial[blockIdx.x] = a;
+    }
+}
+// loss = -sum / numel   (sum[0] may have been all-reduced; numel is the global element count)
+__global__ void bce_loss_kernel(const float* __restrict__ sum, double numel, float* __restrict__ loss) {
+    if (threadIdx.x == 0) loss[0] = (float)(-(double)sum[0] / numel);
+}
+__global__ void __launch_bounds__(kEwThreads)
+bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ gout, float w,
+               float inv_numel, float* __restrict__ dp, long long n) {
+    const float k = -gout[0] * inv_numel;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dp[i] = k * (g[i] / (p[i] + 1e-6f) - w * (1.f - g[i]) / ((1.f + 1e-6f) - p[i]));
+}
+
+// ---------------------------------------------------------------------------------------
 // Weight packing: PyTorch fp32 (Cout, Cin, kd, kh, kw) -> bf16 UMMA B-operand stage images
 //   packed[job][g][tg][tl][kchunk][n][8]  (one contiguous w_stage per (job, g, tg))
 // GEMM view: Wg[tap][k][n].  `kind` selects how (tap,k,n) map into the PyTorch tensor:

@@ -1,7 +1,8 @@
 """Drop-in mirror of the reference's criteria on the hot path (loss.py:64-79, 98-122).
 
-`Dice_loss_joint` keeps the reference's constructor and `criterion(output_list, target_list)`
-call shape (train.py:203-205) and runs as hand-written CUDA reductions (b200_dice_*).  The
+`Dice_loss_joint` and `BCE_Loss` keep the reference's constructors and the
+`criterion(output_list, target_list)` call shape (train.py:203-205) and run as hand-written CUDA
+reductions (b200_dice_*, b200_bce_*).  The
 six per-channel sums are produced without the epsilons so that a data-parallel run can
 all-reduce them before the loss is formed: set `Dice_loss_joint.process_group`.
 """
@@ -57,10 +58,33 @@ class Dice_loss_joint(nn.Module):
             return _DiceFunction.apply(pred.float(), gt, float(self.priority), self.process_group)
 
 
+class _BCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, probs, target, bg_weight, group):
+        probs = probs.contiguous()
+        target = target.contiguous().float()
+        s = ops.bce_sum(probs, target, bg_weight)
+        numel = probs.numel()
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+            numel *= dist.get_world_size(group)          # the mean runs over the global batch
+        ctx.save_for_backward(probs, target)
+        ctx.bg_weight, ctx.numel = bg_weight, numel
+        return ops.bce_loss(s, numel).reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        probs, target = ctx.saved_tensors
+        gout = gout.reshape(1).float().contiguous()
+        return ops.bce_backward(probs, target, gout, ctx.bg_weight, ctx.numel), None, None, None
+
+
 class BCE_Loss(nn.Module):
-    """loss.py:64-79 (the other half of the trainer's criterion).
-    Not part of the north-star hot path; evaluated with elementwise torch ops on the
-    probabilities until it is fused into the Dice/sigmoid kernels."""
+    """loss.py:64-79 — the other half of the trainer's criterion (main.py:127):
+    -mean(g log(p+1e-6) + bg_weight (1-g) log(1+1e-6-p)), as CUDA reductions (b200_bce_*)."""
+
+    process_group = None
 
     def __init__(self, index=0, bg_weight=1):
         super(BCE_Loss, self).__init__()
@@ -71,5 +95,7 @@ class BCE_Loss(nn.Module):
         assert (x[self.label_index].shape == y[self.label_index].shape)
         pred = x[self.label_index]
         gt = y[self.label_index]
-        loss = gt * torch.log(pred + 1e-6) + self.bg_weight * (1. - gt) * torch.log((1. + 1e-6) - pred)
-        return -torch.mean(loss)
+        if not pred.is_cuda:
+            raise RuntimeError("brats2019_b200.BCE_Loss runs on CUDA only (no CPU fallback)")
+        with torch.cuda.device(pred.device):
+            return _BCEFunction.apply(pred.float(), gt, float(self.bg_weight), self.process_group)

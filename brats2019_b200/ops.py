@@ -317,3 +317,29 @@ def dice_backward(probs, target, sums, grad_out, priority, grad_probs=None):
                                         _p(grad_probs), B, Cc, S, _stream()), "b200_dice_backward")
     _count(1)
     return grad_probs
+
+
+def bce_sum(probs, target, bg_weight, workspace=None):
+    L = _lib.lib()
+    s = torch.empty(1, dtype=torch.float32, device=probs.device)
+    if workspace is None:
+        workspace = torch.empty(L.b200_bce_workspace_floats(), dtype=torch.float32, device=probs.device)
+    check(L.b200_bce_sum(_p(probs), _p(target), float(bg_weight), _p(s), _p(workspace), probs.numel(), _stream()),
+          "b200_bce_sum")
+    _count(2)
+    return s
+
+
+def bce_loss(s, global_numel):
+    loss = torch.empty(1, dtype=torch.float32, device=s.device)
+    check(_lib.lib().b200_bce_loss(_p(s), float(global_numel), _p(loss), _stream()), "b200_bce_loss")
+    _count(1)
+    return loss
+
+
+def bce_backward(probs, target, grad_out, bg_weight, global_numel):
+    gp = torch.empty_like(probs)
+    check(_lib.lib().b200_bce_backward(_p(probs), _p(target), _p(grad_out), float(bg_weight), float(global_numel),
+                                       _p(gp), probs.numel(), _stream()), "b200_bce_backward")
+    _count(1)
+    return gp

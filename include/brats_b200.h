@@ -122,6 +122,16 @@ int b200_dice_loss(const float* sums, int C, float priority, float* loss, void* 
 int b200_dice_backward(const float* probs, const float* target, const float* sums, const float* grad_out,
                        float priority, float* grad_probs, int B, int C, long long S, void* stream);
 
+/* ---- BCE_Loss (loss.py:64-79) ------------------------------------------------
+ * sum[1] = sum over elements of g log(p+1e-6) + bg_weight (1-g) log(1+1e-6-p)  (all-reducible);
+ * loss = -sum / global_numel. */
+size_t b200_bce_workspace_floats(void);
+int b200_bce_sum(const float* probs, const float* target, float bg_weight, float* sum, float* workspace,
+                 long long numel, void* stream);
+int b200_bce_loss(const float* sum, double global_numel, float* loss, void* stream);
+int b200_bce_backward(const float* probs, const float* target, const float* grad_out, float bg_weight,
+                      double global_numel, float* grad_probs, long long numel, void* stream);
+
 /* ---- plan introspection (tests): integer dump of the launch plan ---------------- */
 int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);

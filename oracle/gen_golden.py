@@ -100,6 +100,37 @@ def main():
         print(name, "dice", dice.item(), "bce", bce.item(), "->", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def tiling_golden():
+    """Pin the oracle's restatement of the sliding-window arithmetic on the reference's own
+    loader_helper.get_indices/copy/copy_back (nibabel is absent here: stubbed, it is only used by
+    the NIfTI readers of that file)."""
+    import types
+    sys.modules.setdefault("nibabel", types.ModuleType("nibabel"))
+    import loader_helper as LH           # /root/reference/loader_helper.py
+    g = torch.Generator().manual_seed(3)
+    data = torch.randn(1, 2, 21, 13, 10, generator=g)
+    tile, center, border = (10, 8, 6), (4, 4, 2), (3, 2, 2)
+    out = torch.zeros(1, 2, 21, 13, 10)
+    grid = [int(np.ceil(j / i)) for i, j in zip(center, data.shape[2:])]
+    tiles = []
+    for i in range(grid[0]):
+        for j in range(grid[1]):
+            for k in range(grid[2]):
+                imin, imax = LH.get_indices(position=(i, j, k), center_shape=center, border=border)
+                t = LH.copy(data=data, tile_shape=tile, index_min=imin, index_max=imax)
+                tiles.append(t.numpy().copy())
+                f = t * 2.0 + (i * 100 + j * 10 + k)          # stand-in for the model: position-dependent
+                LH.copy_back(data=out, tile=f, center_shape=center, index_min=imin, index_max=imax, border=border)
+    path = os.path.join(REPO, "tests", "golden", "tiling.npz")
+    np.savez_compressed(path, data=data.numpy(), out=out.numpy(), tiles=np.stack(tiles), tile=np.array(tile),
+                        center=np.array(center), border=np.array(border))
+    print("tiling ->", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "tiling":
+        tiling_golden()
+    else:
+        main()
+        tiling_golden()

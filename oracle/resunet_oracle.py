@@ -19,6 +19,8 @@ Reference lines followed:
   loss.py:64-79     BCE_Loss             -> `bce_loss`
   weight_init.py:22-27                   -> `init_params`
   test.py:144, metrics.py:108-133        -> `threshold_masks`, `dice_metric`
+  test.py:115-141                        -> `tta_predict`
+  train.py:145-176, loader_helper.py:34-97 -> `tile_get_indices`, `tile_copy`, `tile_copy_back`, `predict_tiled`
 """
 from __future__ import annotations
 
@@ -255,3 +257,61 @@ def train_step(p, x, target, with_bce=False, cfg=DEFAULT_CFG):
         loss = (loss + bce_loss(probs, [target], bg_weight=1e-2)) / 2
     grads = torch.autograd.grad(loss, list(leaves.values()))
     return loss.detach(), probs[0].detach(), OrderedDict(zip(leaves.keys(), grads))
+
+
+# ----------------------------------------------------------------------------------------
+# inference procedures around the model
+# ----------------------------------------------------------------------------------------
+def tta_predict(p, x, cfg=DEFAULT_CFG):
+    """test.py:115-141: identity, flip D, flip H, flip D+H; un-flip; average."""
+    outs = []
+    for dims in ((), (2,), (3,), (2, 3)):
+        xi = torch.flip(x, dims) if dims else x
+        o = unet_forward(p, [xi], cfg)[0]
+        outs.append(torch.flip(o, dims) if dims else o)
+    return sum(outs) / len(outs)
+
+
+def tile_get_indices(position, center_shape, border):
+    # loader_helper.py:34-39
+    index = [p * c for p, c in zip(position, center_shape)]
+    index_min = [i - b for i, b in zip(index, border)]
+    index_max = [i + c + b for i, c, b in zip(index, center_shape, border)]
+    return index_min, index_max
+
+
+def tile_copy(data, tile_shape, index_min, index_max):
+    # loader_helper.py:42-58: window [index_min, index_max) with zero fill outside the volume
+    ret = torch.zeros(tuple(data.shape[:2]) + tuple(tile_shape), dtype=data.dtype, device=data.device)
+    shape = data.shape[2:]
+    cmin = [max(i, 0) for i in index_min]
+    cmax = [min(i, s) for i, s in zip(index_max, shape)]
+    dmin = [c - i for c, i in zip(cmin, index_min)]
+    dmax = [t - (i - c) for t, c, i in zip(tile_shape, cmax, index_max)]
+    ret[:, :, dmin[0]:dmax[0], dmin[1]:dmax[1], dmin[2]:dmax[2]] = data[:, :, cmin[0]:cmax[0], cmin[1]:cmax[1], cmin[2]:cmax[2]]
+    return ret
+
+
+def tile_copy_back(data, tile, center_shape, index_min, index_max, border):
+    # loader_helper.py:82-97: only the centre of the tile is written, clamped to the volume
+    shape = data.shape[2:]
+    cen_min = [i + b for i, b in zip(index_min, border)]
+    cen_max = [i - b for i, b in zip(index_max, border)]
+    cmin = [max(i, 0) for i in cen_min]
+    cmax = [min(i, s) for i, s in zip(cen_max, shape)]
+    dmin = [b + c - i for b, c, i in zip(border, cmin, cen_min)]
+    dmax = [b + t - (i - c) for b, t, c, i in zip(border, center_shape, cmax, cen_max)]
+    data[:, :, cmin[0]:cmax[0], cmin[1]:cmax[1], cmin[2]:cmax[2]] = tile[:, :, dmin[0]:dmax[0], dmin[1]:dmax[1], dmin[2]:dmax[2]]
+
+
+def predict_tiled(fn, x, output_shape, tile_shape=(192, 192, 192), center_shape=(48, 48, 48), border=(72, 72, 72)):
+    """train.py:145-176 with `fn(tile) -> tile-shaped output` standing for self.model([tile])[0]."""
+    out = torch.zeros(output_shape, dtype=x.dtype, device=x.device)
+    grid = [int(math.ceil(j / i)) for i, j in zip(center_shape, x.shape[2:])]
+    for i in range(grid[0]):
+        for j in range(grid[1]):
+            for k in range(grid[2]):
+                imin, imax = tile_get_indices((i, j, k), center_shape, border)
+                t = tile_copy(x, tile_shape, imin, imax)
+                tile_copy_back(out, fn(t), center_shape, imin, imax, border)
+    return out

@@ -146,6 +146,14 @@ def group_ew():
     report("sigmoid backward", ops.act_to_ncdhw(dl, 3), bf(refdl), tol_rel=1e-2)
     report("sigmoid backward pad channels zero", ops.act_to_ncdhw(dl)[:, 3:], torch.zeros(N, 13, D2, H2, W2, device=dev), tol_abs=0)
     report("bias grad", dbias, refdl.sum(dim=(0, 2, 3, 4)), tol_rel=2e-3)
+    # BCE (loss.py:64-79)
+    pr2 = probs.clone().requires_grad_(True)
+    bref = -torch.mean(target * torch.log(pr2 + 1e-6) + 1e-2 * (1. - target) * torch.log((1. + 1e-6) - pr2))
+    bref.backward()
+    bs = ops.bce_sum(probs, target, 1e-2)
+    report("bce loss", ops.bce_loss(bs, probs.numel()), bref.detach().view(1), tol_abs=1e-5)
+    report("bce backward", ops.bce_backward(probs, target, torch.ones(1, device=dev), 1e-2, probs.numel()), pr2.grad,
+           tol_rel=1e-3)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -66,3 +66,48 @@ def test_dice_closed_form_gradient():
     t = (torch.rand(2, 3, 4, 4, 4) > 0.6).float()
     O.dice_loss_joint([p], [t]).backward()
     np.testing.assert_allclose(O.dice_loss_grad_closed_form(p.detach(), t).numpy(), p.grad.numpy(), rtol=1e-4, atol=1e-8)
+
+
+def test_tiling_restatement_matches_reference_loader_helper(golden):
+    """oracle.tile_* / predict_tiled vs outputs of the reference's loader_helper (tests/golden/tiling.npz)."""
+    g = golden("tiling")
+    data = torch.from_numpy(g["data"])
+    tile, center, border = tuple(int(v) for v in g["tile"]), tuple(int(v) for v in g["center"]), tuple(int(v) for v in g["border"])
+    seen = []
+    state = {"n": 0}
+    grid = [int(np.ceil(j / i)) for i, j in zip(center, data.shape[2:])]
+
+    def fn(t):
+        n = state["n"]
+        state["n"] += 1
+        seen.append(t.numpy().copy())
+        i, rem = divmod(n, grid[1] * grid[2])
+        j, k = divmod(rem, grid[2])
+        return t * 2.0 + (i * 100 + j * 10 + k)
+
+    out = O.predict_tiled(fn, data, data.shape, tile, center, border)
+    np.testing.assert_array_equal(np.stack(seen), g["tiles"])
+    np.testing.assert_array_equal(out.numpy(), g["out"])
+
+
+def test_product_tiler_matches_oracle_tiler_on_cpu_tensors():
+    """brats2019_b200.inference.predict_tiled cuts the same windows and writes the same centres as the
+    reference procedure (checked with a stand-in model on CPU tensors: only tensor indexing runs)."""
+    from brats2019_b200 import inference as I
+    torch.manual_seed(0)
+    x = torch.randn(1, 4, 21, 13, 10)
+    tile, center, border = (10, 8, 6), (4, 4, 2), (3, 2, 2)
+
+    class Fake:
+        def __call__(self, lst):
+            t = lst[0]
+            return [torch.stack([t[:, 0] * 2 + t[:, 1], t[:, 2] - t[:, 3], t[:, 0] * t[:, 3]], dim=1)]
+
+    ref = O.predict_tiled(lambda t: Fake()([t])[0], x, (1, 3, 21, 13, 10), tile, center, border)
+    for bt in (1, 3):
+        got = I.predict_tiled(Fake(), x, 3, tile, center, border, batch_tiles=bt)
+        np.testing.assert_array_equal(got.numpy(), ref.numpy())
+    # padding rule of test.py:92-99
+    xp, l, r = I.pad_to_multiple(x, 16)
+    assert xp.shape[2:] == (32, 16, 16) and torch.equal(I.unpad(xp, l, r), x)
+    assert [I.closest_to_k(v, 16) for v in (155, 240, 160, 16)] == [160, 240, 160, 16]
