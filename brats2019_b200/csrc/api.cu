@@ -11,6 +11,7 @@
 
 #include "../../include/brats_b200.h"
 #include "conv_gemm.cuh"
+#include "conv_march.cuh"
 #include "elementwise.cuh"
 #include "wgrad_gemm.cuh"
 
@@ -238,17 +239,84 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// marching conv (conv_march.cuh): 3x3x3, Cin and Cout in {16, 32}
+// ---------------------------------------------------------------------------------------
+static bool march_enabled() {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("B200_NO_MARCH"); off = (e && atoi(e)) ? 1 : 0; }
+    return !off;
+}
+// returns 0 and fills p when the marching kernel applies to this conv, 1 otherwise (no error text)
+static int plan_march(const b200_conv_desc* d, MarchParams& p) {
+    if (!march_enabled() || d->mode != MODE_K3 || d->Cin_b != 0) return 1;
+    if (!(d->Cin_a == 16 || d->Cin_a == 32) || !(d->Cout == 16 || d->Cout == 32)) return 1;
+    if (d->epi == EPI_SIGMOID && d->Cout != 16) return 1;
+    memset(&p, 0, sizeof(p));
+    const int CO = d->Cout;
+    p.N = d->N; p.D = d->D; p.H = d->H; p.W = d->W;
+    p.Wp = d->W + 2;
+    p.SS = (d->H + 2) * p.Wp;
+    p.by_Wp = make_fastdiv((unsigned)p.Wp);
+    p.Q0 = p.Wp + 1;
+    p.QN = (d->H - 1) * p.Wp + d->W;
+    p.KS = d->Cin_a / 16;
+    p.wtile_bytes = 2u * 5u * CO * 16u;
+    p.w_bytes = (unsigned)p.KS * 9u * p.wtile_bytes;
+    const int nb = ceil_div(p.QN, 128);
+    const int sms = num_sms();
+    const int maxMB = std::min(kMarchMaxMB, 512 / (3 * CO));
+    double best = 1e300;
+    int bMB = 0, bslots = 0;
+    for (int MB = 1; MB <= maxMB; ++MB) {
+        const int TR = 128 * MB;
+        const int SR = TR + 2 * p.Wp + 2;
+        const int SRp = (SR + 7) / 8 * 8;
+        const unsigned slot = (unsigned)(d->Cin_a / 8) * SRp * 16u;
+        if (TR > p.SS + 1000) continue;                       // guard rows cover at most SS + 2*Wp + 1024 of overrun
+        if (slot >= (1u << 20)) continue;
+        const unsigned avail = kMaxSmem - kMarchTailBytes - 1024 - p.w_bytes;
+        int slots = (int)std::min<unsigned>(kMarchMaxSlots, avail / slot);
+        if (slots < 3) continue;
+        const long long strips = ceil_div(nb, MB);
+        const long long units = (long long)d->N * strips * d->D;
+        const double upc = (double)ceil_div(units, std::min<long long>(sms, units));
+        const double steps = upc + 2.0 * (1.0 + upc / d->D);
+        const double cost = steps * MB * (1.0 + 0.12 * ((double)SR / TR - 1.0));
+        if (cost < best) { best = cost; bMB = MB; bslots = slots; }
+    }
+    if (bMB == 0) return 1;
+    p.MB = bMB; p.TR = 128 * bMB;
+    p.SRp = (p.TR + 2 * p.Wp + 2 + 7) / 8 * 8;
+    p.plane_bytes = (unsigned)p.SRp * 16u;
+    p.slot_bytes = (unsigned)(d->Cin_a / 8) * p.plane_bytes;
+    p.nslots = std::min(bslots, 4);
+    p.n_strips = ceil_div(nb, p.MB);
+    p.units = (long long)d->N * p.n_strips * d->D;
+    p.smem_x_off = 0;
+    p.smem_w_off = align_up((unsigned)p.nslots * p.slot_bytes, 128);
+    p.smem_bar_off = align_up(p.smem_w_off + p.w_bytes, 16);
+    p.tmem_cols = pow2_cols((unsigned)(p.MB * 3 * CO));
+    return 0;
+}
+static int march_ctas(const MarchParams& p) { return (int)std::min<long long>(num_sms(), p.units); }
+
 static int conv_grid_ctas(const ConvKParams& p) {
     int per_job = std::max(1, num_sms() / p.n_jobs);
     return std::min(per_job, p.num_tiles);
 }
 
 extern "C" size_t b200_conv_packed_weight_bytes(const b200_conv_desc* d) {
+    MarchParams mp;
+    if (check_conv_desc(d) == 0 && plan_march(d, mp) == 0) return mp.w_bytes;
     ConvKParams p;
     if (plan_conv(d, p)) return 0;
     return (size_t)p.n_jobs * p.KG * p.NTG * p.w_stage_bytes;
 }
 extern "C" int b200_conv_ctas(const b200_conv_desc* d) {
+    MarchParams mp;
+    if (check_conv_desc(d) == 0 && plan_march(d, mp) == 0) return march_ctas(mp);
     ConvKParams p;
     if (plan_conv(d, p)) return -1;
     return conv_grid_ctas(p);
@@ -256,9 +324,24 @@ extern "C" int b200_conv_ctas(const b200_conv_desc* d) {
 
 extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const float* w, int Cout_w, int Cin_w,
                                      int taps_w, int ci_off, int K_real, int N_real, void* packed, void* stream) {
+    if (check_conv_desc(d)) return 1;
+    if (kind < 0 || kind > 3) return fail("bad weight kind %d", kind);
+    {
+        MarchParams mp;
+        if (plan_march(d, mp) == 0) {
+            if (kind > B200_W_DGRAD || taps_w != 27) return fail("marching conv: 3x3x3 forward / data-gradient weights only");
+            if (K_real > d->Cin_a || N_real > d->Cout) return fail("K_real/N_real exceed the GEMM extents");
+            MarchPackParams q;
+            q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.ci_off = ci_off; q.K_real = K_real; q.N_real = N_real;
+            q.KS = mp.KS; q.CO = d->Cout;
+            const int total = q.KS * 9 * 2 * 5 * q.CO;
+            pack_weight_march_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, q);
+            LAUNCH_OK("pack_weight_march_kernel");
+            return 0;
+        }
+    }
     ConvKParams p;
     if (plan_conv(d, p)) return 1;
-    if (kind < 0 || kind > 3) return fail("bad weight kind %d", kind);
     const int taps_g = (d->mode == MODE_K3) ? 27 : 1;
     if ((kind == B200_W_FWD || kind == B200_W_DGRAD) && taps_w != taps_g) return fail("taps mismatch %d vs %d", taps_w, taps_g);
     if ((kind == B200_W_FWD_S2D || kind == B200_W_DGRAD_S2D) && (taps_w != 8 || d->mode != MODE_K1))
@@ -290,9 +373,59 @@ static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream
     return 0;
 }
 
+template <int CO, int EPI>
+static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(conv_march_kernel<CO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        attr_set = true;
+    }
+    conv_march_kernel<CO, EPI><<<grid, kMarchThreads, smem, st>>>(p);
+    LAUNCH_OK("conv_march_kernel");
+    return 0;
+}
+
+static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a, const void* packed, void* out,
+                     const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
+                     float* logits, int n_out_real, cudaStream_t st) {
+    if (!src_a || !packed) return fail("conv: null operand");
+    if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
+    if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
+        return fail("conv: sigmoid epilogue needs bias, probs and 1..4 real outputs");
+    if (stats_partial && d->epi != EPI_BF16) return fail("conv: GroupNorm statistics only for the bf16 epilogue");
+    if (check_ptr16(src_a, "src_a") || check_ptr16(out, "out") || check_ptr16(residual, "residual") ||
+        check_ptr16(packed, "packed weights"))
+        return 1;
+    p.wpacked = (const __nv_bfloat16*)packed;
+    p.lrelu_out = lrelu_out;
+    p.stats_partial = stats_partial;
+    p.bias = bias; p.probs = probs; p.logits = logits; p.n_out_real = n_out_real;
+    {
+        const char* dbg = getenv("B200_CONV_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
+    const int grid = march_ctas(p);
+    if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)grid * p.N * 16 * sizeof(float), st));
+    Vol vol{d->N, d->D, d->H, d->W};
+    p.src = make_act(src_a, vol);
+    p.out = make_act(out, vol);
+    p.residual = make_act(residual, vol);
+    const unsigned smem = p.smem_bar_off + kMarchTailBytes;
+    if (d->epi == EPI_SIGMOID) return launch_march<16, EPI_SIGMOID>(p, smem, grid, st);
+    if (d->Cout == 16) return launch_march<16, EPI_BF16>(p, smem, grid, st);
+    return launch_march<32, EPI_BF16>(p, smem, grid, st);
+}
+
 extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
                              void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
                              float* probs, float* logits, int n_out_real, void* stream) {
+    if (check_conv_desc(d)) return 1;
+    {
+        MarchParams mp;
+        if (plan_march(d, mp) == 0)
+            return run_march(d, mp, src_a, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
+                             n_out_real, (cudaStream_t)stream);
+    }
     ConvKParams p;
     if (plan_conv(d, p)) return 1;
     if (!src_a || !packed) return fail("conv: null operand");
@@ -710,6 +843,25 @@ extern "C" int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out
     if (n_out < nv + kMaxTaps) return fail("plan_debug: need %d ints", nv + kMaxTaps);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];
     for (int i = 0; i < kMaxTaps; ++i) out[nv + i] = p.tap_off[i];
+    return 0;
+}
+
+extern "C" int b200_march_prof_read(unsigned long long* host_out, int n) {
+    if (n > 160 * 16) n = 160 * 16;
+    CUDA_OK(cudaMemcpyFromSymbol(host_out, g_march_prof, (size_t)n * sizeof(unsigned long long)));
+    return 0;
+}
+
+extern "C" int b200_march_plan_debug(const b200_conv_desc* d, int* out, int n_out) {
+    if (check_conv_desc(d)) return 1;
+    MarchParams p;
+    if (plan_march(d, p)) return fail("marching conv does not apply to this descriptor");
+    const int vals[] = {p.MB, p.TR, p.Q0, p.QN, p.n_strips, (int)p.units, p.KS, p.SRp, p.nslots, (int)p.plane_bytes,
+                        (int)p.slot_bytes, (int)p.w_bytes, (int)p.wtile_bytes, (int)p.tmem_cols,
+                        (int)(p.smem_bar_off + kMarchTailBytes), march_ctas(p), p.Wp, p.SS};
+    const int nv = (int)(sizeof(vals) / sizeof(int));
+    if (n_out < nv) return fail("march_plan_debug: need %d ints", nv);
+    for (int i = 0; i < nv; ++i) out[i] = vals[i];
     return 0;
 }
 

@@ -284,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         int cur_n = -1;
-        const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr);
+        const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr) && !(p.debug & 64);
         float* xch = xch_smem + grp * (2 * 4 * 2 * 16);
         int xbuf = 0;
 
@@ -349,10 +349,15 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                         float a0[16], a2[16];
                         {
                             uint32_t r0[16], r1[16], r2[16];
-                            tmem_ld16_nowait(trow + c0, r0);
-                            tmem_ld16_nowait(trow + CO + c0, r1);
-                            tmem_ld16_nowait(trow + 2 * CO + c0, r2);
-                            tmem_ld_wait();
+                            if (!(p.debug & 16)) {
+                                tmem_ld16_nowait(trow + c0, r0);
+                                tmem_ld16_nowait(trow + CO + c0, r1);
+                                tmem_ld16_nowait(trow + 2 * CO + c0, r2);
+                                tmem_ld_wait();
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) { r0[i] = m + i; r1[i] = m - i; r2[i] = m * i; }
+                            }
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 a0[i] = __uint_as_float(r0[i]);
@@ -423,8 +428,10 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i]);
                             }
-                            *reinterpret_cast<uint4*>(p.out.at(ch, orow)) = pack_bf16x8(v);
-                            *reinterpret_cast<uint4*>(p.out.at(ch + 1, orow)) = pack_bf16x8(v + 8);
+                            if (!(p.debug & 32) || v[0] == 123.456f) {
+                                *reinterpret_cast<uint4*>(p.out.at(ch, orow)) = pack_bf16x8(v);
+                                *reinterpret_cast<uint4*>(p.out.at(ch + 1, orow)) = pack_bf16x8(v + 8);
+                            }
                         }
                     } else {  // EPI_SIGMOID: first n_out_real columns are real
                         if (valid && c0 == 0) {

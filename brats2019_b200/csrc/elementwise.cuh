@@ -784,6 +784,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+
+// Marching conv (conv_march.cuh): packed[ks][t = kh*3+kw][k-chunk 2][band*CO + c][8], bands = kd 2,1,0,2,1
+// so that a start offset of 0/1/2 bands rotates which kd tap lands in which accumulator slot.
+struct MarchPackParams {
+    int kind, Cout_w, Cin_w, ci_off, K_real, N_real, KS, CO;
+};
+__global__ void pack_weight_march_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, MarchPackParams q) {
+    const int total = q.KS * 9 * 2 * 5 * q.CO;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int t = i;
+    const int row = t % (5 * q.CO); t /= 5 * q.CO;
+    const int kch = t % 2; t /= 2;
+    const int tap9 = t % 9; t /= 9;
+    const int ks = t;
+    const int band = row / q.CO, c = row - band * q.CO;
+    const int kd = (band == 0 || band == 3) ? 2 : ((band == 1 || band == 4) ? 1 : 0);
+    const int tp = kd * 9 + tap9;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = ks * 16 + kch * 8 + e;
+        float v = 0.f;
+        if (k < q.K_real && c < q.N_real) {
+            if (q.kind == 0) v = w[((size_t)c * q.Cin_w + (k + q.ci_off)) * 27 + tp];
+            else v = w[((size_t)k * q.Cin_w + (c + q.ci_off)) * 27 + (26 - tp)];
+        }
+        f[e] = v;
+    }
+    *reinterpret_cast<uint4*>(packed + (size_t)i * 8) = pack_bf16x8(f);
+}
+
 // ---------------------------------------------------------------------------------------
 // wgrad partial reduction: partial[job][split][nacc][M][Nmma] -> fp32 grad, PyTorch layout.
 //   kind 0: k3 conv  dW[co][ci][kd][kh][kw]           (banded / folded / multi-acc per flags)

@@ -135,6 +135,11 @@ int b200_bce_backward(const float* probs, const float* target, const float* grad
 /* ---- plan introspection (tests): integer dump of the launch plan ---------------- */
 int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
+/* plan of the marching 3x3x3 kernel (Cin, Cout <= 32); error if it does not apply to `d` */
+int b200_march_plan_debug(const b200_conv_desc* d, int* out, int n_out);
+/* perf probes: per-CTA cycle counters of the last marching-conv launch run with B200_CONV_DEBUG bit 256
+ * (host buffer of n <= 2560 counters; synchronises the device) */
+int b200_march_prof_read(unsigned long long* host_out, int n);
 
 #ifdef __cplusplus
 }

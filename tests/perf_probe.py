@@ -71,7 +71,10 @@ def main():
             line("conv3 %d->%d @ %dx%d^3 (+GN stats)" % (Cc, Cc, B, s), timeit(lambda: ops.conv_run(desc, x, pk, y, stats=st)), flops=fl)
         if lvl == 0 and (not only or "conv3" in only) and os.environ.get("B200_CONV_DEBUG") is None:
             for flag, what in ((1, "no activation loads"), (2, "no MMAs"), (3, "neither (epilogue + weights only)"),
-                               (7, "neither, no fold exchange/barrier"), (15, "neither, no exchange, no shuffles")):
+                               (7, "neither, no fold exchange/barrier"), (15, "neither, no exchange, no shuffles"),
+                               (3 + 16, "neither, no tmem ld"), (3 + 32, "neither, no stores"), (3 + 64, "neither, no stats"),
+                               (15 + 16, "neither, no xch/shfl/tmem ld"), (15 + 32, "neither, no xch/shfl/stores"),
+                               (15 + 16 + 32 + 64, "epilogue skeleton only"), (16 + 32 + 64 + 12, "loads+MMA, skeleton epilogue")):
                 env = dict(os.environ, B200_CONV_DEBUG=str(flag), PROBE_ONLY="conv3L0")
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), str(B), str(S)], env=env, capture_output=True, text=True)
                 print("   probe[%s]: %s" % (what, r.stdout.strip().splitlines()[0] if r.stdout.strip() else r.stderr[-300:]), flush=True)
