@@ -216,7 +216,7 @@ def run(args, rank, world, local_rank, dev):
         crit.process_group = net.process_group
     use_graph = not args.no_graph
     opt = torch.optim.Adam(model.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True,
-                           capturable=use_graph)                                            # main.py:133-140
+                           capturable=use_graph, fused=True)                                # main.py:133-140 (stock torch Adam, fused impl)
 
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(Bsz, 4, S, S, S, generator=g).pin_memory()

@@ -27,6 +27,12 @@ class WgradDesc(C.Structure):
                 ("Cin", c_int)]
 
 
+class PackJob(C.Structure):
+    """struct b200_pack_job"""
+    _fields_ = [("desc", ConvDesc), ("kind", c_int), ("Cout_w", c_int), ("Cin_w", c_int), ("taps_w", c_int),
+                ("ci_off", c_int), ("K_real", c_int), ("N_real", c_int), ("w", c_void_p), ("packed", c_void_p)]
+
+
 P = c_void_p
 _PROTOS = {
     # name: (restype, argtypes)
@@ -39,6 +45,9 @@ _PROTOS = {
     "b200_conv_packed_weight_bytes": (c_size_t, [C.POINTER(ConvDesc)]),
     "b200_conv_ctas": (c_int, [C.POINTER(ConvDesc)]),
     "b200_conv_pack_weight": (c_int, [C.POINTER(ConvDesc), c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "b200_pack_table_entry_bytes": (c_size_t, []),
+    "b200_pack_table_build": (c_int, [C.POINTER(PackJob), c_int, P, c_size_t, C.POINTER(c_int)]),
+    "b200_pack_table_run": (c_int, [P, c_int, c_int, P]),
     "b200_conv_run": (c_int, [C.POINTER(ConvDesc), P, P, P, P, P, c_int, P, P, P, P, c_int, P]),
     "b200_wgrad_workspace_bytes": (c_size_t, [C.POINTER(WgradDesc)]),
     "b200_wgrad_run": (c_int, [C.POINTER(WgradDesc), P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
@@ -47,7 +56,8 @@ _PROTOS = {
     "b200_gn_backward_workspace_floats": (c_size_t, [c_int, c_int]),
     "b200_gn_backward": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_upsample2x": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "b200_upsample2x_backward": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200_upsample2x_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "b200_upsample2x_backward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_space_to_depth": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_depth_to_space": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_add": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

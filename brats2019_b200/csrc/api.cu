@@ -13,6 +13,7 @@
 #include "conv_gemm.cuh"
 #include "conv_march.cuh"
 #include "elementwise.cuh"
+#include "elementwise2.cuh"
 #include "wgrad_gemm.cuh"
 
 using namespace b200;
@@ -322,21 +323,22 @@ extern "C" int b200_conv_ctas(const b200_conv_desc* d) {
     return conv_grid_ctas(p);
 }
 
-extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const float* w, int Cout_w, int Cin_w,
-                                     int taps_w, int ci_off, int K_real, int N_real, void* packed, void* stream) {
+// fills the layout parameters of one packing job (no launch); J.w / J.packed are set by the caller
+static int make_pack_job(const b200_conv_desc* d, int kind, int Cout_w, int Cin_w, int taps_w, int ci_off, int K_real,
+                         int N_real, PackJobDev& J, size_t& vectors) {
     if (check_conv_desc(d)) return 1;
     if (kind < 0 || kind > 3) return fail("bad weight kind %d", kind);
+    memset(&J, 0, sizeof(J));
     {
         MarchParams mp;
         if (plan_march(d, mp) == 0) {
             if (kind > B200_W_DGRAD || taps_w != 27) return fail("marching conv: 3x3x3 forward / data-gradient weights only");
             if (K_real > d->Cin_a || N_real > d->Cout) return fail("K_real/N_real exceed the GEMM extents");
-            MarchPackParams q;
+            MarchPackParams& q = J.mq;
             q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.ci_off = ci_off; q.K_real = K_real; q.N_real = N_real;
             q.KS = mp.KS; q.CO = d->Cout;
-            const int total = q.KS * 9 * 2 * 5 * q.CO;
-            pack_weight_march_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, q);
-            LAUNCH_OK("pack_weight_march_kernel");
+            J.layout = 1;
+            vectors = (size_t)q.KS * 9 * 2 * 5 * q.CO;
             return 0;
         }
     }
@@ -347,16 +349,60 @@ extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const fl
     if ((kind == B200_W_FWD_S2D || kind == B200_W_DGRAD_S2D) && (taps_w != 8 || d->mode != MODE_K1))
         return fail("s2d weight kinds need a k1 GEMM and a 2x2x2 kernel");
     if (K_real > d->Cin_a + d->Cin_b || N_real > d->Cout) return fail("K_real/N_real exceed the GEMM extents");
-    PackParams q;
+    PackParams& q = J.q;
     q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
     q.K_real = K_real; q.N_real = N_real;
     q.n_jobs = p.n_jobs; q.KG = p.KG; q.NTG = p.NTG; q.TG = p.TG; q.KC = p.KC; q.Nmma = conv_nmma(d);
     q.fold = conv_fold(d) ? 1 : 0;
     if (q.fold && kind > B200_W_DGRAD) return fail("fold applies to 3x3x3 weights only");
-    const size_t total = (size_t)q.n_jobs * q.KG * q.NTG * q.TG * (q.KC / 8) * q.Nmma;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
-    pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, q);
-    LAUNCH_OK("pack_weight_kernel");
+    J.layout = 0;
+    vectors = pack_weight_total(q);
+    return 0;
+}
+
+extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const float* w, int Cout_w, int Cin_w,
+                                     int taps_w, int ci_off, int K_real, int N_real, void* packed, void* stream) {
+    PackJobDev J;
+    size_t vectors = 0;
+    if (make_pack_job(d, kind, Cout_w, Cin_w, taps_w, ci_off, K_real, N_real, J, vectors)) return 1;
+    const int blocks = (int)((vectors + 255) / 256);
+    if (J.layout == 1) {
+        pack_weight_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.mq);
+        LAUNCH_OK("pack_weight_march_kernel");
+    } else {
+        pack_weight_kernel<<<std::min(blocks, 1024), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.q);
+        LAUNCH_OK("pack_weight_kernel");
+    }
+    return 0;
+}
+
+// ---- all weights in one launch -----------------------------------------------------------------
+extern "C" size_t b200_pack_table_entry_bytes(void) { return sizeof(PackJobDev); }
+extern "C" int b200_pack_table_build(const b200_pack_job* jobs, int n_jobs, void* table_host, size_t table_bytes,
+                                     int* total_blocks) {
+    if (!jobs || n_jobs < 1 || !table_host || !total_blocks) return fail("pack_table_build: bad arguments");
+    if (table_bytes < (size_t)n_jobs * sizeof(PackJobDev)) return fail("pack_table_build: table buffer too small");
+    PackJobDev* T = (PackJobDev*)table_host;
+    int block0 = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        size_t vectors = 0;
+        if (make_pack_job(&jobs[j].desc, jobs[j].kind, jobs[j].Cout_w, jobs[j].Cin_w, jobs[j].taps_w, jobs[j].ci_off,
+                          jobs[j].K_real, jobs[j].N_real, T[j], vectors))
+            return 1;
+        if (check_ptr16(jobs[j].packed, "packed weights")) return 1;
+        T[j].w = jobs[j].w;
+        T[j].packed = (__nv_bfloat16*)jobs[j].packed;
+        T[j].block0 = block0;
+        T[j].nblocks = (int)((vectors + 255) / 256);
+        block0 += T[j].nblocks;
+    }
+    *total_blocks = block0;
+    return 0;
+}
+extern "C" int b200_pack_table_run(const void* table_device, int n_jobs, int total_blocks, void* stream) {
+    if (!table_device || n_jobs < 1 || total_blocks < 1) return fail("pack_table_run: bad arguments");
+    pack_weights_batched_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const PackJobDev*)table_device, n_jobs);
+    LAUNCH_OK("pack_weights_batched_kernel");
     return 0;
 }
 
@@ -672,14 +718,15 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
     return 0;
 }
 
-static int gn_bwd_blocks(int N, int D, int H) {
-    // CTAs per sample for the reduction: ~4 per SM over the batch, each with >= 4 lines of work
-    int per = std::max(1, 4 * num_sms() / std::max(1, N));
-    per = std::max(1, std::min(per, D * H / 4));
-    per = std::max(per, (D * H + kMaxRedLines - 1) / kMaxRedLines);     // row table of the kernel
-    return std::min(per, D * H);
+// reduction grid: ~4 CTAs per SM over the batch; each CTA owns `lpb` consecutive lines (<= kRedLines)
+static void gn_bwd_grid(int N, int D, int H, int& blocks, int& lpb) {
+    const int lines = D * H;
+    int want = std::max(1, 4 * num_sms() / std::max(1, N));
+    want = std::min(want, lines);
+    lpb = std::min(kRedLines, (lines + want - 1) / want);
+    blocks = (lines + lpb - 1) / lpb;
 }
-static int gn_bwd_max_blocks() { return 4 * num_sms() + 2048; }      // >= gn_bwd_blocks() for any volume up to 1M lines
+static int gn_bwd_max_blocks() { return 4 * num_sms() + 8192; }      // >= blocks for any volume up to 1M lines
 extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
     // partial[N][blocks][C][2] + coef[N][C][2]
     return (size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2;
@@ -687,24 +734,25 @@ extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
 extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta,
                                 float* workspace, int N, int D, int H, int W, int C, int do_lrelu, void* stream) {
-    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8) || 1024 % (2 * C)) return fail("gn_backward: C=%d unsupported", C);
+    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8) || C < 16) return fail("gn_backward: C=%d unsupported", C);
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = gn_bwd_blocks(N, D, H);
+    int blocks, rlpb;
+    gn_bwd_grid(N, D, H, blocks, rlpb);
     float* partial = workspace;
     if (blocks > gn_bwd_max_blocks()) return fail("gn_backward: volume too large");
     float* coef = workspace + (size_t)N * gn_bwd_max_blocks() * C * 2;
-    gn_bwd_reduce_kernel<<<dim3(blocks, N), kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                                partial, v, C, do_lrelu, make_fastdiv((unsigned)W));
-    LAUNCH_OK("gn_bwd_reduce_kernel");
+    const FastDiv by_W = make_fastdiv((unsigned)W);
+    gn_bwd_reduce2_kernel<<<dim3(blocks, N), 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                          partial, v, C, do_lrelu, by_W, rlpb);
+    LAUNCH_OK("gn_bwd_reduce2_kernel");
     const double m = (double)(C / 8) * D * H * W;
-    gn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
-    LAUNCH_OK("gn_bwd_finalize_kernel");
+    gn_bwd_finalize2_kernel<<<8, 256, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
+    LAUNCH_OK("gn_bwd_finalize2_kernel");
     const int lpb = lines_per_block(N, D, H);
-    gn_bwd_apply_kernel<<<N * D * H / lpb, kEwThreads, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                               coef, make_act(dx, v), v, C, do_lrelu,
-                                                               make_line_geom(W, C, lpb));
-    LAUNCH_OK("gn_bwd_apply_kernel");
+    gn_bwd_apply2_kernel<<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                         coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb);
+    LAUNCH_OK("gn_bwd_apply2_kernel");
     return 0;
 }
 
@@ -713,19 +761,30 @@ extern "C" int b200_upsample2x(const void* coarse, void* fine, int N, int D, int
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    upsample2x_lrelu_kernel<<<N * 2 * D * 2 * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(coarse, vc),
-                                                                                       make_act(fine, vf), vc, C, do_lrelu);
-    LAUNCH_OK("upsample2x_lrelu_kernel");
+    upsample2x_fwd2_kernel<<<N * 2 * D * 2 * H, 128, 0, (cudaStream_t)stream>>>(make_act(coarse, vc), make_act(fine, vf), vc,
+                                                                               C, do_lrelu, make_fastdiv((unsigned)W));
+    LAUNCH_OK("upsample2x_fwd2_kernel");
     return 0;
 }
-extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out, void* dcoarse, int N, int D, int H,
-                                        int W, int C, int do_lrelu, void* stream) {
+// workspace: the w-reduced intermediate, act layout of volume (N, 2D, 2H, W) with C channels
+extern "C" size_t b200_upsample2x_backward_workspace_bytes(int N, int D, int H, int W, int C) {
+    Vol vt{N, 2 * D, 2 * H, W};
+    return (size_t)(C / 8) * vt.plane_rows() * 16;
+}
+extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out, void* dcoarse, void* workspace, int N,
+                                        int D, int H, int W, int C, int do_lrelu, void* stream) {
     if (check_act(N, D, H, W, C)) return 1;
+    if (!workspace || check_ptr16(workspace, "workspace")) return fail("upsample2x_backward: workspace missing or misaligned");
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    upsample2x_lrelu_bwd_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(
-        make_act(dfine, vf), make_act(fine_out, vf), make_act(dcoarse, vc), vc, C, do_lrelu);
-    LAUNCH_OK("upsample2x_lrelu_bwd_kernel");
+    Vol vt{N, 2 * D, 2 * H, W};
+    cudaStream_t st = (cudaStream_t)stream;
+    const FastDiv by_W = make_fastdiv((unsigned)W);
+    upsample2x_bwd_w_kernel<<<N * 2 * D * 2 * H, 128, 0, st>>>(make_act(dfine, vf), make_act(fine_out, vf),
+                                                              make_act(workspace, vt), vc, C, do_lrelu, by_W);
+    LAUNCH_OK("upsample2x_bwd_w_kernel");
+    upsample2x_bwd_dh_kernel<<<N * D * H, 128, 0, st>>>(make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W);
+    LAUNCH_OK("upsample2x_bwd_dh_kernel");
     return 0;
 }
 

@@ -765,35 +765,38 @@ __device__ __forceinline__ float fetch_weight(const float* w, const PackParams& 
     return w[((size_t)co * q.Cin_w + ci) * q.taps_w + tp];
 }
 
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, PackParams q) {
-    const size_t total = (size_t)q.n_jobs * q.KG * q.NTG * q.TG * (q.KC / 8) * q.Nmma;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t t = i;
-        const int nrow = t % q.Nmma; t /= q.Nmma;
-        const int kch = t % (q.KC / 8); t /= (q.KC / 8);
-        const int tl = t % q.TG; t /= q.TG;
-        const int tg = t % q.NTG; t /= q.NTG;
-        const int g = t % q.KG; t /= q.KG;
-        const int job = (int)t;
-        const int tap = tg * q.TG + tl;
-        const int n = job * q.Nmma + nrow;
-        float f[8];
+__device__ __forceinline__ void pack_weight_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                 const PackParams& q, size_t i) {
+    size_t t = i;
+    const int nrow = t % q.Nmma; t /= q.Nmma;
+    const int kch = t % (q.KC / 8); t /= (q.KC / 8);
+    const int tl = t % q.TG; t /= q.TG;
+    const int tg = t % q.NTG; t /= q.NTG;
+    const int g = t % q.KG; t /= q.KG;
+    const int job = (int)t;
+    const int tap = tg * q.TG + tl;
+    const int n = job * q.Nmma + nrow;
+    float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fetch_weight(w, q, tap, g * q.KC + kch * 8 + e, n);
-        *reinterpret_cast<uint4*>(packed + i * 8) = pack_bf16x8(f);
-    }
+    for (int e = 0; e < 8; ++e) f[e] = fetch_weight(w, q, tap, g * q.KC + kch * 8 + e, n);
+    *reinterpret_cast<uint4*>(packed + i * 8) = pack_bf16x8(f);
 }
-
+__host__ __device__ inline size_t pack_weight_total(const PackParams& q) {
+    return (size_t)q.n_jobs * q.KG * q.NTG * q.TG * (q.KC / 8) * q.Nmma;
+}
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, PackParams q) {
+    const size_t total = pack_weight_total(q);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        pack_weight_elem(w, packed, q, i);
+}
 
 // Marching conv (conv_march.cuh): packed[ks][t = kh*3+kw][k-chunk 2][band*CO + c][8], bands = kd 2,1,0,2,1
 // so that a start offset of 0/1/2 bands rotates which kd tap lands in which accumulator slot.
 struct MarchPackParams {
     int kind, Cout_w, Cin_w, ci_off, K_real, N_real, KS, CO;
 };
-__global__ void pack_weight_march_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, MarchPackParams q) {
-    const int total = q.KS * 9 * 2 * 5 * q.CO;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+__device__ __forceinline__ void pack_weight_march_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                       const MarchPackParams& q, int i) {
     int t = i;
     const int row = t % (5 * q.CO); t /= 5 * q.CO;
     const int kch = t % 2; t /= 2;
@@ -814,6 +817,39 @@ __global__ void pack_weight_march_kernel(const float* __restrict__ w, __nv_bfloa
         f[e] = v;
     }
     *reinterpret_cast<uint4*>(packed + (size_t)i * 8) = pack_bf16x8(f);
+}
+__global__ void pack_weight_march_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, MarchPackParams q) {
+    const int total = q.KS * 9 * 2 * 5 * q.CO;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) pack_weight_march_elem(w, packed, q, i);
+}
+
+// All weights of the model in ONE launch: a device-resident job table (built once on the host by
+// b200_pack_table_build) maps CTA ranges to (weight tensor, packed image, layout parameters).
+struct PackJobDev {
+    const float* w;
+    __nv_bfloat16* packed;
+    int layout;            // 0: conv_gemm.cuh images, 1: conv_march.cuh image
+    int block0, nblocks;   // CTA range of this job (256 vectors per CTA)
+    int pad_;
+    PackParams q;
+    MarchPackParams mq;
+};
+__global__ void pack_weights_batched_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
+    __shared__ int s_job;
+    if (threadIdx.x == 0) {
+        int j = 0;
+        while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
+        s_job = j;
+    }
+    __syncthreads();
+    const PackJobDev& J = jobs[s_job];
+    const size_t i = (size_t)((int)blockIdx.x - J.block0) * blockDim.x + threadIdx.x;
+    if (J.layout == 0) {
+        if (i < pack_weight_total(J.q)) pack_weight_elem(J.w, J.packed, J.q, i);
+    } else {
+        if (i < (size_t)(J.mq.KS * 9 * 2 * 5 * J.mq.CO)) pack_weight_march_elem(J.w, J.packed, J.mq, (int)i);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,398 @@
+// Second-generation memory-bound kernels: GroupNorm backward and trilinear x2 (forward + adjoint).
+//
+// The first versions (elementwise.cuh) were instruction-bound, not HBM-bound (ncu, profiles/r01_*):
+// per-element shared-memory reads of the per-channel constants and scalar FP32 math cost ~125
+// instructions per 16-byte vector.  Here a warp owns ONE 8-channel chunk, so the per-channel
+// constants live in registers, and the arithmetic is packed FP32x2 (FFMA2/FMUL2/FADD2, new on
+// sm_100): ~60 instructions per vector, which puts the kernels back under the HBM roofline.
+//
+// Replaces aten::native_group_norm_backward + leaky_relu_backward (model.py:95-96, 105-112, 338)
+// and aten::upsample_trilinear3d(+_backward) + leaky_relu (model.py:7-14, 422).
+#pragma once
+#include "elementwise.cuh"
+
+namespace b200 {
+
+constexpr int kRedLines = 128;      // lines one gn_bwd_reduce2 CTA may own
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+// bf16x2 word -> two floats (low half first)
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ void unpack4(const uint4& q, float2* f) {
+    f[0] = bf2_to_f2(q.x); f[1] = bf2_to_f2(q.y); f[2] = bf2_to_f2(q.z); f[3] = bf2_to_f2(q.w);
+}
+__device__ __forceinline__ uint4 pack4(const float2* f) {
+    uint4 q;
+    q.x = pack_bf16x2(f[0].x, f[0].y); q.y = pack_bf16x2(f[1].x, f[1].y);
+    q.z = pack_bf16x2(f[2].x, f[2].y); q.w = pack_bf16x2(f[3].x, f[3].y);
+    return q;
+}
+__device__ __forceinline__ float2 lrelu_mask(float2 z) { return make_float2(z.x > 0.f ? 1.f : 0.01f, z.y > 0.f ? 1.f : 0.01f); }
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Warp -> chunk assignment of a 256-thread CTA: with nch = C/8 chunks, nb = min(nch, 8) chunks are
+// processed per pass, 8/nb warps share one chunk (splitting its voxel list), nch/8 passes.
+struct WarpChunk {
+    int nb, wpc, npass, cvb, ws;
+};
+__device__ __forceinline__ WarpChunk warp_chunk(int C) {
+    WarpChunk m;
+    const int nch = C >> 3, w = threadIdx.x >> 5;
+    m.nb = nch < 8 ? nch : 8;
+    m.wpc = 8 / m.nb;
+    m.npass = (nch + 7) >> 3;
+    m.cvb = w % m.nb;
+    m.ws = w / m.nb;
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm (+LeakyReLU) backward, pass 1: per (n, c) sums  S1 = sum dz, S2 = sum dz * xhat
+//   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
+// grid = (blocks, N); CTA b owns lines [b*lpb, b*lpb+lpb) of sample n; partial[n][blocks][C][2].
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3)
+gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
+                      Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
+    __shared__ long long s_rows[kRedLines];
+    __shared__ float s_red[8][16];
+    const int n = blockIdx.y;
+    const int nlines = v.D * v.H;
+    const int line0 = blockIdx.x * lpb;
+    const int nl = min(lpb, nlines - line0);
+    for (int li = threadIdx.x; li < nl; li += blockDim.x) {
+        const int line = line0 + li;
+        const int d = line / v.H, h = line - d * v.H;
+        s_rows[li] = v.row(n, d + 1, h + 1, 1);
+    }
+    __syncthreads();
+    const WarpChunk wc = warp_chunk(C);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gs = C >> 3;
+    const int total = nl * v.W;
+    const int stride = wc.wpc * 32;
+    for (int pass = 0; pass < wc.npass; ++pass) {
+        const int cv = wc.cvb + 8 * pass;
+        float2 a2[4], b2[4], p1[4], p2[4], s1[4], s2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float ka[2], kb[2], k1[2], k2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cv * 8 + 2 * j + e;
+                const int g = c / gs;
+                const float r = rstd[n * 8 + g], m = mean[n * 8 + g];
+                ka[e] = r; kb[e] = -m * r;
+                k1[e] = r * gamma[c]; k2[e] = -m * r * gamma[c] + beta[c];
+            }
+            a2[j] = f2(ka[0], ka[1]); b2[j] = f2(kb[0], kb[1]);
+            p1[j] = f2(k1[0], k1[1]); p2[j] = f2(k2[0], k2[1]);
+            s1[j] = f2(0.f, 0.f); s2[j] = f2(0.f, 0.f);
+        }
+        constexpr int U = 2;
+        for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
+            uint4 qx[U], qd[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = i0 + u * stride;
+                ok[u] = idx < total;
+                if (ok[u]) {
+                    const int li = by_W.div(idx);
+                    const long long r = s_rows[li] + (idx - li * v.W);
+                    qx[u] = ld16(x.at(cv, r));
+                    qd[u] = ld16(dy.at(cv, r));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                float2 fx[4], fd[4];
+                unpack4(qx[u], fx);
+                unpack4(qd[u], fd);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 xh = __ffma2_rn(fx[j], a2[j], b2[j]);
+                    float2 dz = fd[j];
+                    if (do_lrelu) dz = __fmul2_rn(dz, lrelu_mask(__ffma2_rn(fx[j], p1[j], p2[j])));
+                    s1[j] = __fadd2_rn(s1[j], dz);
+                    s2[j] = __ffma2_rn(dz, xh, s2[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s1[j].x = warp_sum(s1[j].x); s1[j].y = warp_sum(s1[j].y);
+            s2[j].x = warp_sum(s2[j].x); s2[j].y = warp_sum(s2[j].y);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s_red[warp][2 * j] = s1[j].x; s_red[warp][2 * j + 1] = s1[j].y;
+                s_red[warp][8 + 2 * j] = s2[j].x; s_red[warp][8 + 2 * j + 1] = s2[j].y;
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < wc.nb * 16) {
+            const int cb = threadIdx.x >> 4, k = threadIdx.x & 15;
+            float acc = 0.f;
+            for (int q = 0; q < wc.wpc; ++q) acc += s_red[cb + q * wc.nb][k];       // fixed order
+            const int c = (cb + 8 * pass) * 8 + (k & 7);
+            partial[(((size_t)n * gridDim.x + blockIdx.x) * C + c) * 2 + (k >> 3)] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2: partial[n][blocks][C][2] -> coef[n][C][2] = (A_g, B_g)/m of the channel's group, and
+// dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.   grid = 8 (one CTA per group), 256 threads.
+// Warp o sums one (channel, which) over the blocks (lanes stride the blocks, double accumulation,
+// fixed shuffle tree): deterministic.
+__global__ void __launch_bounds__(256)
+gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
+                        const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta) {
+    __shared__ double s_sum[64];     // [k][which], k < gs <= 32
+    __shared__ double s_tot[64];
+    const int g = blockIdx.x, gs = C >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nout = gs * 2;
+    if ((int)threadIdx.x < nout) s_tot[threadIdx.x] = 0.0;
+    for (int n = 0; n < N; ++n) {
+        for (int o = warp; o < nout; o += 8) {
+            const int c = g * gs + (o >> 1);
+            const float* src = partial + ((size_t)n * blocks * C + c) * 2 + (o & 1);
+            double a = 0.0;
+            for (int b = lane; b < blocks; b += 32) a += (double)src[(size_t)b * C * 2];
+            a = warp_sum_d(a);
+            if (lane == 0) s_sum[o] = a;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nout) s_tot[threadIdx.x] += s_sum[threadIdx.x];
+        if ((int)threadIdx.x < gs) {
+            double A = 0.0, B = 0.0;
+            for (int k = 0; k < gs; ++k) {
+                A += s_sum[2 * k] * (double)gamma[g * gs + k];
+                B += s_sum[2 * k + 1] * (double)gamma[g * gs + k];
+            }
+            const int c = g * gs + threadIdx.x;
+            coef[((size_t)n * C + c) * 2 + 0] = (float)(A / m);
+            coef[((size_t)n * C + c) * 2 + 1] = (float)(B / m);
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < gs) {
+        dbeta[g * gs + threadIdx.x] = (float)s_tot[2 * threadIdx.x];
+        dgamma[g * gs + threadIdx.x] = (float)s_tot[2 * threadIdx.x + 1];
+    }
+}
+
+// pass 3: dx = rstd * (dz*gamma - A_g - xhat*B_g) = dz*p1 + x*c1 + c0 with per-channel constants
+//   p1 = rstd*gamma, c1 = -rstd^2 B, c0 = -rstd (A + b B), b = -mean*rstd;  z = x*p1 + (b*gamma + beta).
+__global__ void __launch_bounds__(256, 3)
+gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
+                     ActRef dx, Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
+    __shared__ long long s_rows[16];
+    const int line0 = blockIdx.x * lpb;
+    fill_line_rows(v, line0, lpb, s_rows);
+    __syncthreads();
+    const int n = line0 / (v.D * v.H);
+    const WarpChunk wc = warp_chunk(C);
+    const int lane = threadIdx.x & 31;
+    const int gs = C >> 3;
+    const int total = lpb * v.W;
+    const int stride = wc.wpc * 32;
+    for (int pass = 0; pass < wc.npass; ++pass) {
+        const int cv = wc.cvb + 8 * pass;
+        float2 p1[4], p2[4], c1[4], c0[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float k1[2], k2[2], k3[2], k4[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cv * 8 + 2 * j + e;
+                const int g = c / gs;
+                const float r = rstd[n * 8 + g], b = -mean[n * 8 + g] * r;
+                const float A = coef[((size_t)n * C + c) * 2 + 0], B = coef[((size_t)n * C + c) * 2 + 1];
+                k1[e] = r * gamma[c]; k2[e] = b * gamma[c] + beta[c];
+                k3[e] = -r * r * B; k4[e] = -r * (A + b * B);
+            }
+            p1[j] = f2(k1[0], k1[1]); p2[j] = f2(k2[0], k2[1]);
+            c1[j] = f2(k3[0], k3[1]); c0[j] = f2(k4[0], k4[1]);
+        }
+        constexpr int U = 2;
+        for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
+            uint4 qx[U], qd[U];
+            long long rr[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = i0 + u * stride;
+                ok[u] = idx < total;
+                if (ok[u]) {
+                    const int li = by_W.div(idx);
+                    rr[u] = s_rows[li] + (idx - li * v.W);
+                    qx[u] = ld16(x.at(cv, rr[u]));
+                    qd[u] = ld16(dy.at(cv, rr[u]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                float2 fx[4], fd[4];
+                unpack4(qx[u], fx);
+                unpack4(qd[u], fd);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 dz = fd[j];
+                    if (do_lrelu) dz = __fmul2_rn(dz, lrelu_mask(__ffma2_rn(fx[j], p1[j], p2[j])));
+                    fx[j] = __ffma2_rn(dz, p1[j], __ffma2_rn(fx[j], c1[j], c0[j]));
+                }
+                st16(dx.at(cv, rr[u]), pack4(fx));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Trilinear x2 forward (+LeakyReLU): one CTA per fine line (n, fd, fh); a thread owns one coarse
+// voxel column w of one chunk and produces the fine voxels 2w, 2w+1.  The four coarse lines that
+// feed the fine line are blended first (weights shared by the whole CTA), then the w taps.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+upsample2x_fwd2_kernel(ActRef in, ActRef out, Vol vc, int C, int do_lrelu, FastDiv by_Wc) {
+    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
+    int n, d, h;
+    line_coords(vf, blockIdx.x, n, d, h);
+    int d0, d1, h0, h1;
+    float wd0, wd1, wh0, wh1;
+    up_taps(d, vc.D, d0, d1, wd0, wd1);
+    up_taps(h, vc.H, h0, h1, wh0, wh1);
+    const long long rows[4] = {vc.row(n, d0 + 1, h0 + 1, 1), vc.row(n, d0 + 1, h1 + 1, 1), vc.row(n, d1 + 1, h0 + 1, 1),
+                               vc.row(n, d1 + 1, h1 + 1, 1)};
+    const float cwf[4] = {wd0 * wh0, wd0 * wh1, wd1 * wh0, wd1 * wh1};
+    const long long orow0 = vf.row(n, d + 1, h + 1, 1);
+    const int items = vc.W * (C >> 3);
+    const float2 q25 = f2(0.25f, 0.25f), q75 = f2(0.75f, 0.75f), slope = f2(0.01f, 0.01f);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int cv = by_Wc.div(i), w = i - cv * vc.W;
+        const int wm = max(w - 1, 0), wp = min(w + 1, vc.W - 1);
+        float2 tm[4], tc[4], tp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tm[j] = f2(0.f, 0.f); tc[j] = f2(0.f, 0.f); tp[j] = f2(0.f, 0.f); }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint4 qm = ld16(in.at(cv, rows[t] + wm));
+            const uint4 qc = ld16(in.at(cv, rows[t] + w));
+            const uint4 qp = ld16(in.at(cv, rows[t] + wp));
+            const float2 cw = f2(cwf[t], cwf[t]);
+            float2 a[4];
+            unpack4(qm, a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tm[j] = __ffma2_rn(a[j], cw, tm[j]);
+            unpack4(qc, a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tc[j] = __ffma2_rn(a[j], cw, tc[j]);
+            unpack4(qp, a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tp[j] = __ffma2_rn(a[j], cw, tp[j]);
+        }
+        float2 ev[4], od[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 c75 = __fmul2_rn(tc[j], q75);
+            ev[j] = __ffma2_rn(tm[j], q25, c75);
+            od[j] = __ffma2_rn(tp[j], q25, c75);
+            if (do_lrelu) {
+                const float2 se = __fmul2_rn(ev[j], slope), so = __fmul2_rn(od[j], slope);
+                ev[j] = f2(fmaxf(ev[j].x, se.x), fmaxf(ev[j].y, se.y));
+                od[j] = f2(fmaxf(od[j].x, so.x), fmaxf(od[j].y, so.y));
+            }
+        }
+        __nv_bfloat16* o = out.at(cv, orow0 + 2 * w);
+        st16(o, pack4(ev));
+        st16(o + 8, pack4(od));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Trilinear x2 adjoint (+LeakyReLU backward), separable in two passes:
+//   A: T[n, fd, fh, w] = sum_{fw in taps(w)} ww * dy[fd,fh,fw] * lrelu'(y[fd,fh,fw])    (fine d,h; coarse w)
+//   B: dcoarse[n, d, h, w] = sum_{fd in taps(d), fh in taps(h)} wd*wh * T[n, fd, fh, w]
+// T lives in an act-layout workspace of volume (N, 2D, 2H, W).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+upsample2x_bwd_w_kernel(ActRef dy, ActRef y, ActRef T, Vol vc, int C, int do_lrelu, FastDiv by_Wc) {
+    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
+    Vol vt{vc.N, vc.D * 2, vc.H * 2, vc.W};
+    int n, d, h;
+    line_coords(vf, blockIdx.x, n, d, h);
+    const long long irow0 = vf.row(n, d + 1, h + 1, 1);
+    const long long orow0 = vt.row(n, d + 1, h + 1, 1);
+    const int items = vc.W * (C >> 3);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int cv = by_Wc.div(i), w = i - cv * vc.W;
+        int wi[4];
+        float ww[4];
+        const int nw = down_taps(w, vc.W, wi, ww);
+        float2 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = f2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < nw) {
+                float2 g[4];
+                unpack4(ld16(dy.at(cv, irow0 + wi[t])), g);
+                const float2 wt = f2(ww[t], ww[t]);
+                if (do_lrelu) {
+                    float2 yy[4];
+                    unpack4(ld16(y.at(cv, irow0 + wi[t])), yy);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(__fmul2_rn(g[j], lrelu_mask(yy[j])), wt, acc[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(g[j], wt, acc[j]);
+                }
+            }
+        }
+        st16(T.at(cv, orow0 + w), pack4(acc));
+    }
+}
+
+__global__ void __launch_bounds__(128)
+upsample2x_bwd_dh_kernel(ActRef T, ActRef dcoarse, Vol vc, int C, FastDiv by_Wc) {
+    Vol vt{vc.N, vc.D * 2, vc.H * 2, vc.W};
+    int n, d, h;
+    line_coords(vc, blockIdx.x, n, d, h);
+    int di[4], hi[4];
+    float dw[4], hw[4];
+    const int nd = down_taps(d, vc.D, di, dw), nh = down_taps(h, vc.H, hi, hw);
+    const long long orow0 = vc.row(n, d + 1, h + 1, 1);
+    const int items = vc.W * (C >> 3);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int cv = by_Wc.div(i), w = i - cv * vc.W;
+        float2 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = f2(0.f, 0.f);
+        for (int a = 0; a < nd; ++a)
+            for (int b = 0; b < nh; ++b) {
+                float2 g[4];
+                unpack4(ld16(T.at(cv, vt.row(n, di[a] + 1, hi[b] + 1, 1) + w)), g);
+                const float wab = dw[a] * hw[b];
+                const float2 wt = f2(wab, wab);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(g[j], wt, acc[j]);
+            }
+        st16(dcoarse.at(cv, orow0 + w), pack4(acc));
+    }
+}
+
+}  // namespace b200

@@ -85,6 +85,7 @@ class Engine:
             raise RuntimeError("brats2019_b200: at most 4 output channels supported")
         self.plans = {}
         self.packed = {}
+        self.pack_table = ops.PackTable()
         self.last = None          # (plan, generation) of the most recent training forward
 
     # ---------------------------------------------------------------------------------
@@ -105,17 +106,43 @@ class Engine:
         return dict(self.m.named_parameters())
 
     def _pack(self, desc, kind, name, w, ci_off=0, K_real=None, N_real=None):
-        key = (name, kind, ci_off, desc.mode, desc.Cin_a, desc.Cin_b, desc.Cout)
+        """Packed bf16 operand image of one weight.  Images are registered in `self.pack_table` the first
+        time they are needed and from then on refreshed all together by ONE kernel at the start of each
+        forward (`_refresh_packed`); a weight that changed since then is re-packed on the spot."""
+        key = (name, kind, ci_off, desc.mode, desc.epi, desc.N, desc.D, desc.H, desc.W, desc.Cin_a, desc.Cin_b, desc.Cout)
         ent = self.packed.get(key)
         ver = (w._version, w.data_ptr())
-        # while a CUDA graph is being captured the pack kernels must be part of it (the weights
-        # change between replays), so the version cache is bypassed
-        if ent is None or ent[0] != ver or torch.cuda.is_current_stream_capturing():
-            buf = ops.conv_pack_weight(desc, kind, w, ci_off=ci_off, K_real=K_real, N_real=N_real,
-                                       out=None if ent is None else ent[1])
-            ent = (ver, buf)
+        if ent is None:
+            idx, buf = self.pack_table.add(desc, kind, w, ci_off, K_real, N_real)
+            ent = [ver, buf, idx]
             self.packed[key] = ent
+        elif ent[0] != ver and not torch.cuda.is_current_stream_capturing():
+            job = self.pack_table.jobs[ent[2]]
+            if job[2].data_ptr() != w.data_ptr():
+                self.pack_table.table = None          # the parameter's storage moved: rebuild the job table
+            job[2] = w
+            self.pack_table.repack_one(ent[2])
+            ent[0] = ver
         return ent[1]
+
+    def _refresh_packed(self):
+        """One launch re-packs every registered weight image if any parameter changed (always while a CUDA
+        graph is being captured: the weights differ between replays)."""
+        if not self.packed:
+            return
+        capturing = torch.cuda.is_current_stream_capturing()
+        stale = capturing
+        if not stale:
+            for ent in self.packed.values():
+                w = self.pack_table.jobs[ent[2]][2]
+                if ent[0] != (w._version, w.data_ptr()):
+                    stale = True
+                    break
+        if stale:
+            self.pack_table.run()
+            for ent in self.packed.values():
+                w = self.pack_table.jobs[ent[2]][2]
+                ent[0] = (w._version, w.data_ptr())
 
     # ---------------------------------------------------------------------------------
     # building blocks
@@ -164,6 +191,7 @@ class Engine:
     def forward(self, x, want_logits=False, training=False):
         P = self.plan_for(x)
         P.generation += 1
+        self._refresh_packed()
         prm = self._params()
         ch = self.ch
         x = x.contiguous()

@@ -165,6 +165,63 @@ def conv_pack_weight(desc, kind, w, ci_off=0, K_real=None, N_real=None, out=None
     return out
 
 
+class PackTable:
+    """All packed weight images of one model; `run()` refreshes every image with ONE kernel launch
+    (b200_pack_table_run) from a device-resident job table that is rebuilt only when a job is added or
+    a parameter's storage moves."""
+
+    def __init__(self):
+        self.jobs = []          # [desc, kind, w, ci_off, K_real, N_real, buf]
+        self.table = None
+        self.ptrs = None
+        self.total_blocks = 0
+
+    def add(self, desc, kind, w, ci_off, K_real, N_real):
+        buf = conv_pack_weight(desc, kind, w, ci_off=ci_off, K_real=K_real, N_real=N_real)
+        self.jobs.append([desc, kind, w, ci_off, K_real, N_real, buf])
+        self.table = None
+        if not torch.cuda.is_current_stream_capturing():
+            self._build()          # keep the device table current outside graph capture (first step only)
+        return len(self.jobs) - 1, buf
+
+    def repack_one(self, idx):
+        desc, kind, w, ci_off, K_real, N_real, buf = self.jobs[idx]
+        conv_pack_weight(desc, kind, w, ci_off=ci_off, K_real=K_real, N_real=N_real, out=buf)
+
+    def _build(self):
+        L = _lib.lib()
+        n = len(self.jobs)
+        arr = (_lib.PackJob * n)()
+        for i, (desc, kind, w, ci_off, K_real, N_real, buf) in enumerate(self.jobs):
+            assert w.dtype == torch.float32 and w.is_cuda and w.is_contiguous()
+            taps = 1
+            for sdim in w.shape[2:]:
+                taps *= sdim
+            arr[i].desc = desc
+            arr[i].kind, arr[i].Cout_w, arr[i].Cin_w, arr[i].taps_w = kind, w.shape[0], w.shape[1], taps
+            arr[i].ci_off, arr[i].K_real, arr[i].N_real = ci_off, K_real, N_real
+            arr[i].w, arr[i].packed = w.data_ptr(), buf.data_ptr()
+        nbytes = n * L.b200_pack_table_entry_bytes()
+        host = (C.c_uint8 * nbytes)()
+        total = C.c_int(0)
+        check(L.b200_pack_table_build(arr, n, host, nbytes, C.byref(total)), "b200_pack_table_build")
+        dev = self.jobs[0][2].device
+        # pinned staging buffer (kept alive): the copy is legal even while a CUDA graph is being captured
+        self._host = torch.frombuffer(bytearray(host), dtype=torch.uint8).pin_memory()
+        self.table = self._host.to(dev, non_blocking=True)
+        self.total_blocks = total.value
+        self.ptrs = [j[2].data_ptr() for j in self.jobs]
+
+    def run(self):
+        if not self.jobs:
+            return
+        if self.table is None or self.ptrs != [j[2].data_ptr() for j in self.jobs]:
+            self._build()
+        check(_lib.lib().b200_pack_table_run(_p(self.table), len(self.jobs), self.total_blocks, _stream()),
+              "b200_pack_table_run")
+        _count(1)
+
+
 def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=False, stats=None, bias=None,
              probs=None, logits=None, n_out_real=0):
     check(_lib.lib().b200_conv_run(C.byref(desc), _p(src_a), _p(src_b), _p(packed), _p(out), _p(residual),
@@ -242,11 +299,23 @@ def upsample2x(coarse, fine, lrelu=True):
     return fine
 
 
-def upsample2x_backward(dfine, fine_out, dcoarse, lrelu=True):
+_UPS_WS = {}
+
+
+def upsample2x_backward(dfine, fine_out, dcoarse, lrelu=True, workspace=None):
     N, D, H, W, Cc = act_dims(dcoarse)
-    check(_lib.lib().b200_upsample2x_backward(_p(dfine), _p(fine_out), _p(dcoarse), N, D, H, W, Cc,
-                                              1 if lrelu else 0, _stream()), "b200_upsample2x_backward")
-    _count(1)
+    L = _lib.lib()
+    if workspace is None:
+        # one cached scratch buffer per (device, size): allocation-free after the first call (CUDA graphs)
+        nbytes = L.b200_upsample2x_backward_workspace_bytes(N, D, H, W, Cc)
+        key = (dcoarse.device, nbytes)
+        workspace = _UPS_WS.get(key)
+        if workspace is None:
+            workspace = torch.empty(nbytes, dtype=torch.uint8, device=dcoarse.device)
+            _UPS_WS[key] = workspace
+    check(L.b200_upsample2x_backward(_p(dfine), _p(fine_out), _p(dcoarse), _p(workspace), N, D, H, W, Cc,
+                                     1 if lrelu else 0, _stream()), "b200_upsample2x_backward")
+    _count(2)
     return dcoarse
 
 

@@ -62,6 +62,20 @@ int b200_conv_ctas(const b200_conv_desc* d);
  * ci_off: first PyTorch input channel addressed (halves of the cat conv). */
 int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const float* w, int Cout_w, int Cin_w, int taps_w,
                           int ci_off, int K_real, int N_real, void* packed, void* stream);
+/* All packed weights of a model in ONE launch.  The host builds a table once (pointers and layouts are
+ * stable across steps), copies it to the device, and re-runs it whenever the weights changed:
+ *   b200_pack_table_build: fills `table_host` (n_jobs * b200_pack_table_entry_bytes()) and *total_blocks;
+ *   b200_pack_table_run:   launches the packing kernel over a DEVICE copy of that table. */
+typedef struct b200_pack_job {
+    b200_conv_desc desc;
+    int kind, Cout_w, Cin_w, taps_w, ci_off, K_real, N_real;
+    const float* w;      /* device, fp32 PyTorch layout */
+    void* packed;        /* device, b200_conv_packed_weight_bytes(&desc) bytes, 16-byte aligned */
+} b200_pack_job;
+size_t b200_pack_table_entry_bytes(void);
+int b200_pack_table_build(const b200_pack_job* jobs, int n_jobs, void* table_host, size_t table_bytes, int* total_blocks);
+int b200_pack_table_run(const void* table_device, int n_jobs, int total_blocks, void* stream);
+
 /* out = conv(cat[src_a, src_b]) (+ residual) (lrelu optional).
  * stats_partial (optional, epi 0, mode 0): fp32 [b200_conv_ctas][N][16] per-CTA GroupNorm
  *   partial sums (8 group sums, 8 group sums of squares) of the fp32 accumulators.
@@ -98,8 +112,11 @@ int b200_gn_backward(const void* x, const void* dy, const float* mean, const flo
 /* ---- trilinear x2 (aten::upsample_trilinear3d, model.py:7-14) fused with LeakyReLU
  *      (model.py:422); (N,D,H,W) is the COARSE volume -------------------------------------- */
 int b200_upsample2x(const void* coarse, void* fine, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
-int b200_upsample2x_backward(const void* dfine, const void* fine_out, void* dcoarse, int N, int D, int H, int W, int C,
-                             int do_lrelu, void* stream);
+/* backward = adjoint of the interpolation applied to dfine * lrelu'(fine_out); separable in two passes
+ * through `workspace` (b200_upsample2x_backward_workspace_bytes, 16-byte aligned, no initialisation needed) */
+size_t b200_upsample2x_backward_workspace_bytes(int N, int D, int H, int W, int C);
+int b200_upsample2x_backward(const void* dfine, const void* fine_out, void* dcoarse, void* workspace, int N, int D,
+                             int H, int W, int C, int do_lrelu, void* stream);
 
 /* ---- space-to-depth helpers for the 2x2x2 stride-2 conv (model.py:360-363) ---------------
  * (N,D,H,W) is the COARSE volume; coarse has 8*C channels, fine has C. */
