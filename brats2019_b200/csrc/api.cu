@@ -205,7 +205,13 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     } else {
         p.NTG = 1; p.TG = 1;
         p.w_stage_bytes = (unsigned)(p.KC * Nm * 2);
-        p.MB = (Nm <= 128) ? 2 : 1;
+        // rows per tile: as many 128-row blocks as TMEM allows (2 accumulator stages) while every SM still
+        // gets >= 2 tiles: these GEMMs are HBM-bound and need bytes in flight, not tensor throughput
+        p.MB = 1;
+        for (int MB : {4, 2}) {
+            if (2 * MB * Nm > 512) continue;
+            if (ceil_div(p.total_rows, 128 * MB) >= 2 * sms) { p.MB = MB; break; }
+        }
         p.BD = 1; p.whole = 0;
         p.TR = 128 * p.MB;
         p.SRp = p.TR;
@@ -222,14 +228,16 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     unsigned budget = kMaxSmem - bar_bytes;
     p.x_stages = 2; p.w_stages = 2;
     const unsigned w_total = (unsigned)(p.KG * p.NTG) * p.w_stage_bytes;
-    if (d->mode == MODE_K3 && p.KG * p.NTG <= 8 && w_total <= 64 * 1024 && align_up(2 * p.x_stage_bytes, 128) + w_total <= budget) {
+    if (p.KG * p.NTG <= 8 && w_total <= 64 * 1024 && align_up(2 * p.x_stage_bytes, 128) + w_total <= budget) {
         p.w_resident = 1;
         p.w_stages = p.KG * p.NTG;
     }
     auto used = [&]() { return align_up(p.x_stages * p.x_stage_bytes, 128) + p.w_stages * p.w_stage_bytes; };
     if (used() > budget) return fail("conv: shared memory plan does not fit (%u bytes)", used());
-    for (int round = 0; round < 2; ++round) {
-        if (!p.w_resident) { ++p.w_stages; if (used() > budget) --p.w_stages; }
+    // k3: up to 4 stages; k1 (HBM-bound, small stages): up to 8 so that >= ~100 KB are in flight per SM
+    const int rounds = (d->mode == MODE_K1) ? 6 : 2;
+    for (int round = 0; round < rounds; ++round) {
+        if (!p.w_resident && round < 2) { ++p.w_stages; if (used() > budget) --p.w_stages; }
         ++p.x_stages; if (used() > budget) --p.x_stages;
     }
     p.smem_x_off = 0;
@@ -652,8 +660,12 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     q.banded = P.banded; q.folded = P.folded; q.accs = P.accs;
     q.n_jobs = P.k.n_jobs; q.splits = P.k.splits; q.nacc = P.k.nacc; q.M = P.k.M; q.Nmma = P.k.Nmma;
     q.accumulate = accumulate;
-    const int total = q.n_jobs * q.nacc * q.M * q.Nmma;
-    wgrad_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(P.k.partial, grad, q);
+    const int quads = q.n_jobs * q.nacc * q.M * q.Nmma / 4;
+    // split-groups per CTA: enough threads to fill the machine (~2 CTAs per SM), at most 8 and <= splits
+    int SG = 1;
+    while (SG < 8 && SG * 2 <= q.splits && (long long)quads * SG < 2LL * 256 * num_sms()) SG *= 2;
+    const int qpc = 256 / SG;
+    wgrad_reduce_kernel<<<(quads + qpc - 1) / qpc, 256, 0, st>>>(P.k.partial, grad, q, SG);
     LAUNCH_OK("wgrad_reduce_kernel");
     return 0;
 }

@@ -866,30 +866,12 @@ struct WgradReduceParams {
     int accumulate;          // add into grad instead of overwriting
 };
 
-// A 256-thread CTA owns 32 consecutive accumulator elements (job, acc, row, col): warp w sums the
-// K splits s = w, w+8, ... (128-byte coalesced reads of the partials), the 8 warp sums are combined
-// in a fixed order through shared memory (deterministic), and one scattered write goes into the
-// PyTorch-layout gradient.
-__global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q) {
-    __shared__ double s_acc[8][32];
-    const int per_job = q.nacc * q.M * q.Nmma;
-    const int total = q.n_jobs * per_job;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int i = blockIdx.x * 32 + l;
-    double a = 0.0;
-    int job = 0;
-    if (i < total) {
-        job = i / per_job;
-        const float* src = partial + (size_t)job * q.splits * per_job + (size_t)(i - job * per_job);
-        for (int s = w; s < q.splits; s += 8) a += (double)src[(size_t)s * per_job];
-    }
-    s_acc[w][l] = a;
-    __syncthreads();
-    if (w != 0 || i >= total) return;
-    a = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a += s_acc[k][l];
+// A 256-thread CTA owns 256/SG quads of 4 consecutive accumulator elements; thread (sg, quad) sums the
+// K splits s = sg, sg+SG, ... of its quad with float4 loads (4 independent loads in flight), the SG
+// partial sums are combined in a fixed order through shared memory (deterministic), and the quad is
+// scattered into the PyTorch-layout gradient.  The host picks SG (1..8) so that small outputs with
+// many splits (fine levels) and large outputs with few splits (coarse levels) both fill the machine.
+__device__ __forceinline__ void wgrad_scatter(float* __restrict__ grad, const WgradReduceParams& q, int job, int i, double a) {
     const int col = i % q.Nmma;
     int r = i / q.Nmma;
     const int row = r % q.M;
@@ -919,6 +901,53 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
     const size_t o = ((size_t)co * q.Cin_w + ci_w) * q.taps_w + tp;
     if (q.accumulate) grad[o] += (float)a;
     else grad[o] = (float)a;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q, int SG) {
+    __shared__ double s_acc[256][4];
+    const int per_job = q.nacc * q.M * q.Nmma;            // multiple of 4
+    const int quads = q.n_jobs * (per_job >> 2);
+    const int qpc = 256 / SG;                             // quads per CTA
+    const int sg = threadIdx.x / qpc, ql = threadIdx.x - sg * qpc;
+    const int quad = blockIdx.x * qpc + ql;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int job = 0, i = 0;
+    if (quad < quads) {
+        i = quad << 2;
+        job = i / per_job;
+        i -= job * per_job;
+        const float* src = partial + (size_t)job * q.splits * per_job + (size_t)i;
+        int s = sg;
+        for (; s + 3 * SG < q.splits; s += 4 * SG) {
+            const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)s * per_job);
+            const float4 v1 = *reinterpret_cast<const float4*>(src + (size_t)(s + SG) * per_job);
+            const float4 v2 = *reinterpret_cast<const float4*>(src + (size_t)(s + 2 * SG) * per_job);
+            const float4 v3 = *reinterpret_cast<const float4*>(src + (size_t)(s + 3 * SG) * per_job);
+            a0 += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+            a1 += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+            a2 += ((double)v0.z + (double)v1.z) + ((double)v2.z + (double)v3.z);
+            a3 += ((double)v0.w + (double)v1.w) + ((double)v2.w + (double)v3.w);
+        }
+        for (; s < q.splits; s += SG) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * per_job);
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+    }
+    if (SG > 1) {
+        s_acc[threadIdx.x][0] = a0; s_acc[threadIdx.x][1] = a1; s_acc[threadIdx.x][2] = a2; s_acc[threadIdx.x][3] = a3;
+        __syncthreads();
+        if (sg != 0) return;
+        for (int k = 1; k < SG; ++k) {
+            a0 += s_acc[k * qpc + ql][0]; a1 += s_acc[k * qpc + ql][1];
+            a2 += s_acc[k * qpc + ql][2]; a3 += s_acc[k * qpc + ql][3];
+        }
+    }
+    if (quad >= quads) return;
+    wgrad_scatter(grad, q, job, i + 0, a0);
+    wgrad_scatter(grad, q, job, i + 1, a1);
+    wgrad_scatter(grad, q, job, i + 2, a2);
+    wgrad_scatter(grad, q, job, i + 3, a3);
 }
 
 }  // namespace b200

@@ -159,32 +159,44 @@ __global__ void __launch_bounds__(256)
 gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
                         const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
                         float* __restrict__ dbeta) {
-    __shared__ double s_sum[64];     // [k][which], k < gs <= 32
+    __shared__ double s_sum[8][64];     // [n % 8][k*2 + which], k < gs <= 32
     __shared__ double s_tot[64];
     const int g = blockIdx.x, gs = C >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nout = gs * 2;
     if ((int)threadIdx.x < nout) s_tot[threadIdx.x] = 0.0;
-    for (int n = 0; n < N; ++n) {
-        for (int o = warp; o < nout; o += 8) {
+    for (int n0 = 0; n0 < N; n0 += 8) {
+        const int nn = min(8, N - n0);
+        // (sample, output) pairs over the 8 warps; 4 independent loads in flight per lane
+        for (int po = warp; po < nn * nout; po += 8) {
+            const int nl = po / nout, o = po - nl * nout;
             const int c = g * gs + (o >> 1);
-            const float* src = partial + ((size_t)n * blocks * C + c) * 2 + (o & 1);
-            double a = 0.0;
-            for (int b = lane; b < blocks; b += 32) a += (double)src[(size_t)b * C * 2];
-            a = warp_sum_d(a);
-            if (lane == 0) s_sum[o] = a;
+            const float* src = partial + ((size_t)(n0 + nl) * blocks * C + c) * 2 + (o & 1);
+            const size_t bs = (size_t)C * 2;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int b = lane;
+            for (; b + 96 < blocks; b += 128) {
+                const float v0 = src[(size_t)b * bs], v1 = src[(size_t)(b + 32) * bs];
+                const float v2 = src[(size_t)(b + 64) * bs], v3 = src[(size_t)(b + 96) * bs];
+                a0 += (double)v0; a1 += (double)v1; a2 += (double)v2; a3 += (double)v3;
+            }
+            for (; b < blocks; b += 32) a0 += (double)src[(size_t)b * bs];
+            const double a = warp_sum_d((a0 + a1) + (a2 + a3));
+            if (lane == 0) s_sum[nl][o] = a;
         }
         __syncthreads();
-        if ((int)threadIdx.x < nout) s_tot[threadIdx.x] += s_sum[threadIdx.x];
-        if ((int)threadIdx.x < gs) {
+        if ((int)threadIdx.x < nout)
+            for (int nl = 0; nl < nn; ++nl) s_tot[threadIdx.x] += s_sum[nl][threadIdx.x];
+        for (int pc = threadIdx.x; pc < nn * gs; pc += blockDim.x) {
+            const int nl = pc / gs, k0 = pc - nl * gs;
             double A = 0.0, B = 0.0;
             for (int k = 0; k < gs; ++k) {
-                A += s_sum[2 * k] * (double)gamma[g * gs + k];
-                B += s_sum[2 * k + 1] * (double)gamma[g * gs + k];
+                A += s_sum[nl][2 * k] * (double)gamma[g * gs + k];
+                B += s_sum[nl][2 * k + 1] * (double)gamma[g * gs + k];
             }
-            const int c = g * gs + threadIdx.x;
-            coef[((size_t)n * C + c) * 2 + 0] = (float)(A / m);
-            coef[((size_t)n * C + c) * 2 + 1] = (float)(B / m);
+            const int c = g * gs + k0;
+            coef[((size_t)(n0 + nl) * C + c) * 2 + 0] = (float)(A / m);
+            coef[((size_t)(n0 + nl) * C + c) * 2 + 1] = (float)(B / m);
         }
         __syncthreads();
     }

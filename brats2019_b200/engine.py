@@ -41,6 +41,11 @@ class _Plan:
             self.acts[key] = t
         return t
 
+    def alias(self, name, level, view):
+        """Register `view` (Act.chunks of a wider buffer) under the name of a tensor of its own."""
+        self.acts[(name, level, view.C)] = view
+        return view
+
     def f32(self, name, n):
         t = self.misc.get(name)
         if t is None or t.numel() < n:
@@ -197,6 +202,18 @@ class Engine:
         x = x.contiguous()
         if x.dtype != torch.float32:
             x = x.float()
+        # cat([skip, up]) of model.py:424 is ONE 2C-channel buffer per level: the encoder writes the skip
+        # tensor into its first half and the up-sampling its second half (chunk-planar layout: a half is a
+        # tensor of its own), so the cat conv, its data gradient and its weight gradient are single GEMMs.
+        for i in range(self.depth - 1):
+            if ("dec%d.cat" % i, i, 2 * ch[i]) not in P.acts:
+                cat = P.act("dec%d.cat" % i, i, 2 * ch[i])
+                nc = ch[i] // 8
+                P.alias(self._skip_name(i), i, cat.chunks(0, nc))
+                P.alias("dec%d.up" % i, i, cat.chunks(nc, 2 * nc))
+                gcat = P.act("g.cat", i, 2 * ch[i])
+                P.alias("g.skip", i, gcat.chunks(0, nc))
+                P.alias("g.dup", i, gcat.chunks(nc, 2 * nc))
         x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
         c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c")
         h = ops.gn_apply(c, m, r, prm["norm_input.weight"], prm["norm_input.bias"], P.act("in.a", 0, ch[0]),
@@ -217,7 +234,9 @@ class Engine:
             ulo = self._conv1(P, i + 1, wname, prm[wname], ops.W_FWD, h, P.act("dec%d.ulo" % i, i + 1, ch[i]))
             up = ops.upsample2x(ulo, P.act("dec%d.up" % i, i, ch[i]), lrelu=True)         # model.py:421-422
             wname = "decoder_convs1x1.%d.weight" % i
-            h = self._conv1(P, i, wname, prm[wname], ops.W_FWD, skips[i], P.act("dec%d.cc" % i, i, ch[i]), src_b=up)
+            assert up.data_ptr() == P.act("dec%d.cat" % i, i, 2 * ch[i]).chunks(ch[i] // 8, ch[i] // 4).data_ptr()
+            h = self._conv1(P, i, wname, prm[wname], ops.W_FWD, P.act("dec%d.cat" % i, i, 2 * ch[i]),
+                            P.act("dec%d.cc" % i, i, ch[i]))
             for j in range(self.dec[i]):
                 h = self._residual_fwd(P, i, "decoder_convs.%d.%d." % (i, j), h, prm)
         D, H, W = P.dims[0]
@@ -331,13 +350,11 @@ class Engine:
             # cat conv (model.py:424-425): cc = W[:, :C] skip + W[:, C:] up
             wname = "decoder_convs1x1.%d.weight" % i
             w = prm[wname]
-            skip = self._skip_tensor(P, i)
             up = P.act("dec%d.up" % i, i, ch[i])
-            gcat = grads.new(wname, w)
-            self._wgrad(P, i, 1, cur, skip, gcat, ops.G_K1, ci_off=0)
-            self._wgrad(P, i, 1, cur, up, gcat, ops.G_K1, ci_off=ch[i])
-            dskip[i] = self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf("skip", i, ch[i]), ci_off=0)
-            dup = self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf(other(cur_name), i, ch[i]), ci_off=ch[i])
+            self._wgrad(P, i, 1, cur, P.act("dec%d.cat" % i, i, 2 * ch[i]), grads.new(wname, w), ops.G_K1)
+            self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf("cat", i, 2 * ch[i]))       # [dskip | dup] in one GEMM
+            dskip[i] = gbuf("skip", i, ch[i])
+            dup = gbuf("dup", i, ch[i])
             # lrelu + trilinear adjoint (model.py:421-422)
             dulo = ops.upsample2x_backward(dup, up, gbuf("ulo", i + 1, ch[i]), lrelu=True)
             wname = "upsampling.%d.1.weight" % i
@@ -390,6 +407,12 @@ class Engine:
         if self.dec[lvl] > 0:
             return P.act("decoder_convs.%d.%d.out" % (lvl, self.dec[lvl] - 1), lvl, ch[lvl])
         return P.act("dec%d.cc" % lvl, lvl, ch[lvl])
+
+    def _skip_name(self, i):
+        """Name of skip_connections[i] (model.py:417), the level-i encoder output."""
+        if i == 0:
+            return "conv_first.%d.out" % (self.enc[0] - 1) if self.enc[0] > 0 else "in.a"
+        return "encoder_convs.%d.%d.out" % (i - 1, self.enc[i] - 1)
 
     def _skip_tensor(self, P, i):
         """skip_connections[i] of model.py:417: the level-i encoder output."""

@@ -57,6 +57,14 @@ class Act:
     def data_ptr(self):
         return self.t.data_ptr()
 
+    def chunks(self, c0, c1):
+        """View of the 8-channel chunk planes [c0, c1) as an activation tensor of 8*(c1-c0) channels (the
+        layout is chunk-planar, so a channel range that starts on a chunk is itself a valid tensor)."""
+        v = Act.__new__(Act)
+        v.N, v.D, v.H, v.W, v.C, v.G, v.PR = self.N, self.D, self.H, self.W, 8 * (c1 - c0), self.G, self.PR
+        v.t = self.t[c0:c1]
+        return v
+
     @property
     def device(self):
         return self.t.device
