@@ -74,6 +74,7 @@ _PROTOS = {
     "b200_conv_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_march_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
+    "b200_band_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_march_prof_read": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS.keys())

@@ -12,6 +12,7 @@
 #include "../../include/brats_b200.h"
 #include "conv_gemm.cuh"
 #include "conv_march.cuh"
+#include "conv_band.cuh"
 #include "elementwise.cuh"
 #include "elementwise2.cuh"
 #include "wgrad_gemm.cuh"
@@ -292,7 +293,11 @@ static int plan_march(const b200_conv_desc* d, MarchParams& p) {
         const long long units = (long long)d->N * strips * d->D;
         const double upc = (double)ceil_div(units, std::min<long long>(sms, units));
         const double steps = upc + 2.0 * (1.0 + upc / d->D);
-        const double cost = steps * MB * (1.0 + 0.12 * ((double)SR / TR - 1.0));
+        // cycles per step: MMA time of the MB blocks (operand-fetch bound: 46 cycles at N = 48, 56 at N = 96),
+        // stretched by the shared-memory writes of the halo, plus the per-step hand-shake; with a single block
+        // the next step's MMAs additionally wait for the epilogue to drain it (no interleaving)
+        const double t_block = 9.0 * p.KS * (CO == 16 ? 46.0 : 56.0);
+        const double cost = steps * (MB * t_block * (1.0 + 0.12 * ((double)SR / TR - 1.0)) + (MB == 1 ? 400.0 : 100.0));
         if (cost < best) { best = cost; bMB = MB; bslots = slots; }
     }
     if (bMB == 0) return 1;
@@ -311,12 +316,49 @@ static int plan_march(const b200_conv_desc* d, MarchParams& p) {
 }
 static int march_ctas(const MarchParams& p) { return (int)std::min<long long>(num_sms(), p.units); }
 
+
+// ---------------------------------------------------------------------------------------
+// band-marching conv (conv_band.cuh): 3x3x3, 16 -> 16 channels, kd and kh folded (N = 144)
+// ---------------------------------------------------------------------------------------
+static bool band_enabled() {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("B200_NO_BAND"); off = (e && atoi(e)) ? 1 : 0; }
+    return !off;
+}
+static int plan_band(const b200_conv_desc* d, BandParams& p) {
+    if (!band_enabled() || !march_enabled() || d->mode != MODE_K3 || d->Cin_b != 0 || d->Cin_a != 16 || d->Cout != 16) return 1;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.D = d->D; p.H = d->H; p.W = d->W;
+    p.Wp = d->W + 2;
+    p.SS = (d->H + 2) * p.Wp;
+    p.n_bands = ceil_div(d->H, kBandBH);
+    p.n_cols = ceil_div(d->W, 128);
+    // useful fraction of the MMA rows / lines; below ~0.6 the plain marching kernel is the better choice
+    const double eff = ((double)d->W / (128.0 * p.n_cols)) * ((double)d->H / (kBandBH * p.n_bands));
+    if (eff < 0.6) return 1;
+    p.units = (long long)d->N * p.n_bands * p.n_cols * d->D;
+    p.plane_bytes = (unsigned)kBandLines * kBandLineRows * 16u;
+    p.slot_bytes = 2u * p.plane_bytes;
+    p.wimg_bytes = 2u * 144u * 16u;
+    p.w_bytes = 9u * p.wimg_bytes;
+    const unsigned avail = kMaxSmem - kBandTailBytes - 1024 - p.w_bytes;
+    p.nslots = (int)std::min<unsigned>(4, avail / p.slot_bytes);
+    if (p.nslots < 3) return 1;
+    p.smem_x_off = 0;
+    p.smem_w_off = align_up((unsigned)p.nslots * p.slot_bytes, 128);
+    p.smem_bar_off = align_up(p.smem_w_off + p.w_bytes, 16);
+    return 0;
+}
+static int band_ctas(const BandParams& p) { return (int)std::min<long long>(num_sms(), p.units); }
+
 static int conv_grid_ctas(const ConvKParams& p) {
     int per_job = std::max(1, num_sms() / p.n_jobs);
     return std::min(per_job, p.num_tiles);
 }
 
 extern "C" size_t b200_conv_packed_weight_bytes(const b200_conv_desc* d) {
+    BandParams bp;
+    if (check_conv_desc(d) == 0 && plan_band(d, bp) == 0) return bp.w_bytes;
     MarchParams mp;
     if (check_conv_desc(d) == 0 && plan_march(d, mp) == 0) return mp.w_bytes;
     ConvKParams p;
@@ -324,6 +366,8 @@ extern "C" size_t b200_conv_packed_weight_bytes(const b200_conv_desc* d) {
     return (size_t)p.n_jobs * p.KG * p.NTG * p.w_stage_bytes;
 }
 extern "C" int b200_conv_ctas(const b200_conv_desc* d) {
+    BandParams bp;
+    if (check_conv_desc(d) == 0 && plan_band(d, bp) == 0) return band_ctas(bp);
     MarchParams mp;
     if (check_conv_desc(d) == 0 && plan_march(d, mp) == 0) return march_ctas(mp);
     ConvKParams p;
@@ -337,6 +381,19 @@ static int make_pack_job(const b200_conv_desc* d, int kind, int Cout_w, int Cin_
     if (check_conv_desc(d)) return 1;
     if (kind < 0 || kind > 3) return fail("bad weight kind %d", kind);
     memset(&J, 0, sizeof(J));
+    {
+        BandParams bp;
+        if (plan_band(d, bp) == 0) {
+            if (kind > B200_W_DGRAD || taps_w != 27) return fail("band conv: 3x3x3 forward / data-gradient weights only");
+            if (K_real > 16 || N_real > 16) return fail("K_real/N_real exceed the GEMM extents");
+            MarchPackParams& q = J.mq;
+            q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.ci_off = ci_off; q.K_real = K_real; q.N_real = N_real;
+            q.KS = 1; q.CO = 16;
+            J.layout = 2;
+            vectors = 9u * 2u * 144u;
+            return 0;
+        }
+    }
     {
         MarchParams mp;
         if (plan_march(d, mp) == 0) {
@@ -374,7 +431,10 @@ extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const fl
     size_t vectors = 0;
     if (make_pack_job(d, kind, Cout_w, Cin_w, taps_w, ci_off, K_real, N_real, J, vectors)) return 1;
     const int blocks = (int)((vectors + 255) / 256);
-    if (J.layout == 1) {
+    if (J.layout == 2) {
+        pack_weight_band_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.mq);
+        LAUNCH_OK("pack_weight_band_kernel");
+    } else if (J.layout == 1) {
         pack_weight_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.mq);
         LAUNCH_OK("pack_weight_march_kernel");
     } else {
@@ -470,10 +530,58 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
     return launch_march<32, EPI_BF16>(p, smem, grid, st);
 }
 
+template <int EPI>
+static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(conv_band_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        attr_set = true;
+    }
+    conv_band_kernel<EPI><<<grid, kBandThreads, smem, st>>>(p);
+    LAUNCH_OK("conv_band_kernel");
+    return 0;
+}
+
+static int run_band(const b200_conv_desc* d, BandParams& p, const void* src_a, const void* packed, void* out,
+                    const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
+                    float* logits, int n_out_real, cudaStream_t st) {
+    if (!src_a || !packed) return fail("conv: null operand");
+    if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
+    if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
+        return fail("conv: sigmoid epilogue needs bias, probs and 1..4 real outputs");
+    if (stats_partial && d->epi != EPI_BF16) return fail("conv: GroupNorm statistics only for the bf16 epilogue");
+    if (check_ptr16(src_a, "src_a") || check_ptr16(out, "out") || check_ptr16(residual, "residual") ||
+        check_ptr16(packed, "packed weights"))
+        return 1;
+    p.wpacked = (const __nv_bfloat16*)packed;
+    p.lrelu_out = lrelu_out;
+    p.stats_partial = stats_partial;
+    p.bias = bias; p.probs = probs; p.logits = logits; p.n_out_real = n_out_real;
+    {
+        const char* dbg = getenv("B200_CONV_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
+    const int grid = band_ctas(p);
+    if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)grid * p.N * 16 * sizeof(float), st));
+    Vol vol{d->N, d->D, d->H, d->W};
+    p.src = make_act(src_a, vol);
+    p.out = make_act(out, vol);
+    p.residual = make_act(residual, vol);
+    const unsigned smem = p.smem_bar_off + kBandTailBytes;
+    if (d->epi == EPI_SIGMOID) return launch_band<EPI_SIGMOID>(p, smem, grid, st);
+    return launch_band<EPI_BF16>(p, smem, grid, st);
+}
+
 extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
                              void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
                              float* probs, float* logits, int n_out_real, void* stream) {
     if (check_conv_desc(d)) return 1;
+    {
+        BandParams bp;
+        if (plan_band(d, bp) == 0)
+            return run_band(d, bp, src_a, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
+                            n_out_real, (cudaStream_t)stream);
+    }
     {
         MarchParams mp;
         if (plan_march(d, mp) == 0)
@@ -914,6 +1022,18 @@ extern "C" int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out
     if (n_out < nv + kMaxTaps) return fail("plan_debug: need %d ints", nv + kMaxTaps);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];
     for (int i = 0; i < kMaxTaps; ++i) out[nv + i] = p.tap_off[i];
+    return 0;
+}
+
+extern "C" int b200_band_plan_debug(const b200_conv_desc* d, int* out, int n_out) {
+    if (check_conv_desc(d)) return 1;
+    BandParams p;
+    if (plan_band(d, p)) return fail("band-marching conv does not apply to this descriptor");
+    const int vals[] = {kBandBH, p.n_bands, p.n_cols, (int)p.units, p.nslots, (int)p.plane_bytes, (int)p.slot_bytes,
+                        (int)p.w_bytes, (int)p.wimg_bytes, (int)(p.smem_bar_off + kBandTailBytes), band_ctas(p), p.Wp, p.SS};
+    const int nv = (int)(sizeof(vals) / sizeof(int));
+    if (n_out < nv) return fail("band_plan_debug: need %d ints", nv);
+    for (int i = 0; i < nv; ++i) out[i] = vals[i];
     return 0;
 }
 

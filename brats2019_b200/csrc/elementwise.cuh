@@ -824,12 +824,44 @@ __global__ void pack_weight_march_kernel(const float* __restrict__ w, __nv_bfloa
     if (i < total) pack_weight_march_elem(w, packed, q, i);
 }
 
+// Band-marching conv (conv_band.cuh): packed[rot 3][kw 3][k-chunk 2][kh idx 3 (kh = 2,1,0)][kd band 3][16][8],
+// kd of band position b under rotation r = (2,1,0,2,1)[r + b].
+__device__ __forceinline__ void pack_weight_band_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                      const MarchPackParams& q, int i) {
+    int t = i;
+    const int row = t % 144; t /= 144;
+    const int kch = t % 2; t /= 2;
+    const int kw = t % 3; t /= 3;
+    const int rot = t;
+    const int khidx = row / 48, bpos = (row % 48) / 16, c = row % 16;
+    const int kh = 2 - khidx;
+    const int bi = rot + bpos;
+    const int kd = (bi == 0 || bi == 3) ? 2 : ((bi == 1 || bi == 4) ? 1 : 0);
+    const int tp = kd * 9 + kh * 3 + kw;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kch * 8 + e;
+        float v = 0.f;
+        if (k < q.K_real && c < q.N_real) {
+            if (q.kind == 0) v = w[((size_t)c * q.Cin_w + (k + q.ci_off)) * 27 + tp];
+            else v = w[((size_t)k * q.Cin_w + (c + q.ci_off)) * 27 + (26 - tp)];
+        }
+        f[e] = v;
+    }
+    *reinterpret_cast<uint4*>(packed + (size_t)i * 8) = pack_bf16x8(f);
+}
+__global__ void pack_weight_band_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, MarchPackParams q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * 2 * 144) pack_weight_band_elem(w, packed, q, i);
+}
+
 // All weights of the model in ONE launch: a device-resident job table (built once on the host by
 // b200_pack_table_build) maps CTA ranges to (weight tensor, packed image, layout parameters).
 struct PackJobDev {
     const float* w;
     __nv_bfloat16* packed;
-    int layout;            // 0: conv_gemm.cuh images, 1: conv_march.cuh image
+    int layout;            // 0: conv_gemm.cuh images, 1: conv_march.cuh image, 2: conv_band.cuh image
     int block0, nblocks;   // CTA range of this job (256 vectors per CTA)
     int pad_;
     PackParams q;
@@ -847,8 +879,10 @@ __global__ void pack_weights_batched_kernel(const PackJobDev* __restrict__ jobs,
     const size_t i = (size_t)((int)blockIdx.x - J.block0) * blockDim.x + threadIdx.x;
     if (J.layout == 0) {
         if (i < pack_weight_total(J.q)) pack_weight_elem(J.w, J.packed, J.q, i);
-    } else {
+    } else if (J.layout == 1) {
         if (i < (size_t)(J.mq.KS * 9 * 2 * 5 * J.mq.CO)) pack_weight_march_elem(J.w, J.packed, J.mq, (int)i);
+    } else {
+        if (i < (size_t)(9 * 2 * 144)) pack_weight_band_elem(J.w, J.packed, J.mq, (int)i);
     }
 }
 

@@ -154,6 +154,8 @@ int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
 /* plan of the marching 3x3x3 kernel (Cin, Cout <= 32); error if it does not apply to `d` */
 int b200_march_plan_debug(const b200_conv_desc* d, int* out, int n_out);
+/* plan of the band-marching 3x3x3 kernel (16 -> 16 channels, wide lines); error if it does not apply */
+int b200_band_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 /* perf probes: per-CTA cycle counters of the last marching-conv launch run with B200_CONV_DEBUG bit 256
  * (host buffer of n <= 2560 counters; synchronises the device) */
 int b200_march_prof_read(unsigned long long* host_out, int n);

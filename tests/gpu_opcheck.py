@@ -203,23 +203,30 @@ def group_conv3():
     _conv3_case("16->16 32^3", 1, 32, 32, 32, 16, 16)
     _conv3_case("16->16 (8,8,128) long lines", 1, 8, 8, 128, 16, 16)
     _conv3_case("32->32 (4,64,64)", 1, 4, 64, 64, 32, 32)
+    # wide lines: band-marching kernel (kd and kh folded), full / partial bands and window columns
+    _conv3_case("16->16 band (5,16,128)", 1, 5, 16, 128, 16, 16)
+    _conv3_case("16->16 band 2x(3,14,110)", 2, 3, 14, 110, 16, 16)
+    _conv3_case("16->16 band (3,8,240) two window columns", 1, 3, 8, 240, 16, 16)
+    _conv3_case("4->16 band (conv_input) (4,16,128)", 1, 4, 16, 128, 4, 16)
+    _conv3_case("16->16 band res+lrelu (4,24,128)", 1, 4, 24, 128, 16, 16, residual=True, lrelu=True, stats=False)
+    _conv3_case("16->16 band 2x(20,40,128) many CTAs", 2, 20, 40, 128, 16, 16)
     # sigmoid epilogue (conv_output)
     import torch
     import torch.nn.functional as F
     from brats2019_b200 import ops
     dev = "cuda"
     torch.manual_seed(3)
-    N, D, H, W = 2, 8, 8, 16
-    x = bf(torch.randn(N, 16, D, H, W, device=dev))
-    w = bf(torch.randn(3, 16, 3, 3, 3, device=dev) * 0.1)
-    b = torch.randn(3, device=dev)
-    desc = ops.conv_desc(ops.MODE_K3, N, D, H, W, 16, 16, epi=ops.EPI_SIGMOID)
-    packed = ops.conv_pack_weight(desc, ops.W_FWD, w, K_real=16, N_real=3)
-    probs = torch.empty(N, 3, D, H, W, device=dev); logits = torch.empty_like(probs)
-    ops.conv_run(desc, ops.act_from_ncdhw(x), packed, None, bias=b, probs=probs, logits=logits, n_out_real=3)
-    ref = F.conv3d(x, w, b, padding=1)
-    report("conv_output logits", logits, ref, tol_rel=5e-3)
-    report("conv_output probs", probs, torch.sigmoid(ref), tol_abs=2e-3)
+    for (N, D, H, W) in ((2, 8, 8, 16), (1, 4, 16, 128)):
+        x = bf(torch.randn(N, 16, D, H, W, device=dev))
+        w = bf(torch.randn(3, 16, 3, 3, 3, device=dev) * 0.1)
+        b = torch.randn(3, device=dev)
+        desc = ops.conv_desc(ops.MODE_K3, N, D, H, W, 16, 16, epi=ops.EPI_SIGMOID)
+        packed = ops.conv_pack_weight(desc, ops.W_FWD, w, K_real=16, N_real=3)
+        probs = torch.empty(N, 3, D, H, W, device=dev); logits = torch.empty_like(probs)
+        ops.conv_run(desc, ops.act_from_ncdhw(x), packed, None, bias=b, probs=probs, logits=logits, n_out_real=3)
+        ref = F.conv3d(x, w, b, padding=1)
+        report("conv_output logits (%d,%d,%d,%d)" % (N, D, H, W), logits, ref, tol_rel=5e-3)
+        report("conv_output probs (%d,%d,%d,%d)" % (N, D, H, W), probs, torch.sigmoid(ref), tol_abs=2e-3)
 
 
 def group_conv1():
@@ -286,7 +293,8 @@ def group_dgrad():
     dev = "cuda"
     torch.manual_seed(2)
     for (N, D, H, W, Cin, Cout) in ((1, 8, 8, 8, 16, 16), (2, 6, 10, 12, 32, 32), (1, 4, 8, 8, 64, 64),
-                                   (1, 4, 4, 8, 128, 128), (1, 8, 8, 16, 16, 3), (1, 8, 8, 16, 4, 16)):
+                                   (1, 4, 4, 8, 128, 128), (1, 8, 8, 16, 16, 3), (1, 8, 8, 16, 4, 16),
+                                   (1, 4, 16, 128, 16, 16), (1, 3, 8, 128, 16, 3)):
         w = bf(torch.randn(Cout, Cin, 3, 3, 3, device=dev) / (Cin * 27) ** 0.5)
         dy = bf(torch.randn(N, Cout, D, H, W, device=dev))
         ref = F.conv_transpose3d(dy, w, padding=1)

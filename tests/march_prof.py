@@ -24,7 +24,7 @@ desc = ops.conv_desc(ops.MODE_K3, B, S, S, S, Cc, Cc)
 pk = ops.conv_pack_weight(desc, ops.W_FWD, w)
 ctas = ops.conv_ctas(desc)
 st = torch.empty(ctas * B * 16, device=dev)
-for _ in range(3):
+for _ in range(30):      # also ramps the SM clock before the measured launch
     ops.conv_run(desc, x, pk, y, stats=st)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -41,3 +41,7 @@ names = ["prod_total", "prod_wait_empty", "mma_total", "mma_wait_x", "mma_wait_a
 print("flags=%d  C=%d  %dx%d^3  ctas=%d  kernel %.1f us" % (flags, Cc, B, S, ctas, e0.elapsed_time(e1) * 1e3))
 for i, n in enumerate(names):
     print("  %-16s mean %10.0f  max %10.0f" % (n, a[:, i].mean(), a[:, i].max()))
+if a[:, 0].mean() > 0:
+    print("  (band kernel) mma warp span %.1f us -> SM clock %.0f MHz; CTA start skew %.1f us; end spread %.1f us" % (
+        a[:, 0].mean() / 1e3, a[:, 2].mean() / a[:, 0].mean() * 1e3, (a[:, 1].max() - a[:, 1].min()) / 1e3,
+        ((a[:, 1] + a[:, 0]).max() - (a[:, 1] + a[:, 0]).min()) / 1e3))
