@@ -869,10 +869,10 @@ struct PackJobDev {
 };
 __global__ void pack_weights_batched_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
     __shared__ int s_job;
-    if (threadIdx.x == 0) {
-        int j = 0;
-        while (j + 1 < n_jobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
-        s_job = j;
+    // every thread tests a few jobs: one round of independent loads instead of a dependent scan
+    for (int j = threadIdx.x; j < n_jobs; j += blockDim.x) {
+        const int b0 = jobs[j].block0;
+        if ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + jobs[j].nblocks) s_job = j;
     }
     __syncthreads();
     const PackJobDev& J = jobs[s_job];

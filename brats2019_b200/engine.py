@@ -15,6 +15,8 @@ Algebraic restructurings relative to the reference (all exact in real arithmetic
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -91,6 +93,13 @@ class Engine:
         self.plans = {}
         self.packed = {}
         self.pack_table = ops.PackTable()
+        # weight gradients run on a side stream, concurrently with the memory-bound kernels of the
+        # data-gradient chain (GroupNorm backward etc.): a wgrad GEMM at 16/32 channels is bound by MMA issue
+        # latency and leaves HBM and most issue slots idle, and it is off the critical path of backward.
+        self.overlap_wgrad = os.environ.get("B200_NO_WGRAD_OVERLAP", "0") in ("", "0")
+        self._side_stream = None
+        self._side_busy = False
+        self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
         self.last = None          # (plan, generation) of the most recent training forward
 
     # ---------------------------------------------------------------------------------
@@ -255,17 +264,49 @@ class Engine:
     # ---------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------
-    def _wgrad(self, P, lvl, mode, dy, x, grad, kind, ci_off=0, accumulate=False):
+    def _wgrad(self, P, lvl, mode, dy, x, grad, kind, ci_off=0, accumulate=False, overlap=False):
+        """Weight gradient of one conv.  overlap=True: enqueue on the side stream (after everything already on
+        the current stream); the caller must not overwrite `dy` before `_wait_readers(dy)`."""
         D, H, W = P.dims[lvl]
         desc = ops.wgrad_desc(mode, P.N, D, H, W, dy.C, x.C)
-        ws = P.misc.get("wgrad_ws")
+        overlap = overlap and self.overlap_wgrad
+        wsname = "wgrad_ws_side" if overlap else "wgrad_ws"
+        ws = P.misc.get(wsname)
         need = ops._lib.lib().b200_wgrad_workspace_bytes(desc) // 4
         if need == 0:
             ops.check(1, "b200_wgrad_workspace_bytes")
         if ws is None or ws.numel() < need:
+            if ws is not None:
+                self._join_side()          # a larger workspace replaces one the side stream may still use
             ws = torch.empty(need, dtype=torch.float32, device=P.device)
-            P.misc["wgrad_ws"] = ws
-        ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=ws)
+            P.misc[wsname] = ws
+        if not overlap:
+            ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=ws)
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=P.device)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=ws)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._readers[id(dy.t)] = done
+        self._side_busy = True
+
+    def _wait_readers(self, buf):
+        """Order the current stream after the last side-stream kernel that reads `buf` (before overwriting it)."""
+        ev = self._readers.pop(id(buf.t), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _join_side(self):
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._side_busy = False
+            self._readers.clear()
 
     def _dgrad3(self, P, lvl, wname, w, dy, out, residual=None):
         D, H, W = P.dims[lvl]
@@ -286,6 +327,15 @@ class Engine:
                         lrelu=lrelu)
         return dx
 
+    def _dc_buf(self, P, lvl, Cc):
+        """Next buffer of a 3-deep ring for the gradients w.r.t. conv outputs: each is read by a weight-gradient
+        GEMM on the side stream, so it must not be overwritten until that GEMM is done."""
+        k = P.misc.get(("dc_ring", lvl), 0)
+        P.misc[("dc_ring", lvl)] = (k + 1) % 3
+        buf = P.act("tmp.dc%d" % k, lvl, Cc)
+        self._wait_readers(buf)
+        return buf
+
     def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads):
         """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns grad w.r.t. x_in
         (written into d_in_buf), which includes the identity path (model.py:115)."""
@@ -293,17 +343,29 @@ class Engine:
         c1 = P.act(prefix + "c1", lvl, Cc)
         a1 = P.act(prefix + "a1", lvl, Cc)
         c2 = P.act(prefix + "c2", lvl, Cc)
-        t0 = P.act("tmp.g0", lvl, Cc)
         t1 = P.act("tmp.g1", lvl, Cc)
         w1n, w2n = prefix + "conv1.conv1.weight", prefix + "conv2.conv1.weight"
         dc2 = self._gn_bwd(P, lvl, prefix + "c2", c2, d_out, prm[prefix + "norm2.weight"], prm[prefix + "norm2.bias"],
-                           t0, grads, prefix + "norm2.weight", prefix + "norm2.bias")
-        self._wgrad(P, lvl, 0, dc2, a1, grads.new(w2n, prm[w2n]), ops.G_K3)
+                           self._dc_buf(P, lvl, Cc), grads, prefix + "norm2.weight", prefix + "norm2.bias")
+        # Each weight gradient is queued on the side stream AFTER the data-gradient conv that shares its input:
+        # it then runs next to the memory-bound GroupNorm-backward kernels that follow (the two tensor-core
+        # kernels cannot share an SM: both need more than half of its shared memory).
+        g2 = grads.new(w2n, prm[w2n])
         da1 = self._dgrad3(P, lvl, w2n, prm[w2n], dc2, t1)
+        self._wgrad(P, lvl, 0, dc2, a1, g2, ops.G_K3, overlap=True)
         dc1 = self._gn_bwd(P, lvl, prefix + "c1", c1, da1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
-                           t0, grads, prefix + "norm1.weight", prefix + "norm1.bias")
-        self._wgrad(P, lvl, 0, dc1, x_in, grads.new(w1n, prm[w1n]), ops.G_K3)
-        return self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out)
+                           self._dc_buf(P, lvl, Cc), grads, prefix + "norm1.weight", prefix + "norm1.bias")
+        g1 = grads.new(w1n, prm[w1n])
+        dx = self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out)
+        self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3, overlap=True)
+        return dx
+
+    def _mark(self, grads):
+        """Level boundary: a store that ships gradients (BucketedAllReduce) needs them complete, so the side
+        stream is joined first; the default store does nothing here and the side stream keeps running."""
+        if type(grads).mark is not GradStore.mark:
+            self._join_side()
+        grads.mark()
 
     def backward(self, gprobs, store=None):
         """gprobs: fp32 (N, n_out, D, H, W) gradient w.r.t. the returned probabilities.
@@ -327,13 +389,14 @@ class Engine:
         ops.sigmoid_backward(gprobs, probs, dlog, dbias,
                              workspace=P.f32("sig_ws", ops._lib.lib().b200_sigmoid_backward_workspace_floats(P.N, D, H)))
         h_last = P.misc["final_h"]
-        self._wgrad(P, 0, 0, dlog, h_last, grads.new("conv_output.weight", prm["conv_output.weight"]), ops.G_K3)
+        g_out = grads.new("conv_output.weight", prm["conv_output.weight"])
         # ping-pong gradient buffers per level: "g.A"/"g.B"
         def gbuf(name, lvl, Cc):
             return P.act("g." + name, lvl, Cc)
 
         cur = self._dgrad3(P, 0, "conv_output.weight", prm["conv_output.weight"], dlog, gbuf("A", 0, ch[0]))
         cur_name = "A"
+        self._wgrad(P, 0, 0, dlog, h_last, g_out, ops.G_K3, overlap=True)
 
         def other(n):
             return "B" if n == "A" else "A"
@@ -361,7 +424,7 @@ class Engine:
             w = prm[wname]
             h_lo = self._level_output(P, i + 1)
             self._wgrad(P, i + 1, 1, dulo, h_lo, grads.new(wname, w), ops.G_K1)
-            grads.mark()
+            self._mark(grads)
             cur = self._conv1(P, i + 1, wname, w, ops.W_DGRAD, dulo, gbuf("A", i + 1, ch[i + 1]))
             cur_name = "A"
         # At this point `cur` is the gradient w.r.t. the bottleneck output (encoder level depth-1).
@@ -378,7 +441,7 @@ class Engine:
             w = prm[wname]
             s2d = P.act("enc%d.s2d" % i, lvl, 8 * ch[i])
             self._wgrad(P, lvl, 1, cur, s2d, grads.new(wname, w), ops.G_S2D)
-            grads.mark()
+            self._mark(grads)
             ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
             # back to the fine grid, adding the skip-connection gradient from the decoder
             cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
@@ -394,6 +457,7 @@ class Engine:
                             gbuf(other(cur_name), 0, ch[0]), grads, "norm_input.weight", "norm_input.bias", lrelu=False)
         self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), grads.new("conv_input.weight", prm["conv_input.weight"]),
                     ops.G_K3)
+        self._join_side()
         grads.finish()
         return grads.grads
 
