@@ -936,6 +936,12 @@ extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, i
     return 0;
 }
 
+static int sigmoid_lpb(int N, int D, int H) {
+    const long long lines = (long long)N * D * H;
+    int lpb = 1;
+    while (lpb < 16 && lines / (lpb * 2) >= 6LL * num_sms()) lpb *= 2;
+    return lpb;
+}
 extern "C" size_t b200_sigmoid_backward_workspace_floats(int N, int D, int H) { return (size_t)N * D * H * 4; }
 extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs, void* dlogit_act, float* dbias,
                                      float* workspace, int N, int D, int H, int W, int Creal, int Cpad, void* stream) {
@@ -943,9 +949,11 @@ extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs
     (void)Cpad;     // only chunk 0 is written; the other chunks of the destination stay zero
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = N * D * H;
-    sigmoid_bwd_pack_kernel<<<blocks, kEwThreads, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal);
-    LAUNCH_OK("sigmoid_bwd_pack_kernel");
+    const int lpb = sigmoid_lpb(N, D, H);
+    const int blocks = (N * D * H + lpb - 1) / lpb;
+    sigmoid_bwd_pack2_kernel<<<blocks, 256, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+                                                    make_fastdiv((unsigned)W));
+    LAUNCH_OK("sigmoid_bwd_pack2_kernel");
     if (dbias) {
         reduce_partials_kernel<<<Creal, 256, 0, st>>>(workspace, blocks, 4, Creal, dbias);
         LAUNCH_OK("reduce_partials_kernel");
@@ -963,8 +971,8 @@ extern "C" int b200_dice_sums(const float* probs, const float* target, float* su
     const int bx = dice_blocks();
     dice_partial_kernel<<<dim3(bx, B * C), kEwThreads, 0, st>>>(probs, target, workspace, B, C, S);
     LAUNCH_OK("dice_partial_kernel");
-    dice_sums_kernel<<<1, 32, 0, st>>>(workspace, B, C, bx, sums);
-    LAUNCH_OK("dice_sums_kernel");
+    dice_sums2_kernel<<<1, 256, 0, st>>>(workspace, B, C, bx, sums);
+    LAUNCH_OK("dice_sums2_kernel");
     return 0;
 }
 extern "C" int b200_dice_loss(const float* sums, int C, float priority, float* loss, void* stream) {

@@ -274,6 +274,72 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// sigmoid backward + layout (model.py:431 backward): a CTA owns `lpb` lines; thread = voxel.
+//   dlogit = gp * p * (1-p) -> chunk 0 of an act tensor; per-CTA bias-grad partials [blocks][4]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_pack2_kernel(const float* __restrict__ gp, const float* __restrict__ probs, ActRef dlogit,
+                         float* __restrict__ bias_partial, Vol v, int Creal, int lpb, FastDiv by_W) {
+    __shared__ float s_red[8][4];
+    const int line0 = blockIdx.x * lpb;
+    const int nlines = v.N * v.D * v.H;
+    const int nl = min(lpb, nlines - line0);
+    const size_t plane = (size_t)v.D * v.H * v.W;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int idx = threadIdx.x; idx < nl * v.W; idx += blockDim.x) {
+        const int li = by_W.div(idx), w = idx - li * v.W;
+        int n, d, h;
+        line_coords(v, line0 + li, n, d, h);
+        const size_t src = (size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W + w;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            f[i] = 0.f;
+            if (i < Creal) {
+                const float p = probs[src + (size_t)i * plane];
+                f[i] = gp[src + (size_t)i * plane] * p * (1.f - p);
+                if (i < 4) bsum[i] += f[i];
+            }
+        }
+        st16(dlogit.at(0, v.row(n, d + 1, h + 1, 1 + w)), pack_bf16x8(f));
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bsum[c] = warp_sum(bsum[c]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int c = 0; c < 4; ++c) s_red[warp][c] = bsum[c];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float a = 0.f;
+        for (int k = 0; k < 8; ++k) a += s_red[k][threadIdx.x];
+        bias_partial[(size_t)blockIdx.x * 4 + threadIdx.x] = a;
+    }
+}
+
+// partial[B*C][blocks][2] -> sums[8] (I_c at [c], U_c at [4+c]): one CTA, thread (c, which, j) strides
+// the (sample, block) pairs, fixed-order combination through shared memory.
+__global__ void __launch_bounds__(256)
+dice_sums2_kernel(const float* __restrict__ partial, int B, int C, int blocks, float* __restrict__ sums) {
+    __shared__ double s_p[256];
+    const int o = threadIdx.x >> 5, j = threadIdx.x & 31;      // o = c*2 + which (< 8), 32 threads per output
+    const int c = o >> 1, which = o & 1;
+    double a = 0.0;
+    if (c < C)
+        for (int i = j; i < B * blocks; i += 32) {
+            const int b = i / blocks, k = i - b * blocks;
+            a += (double)partial[((size_t)(b * C + c) * blocks + k) * 2 + which];
+        }
+    s_p[threadIdx.x] = a;
+    __syncthreads();
+    if (j == 0 && c < C) {
+        double t = 0.0;
+        for (int q = 0; q < 32; ++q) t += s_p[o * 32 + q];
+        sums[which * 4 + c] = (float)t;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Trilinear x2 forward (+LeakyReLU): one CTA per fine line (n, fd, fh); a thread owns one coarse
 // voxel column w of one chunk and produces the fine voxels 2w, 2w+1.  The four coarse lines that

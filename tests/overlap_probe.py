@@ -70,7 +70,23 @@ def timed(fa, fb, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+big_a = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+big_b = torch.empty_like(big_a)
+
+
+def copy():
+    big_b.copy_(big_a)
+
+
+def gnf():
+    ops.gn_apply(x, mean, rstd, gamma, beta, dx, residual=dy)
+
+
 with torch.cuda.stream(s1):
+    t_copy, t_gnf = timed(copy, None), timed(gnf, None)
+    t_wg = timed(wg, None)
+    print("copy 512MB %.1f us | gn_apply %.1f us | wgrad %.1f us | copy || wgrad %.1f us | gn_apply || wgrad %.1f us | wgrad || wgrad %.1f us"
+          % (t_copy, t_gnf, t_wg, timed(copy, wg), timed(gnf, wg), timed(wg, wg)))
     a = timed(gnb, None)
     b = timed(wg, None)
     c = timed(conv, None)
