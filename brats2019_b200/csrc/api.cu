@@ -783,10 +783,13 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
 // ---------------------------------------------------------------------------------------
 // lines per CTA for the line-walking kernels: a power of two <= 16 that divides D*H (so a CTA
 // never straddles two samples) and still leaves >= ~8 CTAs per SM
-static int lines_per_block(int N, int D, int H) {
+static int lines_per_block(int N, int D, int H, int W = 0, int C = 0) {
     const long long lines = (long long)N * D * H;
     int lpb = 1;
     while (lpb < 16 && (D * H) % (lpb * 2) == 0 && lines / (lpb * 2) >= 8LL * num_sms()) lpb *= 2;
+    // small tensors (W, C given): at least ~16 KB of each operand per CTA, even if that leaves SMs idle
+    if (W > 0 && C > 0)
+        while (lpb < 16 && (D * H) % (lpb * 2) == 0 && (long long)lpb * W * C * 2 < 16384) lpb *= 2;
     return lpb;
 }
 
@@ -839,11 +842,16 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
 }
 
 // reduction grid: ~4 CTAs per SM over the batch; each CTA owns `lpb` consecutive lines (<= kRedLines)
-static void gn_bwd_grid(int N, int D, int H, int& blocks, int& lpb) {
+static void gn_bwd_grid(int N, int D, int H, int W, int C, int& blocks, int& lpb) {
     const int lines = D * H;
     int want = std::max(1, 4 * num_sms() / std::max(1, N));
     want = std::min(want, lines);
-    lpb = std::min(kRedLines, (lines + want - 1) / want);
+    lpb = (lines + want - 1) / want;
+    // small tensors: at least ~64 KB of x+dy per CTA (a CTA costs a few microseconds of fixed latency, and
+    // every extra CTA is another partial for the finalize kernel to add)
+    const int line_bytes = 2 * W * C * 2;
+    lpb = std::max(lpb, (65536 + line_bytes - 1) / line_bytes);
+    lpb = std::min(std::min(lpb, kRedLines), lines);
     blocks = (lines + lpb - 1) / lpb;
 }
 static int gn_bwd_max_blocks() { return 4 * num_sms() + 8192; }      // >= blocks for any volume up to 1M lines
@@ -858,7 +866,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     int blocks, rlpb;
-    gn_bwd_grid(N, D, H, blocks, rlpb);
+    gn_bwd_grid(N, D, H, W, C, blocks, rlpb);
     float* partial = workspace;
     if (blocks > gn_bwd_max_blocks()) return fail("gn_backward: volume too large");
     float* coef = workspace + (size_t)N * gn_bwd_max_blocks() * C * 2;
@@ -869,7 +877,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     const double m = (double)(C / 8) * D * H * W;
     gn_bwd_finalize2_kernel<<<8, 256, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
     LAUNCH_OK("gn_bwd_finalize2_kernel");
-    const int lpb = lines_per_block(N, D, H);
+    const int lpb = lines_per_block(N, D, H, W, C);
     gn_bwd_apply2_kernel<<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
                                                          coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb);
     LAUNCH_OK("gn_bwd_apply2_kernel");

@@ -57,7 +57,7 @@ __device__ __forceinline__ WarpChunk warp_chunk(int C) {
 //   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
 // grid = (blocks, N); CTA b owns lines [b*lpb, b*lpb+lpb) of sample n; partial[n][blocks][C][2].
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
                       Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
@@ -96,7 +96,7 @@ gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const
             p1[j] = f2(k1[0], k1[1]); p2[j] = f2(k2[0], k2[1]);
             s1[j] = f2(0.f, 0.f); s2[j] = f2(0.f, 0.f);
         }
-        constexpr int U = 2;
+        constexpr int U = 4;
         for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
             uint4 qx[U], qd[U];
             bool ok[U];
@@ -208,7 +208,7 @@ gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, in
 
 // pass 3: dx = rstd * (dz*gamma - A_g - xhat*B_g) = dz*p1 + x*c1 + c0 with per-channel constants
 //   p1 = rstd*gamma, c1 = -rstd^2 B, c0 = -rstd (A + b B), b = -mean*rstd;  z = x*p1 + (b*gamma + beta).
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
                      ActRef dx, Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
@@ -240,7 +240,7 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
             p1[j] = f2(k1[0], k1[1]); p2[j] = f2(k2[0], k2[1]);
             c1[j] = f2(k3[0], k3[1]); c0[j] = f2(k4[0], k4[1]);
         }
-        constexpr int U = 2;
+        constexpr int U = 4;
         for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
             uint4 qx[U], qd[U];
             long long rr[U];
