@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrats_b200.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libbrats_b200.so")   # override: A/B perf tests only
 
 c_void_p, c_int, c_float, c_size_t, c_ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 

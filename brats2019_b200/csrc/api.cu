@@ -651,7 +651,8 @@ extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const v
 // ---------------------------------------------------------------------------------------
 struct WgradPlan {
     WgradKParams k;
-    int banded, folded, accs;
+    int banded, folded, accs, dual;
+    int kw_acc;     // 1: accumulators = kw taps (2-row halo), folds = kh taps;  0: accumulators = kh, folds = kw
     unsigned smem;
     int grid;
 };
@@ -671,26 +672,46 @@ static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
         if (d->Cout <= 32) { P.banded = 1; k.M = (d->Cout == 16) ? 64 : 128; }
         else { P.banded = 0; k.M = (d->Cout == 64) ? 64 : 128; }
         if (d->Cout == 48 || d->Cout == 80 || d->Cout == 96 || d->Cout == 112) return fail("wgrad k3: Cout %d unsupported", d->Cout);
-        P.folded = (3 * d->Cin <= 256) ? 1 : 0;
+        // kw in accumulators costs a 2-row halo, kh in N-folds costs 3 copies of X: take the accumulators first
+        // and fold only while the three accumulators of the folded tile still fit TMEM (Cin <= 32)
+        P.folded = (3 * d->Cin <= 256 && 9 * d->Cin <= 512) ? 1 : 0;
         k.Nmma = P.folded ? 3 * d->Cin : d->Cin;
         P.accs = (3 * k.Nmma <= 512) ? 1 : 0;
+        // 16 x 16 channels: an MMA of M=64, N=48 still costs the 46-cycle operand-fetch floor; stacking a second
+        // row range of the same stage in M and N (M=128, N=96, 56 cycles) does twice the work per MMA
+        // (measured on B200: the kernel at 16 x 16 is then bound by the shared-memory ingest of the shifted operand
+        // copies, ~7 TB/s aggregate, and the dual form is 10 % SLOWER than the plain one - it stays opt-in)
+        static int want_dual = -1;
+        if (want_dual < 0) { const char* e = getenv("B200_WGRAD_DUAL"); want_dual = (e && atoi(e)) ? 1 : 0; }
+        P.dual = (want_dual && d->Cout == 16 && d->Cin == 16) ? 1 : 0;
+        if (P.dual) { k.M = 128; k.Nmma = 96; }
         k.nfold = P.folded ? 3 : 1;
         k.nacc = P.accs ? 3 : 1;
         k.nband_loaded = P.banded ? 3 : 1;
+        // tap roles: kd -> M bands (banded) or jobs; one of kh / kw -> N folds (shifted copies of X) and the
+        // other -> TMEM accumulators (X start address + t * acc_shift rows: a halo of 2 * acc_shift rows)
+        static int roles = -1;
+        if (roles < 0) { const char* e = getenv("B200_WGRAD_KH_ACC"); roles = (e && atoi(e)) ? 0 : 1; }
+        P.kw_acc = roles;
+        k.acc_shift = P.kw_acc ? 1 : k.Wp;
+        k.fold_shift = P.kw_acc ? k.Wp : 1;
         int j = 0;
         for (int kd = 0; kd < (P.banded ? 1 : 3); ++kd)
-            for (int kh = 0; kh < (P.accs ? 1 : 3); ++kh)
-                for (int kw = 0; kw < (P.folded ? 1 : 3); ++kw) {
+            for (int ta = 0; ta < (P.accs ? 1 : 3); ++ta)
+                for (int tf = 0; tf < (P.folded ? 1 : 3); ++tf) {
+                    const int kh = P.kw_acc ? tf : ta, kw = P.kw_acc ? ta : tf;
+                    const bool kh_abs = P.kw_acc ? P.folded : P.accs, kw_abs = P.kw_acc ? P.accs : P.folded;
                     k.job_kd[j] = P.banded ? 0 : kd - 1;
-                    k.job_kh[j] = P.accs ? 0 : kh - 1;
-                    k.job_kw[j] = P.folded ? 0 : kw - 1;
+                    k.job_kh[j] = kh_abs ? 0 : kh - 1;
+                    k.job_kw[j] = kw_abs ? 0 : kw - 1;
                     k.job_xch[j] = 0;
                     ++j;
                 }
         k.n_jobs = j;
     } else {
         if (d->Cout > 128) return fail("wgrad k1: Cout <= 128");
-        P.banded = 0; P.folded = 0; P.accs = 0;
+        P.banded = 0; P.folded = 0; P.accs = 0; P.dual = 0; P.kw_acc = 1;
+        k.acc_shift = 1; k.fold_shift = k.Wp;
         k.M = d->Cout <= 64 ? 64 : 128;
         k.Nmma = d->Cin > 256 ? 256 : d->Cin;
         if (d->Cin % k.Nmma) return fail("wgrad k1: Cin %d unsupported", d->Cin);
@@ -699,16 +720,17 @@ static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
         for (int j = 0; j < k.n_jobs; ++j) { k.job_kd[j] = k.job_kh[j] = k.job_kw[j] = 0; k.job_xch[j] = j * k.Nmma; }
     }
     if (k.n_jobs > kMaxJobs) return fail("wgrad: too many jobs");
+    k.nh = P.dual ? 2 : 1;
     k.CoC = d->Cout / 8;
     k.CiC = (d->mode == 0 ? d->Cin : k.Nmma) / 8;
     k.y_planes = k.M / 8;
     k.x_planes = k.Nmma / 8;
-    if (k.nband_loaded * k.CoC > k.y_planes) return fail("wgrad: internal plane count");
+    if (k.nband_loaded * k.CoC * k.nh > k.y_planes) return fail("wgrad: internal plane count");
     // stage size: largest KT in {256,128,64} with >= 2 stages
-    const unsigned bar_bytes = 512;
+    const unsigned bar_bytes = 1024;     // barriers + TMEM slot (first 256 B) + the producer's plane-offset tables
     k.stages = 0;
     for (int KT : {256, 128, 64}) {
-        const int XR = (KT + (k.nacc > 1 ? 2 * k.Wp : 0) + 7) / 8 * 8;
+        const int XR = (KT + (k.nacc > 1 ? 2 * k.acc_shift : 0) + 7) / 8 * 8;
         const unsigned ypl = (unsigned)KT * 16, xpl = (unsigned)XR * 16;
         const unsigned stage = k.y_planes * ypl + k.x_planes * xpl;
         int stages = (int)((kMaxSmem - bar_bytes) / stage);
@@ -720,12 +742,13 @@ static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
         }
     }
     if (k.stages == 0) return fail("wgrad: shared memory plan does not fit (Cout=%d Cin=%d W=%d)", d->Cout, d->Cin, d->W);
-    k.stage_tx_bytes = (unsigned)(k.nband_loaded * k.CoC) * k.y_plane_bytes + (unsigned)(k.nfold * k.CiC) * k.x_plane_bytes;
+    k.stage_tx_bytes = (unsigned)(k.nband_loaded * k.CoC * k.nh) * k.y_plane_bytes +
+                       (unsigned)(k.nfold * k.CiC * k.nh) * k.x_plane_bytes;
     k.smem_bar_off = k.stages * k.stage_bytes;
     P.smem = k.smem_bar_off + bar_bytes;
     k.tmem_cols = pow2_cols((unsigned)(k.nacc * k.Nmma));
     if (k.tmem_cols > 512) return fail("wgrad: TMEM plan does not fit");
-    const int total_stages = ceil_div(k.total_rows, k.KT);
+    const int total_stages = ceil_div(k.total_rows, k.KT * k.nh);
     k.splits = std::max(1, std::min(num_sms() / k.n_jobs, total_stages));
     k.stages_per_split = ceil_div(total_stages, k.splits);
     k.splits = ceil_div(total_stages, k.stages_per_split);
@@ -765,7 +788,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     WgradReduceParams q;
     q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
     q.Cout_g = d->Cout; q.Cin_g = d->Cin;
-    q.banded = P.banded; q.folded = P.folded; q.accs = P.accs;
+    q.banded = P.banded; q.folded = P.folded; q.accs = P.accs; q.dual = P.dual; q.kw_acc = P.kw_acc;
     q.n_jobs = P.k.n_jobs; q.splits = P.k.splits; q.nacc = P.k.nacc; q.M = P.k.M; q.Nmma = P.k.Nmma;
     q.accumulate = accumulate;
     const int quads = q.n_jobs * q.nacc * q.M * q.Nmma / 4;
@@ -1079,7 +1102,7 @@ extern "C" int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_o
     const int vals[] = {k.KT, k.XR, k.nband_loaded, k.CoC, k.CiC, k.nfold, k.nacc, k.M, k.Nmma,
                         k.n_jobs, k.splits, k.stages_per_split, k.y_planes, k.x_planes, (int)k.y_plane_bytes,
                         (int)k.x_plane_bytes, (int)k.stage_bytes, (int)k.stage_tx_bytes, k.stages, (int)k.tmem_cols,
-                        (int)P.smem, P.grid, P.banded, P.folded, P.accs, k.Wp, k.SS};
+                        (int)P.smem, P.grid, P.banded, P.folded, P.accs, k.Wp, k.SS, k.nh, P.kw_acc};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv + 4 * kMaxJobs) return fail("wgrad_plan_debug: need %d ints", nv + 4 * kMaxJobs);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];

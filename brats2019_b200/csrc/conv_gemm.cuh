@@ -145,22 +145,26 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                         mbar_arrive(&x_full[xs]);
                     } else {
                         mbar_arrive_expect_tx(&x_full[xs], p.x_stage_bytes);
+                        // (the issue loop of this single thread must stay well below the MMA / HBM time of a stage:
+                        // one pointer per slice, then a constant stride per chunk - no 64-bit multiplies inside)
                         const ActRef& src = (g < p.KGa) ? p.src_a : p.src_b;
                         const int chunk0 = (g < p.KGa ? g : g - p.KGa) * (p.KC / 8);
                         uint8_t* dst = smem_x + (size_t)xs * p.x_stage_bytes;
                         const uint32_t bytes = (uint32_t)p.SRp * 16;
-                        for (int c = 0; c < p.KC / 8; ++c) {
-                            for (int s = 0; s < p.nslices; ++s) {
-                                long long row0;
-                                if (MODE == MODE_K3) {
-                                    const int dpi = (p.whole ? 0 : tc.d0 + 1) - 1 + s;
-                                    row0 = ((long long)tc.n * (p.D + 2) + dpi) * p.SS + tc.q0 - p.halo_rows;
-                                } else {
-                                    row0 = (long long)t * p.TR;
-                                }
-                                bulk_load_1d(dst + (size_t)c * p.x_plane_bytes + (size_t)s * p.SRp * 16,
-                                             src.at(chunk0 + c, row0), bytes, &x_full[xs]);
+                        const size_t plane_stride = (size_t)src.plane_rows * 8;
+                        const int nch = p.KC / 8;
+                        for (int s = 0; s < p.nslices; ++s) {
+                            long long row0;
+                            if (MODE == MODE_K3) {
+                                const int dpi = (p.whole ? 0 : tc.d0 + 1) - 1 + s;
+                                row0 = ((long long)tc.n * (p.D + 2) + dpi) * p.SS + tc.q0 - p.halo_rows;
+                            } else {
+                                row0 = (long long)t * p.TR;
                             }
+                            const __nv_bfloat16* ps = src.at(chunk0, row0);
+                            uint8_t* pd = dst + (size_t)s * bytes;
+                            for (int c = 0; c < nch; ++c, ps += plane_stride, pd += p.x_plane_bytes)
+                                bulk_load_1d(pd, ps, bytes, &x_full[xs]);
                         }
                     }
                 }

@@ -895,7 +895,7 @@ __global__ void pack_weights_batched_kernel(const PackJobDev* __restrict__ jobs,
 struct WgradReduceParams {
     int kind, Cout_w, Cin_w, taps_w, ci_off;
     int Cout_g, Cin_g;       // channel extents of dY / X as seen by the GEMM (padded)
-    int banded, folded, accs;
+    int banded, folded, accs, dual, kw_acc;
     int n_jobs, splits, nacc, M, Nmma;
     int accumulate;          // add into grad instead of overwriting
 };
@@ -913,16 +913,29 @@ __device__ __forceinline__ void wgrad_scatter(float* __restrict__ grad, const Wg
     const int t = r % q.nacc;
     int co, ci_w, tp;
     if (q.kind == 0) {
+        // jobs enumerate (kd, accumulator-axis tap, fold-axis tap) with the fold axis fastest
         int jj = job;
-        const int jkw = q.folded ? 0 : jj % 3; if (!q.folded) jj /= 3;
-        const int jkh = q.accs ? 0 : jj % 3;   if (!q.accs) jj /= 3;
+        const int jtf = q.folded ? 0 : jj % 3; if (!q.folded) jj /= 3;
+        const int jta = q.accs ? 0 : jj % 3;   if (!q.accs) jj /= 3;
         const int jkd = q.banded ? 0 : jj;
-        const int kd = q.banded ? row / q.Cout_g : jkd;
-        co = q.banded ? row % q.Cout_g : row;
-        const int kw = q.folded ? col / q.Cin_g : jkw;
-        ci_w = q.folded ? col % q.Cin_g : col;
-        const int kh = q.accs ? t : jkh;
-        if (kd > 2 || kw > 2) return;      // unused band / padding of the M or N extent
+        int kd, tf;
+        if (q.dual) {
+            // 8-row blocks (band, chunk, range) and 8-col blocks (fold, chunk, range); the caller only passes
+            // range-0 elements (the range-1 twin at +8 rows, +8 cols has been added to `a`)
+            const int rb = row >> 4, cb = col >> 4;
+            kd = rb / (q.Cout_g >> 3);
+            co = (rb % (q.Cout_g >> 3)) * 8 + (row & 7);
+            tf = cb / (q.Cin_g >> 3);
+            ci_w = (cb % (q.Cin_g >> 3)) * 8 + (col & 7);
+        } else {
+            kd = q.banded ? row / q.Cout_g : jkd;
+            co = q.banded ? row % q.Cout_g : row;
+            tf = q.folded ? col / q.Cin_g : jtf;
+            ci_w = q.folded ? col % q.Cin_g : col;
+        }
+        const int ta = q.accs ? t : jta;
+        const int kh = q.kw_acc ? tf : ta, kw = q.kw_acc ? ta : tf;
+        if (kd > 2 || tf > 2) return;      // unused band / padding of the M or N extent
         tp = (kd * 3 + kh) * 3 + kw;
     } else if (q.kind == 1) {
         if (job * q.Nmma + col >= q.Cin_g) return;
@@ -947,11 +960,25 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
     const int quad = blockIdx.x * qpc + ql;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int job = 0, i = 0;
-    if (quad < quads) {
+    bool active = quad < quads;
+    if (active) {
         i = quad << 2;
         job = i / per_job;
         i -= job * per_job;
+        if (q.dual) {      // only range-0 blocks own an output; their range-1 twin sits 8 rows and 8 columns further
+            const int col = i % q.Nmma, row = (i / q.Nmma) % q.M;
+            active = (((row >> 3) & 1) == 0) && (((col >> 3) & 1) == 0);
+        }
+    }
+    if (active) {
         const float* src = partial + (size_t)job * q.splits * per_job + (size_t)i;
+        if (q.dual) {
+            const float* tw = src + 8 * q.Nmma + 8;
+            for (int s2 = sg; s2 < q.splits; s2 += SG) {
+                const float4 v = *reinterpret_cast<const float4*>(tw + (size_t)s2 * per_job);
+                a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+            }
+        }
         int s = sg;
         for (; s + 3 * SG < q.splits; s += 4 * SG) {
             const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)s * per_job);
@@ -977,7 +1004,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
             a2 += s_acc[k * qpc + ql][2]; a3 += s_acc[k * qpc + ql][3];
         }
     }
-    if (quad >= quads) return;
+    if (!active) return;
     wgrad_scatter(grad, q, job, i + 0, a0);
     wgrad_scatter(grad, q, job, i + 1, a1);
     wgrad_scatter(grad, q, job, i + 2, a2);

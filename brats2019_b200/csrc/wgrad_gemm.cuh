@@ -11,8 +11,11 @@
 // over the plain linear row range, including past either end of the tensor.
 //
 // To fill the 64/128-row M dimension with small channel counts, M stacks `nband` copies of dY
-// shifted by whole slices (one per kd tap) and N stacks `nfold` copies of X shifted by one row
-// (one per kw tap); the three kh taps go to separate TMEM accumulators.  Each CTA owns a
+// shifted by whole slices (one per kd tap) and N stacks `nfold` copies of X shifted by one line
+// (one per kh tap); the three kw taps go to separate TMEM accumulators that read the same X planes
+// at start addresses one row apart (a 2-row halo per stage; folding kw and giving kh to the
+// accumulators instead needs a 2*(W+2)-row halo and doubles the shared-memory ingest, which is the
+// bound of this kernel).  Each CTA owns a
 // (job, K-split) pair, accumulates in TMEM over its row range and writes one fp32 partial;
 // `wgrad_reduce_kernel` sums the partials in a fixed order (deterministic) into the fp32
 // gradient in PyTorch (Cout, Cin, kd, kh, kw) layout.
@@ -27,8 +30,10 @@ constexpr int kMaxJobs = 32;
 struct WgradKParams {
     long long total_rows;
     int Wp, SS;
-    int KT;             // rows per pipeline stage (multiple of 16, <= 256)
-    int XR;             // rows per X plane (KT + 2*Wp when nacc == 3, else KT), multiple of 8
+    int KT;             // rows per plane of a pipeline stage (multiple of 16, <= 256)
+    int nh;             // row ranges per stage: 1, or 2 ("dual": the stage covers rows [r0, r0+KT) and [r0+KT, r0+2KT),
+                        // each with its own planes, stacked in M and N; only the diagonal blocks of D are meaningful)
+    int XR;             // rows per X plane (KT + 2 when nacc == 3, else KT), rounded up to a multiple of 8
     int nband_loaded;   // dY bands actually loaded (3 when banded, else 1)
     int CoC, CiC;       // 8-channel chunks of dY / X per band / fold
     int nfold, nacc;
@@ -44,6 +49,9 @@ struct WgradKParams {
     unsigned tmem_cols;
     ActRef dy, x;               // chunk-planar activations
     float* partial;             // [job][split][nacc][M][Nmma]
+    int acc_shift;              // rows between the X start addresses of consecutive accumulators: 1 (accumulators = kw
+                                // taps, N-folds = kh taps) or Wp (accumulators = kh taps, N-folds = kw taps)
+    int fold_shift;             // rows between consecutive N-fold copies of X: Wp or 1 (the other of the two)
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -71,11 +79,12 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long first_row = (long long)split * p.stages_per_split * p.KT;
+    const int stage_rows = p.KT * p.nh;
+    const long long first_row = (long long)split * p.stages_per_split * stage_rows;
     int nst = p.stages_per_split;
     {
         long long remaining = p.total_rows - first_row;
-        long long need = remaining <= 0 ? 0 : (remaining + p.KT - 1) / p.KT;
+        long long need = remaining <= 0 ? 0 : (remaining + stage_rows - 1) / stage_rows;
         if (need < nst) nst = (int)need;
     }
     const unsigned y_bytes = (unsigned)p.y_planes * p.y_plane_bytes;
@@ -83,28 +92,40 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
     // Whole-warp role code with elect_one() around the issue (see conv_gemm.cuh for why).
     if (warp == 0) {
         // ================= producer =================
+        // Source offset of every plane for r0 = 0, computed once (one lane per plane): the per-stage issue
+        // loop below must stay far below the MMA time of a stage (~2000 cycles), so it is one shared-memory
+        // read and one add per bulk copy instead of the nested band/chunk/range address arithmetic.
+        long long* s_yoff = reinterpret_cast<long long*>(smem + p.smem_bar_off + 256);     // [32] (tail region is 1 KB)
+        long long* s_xoff = s_yoff + 32;                                                   // [32]
+        const int ny = p.nband_loaded * p.CoC * p.nh, nx = p.nfold * p.CiC * p.nh;
+        for (int pl = lane; pl < ny; pl += 32) {
+            const int h = pl % p.nh, c = (pl / p.nh) % p.CoC, b = pl / (p.nh * p.CoC);
+            const int kd = (p.nband_loaded > 1) ? (b - 1) : p.job_kd[job];
+            s_yoff[pl] = ((long long)c * p.dy.plane_rows + p.dy.guard - (long long)kd * p.SS + (long long)h * p.KT) * 16;
+        }
+        for (int pl = lane; pl < nx; pl += 32) {
+            const int h = pl % p.nh, c = (pl / p.nh) % p.CiC, f = pl / (p.nh * p.CiC);
+            // tap of the fold (or the job's fixed tap) along the fold axis, and the accumulator axis start
+            const int ft = (p.nfold > 1) ? (f - 1) : (p.fold_shift == 1 ? p.job_kw[job] : p.job_kh[job]);
+            const int at = (p.nacc > 1) ? -1 : (p.acc_shift == 1 ? p.job_kw[job] : p.job_kh[job]);
+            s_xoff[pl] = ((long long)(p.job_xch[job] / 8 + c) * p.x.plane_rows + p.x.guard + (long long)ft * p.fold_shift +
+                          (long long)at * p.acc_shift + (long long)h * p.KT) * 16;
+        }
+        __syncwarp();
+        const uint8_t* ysrc = reinterpret_cast<const uint8_t*>(p.dy.base);
+        const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(p.x.base);
         int s = 0; uint32_t ph = 0;
         for (int i = 0; i < nst; ++i) {
-            const long long r0 = first_row + (long long)i * p.KT;
+            const long long r0b = (first_row + (long long)i * stage_rows) * 16;
             mbar_wait(&empty[s], ph ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
                 uint8_t* ybase = smem + (size_t)s * p.stage_bytes;
                 uint8_t* xbase = ybase + y_bytes;
-                for (int b = 0; b < p.nband_loaded; ++b) {
-                    const int kd = (p.nband_loaded > 1) ? (b - 1) : p.job_kd[job];
-                    const long long yr = r0 - (long long)kd * p.SS;
-                    for (int c = 0; c < p.CoC; ++c)
-                        bulk_load_1d(ybase + (size_t)(b * p.CoC + c) * p.y_plane_bytes, p.dy.at(c, yr), p.y_plane_bytes,
-                                     &full[s]);
-                }
-                for (int f = 0; f < p.nfold; ++f) {
-                    const int kw = (p.nfold > 1) ? (f - 1) : p.job_kw[job];
-                    const long long xr = r0 + kw + (p.nacc > 1 ? -(long long)p.Wp : (long long)p.job_kh[job] * p.Wp);
-                    for (int c = 0; c < p.CiC; ++c)
-                        bulk_load_1d(xbase + (size_t)(f * p.CiC + c) * p.x_plane_bytes, p.x.at(p.job_xch[job] / 8 + c, xr),
-                                     p.x_plane_bytes, &full[s]);
-                }
+                for (int pl = 0; pl < ny; ++pl)
+                    bulk_load_1d(ybase + (size_t)pl * p.y_plane_bytes, ysrc + s_yoff[pl] + r0b, p.y_plane_bytes, &full[s]);
+                for (int pl = 0; pl < nx; ++pl)
+                    bulk_load_1d(xbase + (size_t)pl * p.x_plane_bytes, xsrc + s_xoff[pl] + r0b, p.x_plane_bytes, &full[s]);
             }
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -128,7 +149,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
                 uint32_t acc = i != 0;
                 for (int t = 0; t < p.nacc; ++t) {
                     uint32_t a16 = ya16;
-                    uint32_t b16 = xa16 + ((p.nacc > 1) ? (uint32_t)(t * p.Wp) : 0u);
+                    uint32_t b16 = xa16 + ((p.nacc > 1) ? (uint32_t)(t * p.acc_shift) : 0u);       // accumulator t = tap kw: X shifted by t rows
                     const uint32_t dtm = tmem_base + (uint32_t)(t * p.Nmma);
                     uint32_t acc_t = acc;
                     for (int ks = 0; ks < ksteps; ++ks) {
@@ -168,10 +189,17 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
                 }
                 if (row_ok) {
                     float4* o = reinterpret_cast<float4*>(dst + ((size_t)t * p.M + row) * p.Nmma + c0);
-                    o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    o[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    o[2] = make_float4(v[8], v[9], v[10], v[11]);
-                    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                    // dual: 8-row / 8-column blocks alternate between the two row ranges; only blocks of the
+                    // same range are products of matching rows, the others are never read
+                    const bool lo = p.nh == 1 || ((row >> 3) & 1) == 0, hi = p.nh == 1 || ((row >> 3) & 1) == 1;
+                    if (lo) {
+                        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                    if (hi) {
+                        o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                        o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                    }
                 }
             }
         }

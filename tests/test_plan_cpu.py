@@ -18,7 +18,7 @@ CONV_FIELDS = ("BD MB TR Q0 QN tiles_q tiles_d num_tiles whole n_jobs KG KGa KC 
                "x_stage_bytes w_stage_bytes x_plane_bytes SRp nslices halo_rows tmem_cols smem ctas Wp SS fold RB").split()
 WGRAD_FIELDS = ("KT XR nband_loaded CoC CiC nfold nacc M Nmma n_jobs splits stages_per_split y_planes "
                 "x_planes y_plane_bytes x_plane_bytes stage_bytes stage_tx_bytes stages tmem_cols smem grid banded "
-                "folded accs Wp SS").split()
+                "folded accs Wp SS nh kw_acc").split()
 
 
 def conv_plan(mode, N, D, H, W, Cin_a, Cout, Cin_b=0, epi=0):
@@ -154,39 +154,48 @@ def test_wgrad3_addressing(cfg):
     total = X.shape[0]
     Wp, SS, KT = p["Wp"], p["SS"], p["KT"]
     guard = _lib.lib().b200_act_guard_rows(D, H, W)
-    M, Nm, nacc = p["M"], p["Nmma"], p["nacc"]
-    partial = torch.zeros(p["n_jobs"], p["splits"], nacc, M, Nm)
+    M, Nm, nacc, nh = p["M"], p["Nmma"], p["nacc"], p["nh"]
+    # dual plans (nh == 2) stack two row ranges of a stage in M and N; the replay keeps the logical tile
+    # [bands*Cout][folds*Cin] and adds the two ranges (the physical interleave is checked on the GPU)
+    Ml, Nl = M // nh, Nm // nh
+    partial = torch.zeros(p["n_jobs"], p["splits"], nacc, Ml, Nl)
+    stage_rows = KT * nh
     for job, (jkd, jkh, jkw, jx) in enumerate(p["jobs"]):
         for split in range(p["splits"]):
-            first = split * p["stages_per_split"] * KT
-            nst = min(p["stages_per_split"], max(0, -(-(total - first) // KT)))
+            first = split * p["stages_per_split"] * stage_rows
+            nst = min(p["stages_per_split"], max(0, -(-(total - first) // stage_rows)))
             for i in range(nst):
-                r0 = first + i * KT
-                A = torch.zeros(KT, M)        # [k][m]; unloaded bands stay zero here (garbage on HW)
-                for b in range(p["nband_loaded"]):
-                    kd = (b - 1) if p["nband_loaded"] > 1 else jkd
-                    A[:, b * Cout:(b + 1) * Cout] = fetch_rows(Y, r0 - kd * SS, KT, guard)
-                XR = p["XR"]
-                Bm = torch.zeros(XR, Nm)
-                for f in range(p["nfold"]):
-                    kw = (f - 1) if p["nfold"] > 1 else jkw
-                    xr = r0 + kw + (-Wp if nacc > 1 else jkh * Wp)
-                    Bm[:, f * Cin:(f + 1) * Cin] = fetch_rows(X, xr, XR, guard)[:, jx:jx + Cin]
-                for t in range(nacc):
-                    xrow = t * Wp if nacc > 1 else 0
-                    assert xrow + KT <= XR
-                    partial[job, split, t] += A.T @ Bm[xrow:xrow + KT]
+                for h in range(nh):
+                    r0 = first + i * stage_rows + h * KT
+                    A = torch.zeros(KT, Ml)        # [k][m]; unloaded bands stay zero here (garbage on HW)
+                    for b in range(p["nband_loaded"]):
+                        kd = (b - 1) if p["nband_loaded"] > 1 else jkd
+                        A[:, b * Cout:(b + 1) * Cout] = fetch_rows(Y, r0 - kd * SS, KT, guard)
+                    XR = p["XR"]
+                    Bm = torch.zeros(XR, Nl)
+                    # one of kh/kw is the fold axis (copies of X), the other the accumulator axis (start shifts)
+                    fsh, ash = (Wp, 1) if p["kw_acc"] else (1, Wp)
+                    jf, ja = (jkh, jkw) if p["kw_acc"] else (jkw, jkh)
+                    for f in range(p["nfold"]):
+                        ft = (f - 1) if p["nfold"] > 1 else jf
+                        xr = r0 + ft * fsh + (-1 if nacc > 1 else ja) * ash
+                        Bm[:, f * Cin:(f + 1) * Cin] = fetch_rows(X, xr, XR, guard)[:, jx:jx + Cin]
+                    for t in range(nacc):
+                        xrow = t * ash if nacc > 1 else 0
+                        assert xrow + KT <= XR
+                        partial[job, split, t] += A.T @ Bm[xrow:xrow + KT]
     red = partial.sum(1)
     got = torch.zeros(co_r, ci_r, 3, 3, 3)
     for co in range(co_r):
         for ci in range(ci_r):
             for tp in range(27):
                 kd, kh, kw = tp // 9, (tp // 3) % 3, tp % 3
-                job = ((0 if p["banded"] else kd) * (1 if p["accs"] else 3) + (0 if p["accs"] else kh)) * \
-                      (1 if p["folded"] else 3) + (0 if p["folded"] else kw)
+                tf, ta = (kh, kw) if p["kw_acc"] else (kw, kh)
+                job = ((0 if p["banded"] else kd) * (1 if p["accs"] else 3) + (0 if p["accs"] else ta)) * \
+                      (1 if p["folded"] else 3) + (0 if p["folded"] else tf)
                 row = (kd * Cout if p["banded"] else 0) + co
-                col = (kw * Cin if p["folded"] else 0) + ci
-                t = kh if p["accs"] else 0
+                col = (tf * Cin if p["folded"] else 0) + ci
+                t = ta if p["accs"] else 0
                 got[co, ci, kd, kh, kw] = red[job, t, row, col]
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-3)
     assert p["smem"] <= 227 * 1024 and p["tmem_cols"] <= 512 and p["nacc"] * p["Nmma"] <= p["tmem_cols"]
