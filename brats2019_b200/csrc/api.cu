@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "elementwise2.cuh"
 #include "wgrad_gemm.cuh"
+#include "elementwise3.cuh"
 
 using namespace b200;
 
@@ -519,7 +520,6 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
         p.debug = dbg ? atoi(dbg) : 0;
     }
     const int grid = march_ctas(p);
-    if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)grid * p.N * 16 * sizeof(float), st));
     Vol vol{d->N, d->D, d->H, d->W};
     p.src = make_act(src_a, vol);
     p.out = make_act(out, vol);
@@ -562,7 +562,6 @@ static int run_band(const b200_conv_desc* d, BandParams& p, const void* src_a, c
         p.debug = dbg ? atoi(dbg) : 0;
     }
     const int grid = band_ctas(p);
-    if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)grid * p.N * 16 * sizeof(float), st));
     Vol vol{d->N, d->D, d->H, d->W};
     p.src = make_act(src_a, vol);
     p.out = make_act(out, vol);
@@ -608,7 +607,6 @@ extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const v
     }
     const int ctas = conv_grid_ctas(p);
     const int grid = ctas * p.n_jobs;
-    if (stats_partial) CUDA_OK(cudaMemsetAsync(stats_partial, 0, (size_t)ctas * p.N * 16 * sizeof(float), st));
     if (check_ptr16(src_a, "src_a") || check_ptr16(src_b, "src_b") || check_ptr16(out, "out") ||
         check_ptr16(residual, "residual") || check_ptr16(packed, "packed weights"))
         return 1;
@@ -877,7 +875,62 @@ static void gn_bwd_grid(int N, int D, int H, int W, int C, int& blocks, int& lpb
     lpb = std::min(std::min(lpb, kRedLines), lines);
     blocks = (lines + lpb - 1) / lpb;
 }
-static int gn_bwd_max_blocks() { return 4 * num_sms() + 8192; }      // >= blocks for any volume up to 1M lines
+static int gn_bwd_max_blocks() { return 4 * num_sms() + 8192; }
+
+// Cluster form of GroupNorm backward (elementwise3.cuh): usable when one sample's slice of a unit, split over the
+// 8 CTAs of a cluster, fits their shared memory.
+static bool plan_gn_cluster(const Vol& v, int C, GnClusterParams& q, unsigned& smem) {
+    // Opt-in (B200_GN_BWD_CLUSTER=1).  Measured on B200 (profiles/r01_ab_gn_cluster.txt): alone the kernel is faster
+    // than reduce -> finalize -> apply at the 16^3 level (26 -> 18 us), but inside the training step it is SLOWER
+    // (6.129 -> 6.157 ms with tiles <= 40 KB, 6.223 ms with tiles <= 160 KB): backward overlaps the data-gradient
+    // chain with weight-gradient GEMMs on a side stream, those CTAs hold ~200 KB of shared memory on every SM, and a
+    // cluster needs 8 SMs of one GPC with room for its tiles at the same time, so it waits where the small
+    // register-only kernels of the three-kernel path slip in beside the GEMM.
+    const char* e = getenv("B200_GN_BWD_CLUSTER");
+    if (!e || atoi(e) == 0) return false;
+    const int gs = C / 8;
+    if (gs < 2 || (gs < 8 && 8 % gs) || (gs >= 8 && gs % 8)) return false;
+    const int ucs = gs >= 8 ? gs / 8 : 1;
+    if (ucs > kGnClusterMaxUcs) return false;
+    const int lines = v.D * v.H;
+    const int lpc = (lines + kGnClusterSize - 1) / kGnClusterSize;
+    if (lpc > kGnClusterMaxLines) return false;
+    const long long nv = (long long)lpc * v.W;
+    const long long bytes = 2LL * ucs * nv * 16;
+    // Tiles larger than ~24 KB cannot share an SM with a weight-gradient CTA of the side stream (200 KB of shared
+    // memory), so the cluster would wait for that kernel to drain; B200_GN_BWD_CLUSTER_MAXKB moves the limit.
+    const char* mk = getenv("B200_GN_BWD_CLUSTER_MAXKB");
+    const long long max_kb = mk ? std::min(160, std::max(0, atoi(mk))) : 160;
+    if (bytes > max_kb * 1024 || nv >= (1 << 24)) return false;
+    static int attr_set = 0, clusters_ok = -1;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gn_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            clusters_ok = 0;
+        }
+        attr_set = 1;
+    }
+    if (clusters_ok < 0) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(kGnClusterSize); cfg.blockDim = dim3(kGnClusterThreads); cfg.dynamicSmemBytes = 160 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kGnClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, gn_bwd_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+        clusters_ok = nc > 0 ? 1 : 0;
+    }
+    if (!clusters_ok) return false;
+    memset(&q, 0, sizeof(q));
+    q.v = v; q.C = C;
+    q.by_W = make_fastdiv((unsigned)v.W);
+    q.lpc = lpc; q.nv = (int)nv; q.ucs = ucs;
+    q.m = (double)gs * v.D * v.H * v.W;
+    smem = (unsigned)bytes;
+    return true;
+}      // >= blocks for any volume up to 1M lines
 extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
     // partial[N][blocks][C][2] + coef[N][C][2]
     return (size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2;
@@ -888,6 +941,30 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8) || C < 16) return fail("gn_backward: C=%d unsupported", C);
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        // small tensors: one cluster launch that keeps x and dy in shared memory (elementwise3.cuh)
+        GnClusterParams q;
+        unsigned smem = 0;
+        if (plan_gn_cluster(v, C, q, smem)) {
+            q.x = make_act(x, v); q.dy = make_act(dy, v); q.dx = make_act(dx, v);
+            q.mean = mean; q.rstd = rstd; q.gamma = gamma; q.beta = beta; q.dgamma = dgamma; q.dbeta = dbeta;
+            q.do_lrelu = do_lrelu;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)((C / 8) / q.ucs * kGnClusterSize));
+            cfg.blockDim = dim3(kGnClusterThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kGnClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            CUDA_OK(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel, q));
+            LAUNCH_OK("gn_bwd_cluster_kernel");
+            return 0;
+        }
+    }
     int blocks, rlpb;
     gn_bwd_grid(N, D, H, W, C, blocks, rlpb);
     float* partial = workspace;

@@ -98,6 +98,10 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc(tmem_slot, 512);
+    // GroupNorm partial sums [ctas][N][16]: this CTA's row starts at zero (samples it never touches must contribute
+    // nothing); the epilogue overwrites the entries of the samples it does touch, after the barrier below.
+    if (p.stats_partial)
+        for (int i = threadIdx.x; i < p.N * 16; i += blockDim.x) p.stats_partial[(size_t)cta * p.N * 16 + i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -297,6 +301,24 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
                 for (int jo = 1 + grp; jo <= kBandBH; jo += kBandEpiGroups) {
                     MARCH_PROF_T(t0);
                     if (prof && t3) t_rest += t0 - t3;
+                    // The residual operand (the identity path of a Residual block's data gradient) is requested
+                    // BEFORE the wait for the accumulator, so its L2/HBM latency hides behind the MMAs of this line;
+                    // loaded after the TMEM read it serialised ~1 us per line and cost the kernel +50 us.
+                    uint4 rq[CO / 8];
+                    bool have_res = false;
+                    if (EPI == EPI_BF16 && p.residual.base) {
+                        const int hp_r = hp0 + jo - 1;
+                        have_res = out_valid && w_ok && hp_r <= p.H;
+                        if (have_res) {
+                            const long long rrow = (((long long)sg.n * (p.D + 2) + dpo) * (p.H + 2) + hp_r) * p.Wp + wp;
+#pragma unroll
+                            for (int c = 0; c < CO / 8; ++c) {
+                                const void* rp = p.residual.at(c, rrow);
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(rq[c].x), "=r"(rq[c].y), "=r"(rq[c].z), "=r"(rq[c].w) : "l"(rp));
+                            }
+                        }
+                    }
                     mbar_wait(&acc_done[jo], k & 1);
                     MARCH_PROF_T(t1);
                     w_done += t1 - t0;
@@ -332,11 +354,11 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
                                 ssq[i / GS] += v[i] * v[i];
                             }
                         }
-                        if (p.residual.base) {
+                        if (have_res) {
 #pragma unroll
                             for (int c = 0; c < CO / 8; ++c) {
                                 float f[8];
-                                unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(c, orow)), f);
+                                unpack_bf16x8(rq[c], f);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[c * 8 + i] += f[i];
                             }

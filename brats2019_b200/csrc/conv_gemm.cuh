@@ -124,6 +124,10 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc(tmem_slot, p.tmem_cols);
+    // GroupNorm partial sums [ctas][N][16]: this CTA's row starts at zero (samples it never touches must contribute
+    // nothing); the epilogue overwrites the entries of the samples it does touch, after the barrier below.
+    if (p.stats_partial)
+        for (int i = threadIdx.x; i < p.N * 16; i += blockDim.x) p.stats_partial[(size_t)cta * p.N * 16 + i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -90,13 +90,20 @@ def group_ew():
                 y = F.leaky_relu(y, 0.01)
             dy = bf(torch.randn_like(y))
             y.backward(dy)
-            dx = ops.act_zeros(N, D, H, W, Cc, dev)
-            dgam = torch.empty(Cc, device=dev); dbet = torch.empty(Cc, device=dev)
-            ws = ops.gn_backward_workspace(N, Cc, dev)
-            ops.gn_backward(xa, ops.act_from_ncdhw(dy), mean, rstd, gamma, beta, dx, dgam, dbet, ws, lrelu=lre)
-            report("gn_backward dx C=%d lrelu=%d" % (Cc, lre), ops.act_to_ncdhw(dx), xr.grad, tol_rel=2e-2)
-            report("gn_backward dgamma C=%d lrelu=%d" % (Cc, lre), dgam, gr.grad, tol_rel=2e-3)
-            report("gn_backward dbeta C=%d lrelu=%d" % (Cc, lre), dbet, br.grad, tol_rel=2e-3)
+            # both forms behind b200_gn_backward: the one-launch cluster kernel (small tensors) and the
+            # reduce -> finalize -> apply path (B200_GN_BWD_CLUSTER=0 forces it)
+            for form in ("cluster", "3-kernel"):
+                os.environ["B200_GN_BWD_CLUSTER"] = "1" if form == "cluster" else "0"
+                dx = ops.act_zeros(N, D, H, W, Cc, dev)
+                dgam = torch.empty(Cc, device=dev); dbet = torch.empty(Cc, device=dev)
+                ws = ops.gn_backward_workspace(N, Cc, dev)
+                ops.gn_backward(xa, ops.act_from_ncdhw(dy), mean, rstd, gamma, beta, dx, dgam, dbet, ws, lrelu=lre)
+                tag = "C=%d lrelu=%d %s" % (Cc, lre, form)
+                report("gn_backward dx " + tag, ops.act_to_ncdhw(dx), xr.grad, tol_rel=2e-2)
+                report("gn_backward dgamma " + tag, dgam, gr.grad, tol_rel=2e-3)
+                report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
+                report("gn_backward halo untouched " + tag, ops.act_outside_absmax(dx).view(1), torch.zeros(1, device=dev), tol_abs=0)
+            os.environ.pop("B200_GN_BWD_CLUSTER", None)
         # upsample
         xr = xc.clone().requires_grad_(True)
         up = F.leaky_relu(F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=False), 0.01)

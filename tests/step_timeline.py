@@ -1,0 +1,51 @@
+"""Timeline of one steady-state training step (CUDA-graph replay): every kernel's start, duration and stream from
+CUPTI (torch.profiler), written as CSV for offline analysis of the main-stream / side-stream overlap.
+
+    python tests/step_timeline.py [B] [S] [out.csv]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+import brats2019_b200 as B  # noqa: E402
+from brats2019_b200.graphs import GraphedTrainStep  # noqa: E402
+
+Bsz = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+out = sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/step_timeline.csv"
+torch.manual_seed(0)
+dev = torch.device("cuda")
+stream = torch.cuda.Stream()
+with torch.cuda.stream(stream):
+    m = B.UNet(**B.DEFAULT_CFG).cuda().train()
+    crit = B.Dice_loss_joint()
+    opt = torch.optim.Adam(m.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True, capturable=True, fused=True)
+    x = torch.randn(Bsz, 4, S, S, S, device=dev)
+    t = (torch.rand(Bsz, 3, S, S, S, device=dev) > 0.7).float()
+    g = GraphedTrainStep(m, crit, opt, x, t, warmup=3)
+    for _ in range(5):
+        g()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(2):
+            g()
+        torch.cuda.synchronize()
+path = out + ".trace.json"
+prof.export_chrome_trace(path)
+import json  # noqa: E402
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+ev.sort(key=lambda e: e["ts"])
+# keep the second replay only
+half = len(ev) // 2
+ev = ev[half:]
+t0 = ev[0]["ts"]
+with open(out, "w") as f:
+    f.write("start_us,dur_us,stream,name\n")
+    for e in ev:
+        name = e["name"].split("(")[0].replace("void ", "").replace("b200::", "")
+        f.write("%.3f,%.3f,%s,%s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), name[:80]))
+os.remove(path)
+print("wrote", out, len(ev), "kernels, span %.1f us" % (ev[-1]["ts"] + ev[-1]["dur"] - t0))
