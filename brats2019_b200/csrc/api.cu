@@ -781,6 +781,11 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     P.k.dy = make_act(dy, vol);
     P.k.x = make_act(x, vol);
     if (P.k.stage_tx_bytes >= (1u << 20)) return fail("wgrad: stage exceeds the mbarrier tx-count range");
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("B200_WGRAD_DEBUG"); dbg = e ? atoi(e) : 0; }
+        P.k.debug = dbg;
+    }
     wgrad_gemm_kernel<<<P.grid, kWgradThreads, P.smem, st>>>(P.k);
     LAUNCH_OK("wgrad_gemm_kernel");
     WgradReduceParams q;
@@ -975,7 +980,9 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
                                                           partial, v, C, do_lrelu, by_W, rlpb);
     LAUNCH_OK("gn_bwd_reduce2_kernel");
     const double m = (double)(C / 8) * D * H * W;
-    gn_bwd_finalize2_kernel<<<8, 256, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
+    // one warp per (sample, channel, S1|S2) sum, up to 32 warps: min(8, N) * (C/8) * 2 sums per CTA
+    const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
+    gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
     LAUNCH_OK("gn_bwd_finalize2_kernel");
     const int lpb = lines_per_block(N, D, H, W, C);
     gn_bwd_apply2_kernel<<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,

@@ -152,10 +152,10 @@ gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const
 }
 
 // pass 2: partial[n][blocks][C][2] -> coef[n][C][2] = (A_g, B_g)/m of the channel's group, and
-// dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.   grid = 8 (one CTA per group), 256 threads.
+// dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.   grid = 8 (one CTA per group), 256-1024 threads.
 // Warp o sums one (channel, which) over the blocks (lanes stride the blocks, double accumulation,
 // fixed shuffle tree): deterministic.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
                         const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
                         float* __restrict__ dbeta) {
@@ -164,11 +164,13 @@ gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, in
     const int g = blockIdx.x, gs = C >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nout = gs * 2;
+    const int nwarps = blockDim.x >> 5;     // the (sample, output) pairs are spread over all warps: the kernel is a chain
+                                            // of dependent-load latencies, so its time is the number of rounds per warp
     if ((int)threadIdx.x < nout) s_tot[threadIdx.x] = 0.0;
     for (int n0 = 0; n0 < N; n0 += 8) {
         const int nn = min(8, N - n0);
         // (sample, output) pairs over the 8 warps; 4 independent loads in flight per lane
-        for (int po = warp; po < nn * nout; po += 8) {
+        for (int po = warp; po < nn * nout; po += nwarps) {
             const int nl = po / nout, o = po - nl * nout;
             const int c = g * gs + (o >> 1);
             const float* src = partial + ((size_t)(n0 + nl) * blocks * C + c) * 2 + (o & 1);

@@ -21,6 +21,7 @@
 // gradient in PyTorch (Cout, Cin, kd, kh, kw) layout.
 #pragma once
 #include "common.cuh"
+#include "conv_march.cuh"     // g_march_prof / MARCH_PROF_T (in-kernel cycle accounting, debug only)
 
 namespace b200 {
 
@@ -52,6 +53,7 @@ struct WgradKParams {
     int acc_shift;              // rows between the X start addresses of consecutive accumulators: 1 (accumulators = kw
                                 // taps, N-folds = kh taps) or Wp (accumulators = kh taps, N-folds = kw taps)
     int fold_shift;             // rows between consecutive N-fold copies of X: Wp or 1 (the other of the two)
+    int debug;                  // 256: per-role cycle counts into g_march_prof (tests/wgrad_prof.py)
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -115,9 +117,15 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
         const uint8_t* ysrc = reinterpret_cast<const uint8_t*>(p.dy.base);
         const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(p.x.base);
         int s = 0; uint32_t ph = 0;
+        const bool prof = (p.debug & 256) != 0;
+        long long t0 = 0, t1 = 0, t2 = 0, tb = 0, w_empty = 0, t_issue = 0;
+        MARCH_PROF_T(tb);
         for (int i = 0; i < nst; ++i) {
             const long long r0b = (first_row + (long long)i * stage_rows) * 16;
+            MARCH_PROF_T(t0);
             mbar_wait(&empty[s], ph ^ 1);
+            MARCH_PROF_T(t1);
+            w_empty += t1 - t0;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
                 uint8_t* ybase = smem + (size_t)s * p.stage_bytes;
@@ -128,7 +136,14 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
                     bulk_load_1d(xbase + (size_t)pl * p.x_plane_bytes, xsrc + s_xoff[pl] + r0b, p.x_plane_bytes, &full[s]);
             }
             __syncwarp();
+            MARCH_PROF_T(t2);
+            t_issue += t2 - t1;
             if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        if (prof && lane == 0 && blockIdx.x < 160) {
+            g_march_prof[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - tb);
+            g_march_prof[blockIdx.x * 16 + 1] = (unsigned long long)w_empty;
+            g_march_prof[blockIdx.x * 16 + 2] = (unsigned long long)t_issue;
         }
     } else if (warp == 2) {
         // ================= MMA issuer =================
@@ -140,8 +155,14 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
         const uint64_t b_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((p.x_plane_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
         const int ksteps = p.KT / 16;
         int s = 0; uint32_t ph = 0;
+        const bool prof = (p.debug & 256) != 0;
+        long long t0 = 0, t1 = 0, t2 = 0, tb = 0, w_full = 0, t_issue = 0;
+        MARCH_PROF_T(tb);
         for (int i = 0; i < nst; ++i) {
+            MARCH_PROF_T(t0);
             mbar_wait(&full[s], ph);
+            MARCH_PROF_T(t1);
+            w_full += t1 - t0;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t ya16 = sbase16 + s * stage16;
@@ -163,10 +184,18 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
             __syncwarp();
             if (elect_one()) umma_commit(&empty[s]);
             __syncwarp();
+            MARCH_PROF_T(t2);
+            t_issue += t2 - t1;
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit(done);
         __syncwarp();
+        if (prof && lane == 0 && blockIdx.x < 160) {
+            g_march_prof[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - tb);
+            g_march_prof[blockIdx.x * 16 + 4] = (unsigned long long)w_full;
+            g_march_prof[blockIdx.x * 16 + 5] = (unsigned long long)t_issue;
+            g_march_prof[blockIdx.x * 16 + 6] = (unsigned long long)nst;
+        }
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> fp32 partial =================
         const int ew = warp - 4;
@@ -174,10 +203,14 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
         int row; bool row_ok;
         if (p.M == 128) { row = ew * 32 + lane; row_ok = true; }
         else            { row = ew * 16 + lane; row_ok = lane < 16; }   // M=64: lanes 0-15 of each quadrant
+        const bool prof = (p.debug & 256) != 0;
+        long long tb = 0, t1 = 0;
+        MARCH_PROF_T(tb);
         if (nst > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
         }
+        MARCH_PROF_T(t1);
         for (int t = 0; t < p.nacc; ++t) {
             for (int c0 = 0; c0 < p.Nmma; c0 += 16) {
                 float v[16];
@@ -202,6 +235,10 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
                     }
                 }
             }
+        }
+        if (prof && lane == 0 && ew == 0 && blockIdx.x < 160) {
+            g_march_prof[blockIdx.x * 16 + 7] = (unsigned long long)(t1 - tb);          // wait for the last MMA
+            g_march_prof[blockIdx.x * 16 + 8] = (unsigned long long)(clock64() - t1);   // TMEM -> global partial
         }
     }
     tc_fence_before();
