@@ -144,7 +144,7 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / max(1, steps)
     v = size ** 3 / dt
     sample = "1 x 4x%d^3 crop per step: fwd + Dice_loss_joint + autograd backward, fp32, torch CPU (oneDNN)" % size
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "voxels/sec fwd+bwd (ResUNet train step, 4x128^3 volumes)", "value": v,
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -153,11 +153,35 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port of /root/reference model.py+loss.py (reference is Python and does not travel to the "
                 "GPU box); excludes the reference's gc.collect() per forward and the optimizer step",
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL prints its version banner to fd 1 when the communicator is
+    created, and the reference-compatible UNet constructor prints 'UNet [...]' (model.py:311): everything except
+    the result line goes to stderr; the result is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -377,7 +401,7 @@ def run(args, rank, world, local_rank, dev):
             "model_tensor_frac_of_sustained": flops_step / (ms_step * 1e-3) / 1e12 / world / peaks["tf_sust"],
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(out))
+        emit(out)
 
 
 if __name__ == "__main__":
