@@ -117,7 +117,7 @@ def train(net, criteria, batches, steps=None, lr=2e-5, weight_decay=1e-6, step_s
         sched.step()
         state.global_step += 1
         if log_every and (idx % log_every == 0):
-            vals = [float(v) for v in loss_val]          # one device->host read per logged step
+            vals = [float(v.detach()) for v in loss_val]          # one device->host read per logged step
             history.append(vals)
             log("step %d  loss %s  lr %.3g  %.2f s" % (state.global_step, ["%.5f" % v for v in vals],
                                                      opt.param_groups[0]["lr"], time.perf_counter() - t0))

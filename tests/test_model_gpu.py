@@ -135,7 +135,9 @@ def test_forward_and_backward_match_reference_golden(golden, case):
     _check_grads(m, ref, yard, case + " dice+bce")
 
 
-@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 32, 48, 64)])
+# (3, 8, 16, 24): odd batch, one slice at the deepest level (D/8 = 1); (1, 24, 40, 72): no dimension a multiple
+# of 16 at level 1+, ragged tiles everywhere; (1, 128, 128, 128): one volume of the benchmark size (config 1/3).
+@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 32, 48, 64), (3, 8, 16, 24), (1, 24, 40, 72), (1, 128, 128, 128)])
 def test_matches_oracle_at_larger_sizes(shape):
     import brats2019_b200 as B
     N, D, H, W = shape
