@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "elementwise2.cuh"
 #include "wgrad_gemm.cuh"
+#include "wgrad_march.cuh"
 #include "elementwise3.cuh"
 
 using namespace b200;
@@ -754,10 +755,64 @@ static int plan_wgrad(const b200_wgrad_desc* d, WgradPlan& P) {
     return 0;
 }
 
+// Marching form (wgrad_march.cuh) for the 3x3x3 16 <-> 16 convs: W a multiple of 16 and a band of lines that fits
+// shared memory.  OPT-IN (B200_WGRAD_MARCH=1): measured on B200 (profiles/r01_ab_wgrad_march.txt) it moves 60 % fewer
+// bytes from L2 but is bound by the same tcgen05.mma issue time as the linear-row kernel (3 MMAs of M=64/N=48 per 16
+// voxels, ~35 cycles each) and pays ~20 us more prologue/epilogue: 137-145 us vs 118-124 us alone, 6.32 vs 6.05 ms per
+// training step.  Kept, with its parity tests, as the starting point for a form that also cuts the MMA count.
+struct WgradMarchPlan {
+    WgradMarchParams k;
+    unsigned smem;
+    int grid;
+};
+static bool plan_wgrad_march(const b200_wgrad_desc* d, WgradMarchPlan& P) {
+    const char* e = getenv("B200_WGRAD_MARCH");         // read per call: tests switch forms in one process
+    const int off = (e && atoi(e)) ? 0 : 1;
+    if (off || d->mode != 0 || d->Cout != 16 || d->Cin != 16 || d->W % 16 || d->W < 16) return false;
+    memset(&P, 0, sizeof(P));
+    WgradMarchParams& k = P.k;
+    k.N = d->N; k.D = d->D; k.H = d->H; k.W = d->W; k.Wp = d->W + 2;
+    k.ksteps = d->W / 16;
+    k.x_blk_bytes = (unsigned)k.Wp * 16u;
+    const unsigned bar_bytes = 1024;
+    // band height: the largest that fits shared memory (3 ring slots + 2 staging slots of dY, 2 stages of X),
+    // preferring one that divides H (equal work per band)
+    auto fits = [&](int BH) {
+        if (BH > d->H || BH * k.Wp > 16383) return false;
+        const unsigned ypl = (unsigned)BH * k.Wp * 16u;
+        const unsigned need = 5u * 2u * ypl + (unsigned)kWgmXStages * (unsigned)(BH + 2) * 2u * k.x_blk_bytes + bar_bytes;
+        return need <= kMaxSmem;
+    };
+    k.BH = 0;
+    for (int BH : {8, 6, 4, 3, 2, 1}) if (fits(BH) && d->H % BH == 0) { k.BH = BH; break; }
+    if (k.BH == 0) for (int BH : {8, 6, 4, 3, 2, 1}) if (fits(BH)) { k.BH = BH; break; }
+    if (k.BH == 0) return false;
+    k.n_bands = ceil_div(d->H, k.BH);
+    k.units = (long long)d->N * k.n_bands * d->D;
+    k.nsub = (k.BH % 2 == 0) ? 2 : 1;
+    k.BHs = k.BH / k.nsub;
+    k.y_plane_bytes = (unsigned)k.BH * k.Wp * 16u;
+    k.y_sub_bytes = (unsigned)k.BHs * k.Wp * 16u;
+    k.y_slot_bytes = 2u * k.y_plane_bytes;
+    k.x_stage_bytes = (unsigned)(k.BH + 2) * 2u * k.x_blk_bytes;
+    if (k.y_slot_bytes >= (1u << 20) || k.x_stage_bytes >= (1u << 20)) return false;
+    k.smem_y_off = 0;
+    k.smem_stg_off = 3u * k.y_slot_bytes;                 // directly after the ring (see the kernel)
+    k.smem_x_off = k.smem_stg_off + 2u * k.y_slot_bytes;
+    k.smem_bar_off = k.smem_x_off + (unsigned)kWgmXStages * k.x_stage_bytes;
+    P.smem = k.smem_bar_off + bar_bytes;
+    P.grid = (int)std::min<long long>(num_sms(), k.units);
+    return true;
+}
+
 extern "C" size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d) {
     WgradPlan P;
     if (plan_wgrad(d, P)) return 0;
-    return (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
+    size_t bytes = (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
+    WgradMarchPlan MP;
+    if (plan_wgrad_march(d, MP))
+        bytes = std::max(bytes, (size_t)MP.grid * kWgmAccs * kWgmM * kWgmN * sizeof(float));
+    return bytes;
 }
 
 extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const void* x, void* workspace, float* grad,
@@ -780,12 +835,29 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     Vol vol{d->N, d->D, d->H, d->W};
     P.k.dy = make_act(dy, vol);
     P.k.x = make_act(x, vol);
-    if (P.k.stage_tx_bytes >= (1u << 20)) return fail("wgrad: stage exceeds the mbarrier tx-count range");
+    static int wdbg = -1;
+    if (wdbg < 0) { const char* e = getenv("B200_WGRAD_DEBUG"); wdbg = e ? atoi(e) : 0; }
     {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("B200_WGRAD_DEBUG"); dbg = e ? atoi(e) : 0; }
-        P.k.debug = dbg;
+        WgradMarchPlan MP;
+        if (kind == B200_G_K3 && plan_wgrad_march(d, MP)) {
+            static bool march_attr_set = false;
+            if (!march_attr_set) {
+                CUDA_OK(cudaFuncSetAttribute(wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                march_attr_set = true;
+            }
+            MP.k.dy = P.k.dy; MP.k.x = P.k.x; MP.k.partial = (float*)workspace; MP.k.debug = wdbg;
+            wgrad_march_kernel<<<MP.grid, kWgmThreads, MP.smem, st>>>(MP.k);
+            LAUNCH_OK("wgrad_march_kernel");
+            WgmReduceParams rq;
+            rq.ctas = MP.grid; rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
+            constexpr int qpb = 256 / kWgmReduceGroups;
+            wgrad_march_reduce_kernel<<<(27 * 16 * 4 + qpb - 1) / qpb, 256, 0, st>>>((const float*)workspace, grad, rq);
+            LAUNCH_OK("wgrad_march_reduce_kernel");
+            return 0;
+        }
     }
+    if (P.k.stage_tx_bytes >= (1u << 20)) return fail("wgrad: stage exceeds the mbarrier tx-count range");
+    P.k.debug = wdbg;
     wgrad_gemm_kernel<<<P.grid, kWgradThreads, P.smem, st>>>(P.k);
     LAUNCH_OK("wgrad_gemm_kernel");
     WgradReduceParams q;
