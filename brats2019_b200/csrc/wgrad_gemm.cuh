@@ -71,7 +71,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }   // full: dY + X producer
         mbar_init(done, 1);
         fence_barrier_init();
     }
@@ -92,8 +92,10 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
     const unsigned y_bytes = (unsigned)p.y_planes * p.y_plane_bytes;
 
     // Whole-warp role code with elect_one() around the issue (see conv_gemm.cuh for why).
-    if (warp == 0) {
-        // ================= producer =================
+    if (warp <= 1) {
+        // ================= producers: warp 0 issues the dY planes of every stage, warp 1 the X planes =================
+        // (one elected thread issues a cp.async.bulk every 42-84 cycles; with 24+ planes per stage a single issuer
+        // was the bound of the 32-channel weight gradient, profiles/r01_wgrad_cycle_probe.txt)
         // Source offset of every plane for r0 = 0, computed once (one lane per plane): the per-stage issue
         // loop below must stay far below the MMA time of a stage (~2000 cycles), so it is one shared-memory
         // read and one add per bulk copy instead of the nested band/chunk/range address arithmetic.
@@ -127,20 +129,24 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
             MARCH_PROF_T(t1);
             w_empty += t1 - t0;
             if (elect_one()) {
-                mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
                 uint8_t* ybase = smem + (size_t)s * p.stage_bytes;
                 uint8_t* xbase = ybase + y_bytes;
-                for (int pl = 0; pl < ny; ++pl)
-                    bulk_load_1d(ybase + (size_t)pl * p.y_plane_bytes, ysrc + s_yoff[pl] + r0b, p.y_plane_bytes, &full[s]);
-                for (int pl = 0; pl < nx; ++pl)
-                    bulk_load_1d(xbase + (size_t)pl * p.x_plane_bytes, xsrc + s_xoff[pl] + r0b, p.x_plane_bytes, &full[s]);
+                if (warp == 0) {
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)ny * p.y_plane_bytes);
+                    for (int pl = 0; pl < ny; ++pl)
+                        bulk_load_1d(ybase + (size_t)pl * p.y_plane_bytes, ysrc + s_yoff[pl] + r0b, p.y_plane_bytes, &full[s]);
+                } else {
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)nx * p.x_plane_bytes);
+                    for (int pl = 0; pl < nx; ++pl)
+                        bulk_load_1d(xbase + (size_t)pl * p.x_plane_bytes, xsrc + s_xoff[pl] + r0b, p.x_plane_bytes, &full[s]);
+                }
             }
             __syncwarp();
             MARCH_PROF_T(t2);
             t_issue += t2 - t1;
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (prof && lane == 0 && blockIdx.x < 160) {
+        if (prof && lane == 0 && blockIdx.x < 160 && warp == 1) {
             g_march_prof[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - tb);
             g_march_prof[blockIdx.x * 16 + 1] = (unsigned long long)w_empty;
             g_march_prof[blockIdx.x * 16 + 2] = (unsigned long long)t_issue;
