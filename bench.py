@@ -120,6 +120,14 @@ def run_reference(args, rank):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm is rank 0 alone on the host, so it takes
+    # every core this process may run on ("all the host threads it can use")
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     steps, warm = args.steps, args.warmup
     # bounded sample: pick the largest cube whose (K+W) steps fit ~150 s, from a 32^3 calibration
