@@ -236,3 +236,28 @@ def test_fastdiv_formula_is_exact_for_planner_divisors():
         n = n[n < (1 << 24)]
         q = ((n * np.uint64(m)) >> np.uint64(32)) >> np.uint64(sh - 1)
         assert (q == n // np.uint64(d)).all(), d
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No fallback of any kind: without the built CUDA library the first native call raises."""
+    import pytest as _pytest
+    from brats2019_b200 import _lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "libbrats_b200.so"))
+    with _pytest.raises(RuntimeError, match="no fallback"):
+        L.lib()
+
+
+def test_cpu_tensor_is_rejected_not_computed():
+    """The drop-in module refuses CPU inputs instead of falling back to ATen (model.py::UNet.forward)."""
+    import contextlib
+    import sys
+    import pytest as _pytest
+    import torch
+    import brats2019_b200 as B
+    with contextlib.redirect_stdout(sys.stderr):
+        m = B.UNet(**B.DEFAULT_CFG)
+    with _pytest.raises(RuntimeError, match="no CPU"):
+        m([torch.zeros(1, 4, 16, 16, 16)])
+    with _pytest.raises(RuntimeError, match="CUDA only"):
+        B.Dice_loss_joint()([torch.zeros(1, 3, 8, 8, 8)], [torch.zeros(1, 3, 8, 8, 8)])
