@@ -18,6 +18,7 @@
 #include "wgrad_gemm.cuh"
 #include "wgrad_march.cuh"
 #include "elementwise3.cuh"
+#include "elementwise4.cuh"
 
 using namespace b200;
 
@@ -1068,9 +1069,9 @@ extern "C" int b200_upsample2x(const void* coarse, void* fine, int N, int D, int
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    upsample2x_fwd2_kernel<<<N * 2 * D * 2 * H, 128, 0, (cudaStream_t)stream>>>(make_act(coarse, vc), make_act(fine, vf), vc,
-                                                                               C, do_lrelu, make_fastdiv((unsigned)W));
-    LAUNCH_OK("upsample2x_fwd2_kernel");
+    upsample2x_fwd3_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(make_act(coarse, vc), make_act(fine, vf), vc, C,
+                                                                       do_lrelu, make_fastdiv((unsigned)W));
+    LAUNCH_OK("upsample2x_fwd3_kernel");
     return 0;
 }
 // workspace: the w-reduced intermediate, act layout of volume (N, 2D, 2H, W) with C channels
@@ -1087,11 +1088,11 @@ extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out,
     Vol vt{N, 2 * D, 2 * H, W};
     cudaStream_t st = (cudaStream_t)stream;
     const FastDiv by_W = make_fastdiv((unsigned)W);
-    upsample2x_bwd_w_kernel<<<N * 2 * D * 2 * H, 128, 0, st>>>(make_act(dfine, vf), make_act(fine_out, vf),
-                                                              make_act(workspace, vt), vc, C, do_lrelu, by_W);
-    LAUNCH_OK("upsample2x_bwd_w_kernel");
-    upsample2x_bwd_dh_kernel<<<N * D * H, 128, 0, st>>>(make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W);
-    LAUNCH_OK("upsample2x_bwd_dh_kernel");
+    upsample2x_bwd_w3_kernel<<<N * 2 * D * 2 * H, 128, 0, st>>>(make_act(dfine, vf), make_act(fine_out, vf),
+                                                               make_act(workspace, vt), vc, C, do_lrelu, by_W);
+    LAUNCH_OK("upsample2x_bwd_w3_kernel");
+    upsample2x_bwd_dh3_kernel<<<N * D * H, 128, 0, st>>>(make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W);
+    LAUNCH_OK("upsample2x_bwd_dh3_kernel");
     return 0;
 }
 
