@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -908,11 +909,26 @@ static int check_act(int N, int D, int H, int W, int C) {
     return 0;
 }
 
+// lines per CTA of the four-voxels-per-thread layout kernels: up to 16, while ~6 CTAs per SM remain
+static int quad_lpb(int N, int D, int H) {
+    const long long lines = (long long)N * D * H;
+    int lpb = 1;
+    while (lpb < 16 && lines / (lpb * 2) >= 6LL * num_sms()) lpb *= 2;
+    return lpb;
+}
+
 extern "C" int b200_pack_input(const float* x, void* act_out, int N, int D, int H, int W, int Creal, int Cpad,
                                void* stream) {
     if (check_act(N, D, H, W, Cpad) || Creal > Cpad) return fail("pack_input: bad channels %d -> %d", Creal, Cpad);
     Vol v{N, D, H, W};
     if (Creal > 8) return fail("pack_input: at most 8 real channels");
+    if (W % 4 == 0 && ((uintptr_t)x & 15) == 0) {
+        const int lpb = quad_lpb(N, D, H);
+        pack_input4_kernel<<<(N * D * H + lpb - 1) / lpb, 256, 0, (cudaStream_t)stream>>>(x, make_act(act_out, v), v, Creal, lpb,
+                                                                                         make_fastdiv((unsigned)(W / 4)));
+        LAUNCH_OK("pack_input4_kernel");
+        return 0;
+    }
     pack_input_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(x, make_act(act_out, v), v, Creal);
     LAUNCH_OK("pack_input_kernel");
     return 0;
@@ -1139,9 +1155,15 @@ extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs
     cudaStream_t st = (cudaStream_t)stream;
     const int lpb = sigmoid_lpb(N, D, H);
     const int blocks = (N * D * H + lpb - 1) / lpb;
-    sigmoid_bwd_pack2_kernel<<<blocks, 256, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
-                                                    make_fastdiv((unsigned)W));
-    LAUNCH_OK("sigmoid_bwd_pack2_kernel");
+    if (W % 4 == 0 && (((uintptr_t)grad_probs | (uintptr_t)probs) & 15) == 0) {
+        sigmoid_bwd_pack4_kernel<<<blocks, 256, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+                                                        make_fastdiv((unsigned)(W / 4)));
+        LAUNCH_OK("sigmoid_bwd_pack4_kernel");
+    } else {
+        sigmoid_bwd_pack2_kernel<<<blocks, 256, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+                                                        make_fastdiv((unsigned)W));
+        LAUNCH_OK("sigmoid_bwd_pack2_kernel");
+    }
     if (dbias) {
         reduce_partials_kernel<<<Creal, 256, 0, st>>>(workspace, blocks, 4, Creal, dbias);
         LAUNCH_OK("reduce_partials_kernel");

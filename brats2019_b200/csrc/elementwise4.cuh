@@ -203,4 +203,101 @@ upsample2x_bwd_dh3_kernel(ActRef T, ActRef dcoarse, Vol vc, int C, FastDiv by_Wc
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Layout conversions at the two ends of the model, four voxels per thread with 16-byte fp32 loads (the
+// one-voxel-per-thread forms spent ~260 instructions per voxel on index arithmetic and scalar loads: 70 % issue-slot
+// utilisation at half of the HBM bandwidth, profiles/r01_ncu_upsample_issue_bound.txt).  A CTA owns `lpb` <= 16 lines
+// whose source offsets and destination rows are computed once into shared memory.  W % 4 == 0 and 16-byte aligned
+// fp32 tensors are required (the entry points fall back to the scalar kernels otherwise).
+// ---------------------------------------------------------------------------------------
+// (B,Creal,D,H,W) fp32 NCDHW -> chunk 0 of an act tensor (model.py:407-412), Creal <= 8.
+__global__ void __launch_bounds__(256)
+pack_input4_kernel(const float* __restrict__ x, ActRef out, Vol v, int Creal, int lpb, FastDiv by_Q) {
+    __shared__ long long s_src[16], s_row[16];
+    const int line0 = blockIdx.x * lpb;
+    const int nl = min(lpb, v.N * v.D * v.H - line0);
+    const size_t plane = (size_t)v.D * v.H * v.W;
+    if ((int)threadIdx.x < nl) {
+        int n, d, h;
+        line_coords(v, line0 + threadIdx.x, n, d, h);
+        s_src[threadIdx.x] = (long long)((size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W);
+        s_row[threadIdx.x] = v.row(n, d + 1, h + 1, 1);
+    }
+    __syncthreads();
+    const int Q = v.W >> 2;
+    for (int idx = threadIdx.x; idx < nl * Q; idx += blockDim.x) {
+        const int li = by_Q.div(idx), q = idx - li * Q;
+        const float* src = x + s_src[li] + 4 * q;
+        float4 c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            c[i] = (i < Creal) ? *reinterpret_cast<const float4*>(src + (size_t)i * plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __nv_bfloat16* dst = out.at(0, s_row[li] + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = k == 0 ? c[i].x : k == 1 ? c[i].y : k == 2 ? c[i].z : c[i].w;
+            st16(dst + k * 8, pack_bf16x8(f));
+        }
+    }
+}
+
+// sigmoid backward + layout (model.py:431 backward): dlogit = gp * p * (1 - p) -> chunk 0 of an act tensor
+// (channels >= Creal stay zero), per-CTA bias-gradient partials [blocks][4].  Creal <= 4.
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_pack4_kernel(const float* __restrict__ gp, const float* __restrict__ probs, ActRef dlogit,
+                         float* __restrict__ bias_partial, Vol v, int Creal, int lpb, FastDiv by_Q) {
+    __shared__ long long s_src[16], s_row[16];
+    __shared__ float s_red[8][4];
+    const int line0 = blockIdx.x * lpb;
+    const int nl = min(lpb, v.N * v.D * v.H - line0);
+    const size_t plane = (size_t)v.D * v.H * v.W;
+    if ((int)threadIdx.x < nl) {
+        int n, d, h;
+        line_coords(v, line0 + threadIdx.x, n, d, h);
+        s_src[threadIdx.x] = (long long)((size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W);
+        s_row[threadIdx.x] = v.row(n, d + 1, h + 1, 1);
+    }
+    __syncthreads();
+    const int Q = v.W >> 2;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int idx = threadIdx.x; idx < nl * Q; idx += blockDim.x) {
+        const int li = by_Q.div(idx), q = idx - li * Q;
+        const long long src = s_src[li] + 4 * q;
+        float4 g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < Creal) {
+                const float4 pr = *reinterpret_cast<const float4*>(probs + src + (size_t)i * plane);
+                const float4 gg = *reinterpret_cast<const float4*>(gp + src + (size_t)i * plane);
+                g[i] = make_float4(gg.x * pr.x * (1.f - pr.x), gg.y * pr.y * (1.f - pr.y), gg.z * pr.z * (1.f - pr.z),
+                                   gg.w * pr.w * (1.f - pr.w));
+                bsum[i] += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            }
+        }
+        __nv_bfloat16* dst = dlogit.at(0, s_row[li] + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                f[i] = i < 4 ? (k == 0 ? g[i].x : k == 1 ? g[i].y : k == 2 ? g[i].z : g[i].w) : 0.f;
+            st16(dst + k * 8, pack_bf16x8(f));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bsum[c] = warp_sum(bsum[c]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int c = 0; c < 4; ++c) s_red[warp][c] = bsum[c];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float a = 0.f;
+        for (int k = 0; k < 8; ++k) a += s_red[k][threadIdx.x];
+        bias_partial[(size_t)blockIdx.x * 4 + threadIdx.x] = a;
+    }
+}
+
 }  // namespace b200

@@ -58,6 +58,12 @@ def group_ew():
     report("pack_input interior", ops.act_to_ncdhw(a, 4), bf(x), tol_abs=0)
     report("pack_input halo+guard zero", ops.act_outside_absmax(a).view(1), torch.zeros(1, device=dev), tol_abs=0)
     report("pack_input pad channels zero", ops.act_to_ncdhw(a)[:, 4:], torch.zeros(N, 12, D, H, W, device=dev), tol_abs=0)
+    # W % 4 == 0 takes the four-voxels-per-thread kernel (W = 10 above takes the scalar one); odd line count per CTA
+    x4 = torch.randn(3, 4, 5, 7, 24, device=dev)
+    a4 = ops.pack_input(x4, 16)
+    report("pack_input quad interior", ops.act_to_ncdhw(a4, 4), bf(x4), tol_abs=0)
+    report("pack_input quad halo+guard zero", ops.act_outside_absmax(a4).view(1), torch.zeros(1, device=dev), tol_abs=0)
+    report("pack_input quad pad channels zero", ops.act_to_ncdhw(a4)[:, 4:], torch.zeros(3, 12, 5, 7, 24, device=dev), tol_abs=0)
 
     for Cc in (16, 32, 64, 128):
         xc = bf(torch.randn(N, Cc, D, H, W, device=dev) * 2 + 0.5)
