@@ -869,9 +869,9 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     q.n_jobs = P.k.n_jobs; q.splits = P.k.splits; q.nacc = P.k.nacc; q.M = P.k.M; q.Nmma = P.k.Nmma;
     q.accumulate = accumulate;
     const int quads = q.n_jobs * q.nacc * q.M * q.Nmma / 4;
-    // split-groups per CTA: enough threads to fill the machine (~2 CTAs per SM), at most 8 and <= splits
+    // split-groups per CTA: enough threads to fill the machine (~2 CTAs per SM), at most 32 and <= splits
     int SG = 1;
-    while (SG < 8 && SG * 2 <= q.splits && (long long)quads * SG < 2LL * 256 * num_sms()) SG *= 2;
+    while (SG < 32 && SG * 2 <= q.splits && (long long)quads * SG < 2LL * 256 * num_sms()) SG *= 2;
     const int qpc = 256 / SG;
     wgrad_reduce_kernel<<<(quads + qpc - 1) / qpc, 256, 0, st>>>(P.k.partial, grad, q, SG);
     LAUNCH_OK("wgrad_reduce_kernel");
