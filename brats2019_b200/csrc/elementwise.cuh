@@ -160,304 +160,7 @@ gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restric
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// GroupNorm (+LeakyReLU) backward, pass 1: per (n, c) sums  S1 = sum dz, S2 = sum dz * xhat
-//   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
-// grid = (blocks_per_sample, N); each CTA walks lines blockIdx.x, +gridDim.x, ... of sample n,
-// one 8-channel chunk plane at a time, and writes partial[n][blockIdx.x][C][2].
-// Fixed summation order -> deterministic.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads)
-gn_bwd_reduce_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
-                     Vol v, int C, int do_lrelu, FastDiv by_W) {
-    __shared__ float s_a[256], s_b[256], s_g[256], s_be[256];
-    __shared__ float s_red[kEwThreads / 32][16];
-    const int n = blockIdx.y;
-    const int gs = C / 8;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / gs;
-        s_a[c] = rstd[n * 8 + g];
-        s_b[c] = -mean[n * 8 + g] * rstd[n * 8 + g];
-        s_g[c] = gamma[c];
-        s_be[c] = beta[c];
-    }
-    __syncthreads();
-    const int nlines = v.D * v.H;
-    const int my_lines = (nlines - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int items = my_lines * v.W;
-    // first row of each of this CTA's lines, computed once (kMaxRedLines bounds the table; the
-    // host sizes the grid so that my_lines never exceeds it)
-    __shared__ long long s_rows[kMaxRedLines];
-    for (int li = threadIdx.x; li < my_lines; li += blockDim.x) {
-        const int line = blockIdx.x + li * gridDim.x;
-        const int d = line / v.H, h = line - d * v.H;
-        s_rows[li] = v.row(n, d + 1, h + 1, 1);
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int cv = 0; cv < C / 8; ++cv) {
-        const int cb = cv * 8;
-        float s1[8], s2[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-        for (int idx0 = threadIdx.x; idx0 < items; idx0 += blockDim.x * kUnroll) {
-            uint4 qx[kUnroll], qd[kUnroll];
-            bool ok[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int idx = idx0 + u * blockDim.x;
-                ok[u] = idx < items;
-                if (ok[u]) {
-                    const int li = by_W.div(idx);
-                    const long long r = s_rows[li] + (idx - li * v.W);
-                    qx[u] = ld16(x.at(cv, r));
-                    qd[u] = ld16(dy.at(cv, r));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (!ok[u]) continue;
-                float fx[8], fd[8];
-                unpack_bf16x8(qx[u], fx);
-                unpack_bf16x8(qd[u], fd);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
-                    float dz = fd[k];
-                    if (do_lrelu) {
-                        const float z = xh * s_g[cb + k] + s_be[cb + k];
-                        dz = z > 0.f ? dz : 0.01f * dz;
-                    }
-                    s1[k] += dz;
-                    s2[k] += dz * xh;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { s1[k] = warp_sum(s1[k]); s2[k] = warp_sum(s2[k]); }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { s_red[warp][k] = s1[k]; s_red[warp][8 + k] = s2[k]; }
-        }
-        __syncthreads();
-        if (threadIdx.x < 16) {
-            float acc = 0.f;
-            for (int q = 0; q < kEwThreads / 32; ++q) acc += s_red[q][threadIdx.x];
-            const int k = threadIdx.x & 7, which = threadIdx.x >> 3;
-            partial[(((size_t)n * gridDim.x + blockIdx.x) * C + cb + k) * 2 + which] = acc;
-        }
-        __syncthreads();
-    }
-}
-
-// pass 2: partial[n][blocks][C][2] -> coef[n][C][2] = (A_g, B_g) per channel's group, and
-//         dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.   grid = 1, block = 1024 threads, C <= 256.
-// Each of the 2C per-sample sums is split over T = 1024/(2C) threads (strided, fixed order) and
-// combined in a fixed order, so the result is deterministic and the latency is ~blocks/T loads.
-__global__ void __launch_bounds__(1024)
-gn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
-                       const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
-    __shared__ double s_part[1024];
-    __shared__ double s_sum[512];      // [c][which]
-    __shared__ double s_tot[512];      // running sum over n
-    const int t = threadIdx.x;
-    const int nout = 2 * C;
-    const int T = 1024 / nout;         // threads per output (C in {16..256} -> T in {32..2})
-    const int o = t / T, j = t - o * T;
-    const int gs = C / 8;
-    if (t < nout) s_tot[t] = 0.0;
-    for (int n = 0; n < N; ++n) {
-        double a = 0.0;
-        if (o < nout) {
-            const float* src = partial + ((size_t)n * blocks * C) * 2 + o;      // o = c*2 + which
-            for (int k = j; k < blocks; k += T) a += (double)src[(size_t)k * C * 2];
-        }
-        s_part[t] = a;
-        __syncthreads();
-        if (t < nout) {
-            double acc = 0.0;
-            for (int q = 0; q < T; ++q) acc += s_part[t * T + q];
-            s_sum[t] = acc;
-            s_tot[t] += acc;
-        }
-        __syncthreads();
-        if (t < C) {
-            const int g0 = (t / gs) * gs;
-            double A = 0.0, B = 0.0;
-            for (int k = 0; k < gs; ++k) {
-                A += s_sum[(g0 + k) * 2 + 0] * (double)gamma[g0 + k];
-                B += s_sum[(g0 + k) * 2 + 1] * (double)gamma[g0 + k];
-            }
-            coef[((size_t)n * C + t) * 2 + 0] = (float)(A / m);
-            coef[((size_t)n * C + t) * 2 + 1] = (float)(B / m);
-        }
-        __syncthreads();
-    }
-    if (t < C) {
-        dbeta[t] = (float)s_tot[t * 2 + 0];
-        dgamma[t] = (float)s_tot[t * 2 + 1];
-    }
-}
-
-// pass 3: dx = rstd * (dz*gamma - A_g - xhat*B_g)
-__global__ void __launch_bounds__(kEwThreads)
-gn_bwd_apply_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
-                    ActRef dx, Vol v, int C, int do_lrelu, LineGeom lg) {
-    __shared__ float s_a[256], s_b[256], s_g[256], s_be[256], s_A[256], s_B[256];
-    __shared__ long long s_rows[16];
-    const int lpb = lg.lpb;
-    const int line0 = blockIdx.x * lpb;
-    fill_line_rows(v, line0, lpb, s_rows);
-    const int n = line0 / (v.D * v.H);
-    const int gs = C / 8;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / gs;
-        s_a[c] = rstd[n * 8 + g];
-        s_b[c] = -mean[n * 8 + g] * rstd[n * 8 + g];
-        s_g[c] = gamma[c];
-        s_be[c] = beta[c];
-        s_A[c] = coef[((size_t)n * C + c) * 2 + 0];
-        s_B[c] = coef[((size_t)n * C + c) * 2 + 1];
-    }
-    __syncthreads();
-    const int nvec = v.W * (C / 8);
-    const int total = lpb * nvec;
-    for (int j0 = threadIdx.x; j0 < total; j0 += blockDim.x * kUnroll) {
-        LineVec lv[kUnroll];
-        uint4 qx[kUnroll], qd[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            lv[u] = line_vec(lg, s_rows, j0 + u * blockDim.x);
-            if (lv[u].ok) {
-                qx[u] = ld16(x.at(lv[u].cv, lv[u].row));
-                qd[u] = ld16(dy.at(lv[u].cv, lv[u].row));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (!lv[u].ok) continue;
-            const int cb = lv[u].cv * 8;
-            float fx[8], fd[8];
-            unpack_bf16x8(qx[u], fx);
-            unpack_bf16x8(qd[u], fd);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float xh = fx[k] * s_a[cb + k] + s_b[cb + k];
-                float dz = fd[k];
-                if (do_lrelu) {
-                    const float z = xh * s_g[cb + k] + s_be[cb + k];
-                    dz = z > 0.f ? dz : 0.01f * dz;
-                }
-                fx[k] = s_a[cb + k] * (dz * s_g[cb + k] - s_A[cb + k] - xh * s_B[cb + k]);
-            }
-            st16(dx.at(lv[u].cv, lv[u].row), pack_bf16x8(fx));
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Trilinear x2, align_corners=False (model.py:7-14; aten::upsample_trilinear3d) + LeakyReLU
-// (model.py:422).  out[2k] = .25 in[k-1] + .75 in[k], out[2k+1] = .75 in[k] + .25 in[k+1],
-// indices clamped.  `vc` = coarse volume, output volume is 2x in each dim.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void up_taps(int i, int K, int& i0, int& i1, float& w0, float& w1) {
-    const int k = i >> 1;
-    if (i & 1) { i0 = k; i1 = min(k + 1, K - 1); w0 = 0.75f; w1 = 0.25f; }
-    else       { i0 = max(k - 1, 0); i1 = k; w0 = 0.25f; w1 = 0.75f; }
-}
-
-__global__ void __launch_bounds__(kEwThreads)
-upsample2x_lrelu_kernel(ActRef in, ActRef out, Vol vc, int C, int do_lrelu) {
-    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
-    int n, d, h;
-    line_coords(vf, blockIdx.x, n, d, h);
-    int d0, d1, h0, h1;
-    float wd0, wd1, wh0, wh1;
-    up_taps(d, vc.D, d0, d1, wd0, wd1);
-    up_taps(h, vc.H, h0, h1, wh0, wh1);
-    const long long rows[4] = {vc.row(n, d0 + 1, h0 + 1, 1), vc.row(n, d0 + 1, h1 + 1, 1), vc.row(n, d1 + 1, h0 + 1, 1),
-                               vc.row(n, d1 + 1, h1 + 1, 1)};
-    const float cw[4] = {wd0 * wh0, wd0 * wh1, wd1 * wh0, wd1 * wh1};
-    const long long orow0 = vf.row(n, d + 1, h + 1, 1);
-    const int nvec = vf.W * (C / 8);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = i / vf.W, w = i - cv * vf.W;
-        int w0, w1;
-        float ww0, ww1;
-        up_taps(w, vc.W, w0, w1, ww0, ww1);
-        float acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            float a[8], b[8];
-            unpack_bf16x8(ld16(in.at(cv, rows[t] + w0)), a);
-            unpack_bf16x8(ld16(in.at(cv, rows[t] + w1)), b);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += cw[t] * (ww0 * a[k] + ww1 * b[k]);
-        }
-        if (do_lrelu) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = lrelu(acc[k]);
-        }
-        st16(out.at(cv, orow0 + w), pack_bf16x8(acc));
-    }
-}
-
-// Adjoint of the above (aten::upsample_trilinear3d_backward fused with leaky_relu_backward):
-// dcoarse[k] = sum_i wt(i -> k) * dy[i] * lrelu'(y[i]); `y` is the forward output (its sign
-// equals the sign of the pre-activation).  One CTA per coarse line.
-__device__ __forceinline__ int down_taps(int k, int K, int* idx, float* wt) {
-    int n = 0;
-    if (k > 0) { idx[n] = 2 * k - 1; wt[n] = 0.25f; ++n; }
-    idx[n] = 2 * k;     wt[n] = 0.75f + (k == 0 ? 0.25f : 0.f);     ++n;
-    idx[n] = 2 * k + 1; wt[n] = 0.75f + (k == K - 1 ? 0.25f : 0.f); ++n;
-    if (k < K - 1) { idx[n] = 2 * k + 2; wt[n] = 0.25f; ++n; }
-    return n;
-}
-
-__global__ void __launch_bounds__(kEwThreads)
-upsample2x_lrelu_bwd_kernel(ActRef dy, ActRef y, ActRef dcoarse, Vol vc, int C, int do_lrelu) {
-    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
-    int n, d, h;
-    line_coords(vc, blockIdx.x, n, d, h);
-    int di[4], hi[4];
-    float dw[4], hw[4];
-    const int nd = down_taps(d, vc.D, di, dw), nh = down_taps(h, vc.H, hi, hw);
-    const long long orow0 = vc.row(n, d + 1, h + 1, 1);
-    const int nvec = vc.W * (C / 8);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = i / vc.W, w = i - cv * vc.W;
-        int wi[4];
-        float ww[4];
-        const int nw = down_taps(w, vc.W, wi, ww);
-        float acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        for (int a = 0; a < nd; ++a)
-            for (int b = 0; b < nh; ++b) {
-                const long long rb = vf.row(n, di[a] + 1, hi[b] + 1, 1);
-                const float wab = dw[a] * hw[b];
-                for (int c = 0; c < nw; ++c) {
-                    float g[8], yy[8];
-                    unpack_bf16x8(ld16(dy.at(cv, rb + wi[c])), g);
-                    const float wt = wab * ww[c];
-                    if (do_lrelu) {
-                        unpack_bf16x8(ld16(y.at(cv, rb + wi[c])), yy);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] += wt * (yy[k] > 0.f ? g[k] : 0.01f * g[k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] += wt * g[k];
-                    }
-                }
-            }
-        st16(dcoarse.at(cv, orow0 + w), pack_bf16x8(acc));
-    }
-}
+// (Trilinear x2 and its adjoint: elementwise4.cuh.)
 
 // ---------------------------------------------------------------------------------------
 // space-to-depth / depth-to-space for the k2 s2 conv (model.py:360-363):
@@ -548,48 +251,6 @@ add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, LineGeom lg) {
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// sigmoid backward + layout: gp (grad wrt probs, fp32 NCDHW, Creal <= 4 channels), probs ->
-// dlogit = gp * p * (1-p) into chunk 0 of an act tensor (other chunks stay zero) + per-CTA
-// bias-grad partials (model.py:431 backward; conv_output.bias grad).  partial[blocks][4]
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads)
-sigmoid_bwd_pack_kernel(const float* __restrict__ gp, const float* __restrict__ probs, ActRef dlogit,
-                        float* __restrict__ bias_partial, Vol v, int Creal) {
-    __shared__ float s_red[kEwThreads / 32][4];
-    int n, d, h;
-    line_coords(v, blockIdx.x, n, d, h);
-    const size_t plane = (size_t)v.D * v.H * v.W;
-    const size_t src0 = (size_t)n * Creal * plane + ((size_t)d * v.H + h) * v.W;
-    const long long row0 = v.row(n, d + 1, h + 1, 1);
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int w = threadIdx.x; w < v.W; w += blockDim.x) {
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            f[i] = 0.f;
-            if (i < Creal) {
-                const size_t o = src0 + (size_t)i * plane + w;
-                const float p = probs[o];
-                f[i] = gp[o] * p * (1.f - p);
-                if (i < 4) bsum[i] += f[i];
-            }
-        }
-        st16(dlogit.at(0, row0 + w), pack_bf16x8(f));
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) bsum[c] = warp_sum(bsum[c]);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0)
-        for (int c = 0; c < 4; ++c) s_red[warp][c] = bsum[c];
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        float a = 0.f;
-        for (int k = 0; k < kEwThreads / 32; ++k) a += s_red[k][threadIdx.x];
-        bias_partial[(size_t)blockIdx.x * 4 + threadIdx.x] = a;
-    }
-}
-
 // out[j] = sum_i partial[i*stride + j], j < n_out, in double, fixed order.
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int count, int stride, int n_out,
                                        float* __restrict__ out) {
@@ -644,21 +305,6 @@ dice_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, fl
         o[1] = b;
         (void)c;
     }
-}
-
-// partial[B*C][blocks][2] -> sums[8] (I_c at [c], U_c at [4+c]), no epsilons yet (so that a
-// data-parallel all-reduce can be applied to `sums` before the loss is formed).
-__global__ void dice_sums_kernel(const float* __restrict__ partial, int B, int C, int blocks, float* __restrict__ sums) {
-    const int c = threadIdx.x;
-    if (c >= C) return;
-    double si = 0.0, su = 0.0;
-    for (int b = 0; b < B; ++b)
-        for (int k = 0; k < blocks; ++k) {
-            si += (double)partial[((size_t)(b * C + c) * blocks + k) * 2 + 0];
-            su += (double)partial[((size_t)(b * C + c) * blocks + k) * 2 + 1];
-        }
-    sums[c] = (float)si;
-    sums[4 + c] = (float)su;
 }
 
 // loss = priority * (1 - mean_c 2 (I_c + 1e-6) / (U_c + 2e-6))

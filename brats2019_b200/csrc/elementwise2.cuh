@@ -1,4 +1,5 @@
-// Second-generation memory-bound kernels: GroupNorm backward and trilinear x2 (forward + adjoint).
+// Second-generation memory-bound kernels: GroupNorm backward, the Dice sums and (until elementwise4.cuh replaced
+// them) trilinear x2.
 //
 // The first versions (elementwise.cuh) were instruction-bound, not HBM-bound (ncu, profiles/r01_*):
 // per-element shared-memory reads of the per-channel constants and scalar FP32 math cost ~125
@@ -6,8 +7,7 @@
 // constants live in registers, and the arithmetic is packed FP32x2 (FFMA2/FMUL2/FADD2, new on
 // sm_100): ~60 instructions per vector, which puts the kernels back under the HBM roofline.
 //
-// Replaces aten::native_group_norm_backward + leaky_relu_backward (model.py:95-96, 105-112, 338)
-// and aten::upsample_trilinear3d(+_backward) + leaky_relu (model.py:7-14, 422).
+// Replaces aten::native_group_norm_backward + leaky_relu_backward (model.py:95-96, 105-112, 338).
 #pragma once
 #include "elementwise.cuh"
 
@@ -339,139 +339,6 @@ dice_sums2_kernel(const float* __restrict__ partial, int B, int C, int blocks, f
         double t = 0.0;
         for (int q = 0; q < 32; ++q) t += s_p[o * 32 + q];
         sums[which * 4 + c] = (float)t;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Trilinear x2 forward (+LeakyReLU): one CTA per fine line (n, fd, fh); a thread owns one coarse
-// voxel column w of one chunk and produces the fine voxels 2w, 2w+1.  The four coarse lines that
-// feed the fine line are blended first (weights shared by the whole CTA), then the w taps.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-upsample2x_fwd2_kernel(ActRef in, ActRef out, Vol vc, int C, int do_lrelu, FastDiv by_Wc) {
-    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
-    int n, d, h;
-    line_coords(vf, blockIdx.x, n, d, h);
-    int d0, d1, h0, h1;
-    float wd0, wd1, wh0, wh1;
-    up_taps(d, vc.D, d0, d1, wd0, wd1);
-    up_taps(h, vc.H, h0, h1, wh0, wh1);
-    const long long rows[4] = {vc.row(n, d0 + 1, h0 + 1, 1), vc.row(n, d0 + 1, h1 + 1, 1), vc.row(n, d1 + 1, h0 + 1, 1),
-                               vc.row(n, d1 + 1, h1 + 1, 1)};
-    const float cwf[4] = {wd0 * wh0, wd0 * wh1, wd1 * wh0, wd1 * wh1};
-    const long long orow0 = vf.row(n, d + 1, h + 1, 1);
-    const int items = vc.W * (C >> 3);
-    const float2 q25 = f2(0.25f, 0.25f), q75 = f2(0.75f, 0.75f), slope = f2(0.01f, 0.01f);
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int cv = by_Wc.div(i), w = i - cv * vc.W;
-        const int wm = max(w - 1, 0), wp = min(w + 1, vc.W - 1);
-        float2 tm[4], tc[4], tp[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { tm[j] = f2(0.f, 0.f); tc[j] = f2(0.f, 0.f); tp[j] = f2(0.f, 0.f); }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const uint4 qm = ld16(in.at(cv, rows[t] + wm));
-            const uint4 qc = ld16(in.at(cv, rows[t] + w));
-            const uint4 qp = ld16(in.at(cv, rows[t] + wp));
-            const float2 cw = f2(cwf[t], cwf[t]);
-            float2 a[4];
-            unpack4(qm, a);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tm[j] = __ffma2_rn(a[j], cw, tm[j]);
-            unpack4(qc, a);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tc[j] = __ffma2_rn(a[j], cw, tc[j]);
-            unpack4(qp, a);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tp[j] = __ffma2_rn(a[j], cw, tp[j]);
-        }
-        float2 ev[4], od[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 c75 = __fmul2_rn(tc[j], q75);
-            ev[j] = __ffma2_rn(tm[j], q25, c75);
-            od[j] = __ffma2_rn(tp[j], q25, c75);
-            if (do_lrelu) {
-                const float2 se = __fmul2_rn(ev[j], slope), so = __fmul2_rn(od[j], slope);
-                ev[j] = f2(fmaxf(ev[j].x, se.x), fmaxf(ev[j].y, se.y));
-                od[j] = f2(fmaxf(od[j].x, so.x), fmaxf(od[j].y, so.y));
-            }
-        }
-        __nv_bfloat16* o = out.at(cv, orow0 + 2 * w);
-        st16(o, pack4(ev));
-        st16(o + 8, pack4(od));
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Trilinear x2 adjoint (+LeakyReLU backward), separable in two passes:
-//   A: T[n, fd, fh, w] = sum_{fw in taps(w)} ww * dy[fd,fh,fw] * lrelu'(y[fd,fh,fw])    (fine d,h; coarse w)
-//   B: dcoarse[n, d, h, w] = sum_{fd in taps(d), fh in taps(h)} wd*wh * T[n, fd, fh, w]
-// T lives in an act-layout workspace of volume (N, 2D, 2H, W).
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-upsample2x_bwd_w_kernel(ActRef dy, ActRef y, ActRef T, Vol vc, int C, int do_lrelu, FastDiv by_Wc) {
-    Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
-    Vol vt{vc.N, vc.D * 2, vc.H * 2, vc.W};
-    int n, d, h;
-    line_coords(vf, blockIdx.x, n, d, h);
-    const long long irow0 = vf.row(n, d + 1, h + 1, 1);
-    const long long orow0 = vt.row(n, d + 1, h + 1, 1);
-    const int items = vc.W * (C >> 3);
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int cv = by_Wc.div(i), w = i - cv * vc.W;
-        int wi[4];
-        float ww[4];
-        const int nw = down_taps(w, vc.W, wi, ww);
-        float2 acc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = f2(0.f, 0.f);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (t < nw) {
-                float2 g[4];
-                unpack4(ld16(dy.at(cv, irow0 + wi[t])), g);
-                const float2 wt = f2(ww[t], ww[t]);
-                if (do_lrelu) {
-                    float2 yy[4];
-                    unpack4(ld16(y.at(cv, irow0 + wi[t])), yy);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(__fmul2_rn(g[j], lrelu_mask(yy[j])), wt, acc[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(g[j], wt, acc[j]);
-                }
-            }
-        }
-        st16(T.at(cv, orow0 + w), pack4(acc));
-    }
-}
-
-__global__ void __launch_bounds__(128)
-upsample2x_bwd_dh_kernel(ActRef T, ActRef dcoarse, Vol vc, int C, FastDiv by_Wc) {
-    Vol vt{vc.N, vc.D * 2, vc.H * 2, vc.W};
-    int n, d, h;
-    line_coords(vc, blockIdx.x, n, d, h);
-    int di[4], hi[4];
-    float dw[4], hw[4];
-    const int nd = down_taps(d, vc.D, di, dw), nh = down_taps(h, vc.H, hi, hw);
-    const long long orow0 = vc.row(n, d + 1, h + 1, 1);
-    const int items = vc.W * (C >> 3);
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int cv = by_Wc.div(i), w = i - cv * vc.W;
-        float2 acc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = f2(0.f, 0.f);
-        for (int a = 0; a < nd; ++a)
-            for (int b = 0; b < nh; ++b) {
-                float2 g[4];
-                unpack4(ld16(T.at(cv, vt.row(n, di[a] + 1, hi[b] + 1, 1) + w)), g);
-                const float wab = dw[a] * hw[b];
-                const float2 wt = f2(wab, wab);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(g[j], wt, acc[j]);
-            }
-        st16(dcoarse.at(cv, orow0 + w), pack4(acc));
     }
 }
 
