@@ -73,6 +73,7 @@ _PROTOS = {
     "b200_bce_backward": (c_int, [P, P, P, c_float, C.c_double, P, c_ll, P]),
     "b200_conv_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
+    "b200_wgrad_march_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_march_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_band_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_march_prof_read": (c_int, [C.POINTER(C.c_ulonglong), c_int]),

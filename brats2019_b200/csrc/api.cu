@@ -767,9 +767,9 @@ struct WgradMarchPlan {
     unsigned smem;
     int grid;
 };
-static bool plan_wgrad_march(const b200_wgrad_desc* d, WgradMarchPlan& P) {
+static bool plan_wgrad_march(const b200_wgrad_desc* d, WgradMarchPlan& P, bool ignore_switch = false) {
     const char* e = getenv("B200_WGRAD_MARCH");         // read per call: tests switch forms in one process
-    const int off = (e && atoi(e)) ? 0 : 1;
+    const int off = (ignore_switch || (e && atoi(e))) ? 0 : 1;
     if (off || d->mode != 0 || d->Cout != 16 || d->Cin != 16 || d->W % 16 || d->W < 16) return false;
     memset(&P, 0, sizeof(P));
     WgradMarchParams& k = P.k;
@@ -1270,6 +1270,20 @@ extern "C" int b200_march_plan_debug(const b200_conv_desc* d, int* out, int n_ou
                         (int)(p.smem_bar_off + kMarchTailBytes), march_ctas(p), p.Wp, p.SS};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv) return fail("march_plan_debug: need %d ints", nv);
+    for (int i = 0; i < nv; ++i) out[i] = vals[i];
+    return 0;
+}
+
+extern "C" int b200_wgrad_march_plan_debug(const b200_wgrad_desc* d, int* out, int n_out) {
+    WgradMarchPlan P;
+    const bool ok = plan_wgrad_march(d, P, true);       // the plan itself does not depend on the opt-in switch
+    if (!ok) return fail("wgrad_march: does not apply (needs mode 0, 16 x 16 channels, W %% 16 == 0)");
+    const WgradMarchParams& k = P.k;
+    const int vals[] = {k.BH, k.n_bands, (int)k.units, k.ksteps, k.BHs, k.nsub, k.Wp, (int)k.y_plane_bytes,
+                        (int)k.y_sub_bytes, (int)k.y_slot_bytes, (int)k.x_blk_bytes, (int)k.x_stage_bytes,
+                        (int)k.smem_y_off, (int)k.smem_stg_off, (int)k.smem_x_off, (int)P.smem, P.grid};
+    const int nv = (int)(sizeof(vals) / sizeof(int));
+    if (n_out < nv) return fail("wgrad_march_plan_debug: need %d ints", nv);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];
     return 0;
 }

@@ -152,6 +152,8 @@ int b200_bce_backward(const float* probs, const float* target, const float* grad
 /* ---- plan introspection (tests): integer dump of the launch plan ---------------- */
 int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
+/* plan of the marching weight-gradient kernel (3x3x3, 16 x 16 channels, W % 16 == 0); error if it does not apply */
+int b200_wgrad_march_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
 /* plan of the marching 3x3x3 kernel (Cin, Cout <= 32); error if it does not apply to `d` */
 int b200_march_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 /* plan of the band-marching 3x3x3 kernel (16 -> 16 channels, wide lines); error if it does not apply */
