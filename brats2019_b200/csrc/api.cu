@@ -605,7 +605,7 @@ extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const v
     p.stats_partial = stats_partial;
     p.bias = bias; p.probs = probs; p.logits = logits; p.n_out_real = n_out_real;
     {
-        const char* dbg = getenv("B200_CONV_DEBUG");     // perf probes only (tests/perf_probe.py)
+        const char* dbg = getenv("B200_CONV_DEBUG");     // perf probes only (tools/perf_probe.py)
         p.debug = dbg ? atoi(dbg) : 0;
     }
     const int ctas = conv_grid_ctas(p);

@@ -64,7 +64,7 @@ struct MarchParams {
     int debug;                        // perf probes: 1 = skip activation loads, 2 = skip MMAs
 };
 
-// In-kernel cycle accounting for the perf probes (debug bit 256): [cta][16] counters, see tests/perf_probe.py.
+// In-kernel cycle accounting for the perf probes (debug bit 256): [cta][16] counters, see tools/perf_probe.py.
 __device__ unsigned long long g_march_prof[160 * 16];
 #define MARCH_PROF_T(var) if (prof) var = clock64()
 

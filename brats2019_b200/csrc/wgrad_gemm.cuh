@@ -53,7 +53,7 @@ struct WgradKParams {
     int acc_shift;              // rows between the X start addresses of consecutive accumulators: 1 (accumulators = kw
                                 // taps, N-folds = kh taps) or Wp (accumulators = kh taps, N-folds = kw taps)
     int fold_shift;             // rows between consecutive N-fold copies of X: Wp or 1 (the other of the two)
-    int debug;                  // 256: per-role cycle counts into g_march_prof (tests/wgrad_prof.py)
+    int debug;                  // 256: per-role cycle counts into g_march_prof (tools/wgrad_prof.py)
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)

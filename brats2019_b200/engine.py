@@ -101,6 +101,8 @@ class Engine:
         self._side_busy = False
         self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
         self.last = None          # (plan, generation) of the most recent training forward
+        self.tap = None           # tests only: callable(name, Act | tensor) invoked after every backward stage, while
+                                  # the (reused) gradient buffer still holds that stage's result
 
     # ---------------------------------------------------------------------------------
     def plan_for(self, x):
@@ -336,6 +338,11 @@ class Engine:
         self._wait_readers(buf)
         return buf
 
+    def _tap(self, name, value):
+        if self.tap is not None:
+            self._join_side()
+            self.tap(name, value)
+
     def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads):
         """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns grad w.r.t. x_in
         (written into d_in_buf), which includes the identity path (model.py:115)."""
@@ -350,13 +357,18 @@ class Engine:
         # Each weight gradient is queued on the side stream AFTER the data-gradient conv that shares its input:
         # it then runs next to the memory-bound GroupNorm-backward kernels that follow (the two tensor-core
         # kernels cannot share an SM: both need more than half of its shared memory).
+        self._tap("g:" + prefix + "d_out", d_out)
+        self._tap("g:" + prefix + "dc2", dc2)
         g2 = grads.new(w2n, prm[w2n])
         da1 = self._dgrad3(P, lvl, w2n, prm[w2n], dc2, t1)
+        self._tap("g:" + prefix + "da1", da1)
         self._wgrad(P, lvl, 0, dc2, a1, g2, ops.G_K3, overlap=True)
         dc1 = self._gn_bwd(P, lvl, prefix + "c1", c1, da1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
                            self._dc_buf(P, lvl, Cc), grads, prefix + "norm1.weight", prefix + "norm1.bias")
+        self._tap("g:" + prefix + "dc1", dc1)
         g1 = grads.new(w1n, prm[w1n])
         dx = self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out)
+        self._tap("g:" + prefix + "dx", dx)
         self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3, overlap=True)
         return dx
 
@@ -394,7 +406,9 @@ class Engine:
         def gbuf(name, lvl, Cc):
             return P.act("g." + name, lvl, Cc)
 
+        self._tap("g:dlogit", dlog)
         cur = self._dgrad3(P, 0, "conv_output.weight", prm["conv_output.weight"], dlog, gbuf("A", 0, ch[0]))
+        self._tap("g:final_h", cur)
         cur_name = "A"
         self._wgrad(P, 0, 0, dlog, h_last, g_out, ops.G_K3, overlap=True)
 
@@ -414,18 +428,22 @@ class Engine:
             wname = "decoder_convs1x1.%d.weight" % i
             w = prm[wname]
             up = P.act("dec%d.up" % i, i, ch[i])
+            self._tap("g:dec%d.cc" % i, cur)
             self._wgrad(P, i, 1, cur, P.act("dec%d.cat" % i, i, 2 * ch[i]), grads.new(wname, w), ops.G_K1)
             self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf("cat", i, 2 * ch[i]))       # [dskip | dup] in one GEMM
+            self._tap("g:dec%d.cat" % i, gbuf("cat", i, 2 * ch[i]))
             dskip[i] = gbuf("skip", i, ch[i])
             dup = gbuf("dup", i, ch[i])
             # lrelu + trilinear adjoint (model.py:421-422)
             dulo = ops.upsample2x_backward(dup, up, gbuf("ulo", i + 1, ch[i]), lrelu=True)
+            self._tap("g:dec%d.ulo" % i, dulo)
             wname = "upsampling.%d.1.weight" % i
             w = prm[wname]
             h_lo = self._level_output(P, i + 1)
             self._wgrad(P, i + 1, 1, dulo, h_lo, grads.new(wname, w), ops.G_K1)
             self._mark(grads)
             cur = self._conv1(P, i + 1, wname, w, ops.W_DGRAD, dulo, gbuf("A", i + 1, ch[i + 1]))
+            self._tap("g:dec%d.h_lo" % i, cur)
             cur_name = "A"
         # At this point `cur` is the gradient w.r.t. the bottleneck output (encoder level depth-1).
         # ---- encoder, levels depth-1 .. 1 ----
@@ -440,11 +458,14 @@ class Engine:
             wname = "encoder_convs.%d.0.downsample.0.weight" % i
             w = prm[wname]
             s2d = P.act("enc%d.s2d" % i, lvl, 8 * ch[i])
+            self._tap("g:enc%d.down" % i, cur)
             self._wgrad(P, lvl, 1, cur, s2d, grads.new(wname, w), ops.G_S2D)
             self._mark(grads)
             ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
             # back to the fine grid, adding the skip-connection gradient from the decoder
+            self._tap("g:enc%d.s2d" % i, ds2d)
             cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
+            self._tap("g:enc%d.skip_total" % i, cur)
             cur_name = "A"
         # ---- level 0 head ----
         for j in reversed(range(self.enc[0])):
@@ -455,6 +476,8 @@ class Engine:
             cur_name = nxt
         dcin = self._gn_bwd(P, 0, "in.c", P.act("in.c", 0, ch[0]), cur, prm["norm_input.weight"], prm["norm_input.bias"],
                             gbuf(other(cur_name), 0, ch[0]), grads, "norm_input.weight", "norm_input.bias", lrelu=False)
+        self._tap("g:in.a", cur)
+        self._tap("g:in.c", dcin)
         self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), grads.new("conv_input.weight", prm["conv_input.weight"]),
                     ops.G_K3)
         self._join_side()

@@ -2,19 +2,31 @@
 against (a) golden vectors produced by the real reference and (b) the fp32 oracle at larger
 sizes.
 
-Stated tolerance.  The kernels store activations in bf16 and accumulate in fp32; the reference
-is fp32.  The yardstick for "bf16-correct" is the reference arithmetic itself under
-torch.autocast(bfloat16) on the same GPU (the oracle run under autocast): SURVEY.md 7.2 measured
-that even this differs from fp32 by ~1% of max|logit| and flips ~0.3% of thresholded voxels.
-Every statistic must satisfy BOTH an absolute cap and "<= 1.5x the yardstick's own error"
-(2x for the two max-over-all-voxels statistics, which are single-sample extremes):
+Three layers of evidence, tightest first:
+
+ 1. tests/test_layer_parity_gpu.py - every stage of the engine, forward and backward, against the oracle's
+    restatement applied to the engine's own inputs: one-ulp-exact (rel-L2 <= 5e-4 per stored tensor, <= 2e-4 per
+    weight gradient).  That is the pin that can see a wrong tap.
+ 2. Here, whole model vs the bf16-storage EMULATION of itself (oracle.train_step_bf16_emulated): not limited by
+    the storage format, but by the chaotic amplification of one-ulp rounding flips through 60 stored tensors
+    (profiles/r02_layer_trace.txt), so it can only be required to be CLOSER than the fp32 comparison:
+    mean logit error <= 0.85x and median gradient error <= 0.9x of the respective error against fp32.
+ 3. Here, whole model vs the fp32 reference (golden vectors of the real reference / the fp32 oracle).  The
+    kernels store activations in bf16 and accumulate in fp32; the reference is fp32.  The yardstick for
+    "bf16-correct" is the reference arithmetic itself under torch.autocast(bfloat16) on the same GPU
+    (even that differs from fp32 by ~1% of max|logit| and flips ~0.3% of thresholded voxels).
+    Every statistic must satisfy BOTH an absolute cap and "<= 1.5x the yardstick's own error" (2x for the two
+    max-over-all-voxels statistics, which are single-sample extremes):
 
     logits     max-abs err <= 3% of max|logit|;  mean-abs err <= 2% of mean|logit|
     probs      max-abs err <= 0.08
     masks      Dice(mask_cuda, mask_ref) >= 0.98 per channel (threshold 0.5, test.py:144)
-    Dice loss  |loss - ref| <= 2e-3
-    gradients  per-tensor relative L2 err: max <= 0.20, median <= 0.06
-(profiles/r01_parity_report.txt holds the measured numbers next to the yardstick.)
+    metrics.Dice(mask, target) (metrics.py:108-133): |cuda - ref| <= 5e-3 per sample and channel (<= 2.5e-3 at
+               the config-3 shape; measured 1.6e-3 there - the north star's 1e-3 is not reachable with bf16
+               storage, the yardstick misses it too)
+    Dice loss  |loss - ref| <= 1e-3   (north star: 1e-3; measured <= 4e-4)
+    gradients  per-tensor relative L2 err: max <= 0.20, median <= 0.06 (<= 0.08 / 0.02 at the config-3 shape)
+(profiles/r02_parity_report.txt holds the measured numbers next to the yardstick.)
 """
 import numpy as np
 import pytest
@@ -24,7 +36,8 @@ from oracle import resunet_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-CAP = dict(logit_max=0.03, logit_mean=0.02, prob=0.08, mask_dice=0.98, loss=2e-3, grad_max=0.20, grad_median=0.06)
+CAP = dict(logit_max=0.03, logit_mean=0.02, prob=0.08, mask_dice=0.98, loss=1e-3, grad_max=0.20, grad_median=0.06,
+           metric=5e-3)
 YARD = 1.5
 
 
@@ -62,6 +75,47 @@ def _yardstick(sd, x, t):
     st = _fwd_stats(lb, ref_logits)
     st.update(grad_max=rel.max().item(), grad_median=rel.median().item())
     return st
+
+
+def _grad_rels(model, ref_grads):
+    out = {}
+    for n, p in model.named_parameters():
+        if p.grad is not None and n in ref_grads:
+            ref = torch.as_tensor(ref_grads[n]).to(p.grad.device).float()
+            out[n] = ((p.grad - ref).norm() / ref.norm().clamp_min(1e-20)).item()
+    return out
+
+
+def _emulated(sd, x, t, with_bce=False):
+    """The bf16-storage emulation of the CUDA pipeline (oracle), fp32 torch ops on this GPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    loss, probs, logits, grads = O.train_step_bf16_emulated(sdc, x.cuda(), t.cuda(), with_bce=with_bce)
+    return loss, logits, grads
+
+
+def _check_closer_to_emulation(model, logits, ref_logits, ref_grads, em_logits, em_grads, tag):
+    """Evidence layer 2 of the module docstring."""
+    ref_logits = ref_logits.to(logits.device)
+    e_ref = (logits - ref_logits).abs().mean().item()
+    e_em = (logits - em_logits).abs().mean().item()
+    r_ref = torch.tensor(list(_grad_rels(model, ref_grads).values())).median().item()
+    r_em = torch.tensor(list(_grad_rels(model, em_grads).values())).median().item()
+    print(tag, "mean |dlogit| vs fp32 %.5f vs bf16-emulated %.5f | median grad rel-L2 vs fp32 %.5f vs emulated %.5f" % (
+        e_ref, e_em, r_ref, r_em))
+    assert e_em <= 0.85 * e_ref, (tag, e_em, e_ref)
+    assert r_em <= 0.9 * r_ref, (tag, r_em, r_ref)
+
+
+def _check_metric(probs, ref_probs, target, tag, cap=None):
+    """metrics.Dice (metrics.py:108-133) of the thresholded masks against the target: CUDA vs reference."""
+    ref_probs, target = ref_probs.to(probs.device), target.to(probs.device)
+    a = O.dice_metric(O.threshold_masks(probs), target > 0.5)
+    b = O.dice_metric(O.threshold_masks(ref_probs), target > 0.5)
+    d = (a - b).abs().max().item()
+    print(tag, "metrics.Dice(mask, target): max |cuda - ref| %.2e (ref values %s)" % (d, [round(v, 4) for v in b.flatten().tolist()]))
+    assert d <= (cap or CAP["metric"]), (tag, d)
 
 
 def _check_forward(probs, logits, ref_logits, yard, tag):
@@ -120,6 +174,9 @@ def test_forward_and_backward_match_reference_golden(golden, case):
     loss.backward()
     ref = {k[len("gdice::"):]: g[k] for k in g.files if k.startswith("gdice::")}
     _check_grads(m, ref, yard, case)
+    _check_metric(out[0].detach(), torch.from_numpy(g["probs"]), t, case)
+    _, em_logits, em_grads = _emulated(sd, torch.from_numpy(g["x"]), t)
+    _check_closer_to_emulation(m, logits, torch.from_numpy(g["logits"]), ref, em_logits, em_grads, case)
     names = [str(n) for n in g["live_names"]]
     prm = dict(m.named_parameters())
     got = np.array([prm[n].grad.double().norm().item() for n in names])
@@ -137,7 +194,9 @@ def test_forward_and_backward_match_reference_golden(golden, case):
 
 # (3, 8, 16, 24): odd batch, one slice at the deepest level (D/8 = 1); (1, 24, 40, 72): no dimension a multiple
 # of 16 at level 1+, ragged tiles everywhere; (1, 128, 128, 128): one volume of the benchmark size (config 1/3).
-@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 32, 48, 64), (3, 8, 16, 24), (1, 24, 40, 72), (1, 128, 128, 128)])
+# (2, 128, 128, 128): BASELINE config 3 exactly.
+@pytest.mark.parametrize("shape", [(1, 32, 32, 32), (2, 32, 48, 64), (3, 8, 16, 24), (1, 24, 40, 72), (1, 128, 128, 128),
+                                   (2, 128, 128, 128)])
 def test_matches_oracle_at_larger_sizes(shape):
     import brats2019_b200 as B
     N, D, H, W = shape
@@ -156,6 +215,15 @@ def test_matches_oracle_at_larger_sizes(shape):
     assert abs(loss.item() - loss_ref.item()) <= CAP["loss"]
     loss.backward()
     _check_grads(m, grads_ref, yard, "oracle %s" % (shape,))
+    big = D * H * W >= 128 ** 3
+    _check_metric(out[0].detach(), probs_ref, t, "oracle %s" % (shape,), cap=2.5e-3 if big else None)
+    if big:          # the benchmark shape: enough voxels per weight for much tighter gradient statistics
+        rels = torch.tensor(list(_grad_rels(m, grads_ref).values()))
+        assert rels.max().item() <= 0.08 and rels.median().item() <= 0.02, (rels.max().item(), rels.median().item())
+    _, em_logits, em_grads = _emulated(sd, x, t)
+    _check_closer_to_emulation(m, logits, logits_ref, grads_ref, em_logits, em_grads, "oracle %s" % (shape,))
+    del m
+    torch.cuda.empty_cache()
 
 
 def test_eval_and_train_paths_agree_and_are_repeatable():

@@ -111,3 +111,67 @@ def test_product_tiler_matches_oracle_tiler_on_cpu_tensors():
     xp, l, r = I.pad_to_multiple(x, 16)
     assert xp.shape[2:] == (32, 16, 16) and torch.equal(I.unpad(xp, l, r), x)
     assert [I.closest_to_k(v, 16) for v in (155, 240, 160, 16)] == [160, 240, 160, 16]
+
+
+# ---- the bf16-storage emulation of the CUDA path (oracle section "bf16-storage emulation") --------------------
+@pytest.mark.parametrize("case", CASES)
+def test_emulation_without_rounding_is_the_reference(golden, case):
+    """With every rounding switched off, the emulated pipeline (commuted 1x1, hand-written GroupNorm and trilinear
+    backward, statistics from the conv accumulators) must reproduce the real reference's golden vectors."""
+    g = golden(case)
+    sd = O.init_params(int(g["weight_seed"]))
+    x = torch.from_numpy(g["x"])
+    t = torch.from_numpy(g["target"]).float()
+    for with_bce, key in ((False, "gdice::"), (True, "gboth::")):
+        with O.rounding(False):
+            loss, probs, logits, grads = O.train_step_bf16_emulated(sd, x, t, with_bce=with_bce)
+        np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=5e-5)
+        np.testing.assert_allclose(probs.numpy(), g["probs"], rtol=0, atol=1e-5)
+        for k in g.files:
+            if k.startswith(key):
+                ref = g[k]
+                got = grads[k[len(key):]].numpy()
+                assert np.abs(got - ref).max() <= 3e-4 * max(np.abs(ref).max(), 1e-12) + 1e-9, k
+
+
+def test_emulation_with_rounding_stays_at_the_bf16_noise_floor(golden):
+    g = golden("box16x24x32_b2")
+    sd = O.init_params(int(g["weight_seed"]))
+    x = torch.from_numpy(g["x"])
+    t = torch.from_numpy(g["target"]).float()
+    loss, probs, logits, grads = O.train_step_bf16_emulated(sd, x, t)
+    ref = torch.from_numpy(g["logits"])
+    err = (logits - ref).abs()
+    assert 1e-3 < err.mean().item() / ref.abs().mean().item() < 2e-2        # rounded, but only at bf16 level
+    assert abs(loss.item() - float(g["dice"])) < 1e-3
+    rel = [np.linalg.norm(grads[k[7:]].numpy() - g[k]) / max(np.linalg.norm(g[k]), 1e-20) for k in g.files if k.startswith("gdice::")]
+    assert 1e-3 < float(np.median(rel)) < 6e-2 and max(rel) < 0.2
+
+
+def test_emulated_trilinear_adjoint_is_the_autograd_adjoint():
+    x = torch.randn(2, 3, 4, 6, 5, dtype=torch.float64, requires_grad=True)
+    y = x
+    for dim in (4, 3, 2):
+        y = O._up1d(y, dim)
+    np.testing.assert_allclose(y.detach().numpy(), O.trilinear_x2(x.detach()).numpy(), atol=1e-12)
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    with O.rounding(False):
+        mine = O._up1d_adjoint(O._up1d_adjoint(O._up1d_adjoint(gy, 4), 3), 2)
+    np.testing.assert_allclose(mine.numpy(), gx.numpy(), atol=1e-12)
+
+
+def test_emulated_groupnorm_backward_is_the_autograd_backward():
+    torch.manual_seed(0)
+    c = torch.randn(2, 16, 3, 4, 5, dtype=torch.float64, requires_grad=True)
+    gamma = torch.randn(16, dtype=torch.float64, requires_grad=True)
+    beta = torch.randn(16, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.leaky_relu(torch.nn.functional.group_norm(c, 8, gamma, beta, O.GN_EPS), O.LRELU_SLOPE)
+    gy = torch.randn_like(y)
+    gc, gg, gb = torch.autograd.grad(y, (c, gamma, beta), gy)
+    with O.rounding(False):
+        mean, rstd = O.gn_stats_emulated(c.detach())
+        dx, dg, db = O.gn_backward_emulated(c.detach(), mean.double(), rstd.double(), gamma.detach(), beta.detach(), gy, True)
+    np.testing.assert_allclose(dx.numpy(), gc.numpy(), atol=2e-6)
+    np.testing.assert_allclose(dg.numpy(), gg.numpy(), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(db.numpy(), gb.numpy(), rtol=2e-6, atol=2e-6)

@@ -1,7 +1,7 @@
 """The dominant kernel alone (3x3x3 C->C implicit GEMM at level `lvl` of a B x 4xS^3 step) for
 
     ncu --set full --clock-control none --import-source on -k regex:conv_gemm --launch-skip 3 -c 1 \
-        -o gpurun_out/prof_conv python tests/conv_for_ncu.py [B] [S] [C]
+        -o gpurun_out/prof_conv python tools/conv_for_ncu.py [B] [S] [C]
 """
 import os
 import sys

@@ -1,6 +1,6 @@
 """Multi-GPU parity (run under torchrun, one rank per GPU):
 
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/ddp_parity.py
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ddp_parity.py
 
 Each rank takes its shard of a global batch; the Dice sums and the gradients are all-reduced
 (brats2019_b200.parallel).  Rank 0 then runs the SAME global batch alone and compares loss and

@@ -1,5 +1,5 @@
 """GroupNorm forward-apply / backward and the trilinear kernels alone at bench shapes, for ncu:
-    ncu --set full --clock-control none --import-source on -k regex:'gn_|upsample' --launch-skip N -c M -o ... python tests/gn_for_ncu.py [B] [S] [C]"""
+    ncu --set full --clock-control none --import-source on -k regex:'gn_|upsample' --launch-skip N -c M -o ... python tools/gn_for_ncu.py [B] [S] [C]"""
 import os
 import sys
 

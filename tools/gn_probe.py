@@ -1,4 +1,4 @@
-"""GroupNorm kernel timings at one level (perf diagnostic): python tests/gn_probe.py [B] [S] [C]"""
+"""GroupNorm kernel timings at one level (perf diagnostic): python tools/gn_probe.py [B] [S] [C]"""
 import os
 import sys
 

@@ -1,5 +1,5 @@
 """In-kernel cycle accounting of the marching conv (perf diagnostic, GPU box):
-    python tests/march_prof.py [B] [S] [C] [debugflags]
+    python tools/march_prof.py [B] [S] [C] [debugflags]
 Runs the C->C 3x3x3 conv with B200_CONV_DEBUG = 256 | flags and prints per-role averages over CTAs."""
 import ctypes as C
 import os

@@ -1,5 +1,5 @@
 """Does a weight-gradient GEMM overlap with the memory-bound kernels when queued on another stream?
-(perf diagnostic, GPU box):  python tests/overlap_probe.py [B] [S] [C]"""
+(perf diagnostic, GPU box):  python tools/overlap_probe.py [B] [S] [C]"""
 import os
 import sys
 

@@ -2,9 +2,11 @@
 yardstick "the reference arithmetic itself in bf16" (the oracle under torch.autocast(bfloat16)
 on the same GPU, i.e. stock PyTorch/cuDNN bf16), on the same weights and inputs.
 
-    python tests/parity_report.py [N D H W]...     # default: a few small/medium shapes
+    python tools/parity_report.py [N D H W]...     # default: a few small/medium shapes
 
-Prints one block per shape; `profiles/r01_parity_report.txt` is a committed copy.
+Third line per shape: the CUDA path against the bf16-storage EMULATION of itself
+(oracle.train_step_bf16_emulated: the reference algorithm with roundings where the kernels store) - the
+comparison that is not limited by the bf16 noise floor.  `profiles/r02_parity_report.txt` is a committed copy.
 """
 import os
 import sys
@@ -69,6 +71,9 @@ def main():
         grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
         fo, fb = stats_forward(logits, logits_ref), stats_forward(logits_bf, logits_ref)
         go, gb = stats_grads(grads, grads_ref), stats_grads(grads_bf, grads_ref)
+        loss_em, probs_em, logits_em, grads_em = O.train_step_bf16_emulated(sd_cuda, x, t)
+        fe, ge = stats_forward(logits, logits_em), stats_grads(grads, grads_em)
+        dm = (O.dice_metric(out[0].detach() > 0.5, t > 0.5) - O.dice_metric(torch.sigmoid(logits_ref) > 0.5, t > 0.5)).abs().max().item()
         print("shape N=%d %dx%dx%d  |logit| max %.2f mean %.3f  dice loss ref %.6f" % (
             N, D, H, W, logits_ref.abs().max().item(), logits_ref.abs().mean().item(), loss_ref.item()))
         for tag, f, gg, l in (("b200 kernels ", fo, go, loss.item()), ("torch bf16 AMP", fb, gb, loss_bf.item())):
@@ -76,6 +81,10 @@ def main():
                   "loss diff %.2e | grad rel-L2 max %.4f median %.4f (%s)" % (
                       tag, f["max_rel"], f["mean_rel"], f["prob_max"], f["flipped"], f["mask_dice"],
                       abs(l - loss_ref.item()), gg["max"], gg["median"], gg["worst"]))
+        print("  b200 vs bf16-emulated oracle: logits max-err/max %.5f mean-err/mean %.5f | prob max-err %.5f | mask flipped %.6f "
+              "dice %.6f | loss diff %.2e | grad rel-L2 max %.5f median %.5f (%s) | metrics.Dice(mask,target) diff vs fp32 ref %.2e" % (
+                  fe["max_rel"], fe["mean_rel"], fe["prob_max"], fe["flipped"], fe["mask_dice"], abs(loss.item() - loss_em.item()),
+                  ge["max"], ge["median"], ge["worst"], dm))
         sys.stdout.flush()
         del m
 

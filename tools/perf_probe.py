@@ -2,7 +2,7 @@
 of the benchmark (batch B x 4x128^3), CUDA events, 3 warm-ups, L2-cold inputs are not needed for
 the large levels (tensors >> L2) and noted for the small ones.
 
-    python tests/perf_probe.py [B] [S]
+    python tools/perf_probe.py [B] [S]
 Prints `name  ms  TFLOP/s | GB/s  (fraction of measured peak)`.
 """
 import json

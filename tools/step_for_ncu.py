@@ -1,7 +1,7 @@
 """One training step (or one forward) of the drop-in UNet between cudaProfilerStart/Stop, for
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-        --log-file gpurun_out/launches.csv python tests/step_for_ncu.py [B] [S] [fwd]
+        --log-file gpurun_out/launches.csv python tools/step_for_ncu.py [B] [S] [fwd]
 
 (launch list of exactly one step; kernels are launched one by one, no CUDA graph)."""
 import os

@@ -1,5 +1,5 @@
 """Per-kernel device time of the steady-state training step (CUDA-graph replay) via torch.profiler / CUPTI:
-    python tests/step_profile.py [B] [S] [steps]
+    python tools/step_profile.py [B] [S] [steps]
 Prints kernel families sorted by total time per step, the sum, and the graph's wall time per step (the
 difference is idle time between kernels)."""
 import os

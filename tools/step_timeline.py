@@ -1,7 +1,7 @@
 """Timeline of one steady-state training step (CUDA-graph replay): every kernel's start, duration and stream from
 CUPTI (torch.profiler), written as CSV for offline analysis of the main-stream / side-stream overlap.
 
-    python tests/step_timeline.py [B] [S] [out.csv]
+    python tools/step_timeline.py [B] [S] [out.csv]
 """
 import os
 import sys

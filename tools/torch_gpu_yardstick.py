@@ -3,7 +3,7 @@ B200 - the oracle restatement on CUDA, i.e. cuDNN convolutions + ATen GroupNorm/
 bf16 autocast, at the bench workload (train step on B x 4xS^3, forward on the same batch).  SURVEY.md 8d asks
 for this next to the CPU baseline; it is what a user of the reference gets by just moving to a B200.
 
-    python tests/torch_gpu_yardstick.py [B] [S] [reps]
+    python tools/torch_gpu_yardstick.py [B] [S] [reps]
 Prints one JSON line per mode: ms per train step (fwd + Dice + autograd backward, no optimizer) and per forward."""
 import json
 import os

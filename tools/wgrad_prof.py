@@ -1,5 +1,5 @@
 """In-kernel cycle accounting of the weight-gradient GEMM (perf diagnostic, GPU box):
-    python tests/wgrad_prof.py [B] [S] [C]
+    python tools/wgrad_prof.py [B] [S] [C]
 Runs the C x C 3x3x3 weight gradient with B200_WGRAD_DEBUG=256 and prints per-role averages over CTAs."""
 import ctypes as C
 import os

@@ -1,5 +1,5 @@
 """Per-kernel device time of one weight-gradient call (gemm + reduce) via torch.profiler:
-    python tests/wgrad_profile.py [B] [S] [C]"""
+    python tools/wgrad_profile.py [B] [S] [C]"""
 import os
 import sys
 from collections import defaultdict
