@@ -127,11 +127,19 @@ def test_emulation_without_rounding_is_the_reference(golden, case):
             loss, probs, logits, grads = O.train_step_bf16_emulated(sd, x, t, with_bce=with_bce)
         np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=5e-5)
         np.testing.assert_allclose(probs.numpy(), g["probs"], rtol=0, atol=1e-5)
+        # Gradients: the fp32 autograd of the reference itself carries up to ~1 % error on a few tensors of this tiny
+        # case (its GroupNorm backward cancels badly on 128-element groups: fp32 oracle vs float64 oracle differ by
+        # 9e-3), so the tight comparison is against the oracle in float64 and the golden comparison is loose.
+        sdd = {k: v.double() for k, v in sd.items()}
+        _, _, g64 = O.train_step(sdd, x.double(), t.double(), with_bce=with_bce)
+        for k, ref in g64.items():
+            got = grads[k].double()
+            assert ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item() <= 1e-4, k
         for k in g.files:
             if k.startswith(key):
                 ref = g[k]
                 got = grads[k[len(key):]].numpy()
-                assert np.abs(got - ref).max() <= 3e-4 * max(np.abs(ref).max(), 1e-12) + 1e-9, k
+                assert np.linalg.norm(got - ref) <= 2e-2 * max(np.linalg.norm(ref), 1e-12), k
 
 
 def test_emulation_with_rounding_stays_at_the_bf16_noise_floor(golden):
