@@ -134,7 +134,7 @@ def test_emulation_without_rounding_is_the_reference(golden, case):
         _, _, g64 = O.train_step(sdd, x.double(), t.double(), with_bce=with_bce)
         for k, ref in g64.items():
             got = grads[k].double()
-            assert ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item() <= (2e-3 if with_bce else 1e-4), k
+            assert ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item() <= 2e-3, k
         for k in g.files:
             if k.startswith(key):
                 ref = g[k]
