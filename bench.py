@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of one CUDA graph per step")
+    ap.add_argument("--torch-adam", action="store_true", help="stock torch.optim.Adam(fused=True) instead of brats2019_b200.optim.FusedAdam")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,8 +248,13 @@ def run(args, rank, world, local_rank, dev):
         net = DistributedUNet(model)
         crit.process_group = net.process_group
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True,
-                           capturable=use_graph, fused=True)                                # main.py:133-140 (stock torch Adam, fused impl)
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True,
+                               capturable=use_graph, fused=True)                            # main.py:133-140 (stock torch Adam, fused impl)
+    else:
+        from brats2019_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True, lr_step_size=16000, lr_gamma=0.5,
+                        model=net)                                                          # main.py:133-142 as one kernel
 
     g = torch.Generator().manual_seed(100 + rank)
     x_host = torch.randn(Bsz, 4, S, S, S, generator=g).pin_memory()

@@ -71,6 +71,8 @@ _PROTOS = {
     "b200_bce_sum": (c_int, [P, P, c_float, P, P, c_ll, P]),
     "b200_bce_loss": (c_int, [P, C.c_double, P, P]),
     "b200_bce_backward": (c_int, [P, P, P, c_float, C.c_double, P, c_ll, P]),
+    "b200_adam_step": (c_int, [P, P, P, P, P, C.POINTER(c_ll), C.POINTER(c_ll), c_int, P, P, P, C.c_double, C.c_double, c_float,
+                               c_float, c_int, c_float, P]),
     "b200_conv_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_march_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),

@@ -20,6 +20,7 @@
 #include "wgrad_march.cuh"
 #include "elementwise3.cuh"
 #include "elementwise4.cuh"
+#include "optimizer.cuh"
 
 using namespace b200;
 
@@ -1225,6 +1226,43 @@ extern "C" int b200_bce_backward(const float* probs, const float* target, const 
     bce_bwd_kernel<<<dice_blocks() * 2, kEwThreads, 0, (cudaStream_t)stream>>>(probs, target, grad_out, bg_weight,
                                                                               (float)(1.0 / global_numel), grad_probs, numel);
     LAUNCH_OK("bce_bwd_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused Adam (optimizer.cuh): main.py:133-138, train.py:220
+// ---------------------------------------------------------------------------------------
+extern "C" int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                              const long long* seg_begin, const long long* seg_len, int n_segs, const float* lr,
+                              float* step, unsigned* ticket, double beta1, double beta2, float eps, float weight_decay,
+                              int lr_step_size, float lr_gamma, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step || !ticket) return fail("adam: null argument");
+    if (n_segs < 1 || n_segs > kAdamMaxSegs) return fail("adam: 1..%d segments supported, got %d", kAdamMaxSegs, n_segs);
+    if (check_ptr16(params, "adam params") || check_ptr16(grads, "adam grads") || check_ptr16(exp_avg, "adam exp_avg") ||
+        check_ptr16(exp_avg_sq, "adam exp_avg_sq") || check_ptr16(max_exp_avg_sq, "adam max_exp_avg_sq"))
+        return 1;
+    AdamParams q;
+    memset(&q, 0, sizeof(q));
+    q.p = params; q.g = grads; q.m = exp_avg; q.v = exp_avg_sq; q.vmax = max_exp_avg_sq;
+    q.lr = lr; q.step = step; q.ticket = ticket;
+    q.beta1 = (float)beta1; q.beta2 = (float)beta2; q.eps = eps; q.weight_decay = weight_decay;
+    q.beta1d = beta1; q.beta2d = beta2;
+    q.one_minus_beta1 = (float)(1.0 - beta1); q.one_minus_beta2 = (float)(1.0 - beta2);
+    q.lr_step_size = lr_step_size; q.lr_gamma = lr_gamma;
+    q.segs.n = n_segs;
+    long long cum = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        if (seg_begin[i] % 4 || seg_len[i] % 4 || seg_len[i] <= 0) return fail("adam: segments must be non-empty multiples of 4 floats");
+        q.segs.begin[i] = seg_begin[i] / 4;
+        q.segs.cum[i] = cum;
+        cum += seg_len[i] / 4;
+    }
+    q.segs.cum[n_segs] = cum;
+    // ~2 float4 per thread per pass, at most 4 CTAs per SM: the kernel is a pure stream over 36 bytes per element
+    const long long want = (cum + 2LL * kAdamThreads - 1) / (2LL * kAdamThreads);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, 4LL * num_sms()));
+    adam_step_kernel<<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(q);
+    LAUNCH_OK("adam_step_kernel");
     return 0;
 }
 

@@ -33,6 +33,7 @@ class _Plan:
         self.acts = {}
         self.misc = {}
         self.generation = 0
+        self.pinned = False
 
     def act(self, name, level, Cc):
         key = (name, level, Cc)
@@ -90,8 +91,15 @@ class Engine:
             raise RuntimeError("brats2019_b200: channel counts must be multiples of 16 and <= 128, got %s" % self.ch)
         if self.n_out > 4:
             raise RuntimeError("brats2019_b200: at most 4 output channels supported")
+        supported = (16, 32, 64, 128)
+        if any(c not in supported for c in self.ch):
+            raise RuntimeError("brats2019_b200: the conv kernels exist for %s channels only, got %s" % (supported, self.ch))
         self.plans = {}
+        self.max_plans = 4        # input shapes whose buffers stay resident (least recently used are freed)
         self.packed = {}
+        self._packed_dirty = False
+        self._checked_devices = set()
+        self.grad_order = None    # parameter names in the order Engine.backward produces their gradients
         self.pack_table = ops.PackTable()
         # weight gradients run on a side stream, concurrently with the memory-bound kernels of the
         # data-gradient chain (GroupNorm backward etc.): a wgrad GEMM at 16/32 channels is bound by MMA issue
@@ -112,11 +120,38 @@ class Engine:
             raise RuntimeError("brats2019_b200: input must be (N,4,D,H,W) with D,H,W divisible by %d, got %s"
                                % (q, tuple(x.shape)))
         key = (N, D, H, W, x.device.index)
-        p = self.plans.get(key)
+        p = self.plans.pop(key, None)
         if p is None:
+            if x.device.index not in self._checked_devices:
+                ops.check(ops._lib.lib().b200_device_check(x.device.index), "b200_device_check")
+                self._checked_devices.add(x.device.index)
             p = _Plan(N, D, H, W, self.depth, x.device)
-            self.plans[key] = p
+            # test.py crops every case to its own bounding box: a validation sweep sees many shapes, each worth GBs of
+            # buffers.  Keep the most recently used few; a plan with a pending backward is never the oldest.
+            while len(self.plans) >= self.max_plans and not torch.cuda.is_current_stream_capturing():
+                victim = next((k for k, q in self.plans.items() if not q.pinned), None)
+                if victim is None:
+                    break
+                self._join_side()
+                self.plans.pop(victim)
+        if torch.cuda.is_current_stream_capturing():
+            p.pinned = True            # a CUDA graph holds raw pointers into these buffers
+        self.plans[key] = p            # most recently used last
         return p
+
+    def free_plans(self):
+        """Drop every cached activation buffer (they are re-allocated on the next forward)."""
+        self._join_side()
+        self.plans.clear()
+        self.last = None
+        ops.free_workspaces()
+
+    def invalidate_packed(self):
+        """The packed bf16 weight images are refreshed when a parameter's version counter or storage changes.
+        Anything that rewrites weights WITHOUT bumping the version - `p.data` edits (weight_init.py:22-27 does
+        `init.kaiming_normal_(m.weight.data)`), `dist.broadcast(p.data)`, a CUDA-graph replay that contains an
+        optimizer step - must call this; the model's own hooks do so for load_state_dict / apply / _apply."""
+        self._packed_dirty = True
 
     def _params(self):
         return dict(self.m.named_parameters())
@@ -147,7 +182,7 @@ class Engine:
         if not self.packed:
             return
         capturing = torch.cuda.is_current_stream_capturing()
-        stale = capturing
+        stale = capturing or self._packed_dirty
         if not stale:
             for ent in self.packed.values():
                 w = self.pack_table.jobs[ent[2]][2]
@@ -159,6 +194,8 @@ class Engine:
             for ent in self.packed.values():
                 w = self.pack_table.jobs[ent[2]][2]
                 ent[0] = (w._version, w.data_ptr())
+            if not capturing:
+                self._packed_dirty = False
 
     # ---------------------------------------------------------------------------------
     # building blocks
@@ -262,6 +299,11 @@ class Engine:
         if training:
             self.last = (P, P.generation, probs)
         return (probs, logits) if want_logits else probs
+
+    def saved_state(self):
+        """(plan, generation, probs) of the training forward that just ran: what its autograd node must hand back
+        to `backward` (the activations live in the plan's buffers, not in the node)."""
+        return self.last
 
     # ---------------------------------------------------------------------------------
     # backward
@@ -379,17 +421,26 @@ class Engine:
             self._join_side()
         grads.mark()
 
-    def backward(self, gprobs, store=None):
+    def backward(self, gprobs, store=None, state=None):
         """gprobs: fp32 (N, n_out, D, H, W) gradient w.r.t. the returned probabilities.
         Returns {parameter name: fp32 gradient} for the live parameters.  `store` decides where
         gradients live (GradStore: fresh tensors; parallel.BucketedAllReduce: views of one flat
-        buffer, all-reduced bucket by bucket while the rest of backward still runs)."""
-        if self.last is None:
+        buffer, all-reduced bucket by bucket while the rest of backward still runs).
+        `state`: the `saved_state()` of the forward this backward belongs to (default: the latest)."""
+        state = state if state is not None else self.last
+        if state is None:
             raise RuntimeError("brats2019_b200: backward without a training forward")
-        P, gen, probs = self.last
+        P, gen, probs = state
         if gen != P.generation:
-            raise RuntimeError("brats2019_b200: activations were overwritten by a later forward of the same shape; "
-                               "run backward before the next forward")
+            raise RuntimeError(
+                "brats2019_b200: the activations of this forward were overwritten by a later forward of the same "
+                "input shape (the engine keeps ONE set of activation buffers per shape).  Call backward() before the "
+                "next forward of that shape - e.g. accumulate gradients as `for xb: loss(model([xb])).backward()` "
+                "instead of summing losses of several forwards first - and run eval forwards under torch.no_grad() "
+                "after backward.")
+        if tuple(gprobs.shape) != tuple(probs.shape):
+            raise RuntimeError("brats2019_b200: gradient of shape %s for an output of shape %s"
+                               % (tuple(gprobs.shape), tuple(probs.shape)))
         prm = {k: v.detach() for k, v in self._params().items()}
         ch = self.ch
         grads = store if store is not None else GradStore()
@@ -482,6 +533,7 @@ class Engine:
                     ops.G_K3)
         self._join_side()
         grads.finish()
+        self.grad_order = list(grads.grads.keys())
         return grads.grads
 
     # forward-activation lookups used by backward ---------------------------------------

@@ -44,8 +44,19 @@ class GraphedTrainStep:
             self.x.copy_(x, non_blocking=True)
         if t is not None:
             self.t.copy_(t, non_blocking=True)
-        self.graph.replay()
+        self._replay()
         return self.loss
+
+    def _replay(self):
+        sync_lr = getattr(self.optimizer, "sync_lr", None)
+        if sync_lr is not None:
+            sync_lr()                    # a host LR scheduler may have rewritten param_groups[0]['lr']
+        self.graph.replay()
+        # the replayed optimizer step rewrote the weights without touching their version counters: the next EAGER
+        # forward (an eval pass between training phases) must re-pack its bf16 weight images
+        m = self.model.module if hasattr(self.model, "module") else self.model
+        if hasattr(m, "invalidate_packed_weights"):
+            m.invalidate_packed_weights()
 
     # -- host-input pipeline: the H2D copy of step i+1 overlaps the compute of step i -------------
     def prefetch(self, x_host, t_host):
@@ -75,7 +86,7 @@ class GraphedTrainStep:
         self.t.copy_(self._stage[k][1], non_blocking=True)
         self._free[k].record()
         self._slot_out = k ^ 1
-        self.graph.replay()
+        self._replay()
         return self.loss
 
 

@@ -33,6 +33,8 @@ import torch.nn as nn
 
 from . import BCE_Loss, DEFAULT_CFG, Dice_loss_joint, UNet
 from . import checkpoint as ckpt
+from .graphs import GraphedTrainStep
+from .optim import FusedAdam
 from .parallel import DistributedUNet
 
 PATCH = (144, 144, 128)        # main.py:115
@@ -90,37 +92,79 @@ def build(device, cfg=DEFAULT_CFG, seed=1337, distributed=None):
     return net, criteria, group
 
 
+class MeanCriterion:
+    """train.py:203-205: `loss_val = [c(output, target) for c in criterion]; loss = sum(loss_val) / len(loss_val)`.
+    Keeps the per-criterion values of the last call (static tensors under a CUDA graph) for logging."""
+
+    def __init__(self, criteria):
+        self.criteria, self.vals = list(criteria), []
+
+    def __call__(self, output, target):
+        vals = [c(output, target) for c in self.criteria]
+        self.vals = [v.detach() for v in vals]       # no reference to the autograd graph survives the step
+        return sum(vals) / len(vals)
+
+
 def train(net, criteria, batches, steps=None, lr=2e-5, weight_decay=1e-6, step_size=16000, gamma=0.5,
-          log_every=10, log=print, state=None):
+          log_every=10, log=print, state=None, fused=True, graph=True, eager_steps=2):
     """The batch loop of train.py:188-223: forward, mean of the criteria, backward, Adam step, scheduler step.
-    Returns the list of per-step (loss values per criterion) as Python floats."""
+
+    fused=True (default): optim.FusedAdam - Adam(amsgrad, weight decay) and the StepLR schedule as one kernel over flat
+    buffers; graph=True: from batch `eager_steps` on, the whole step (forward, criteria, backward, gradient all-reduce,
+    optimizer) is ONE CUDA-graph replay per batch (a new graph is captured if the batch shape changes).  fused=False:
+    the stock torch.optim.Adam(fused=True) + StepLR of round 1, eager.
+    Returns (per-logged-step loss values per criterion as Python floats, TrainingState)."""
+    if fused and graph and torch.cuda.current_stream() == torch.cuda.default_stream():
+        # CUDA-graph capture cannot involve the legacy default stream (autograd's AccumulateGrad nodes run on the stream
+        # they were created on): run the whole loop on a stream of our own, ordered after / before the caller's work
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            out = train(net, criteria, batches, steps, lr, weight_decay, step_size, gamma, log_every, log, state, fused, graph,
+                        eager_steps)
+        torch.cuda.current_stream().wait_stream(side)
+        return out
     module = net.module if hasattr(net, "module") else net
-    opt = torch.optim.Adam(module.parameters(), lr=lr, weight_decay=weight_decay, amsgrad=True, fused=True)   # main.py:133-138
-    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=gamma)                             # main.py:139-142
+    if fused:
+        opt = FusedAdam(module.parameters(), lr=lr, weight_decay=weight_decay, amsgrad=True, lr_step_size=step_size,
+                        lr_gamma=gamma, model=net)                                                                 # main.py:133-142
+        sched = None
+    else:
+        opt = torch.optim.Adam(module.parameters(), lr=lr, weight_decay=weight_decay, amsgrad=True, fused=True)   # main.py:133-138
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=gamma)                             # main.py:139-142
     state = state if state is not None else ckpt.TrainingState()
     if state.optimizer_state is not None:
         opt.load_state_dict(state.optimizer_state)                                                            # train.py:83-84
+    crit = MeanCriterion(criteria)
     history = []
     net.train()
     opt.zero_grad(set_to_none=True)
+    gstep, gshape = None, None
     t0 = time.perf_counter()
     for idx, (data, target) in enumerate(batches):
         if steps is not None and idx >= steps:
             break
         assert isinstance(data, list) and isinstance(target, list)                                             # train.py:193
-        output = net(data)
-        loss_val = [c(output, target) for c in criteria]
-        loss = sum(loss_val) / len(loss_val)                                                                   # train.py:203-205
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        sched.step()
+        if fused and graph and idx >= eager_steps:
+            shape = (tuple(data[0].shape), tuple(target[0].shape))
+            if gstep is None or shape != gshape:
+                gstep, gshape = GraphedTrainStep(net, crit, opt, data[0], target[0], warmup=0), shape
+            gstep(data[0], target[0])
+        else:
+            output = net(data)
+            loss = crit(output, target)                                                                        # train.py:203-205
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            if sched is not None:
+                sched.step()
         state.global_step += 1
         if log_every and (idx % log_every == 0):
-            vals = [float(v.detach()) for v in loss_val]          # one device->host read per logged step
+            vals = [float(v.detach()) for v in crit.vals]         # one device->host read per logged step
             history.append(vals)
-            log("step %d  loss %s  lr %.3g  %.2f s" % (state.global_step, ["%.5f" % v for v in vals],
-                                                     opt.param_groups[0]["lr"], time.perf_counter() - t0))
+            lr_now = opt.param_groups[0]["lr"] * (gamma ** ((state.global_step - 1) // step_size) if fused else 1.0)
+            log("step %d  loss %s  lr %.3g  %.2f s" % (state.global_step, ["%.5f" % v for v in vals], lr_now,
+                                                     time.perf_counter() - t0))
     state.optimizer_state = opt.state_dict()                                                                   # train.py:315
     return history, state
 
@@ -134,6 +178,8 @@ def main(argv=None):
     ap.add_argument("--models_path", default="")
     ap.add_argument("--resume", default="", help="checkpoint in the reference layout (train.py:320-324)")
     ap.add_argument("--log-every", type=int, default=10)
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph per step")
+    ap.add_argument("--torch-adam", action="store_true", help="stock torch.optim.Adam(fused=True) + StepLR instead of FusedAdam")
     opt = ap.parse_args(argv)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -155,7 +201,8 @@ def main(argv=None):
             state = ckpt.load_state_dict_into(net, opt.resume)
         batches = synthetic_batches(opt.batchSize // world, tuple(opt.patch), opt.steps, 100 + rank, dev)
         log = print if rank == 0 else (lambda *a, **k: None)
-        _, state = train(net, criteria, batches, log_every=opt.log_every, log=log, state=state)
+        _, state = train(net, criteria, batches, log_every=opt.log_every, log=log, state=state,
+                         fused=not opt.torch_adam, graph=not opt.no_graph)
         torch.cuda.synchronize()
         if rank == 0 and opt.name and opt.models_path:
             d = os.path.join(opt.models_path, opt.name)

@@ -74,13 +74,15 @@ class _UNetFunction(torch.autograd.Function):
         probs = eng.forward(x, training=True)
         ctx.module = module
         ctx.names = names
+        ctx.state = eng.saved_state()       # (plan, generation, probs): which activations this node owns
         return probs
 
     @staticmethod
     def backward(ctx, gprobs):
         eng = ctx.module._engine()
         factory = ctx.module._grad_store_factory
-        grads = eng.backward(gprobs, factory() if factory is not None else None)
+        grads = eng.backward(gprobs, factory() if factory is not None else None, state=ctx.state)
+        ctx.state = None
         return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
@@ -173,6 +175,29 @@ class UNet(nn.Module):
         d.pop("_eng", None)                  # buffers/plans are rebuilt lazily after unpickling
         d["_grad_store_factory"] = None
         return d
+
+    # Weight edits that do not bump a parameter's version counter (engine.Engine.invalidate_packed): the paths the
+    # reference itself uses are covered here - `model.apply(weight_init)` (main.py:60; weight_init.py:22-27 writes
+    # through `.data`), `.cuda()` / `.to()` (train.py:54-56) and `load_state_dict` (train.py:333).
+    def invalidate_packed_weights(self):
+        eng = self.__dict__.get("_eng")
+        if eng is not None:
+            eng.invalidate_packed()
+
+    def apply(self, fn):
+        out = super(UNet, self).apply(fn)
+        self.invalidate_packed_weights()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super(UNet, self)._apply(fn, *args, **kwargs)
+        self.invalidate_packed_weights()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super(UNet, self).load_state_dict(*args, **kwargs)
+        self.invalidate_packed_weights()
+        return out
 
     def dead_parameter_names(self):
         """Parameters the reference builds but never uses (model.py:379-395 vs :420)."""

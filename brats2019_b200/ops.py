@@ -310,6 +310,11 @@ def upsample2x(coarse, fine, lrelu=True):
 _UPS_WS = {}
 
 
+def free_workspaces():
+    """Drop the cached scratch buffers of this module (Engine.free_plans)."""
+    _UPS_WS.clear()
+
+
 def upsample2x_backward(dfine, fine_out, dcoarse, lrelu=True, workspace=None):
     N, D, H, W, Cc = act_dims(dcoarse)
     L = _lib.lib()

@@ -76,14 +76,18 @@ class DistributedUNet(nn.Module):
         if broadcast:
             for p in module.parameters():
                 dist.broadcast(p.data, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+            module.invalidate_packed_weights()       # `.data` writes do not bump version counters
         module._grad_store_factory = self._make_store
+        self.flat_provider = None      # optim.FusedAdam.bind(): persistent flat gradient buffer shared with the optimizer
         self.last_buckets = []
 
     def _make_store(self):
         dev = next(self.module.parameters()).device
         # A fresh flat buffer per step (18 MB from the caching allocator): autograd may adopt the
         # returned views as `.grad`, so the storage must not be reused by the next backward.
-        flat = torch.empty(flat_grad_elems(self.module), dtype=torch.float32, device=dev)
+        flat = self.flat_provider() if self.flat_provider is not None else None
+        if flat is None:
+            flat = torch.empty(flat_grad_elems(self.module), dtype=torch.float32, device=dev)
         store = BucketedAllReduce(flat, self.process_group, self.min_bucket_elems)
         self.last_buckets = store.buckets
         return store

@@ -149,6 +149,19 @@ int b200_bce_loss(const float* sum, double global_numel, float* loss, void* stre
 int b200_bce_backward(const float* probs, const float* target, const float* grad_out, float bg_weight,
                       double global_numel, float* grad_probs, long long numel, void* stream);
 
+/* ---- fused Adam step (torch.optim.Adam(amsgrad, weight_decay) of main.py:133-138, stepped at
+ *      train.py:220) ------------------------------------------------------------
+ * One launch over flat fp32 buffers that share offsets: params, grads, exp_avg, exp_avg_sq and (amsgrad, may be
+ * NULL) max_exp_avg_sq.  Only the element ranges [seg_begin[i], seg_begin[i] + seg_len[i]) are touched (host
+ * arrays, multiples of 4 floats, <= 64 ranges): parameters without a gradient are skipped like torch does.
+ * `lr`, `step` (fp32 count of steps taken, advanced by the kernel) and `ticket` (unsigned, zero) are DEVICE
+ * scalars so the launch is CUDA-graph replayable.  lr_step_size > 0 applies StepLR(lr_step_size, lr_gamma)
+ * stepped once per call (main.py:139-142, train.py:222-223) inside the kernel. */
+int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                   const long long* seg_begin, const long long* seg_len, int n_segs, const float* lr, float* step,
+                   unsigned* ticket, double beta1, double beta2, float eps, float weight_decay, int lr_step_size,
+                   float lr_gamma, void* stream);
+
 /* ---- plan introspection (tests): integer dump of the launch plan ---------------- */
 int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);
 int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
