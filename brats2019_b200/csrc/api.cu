@@ -48,18 +48,37 @@ static int fail(const char* fmt, ...) {
 
 extern "C" const char* b200_last_error(void) { return g_err; }
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_num_sms = n;
-        else
-            g_num_sms = 148;   // B200; used for planning queries on a machine without a GPU
-    }
-    return g_num_sms;
+static const unsigned kMaxSmem = 227 * 1024;
+// Per-device caches (one process may drive several GPUs: tests on cuda:1 after cuda:0, DataParallel-style use):
+// the SM count sizes grids and partial-sum buffers, and cudaFuncAttributeMaxDynamicSharedMemorySize is a
+// per-device function attribute.
+static const int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
 }
+static int num_sms() {
+    static int cache[kMaxDevices];
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return 148;   // B200; planning queries on a machine without a GPU
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cache[dev] = n;
+        else { cudaGetLastError(); cache[dev] = 148; }
+    }
+    return cache[dev];
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
+#define SET_MAX_SMEM_ONCE(...)                                                                                     \
+    do {                                                                                                           \
+        static bool done_[kMaxDevices];                                                                            \
+        const int dev_ = current_device();                                                                         \
+        if (dev_ < 0 || dev_ >= kMaxDevices || !done_[dev_]) {                                                     \
+            CUDA_OK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
+            if (dev_ >= 0 && dev_ < kMaxDevices) done_[dev_] = true;                                               \
+        }                                                                                                          \
+    } while (0)
 extern "C" int b200_num_sms(void) { return num_sms(); }
 
 extern "C" int b200_device_check(int dev) {
@@ -93,7 +112,6 @@ static unsigned pow2_cols(unsigned c) {
     while (p < c) p <<= 1;
     return p;
 }
-static const unsigned kMaxSmem = 227 * 1024;
 
 // ---------------------------------------------------------------------------------------
 // conv planning
@@ -481,12 +499,7 @@ extern "C" int b200_pack_table_run(const void* table_device, int n_jobs, int tot
 
 template <int MODE, int EPI, int NM, int FOLD>
 static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<MODE, EPI, NM, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kMaxSmem));
-        attr_set = true;
-    }
+    SET_MAX_SMEM_ONCE(conv_gemm_kernel<MODE, EPI, NM, FOLD>);
     conv_gemm_kernel<MODE, EPI, NM, FOLD><<<grid, kConvThreads, smem, st>>>(p);
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
@@ -494,11 +507,7 @@ static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream
 
 template <int CO, int EPI>
 static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(conv_march_kernel<CO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        attr_set = true;
-    }
+    SET_MAX_SMEM_ONCE(conv_march_kernel<CO, EPI>);
     conv_march_kernel<CO, EPI><<<grid, kMarchThreads, smem, st>>>(p);
     LAUNCH_OK("conv_march_kernel");
     return 0;
@@ -536,11 +545,7 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
 
 template <int EPI>
 static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(conv_band_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        attr_set = true;
-    }
+    SET_MAX_SMEM_ONCE(conv_band_kernel<EPI>);
     conv_band_kernel<EPI><<<grid, kBandThreads, smem, st>>>(p);
     LAUNCH_OK("conv_band_kernel");
     return 0;
@@ -828,11 +833,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     if (kind == B200_G_S2D && (d->mode != 1 || taps_w != 8 || d->Cin != 8 * Cin_w)) return fail("wgrad: s2d kind mismatch");
     if (Cout_w > d->Cout) return fail("wgrad: Cout_w > Cout");
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        attr_set = true;
-    }
+    SET_MAX_SMEM_ONCE(wgrad_gemm_kernel);
     P.k.partial = (float*)workspace;
     if (check_ptr16(dy, "dy") || check_ptr16(x, "x")) return 1;
     Vol vol{d->N, d->D, d->H, d->W};
@@ -843,11 +844,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     {
         WgradMarchPlan MP;
         if (kind == B200_G_K3 && plan_wgrad_march(d, MP)) {
-            static bool march_attr_set = false;
-            if (!march_attr_set) {
-                CUDA_OK(cudaFuncSetAttribute(wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-                march_attr_set = true;
-            }
+            SET_MAX_SMEM_ONCE(wgrad_march_kernel);
             MP.k.dy = P.k.dy; MP.k.x = P.k.x; MP.k.partial = (float*)workspace; MP.k.debug = wdbg;
             wgrad_march_kernel<<<MP.grid, kWgmThreads, MP.smem, st>>>(MP.k);
             LAUNCH_OK("wgrad_march_kernel");
@@ -1181,7 +1178,6 @@ extern "C" size_t b200_dice_workspace_floats(int B, int C) { return (size_t)B * 
 extern "C" int b200_dice_sums(const float* probs, const float* target, float* sums, float* workspace, int B, int C,
                               long long S, void* stream) {
     if (C < 1 || C > 4) return fail("dice: C=%d unsupported (1..4)", C);
-    if (S % 4) return fail("dice: spatial size must be a multiple of 4");
     cudaStream_t st = (cudaStream_t)stream;
     const int bx = dice_blocks();
     dice_partial_kernel<<<dim3(bx, B * C), kEwThreads, 0, st>>>(probs, target, workspace, B, C, S);

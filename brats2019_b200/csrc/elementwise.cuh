@@ -280,18 +280,19 @@ dice_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, fl
     const float* pp = p + (size_t)bc * S;
     const float* gg = g + (size_t)bc * S;
     float si = 0.f, su = 0.f;
-    const long long nv = (S % 4 == 0) ? S / 4 : 0;
+    // 16-byte loads only when both rows really are 16-byte aligned (a sliced batch is contiguous but may start anywhere)
+    const bool vec = (S % 4 == 0) && (((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(gg)) & 15) == 0);
+    const long long nv = vec ? S / 4 : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         const float4 a = reinterpret_cast<const float4*>(pp)[i];
         const float4 b = reinterpret_cast<const float4*>(gg)[i];
         si += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
         su += (a.x * a.x + b.x) + (a.y * a.y + b.y) + (a.z * a.z + b.z) + (a.w * a.w + b.w);
     }
-    if (blockIdx.x == 0)
-        for (long long i = nv * 4 + threadIdx.x; i < S; i += blockDim.x) {
-            si += pp[i] * gg[i];
-            su += pp[i] * pp[i] + gg[i];
-        }
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x) {
+        si += pp[i] * gg[i];
+        su += pp[i] * pp[i] + gg[i];
+    }
     __shared__ float s_i[kEwThreads / 32], s_u[kEwThreads / 32];
     si = warp_sum(si);
     su = warp_sum(su);
@@ -340,7 +341,8 @@ __global__ void __launch_bounds__(kEwThreads)
 bce_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, float w, float* __restrict__ partial,
                    long long n) {
     float acc = 0.f;
-    const long long nv = ((n & 3) == 0) ? n / 4 : 0;
+    const bool vec = ((n & 3) == 0) && (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15) == 0);
+    const long long nv = vec ? n / 4 : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         const float4 a = reinterpret_cast<const float4*>(p)[i];
         const float4 b = reinterpret_cast<const float4*>(g)[i];

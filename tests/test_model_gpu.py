@@ -313,3 +313,22 @@ def test_reference_training_patch_shape_144x144x128():
     assert rels.max().item() <= CAP["grad_max"] and rels.median().item() <= CAP["grad_median"]
     del m
     torch.cuda.empty_cache()
+
+
+def test_losses_accept_contiguous_views_that_are_not_16_byte_aligned():
+    """ADVICE r1: `.contiguous()` is a no-op for a sliced batch whose storage offset is not a multiple of 4 floats;
+    the 16-byte load path must not be taken for it (and odd spatial sizes must work)."""
+    import brats2019_b200 as B
+    for S, off in ((1000, 1), (1000, 2), (999, 0), (1001, 3)):
+        g = torch.Generator().manual_seed(S + off)
+        p = torch.rand(off + 2 * 3 * S, generator=g).cuda()[off:].view(2, 3, S, 1, 1).requires_grad_(True)
+        t = (torch.rand(off + 2 * 3 * S, generator=g) > 0.6).float().cuda()[off:].view(2, 3, S, 1, 1)
+        assert p.is_contiguous() and (p.data_ptr() % 16 != 0 or S % 4)
+        for crit, ref in ((B.Dice_loss_joint(), O.dice_loss_joint), (B.BCE_Loss(bg_weight=1e-2), lambda a, b: O.bce_loss(a, b, bg_weight=1e-2))):
+            loss = crit([p], [t])
+            want = ref([p.detach().cpu().double()], [t.cpu().double()])
+            assert abs(loss.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item())), (S, off, loss.item(), want.item())
+            (gp,) = torch.autograd.grad(loss, p)
+            pr = p.detach().cpu().double().requires_grad_(True)
+            (gr,) = torch.autograd.grad(ref([pr], [t.cpu().double()]), pr)
+            assert (gp.cpu().double() - gr).abs().max().item() <= 1e-5 * gr.abs().max().item() + 1e-9
