@@ -75,6 +75,7 @@ _PROTOS = {
                                c_float, c_int, c_float, P]),
     "b200_conv_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
+    "b200_wgrad_line_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_march_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_march_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_band_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),

@@ -20,12 +20,18 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+PROBES_OUT = os.path.join(HERE, "libbrats_b200_probes.so")
+
+
+def build(force=False, verbose=False, probes=False):
+    """probes=True: a second library with -DB200_PROBES (in-kernel cycle accounting and skip-a-stage switches for the
+    profiling scripts under tools/; select it with B200_LIB_PATH).  The default library carries none of that code."""
+    out = PROBES_OUT if probes else OUT
+    if not force and not probes and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "-o", OUT] + SOURCES
+           "-Xcompiler", "-fPIC", "-o", out] + (["-DB200_PROBES"] if probes else []) + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -33,8 +39,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv))

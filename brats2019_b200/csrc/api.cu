@@ -18,6 +18,7 @@
 #include "elementwise2.cuh"
 #include "wgrad_gemm.cuh"
 #include "wgrad_march.cuh"
+#include "wgrad_line.cuh"
 #include "elementwise3.cuh"
 #include "elementwise4.cuh"
 #include "optimizer.cuh"
@@ -813,10 +814,75 @@ static bool plan_wgrad_march(const b200_wgrad_desc* d, WgradMarchPlan& P, bool i
     return true;
 }
 
+// Line-marching form (wgrad_line.cuh) for the 3x3x3 16 <-> 16 convs: W a multiple of 16 and a band of >= 2 lines whose
+// ring fits shared memory.  Default; B200_NO_WGRAD_LINE=1 falls back to the linear-row kernel (A/B measurements).
+struct WgradLinePlan {
+    WgradLineParams k;
+    unsigned smem;
+    int grid;
+};
+static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ignore_switch = false) {
+    const char* e = getenv("B200_NO_WGRAD_LINE");        // read per call: tests switch forms in one process
+    if (!ignore_switch && e && atoi(e)) return false;
+    if (d->mode != 0 || d->Cout != 16 || d->Cin != 16 || d->W % 16 || d->W < 16) return false;
+    memset(&P, 0, sizeof(P));
+    WgradLineParams& k = P.k;
+    k.N = d->N; k.D = d->D; k.H = d->H; k.W = d->W; k.Wp = d->W + 2;
+    k.ksteps = d->W / 16;
+    k.Lp = (unsigned)k.Wp * 16u;
+    if (k.Lp >= (1u << 18)) return false;               // descriptor stride field
+    const unsigned bar_bytes = 1024;
+    // Shared memory: the X ring, NR raw dY lines, Ny expanded dY lines.  ~12 KB per SM stay free on purpose: in the training
+    // step this kernel runs beside the memory-bound GroupNorm-backward kernels (engine.py, side stream), whose CTAs need a
+    // few KB each to be co-resident - with the whole 227 KB taken they queue behind this kernel and the overlap is lost
+    // (measured: step 5.89 ms vs 5.81 ms).
+    const unsigned budget = kMaxSmem - 12 * 1024;
+    auto need = [&](int LH, int NR, int Ny) {
+        const unsigned R = 3u * (LH + 2) + 1u;
+        return (unsigned long long)(R + kWglMirror) * 2u * k.Lp + 128u + (unsigned long long)NR * 2u * k.Lp +
+               ((unsigned long long)Ny * 6u + 2u) * k.Lp + bar_bytes;
+    };
+    k.LH = 0;
+    {   // diagnostics: B200_WGL_LH / B200_WGL_NR / B200_WGL_NY force the plan (tools/wgrad_ab.py sweeps them)
+        const char* el = getenv("B200_WGL_LH");
+        const char* er = getenv("B200_WGL_NR");
+        const char* en = getenv("B200_WGL_NY");
+        if (el && er && en) {
+            const int LH = atoi(el), NR = atoi(er), Ny = atoi(en);
+            if (LH >= 1 && LH <= d->H && LH + 2 <= kWglND && NR >= 2 && NR <= kWglMaxNy && Ny >= 2 && Ny <= kWglMaxNy &&
+                need(LH, NR, Ny) <= kMaxSmem) { k.LH = LH; k.NR = NR; k.Ny = Ny; }
+        }
+    }
+    // band height: prefer one that divides H (equal work per band), then the tallest; 3 expanded lines (two steps of
+    // slack for the copy warps), as many raw lines as fit (>= 3)
+    for (int pass = 0; pass < 2 && k.LH == 0; ++pass)
+        for (int LH = 8; LH >= 2 && k.LH == 0; --LH) {
+            if (LH > d->H || LH + 2 > kWglND) continue;     // a producer polls a step_done barrier at most LH steps late
+            if (pass == 0 && d->H % LH) continue;
+            for (int NR = kWglMaxNy; NR >= 3; --NR)
+                if (need(LH, NR, 3) <= budget) { k.LH = LH; k.NR = NR; k.Ny = 3; break; }
+        }
+    if (k.LH == 0) return false;
+    k.R = 3 * (k.LH + 2) + 1;
+    k.n_bands = ceil_div(d->H, k.LH);
+    k.units = (long long)d->N * k.n_bands * d->D;
+    k.smem_x_off = 0;
+    k.smem_raw_off = align_up((unsigned)(k.R + kWglMirror) * 2u * k.Lp, 128);
+    k.smem_y_off = k.smem_raw_off + (unsigned)k.NR * 2u * k.Lp;
+    k.smem_bar_off = align_up(k.smem_y_off + ((unsigned)k.Ny * 6u + 2u) * k.Lp, 16);
+    P.smem = k.smem_bar_off + bar_bytes;
+    if (P.smem > kMaxSmem) return false;
+    P.grid = (int)std::min<long long>(num_sms(), k.units);
+    return true;
+}
+
 extern "C" size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d) {
     WgradPlan P;
     if (plan_wgrad(d, P)) return 0;
     size_t bytes = (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
+    WgradLinePlan LP;
+    if (plan_wgrad_line(d, LP, true))
+        bytes = std::max(bytes, (size_t)LP.grid * kWglRows * kWglN * sizeof(float));
     WgradMarchPlan MP;
     if (plan_wgrad_march(d, MP))
         bytes = std::max(bytes, (size_t)MP.grid * kWgmAccs * kWgmM * kWgmN * sizeof(float));
@@ -841,6 +907,25 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     P.k.x = make_act(x, vol);
     static int wdbg = -1;
     if (wdbg < 0) { const char* e = getenv("B200_WGRAD_DEBUG"); wdbg = e ? atoi(e) : 0; }
+    {
+        WgradLinePlan LP;
+        const char* em = getenv("B200_WGRAD_MARCH");
+        if (kind == B200_G_K3 && !(em && atoi(em)) && plan_wgrad_line(d, LP)) {
+            SET_MAX_SMEM_ONCE(wgrad_line_kernel);
+            LP.k.dy = P.k.dy; LP.k.x = P.k.x; LP.k.partial = (float*)workspace;
+#ifdef B200_PROBES
+            { const char* e2 = getenv("B200_WGL_DEBUG"); LP.k.debug = e2 ? atoi(e2) : 0; }
+#endif
+            wgrad_line_kernel<<<LP.grid, kWglThreads, LP.smem, st>>>(LP.k);
+            LAUNCH_OK("wgrad_line_kernel");
+            WglReduceParams rq;
+            rq.ctas = LP.grid; rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
+            constexpr int qpb = 256 / kWglReduceGroups;
+            wgrad_line_reduce_kernel<<<(27 * 16 * 4 + qpb - 1) / qpb, 256, 0, st>>>((const float*)workspace, grad, rq);
+            LAUNCH_OK("wgrad_line_reduce_kernel");
+            return 0;
+        }
+    }
     {
         WgradMarchPlan MP;
         if (kind == B200_G_K3 && plan_wgrad_march(d, MP)) {
@@ -1293,6 +1378,13 @@ extern "C" int b200_band_plan_debug(const b200_conv_desc* d, int* out, int n_out
     return 0;
 }
 
+#ifdef B200_PROBES
+extern "C" int b200_wgl_prof_read(unsigned long long* host_out, int n) {
+    if (n > 160 * 8) n = 160 * 8;
+    CUDA_OK(cudaMemcpyFromSymbol(host_out, g_wgl_prof, (size_t)n * sizeof(unsigned long long)));
+    return 0;
+}
+#endif
 extern "C" int b200_march_prof_read(unsigned long long* host_out, int n) {
     if (n > 160 * 16) n = 160 * 16;
     CUDA_OK(cudaMemcpyFromSymbol(host_out, g_march_prof, (size_t)n * sizeof(unsigned long long)));
@@ -1322,6 +1414,19 @@ extern "C" int b200_wgrad_march_plan_debug(const b200_wgrad_desc* d, int* out, i
                         (int)k.smem_y_off, (int)k.smem_stg_off, (int)k.smem_x_off, (int)P.smem, P.grid};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv) return fail("wgrad_march_plan_debug: need %d ints", nv);
+    for (int i = 0; i < nv; ++i) out[i] = vals[i];
+    return 0;
+}
+
+extern "C" int b200_wgrad_line_plan_debug(const b200_wgrad_desc* d, int* out, int n_out) {
+    WgradLinePlan P;
+    if (!plan_wgrad_line(d, P, true)) return fail("wgrad_line: does not apply (needs mode 0, 16 x 16 channels, W %% 16 == 0)");
+    const WgradLineParams& k = P.k;
+    const int vals[] = {k.LH, k.n_bands, (int)k.units, k.ksteps, k.R, k.Ny, k.Wp, (int)k.Lp, (int)k.smem_x_off,
+                        (int)k.smem_y_off, (int)k.smem_bar_off, (int)P.smem, P.grid, kWglMirror, kWglNB, kWglND, k.NR,
+                        (int)k.smem_raw_off};
+    const int nv = (int)(sizeof(vals) / sizeof(int));
+    if (n_out < nv) return fail("wgrad_line_plan_debug: need %d ints", nv);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];
     return 0;
 }

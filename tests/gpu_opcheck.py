@@ -324,29 +324,33 @@ def group_wgrad():
     from brats2019_b200 import ops
     dev = "cuda"
     torch.manual_seed(4)
-    # 16 <-> 16 channels with W % 16 == 0 can take the marching kernel (wgrad_march.cuh, opt-in with B200_WGRAD_MARCH=1);
-    # those shapes are checked in both forms: odd D, H not a multiple of the 4-line band, batch 2,
-    # the real level-0 width 128, 3 and 4 real channels (conv_output / conv_input)
+    # 16 <-> 16 channels with W % 16 == 0 take the line-marching kernel (wgrad_line.cuh, the default), or the older
+    # marching kernel (wgrad_march.cuh, opt-in with B200_WGRAD_MARCH=1), or the linear-row kernel
+    # (B200_NO_WGRAD_LINE=1); those shapes are checked in all three forms: odd D, H not a multiple of the band,
+    # batch 2, the real level-0 width 128, 3 and 4 real channels (conv_output / conv_input), one-line volumes
     for (N, D, H, W, Cin, Cout) in ((1, 8, 8, 8, 16, 16), (2, 6, 10, 12, 16, 16), (2, 6, 10, 12, 32, 32),
                                    (1, 6, 8, 8, 64, 64), (2, 4, 4, 8, 128, 128), (1, 8, 8, 16, 16, 3),
                                    (1, 8, 8, 16, 4, 16), (1, 16, 16, 64, 16, 16), (2, 5, 7, 32, 16, 16),
-                                   (1, 3, 6, 128, 16, 16), (2, 12, 9, 48, 16, 16), (3, 1, 1, 16, 16, 16)):
+                                   (1, 3, 6, 128, 16, 16), (2, 12, 9, 48, 16, 16), (3, 1, 1, 16, 16, 16),
+                                   (1, 20, 37, 128, 16, 16), (2, 7, 16, 144, 16, 16)):
         x = bf(torch.randn(N, Cin, D, H, W, device=dev))
         dy = bf(torch.randn(N, Cout, D, H, W, device=dev))
         w = torch.zeros(Cout, Cin, 3, 3, 3, device=dev, requires_grad=True)
         F.conv3d(x, w, padding=1).backward(dy)
         desc = ops.wgrad_desc(0, N, D, H, W, ops.pad16(Cout), ops.pad16(Cin))
-        forms = ("march", "linear") if (ops.pad16(Cin) == 16 and ops.pad16(Cout) == 16 and W % 16 == 0) else ("linear",)
+        forms = ("line", "march", "linear") if (ops.pad16(Cin) == 16 and ops.pad16(Cout) == 16 and W % 16 == 0) else ("linear",)
         for form in forms:
             os.environ["B200_WGRAD_MARCH"] = "1" if form == "march" else "0"
+            os.environ["B200_NO_WGRAD_LINE"] = "0" if form == "line" else "1"
             g = torch.full((Cout, Cin, 3, 3, 3), 5.0, device=dev)
             ops.wgrad_run(desc, ops.act_from_ncdhw(dy), ops.act_from_ncdhw(x), g, ops.G_K3)
             report("wgrad3 %dx%d (%d,%d,%d,%d) %s" % (Cout, Cin, N, D, H, W, form), g, w.grad, tol_rel=1e-2)
-            if form == "march":      # accumulate into an existing gradient
+            if form in ("march", "line"):      # accumulate into an existing gradient
                 g2 = g.clone()
                 ops.wgrad_run(desc, ops.act_from_ncdhw(dy), ops.act_from_ncdhw(x), g2, ops.G_K3, accumulate=True)
-                report("wgrad3 %dx%d (%d,%d,%d,%d) march accumulate" % (Cout, Cin, N, D, H, W), g2, 2 * w.grad, tol_rel=1e-2)
+                report("wgrad3 %dx%d (%d,%d,%d,%d) %s accumulate" % (Cout, Cin, N, D, H, W, form), g2, 2 * w.grad, tol_rel=1e-2)
         os.environ.pop("B200_WGRAD_MARCH", None)
+        os.environ.pop("B200_NO_WGRAD_LINE", None)
     N, D, H, W = 2, 6, 8, 12
     for Cin, Cout in ((32, 16), (128, 64), (16, 16), (64, 128)):
         x = bf(torch.randn(N, Cin, D, H, W, device=dev)); dy = bf(torch.randn(N, Cout, D, H, W, device=dev))

@@ -1,0 +1,199 @@
+"""CPU replay of the line-marching weight-gradient kernel (brats2019_b200/csrc/wgrad_line.cuh): the planner's
+numbers (b200_wgrad_line_plan_debug) drive a numpy emulation of what a CTA does, including its asynchronous
+structure - four actors (X producer, dY producer, the copy warps that expand a raw dY line into its three kw copies,
+MMA issuer) that only advance when the kernel's own wait rules allow it, scheduled in random order with the producers as greedy as the rules let them be:
+
+  * shared-memory ring: slot (3*line + slice) mod R with the first 8 slots mirrored behind the ring; every 9-slot
+    window the MMA reads must hold exactly the lines (kh, kd) of the step, i.e. no load may land in a slot that a
+    later step still reads (the reuse rule `step (s-3)*nl + min(line+1, nl-1) done`) and no window may wrap;
+  * mbarrier rings: a waiter is never two phases behind the barrier it polls (x_full[64], step_done[16], y[Ny]);
+  * operands: the (kw, chunk) copies of a dY line and the K range over the interior voxels of a line;
+  * the reduce kernel's index map back to the PyTorch (Cout, Cin, 3, 3, 3) gradient, against torch autograd.
+No GPU: what the hardware does with the descriptors is covered by tests/gpu_opcheck.py (wgrad group) and
+tests/test_layer_parity_gpu.py."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from brats2019_b200 import _lib
+from brats2019_b200._lib import WgradDesc
+
+FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off".split()
+
+
+def line_plan(N, D, H, W):
+    d = WgradDesc(0, N, D, H, W, 16, 16)
+    out = (C.c_int * 32)()
+    assert _lib.lib().b200_wgrad_line_plan_debug(C.byref(d), out, 32) == 0, _lib.lib().b200_last_error()
+    return {k: out[i] for i, k in enumerate(FIELDS)}
+
+
+def padded(x):
+    """(N,C,D,H,W) -> (N, D+2, H+2, W+2, C) with the zero halo the activation layout keeps in HBM."""
+    N, Cc, D, H, W = x.shape
+    a = np.zeros((N, D + 2, H + 2, W + 2, Cc), np.float64)
+    a[:, 1:-1, 1:-1, 1:-1] = x.permute(0, 2, 3, 4, 1).numpy()
+    return a
+
+
+def segments(p, cta, N, D, H):
+    units, grid, nb, LH = p["units"], p["grid"], p["n_bands"], p["LH"]
+    u, u_end = units * cta // grid, units * (cta + 1) // grid
+    out = []
+    while u < u_end:
+        d0, band, n = u % D, (u // D) % nb, u // D // nb
+        length = min(D - d0, u_end - u)
+        out.append(dict(n=n, band=band, d0=d0, len=length, nl=min(LH, H - band * LH)))
+        u += length
+    return out
+
+
+def replay_cta(p, segs, Y, X, W, rng):
+    """One CTA.  Returns its 64 x 144 accumulator."""
+    R, Ny, NR, NB, ND, MIR, LH = p["R"], p["Ny"], p["NR"], p["NB"], p["ND"], p["mirror"], p["LH"]
+    ring = [None] * (R + MIR)                    # slot -> (seg index, slice s, line lam) currently stored
+    rawslot = [None] * NR                        # raw dY ring: slot -> line index it holds
+    yslot = [None] * Ny                          # slot -> step index whose expanded line it holds
+    acc = np.zeros((64, 144))
+    # ---- static schedules of the three actors (exactly the kernel's loops) ----
+    xloads, steps = [], []                       # (seg, s, lam, wait_step or None) ; (seg, sd, l, k_need)
+    t_base, seg_k0 = 0, 0
+    for si, sg in enumerate(segs):
+        nl = sg["nl"]
+        for s in range(sg["len"] + 2):
+            for lam in range(nl + 2):
+                wait = None
+                if s >= 3:
+                    wait = t_base + (s - 3) * nl + min(lam + 1, nl - 1)
+                if s == 0 and lam == 0 and t_base > 0:
+                    wait = t_base - 1
+                xloads.append((si, s, lam, wait))
+        for sd in range(1, sg["len"] + 1):
+            for l in range(nl):
+                steps.append((si, sd, l, seg_k0 + (sd + 1) * (nl + 2) + l + 2))
+        t_base += sg["len"] * nl
+        seg_k0 += (sg["len"] + 2) * (nl + 2)
+    nsteps = len(steps)
+    kx = ky = kc = t = 0                         # progress of X producer, dY producer, copy warps, MMA
+    max_ahead_x = 0
+    guard = 0
+    while t < nsteps:
+        guard += 1
+        assert guard < 50 * (len(xloads) + 2 * nsteps) + 1000, "deadlock: no actor can advance"
+        order = [0, 0, 0, 1, 1, 3, 3, 2]         # producers greedy, MMA lazy: the hardest interleaving for slot reuse
+        rng.shuffle(order)
+        for who in order:
+            if who == 0 and kx < len(xloads):
+                si, s, lam, wait = xloads[kx]
+                if wait is not None and wait >= t:
+                    continue                                     # step `wait` not done yet
+                if wait is not None:
+                    assert t - 1 - wait < ND, "step_done phase ambiguity for the X producer"
+                waited = steps[t - 1][3] + 1 if t > 0 else 0      # loads the MMA warp has certainly waited for
+                assert kx - waited < NB, "x_full ring lapped"
+                q = (3 * lam + s) % R
+                ring[q] = (si, s, lam)
+                if q < MIR:
+                    ring[q + R] = (si, s, lam)
+                kx += 1
+            elif who == 1 and ky < nsteps:
+                if ky >= NR and ky - NR >= kc:
+                    continue                                     # raw slot not read yet (raw_free)
+                rawslot[ky % NR] = ky
+                ky += 1
+            elif who == 3 and kc < nsteps:
+                if ky <= kc:
+                    continue                                     # raw line not landed (y_raw)
+                if kc >= Ny and kc - Ny >= t:
+                    continue                                     # expanded slot still read by the MMAs (step_done)
+                if kc >= Ny:
+                    assert t - 1 - (kc - Ny) < ND, "step_done phase ambiguity for the copy warps"
+                assert rawslot[kc % NR] == kc
+                yslot[kc % Ny] = kc
+                kc += 1
+            elif who == 2 and t < nsteps:
+                si, sd, l, k_need = steps[t]
+                if kx <= k_need or kc <= t:
+                    continue
+                max_ahead_x = max(max_ahead_x, kx - (k_need + 1))
+                sg = segs[si]
+                assert yslot[t % Ny] == t
+                q0 = (3 * l + sd - 1) % R
+                assert q0 + 9 <= R + MIR                         # the window never wraps
+                for kh in range(3):
+                    for kd in range(3):
+                        assert ring[q0 + 3 * kh + kd] == (si, sd - 1 + kd, l + kh), (t, kh, kd, ring[q0 + 3 * kh + kd])
+                # ---- operands of this step, as the descriptors address them ----
+                n, band, d0 = sg["n"], sg["band"], sg["d0"]
+                dp = d0 + sd                                     # padded slice of the dY line (sd = 1 <-> interior slice d0)
+                hp = band * LH + 1 + l
+                yl = Y[n, dp, hp]                                # (W+2, 16)
+                A = np.zeros((64, W))                            # rows kw*16 + co, K = X rows 1 .. W
+                for kw in range(3):
+                    A[kw * 16:(kw + 1) * 16] = yl[1 - kw + 1:1 - kw + 1 + W].T      # A_kw[r] = dY[r - kw + 1]
+                B = np.zeros((144, W))
+                for kh in range(3):
+                    for kd in range(3):
+                        xl = X[n, d0 + sd - 1 + kd, band * LH + l + kh]              # slice s = sd-1+kd <-> padded d0+s
+                        B[(3 * kh + kd) * 16:(3 * kh + kd + 1) * 16] = xl[1:1 + W].T
+                acc += A @ B.T
+                t += 1
+    assert max_ahead_x < NB
+    return acc
+
+
+def replay(dy, x, p, seed=0):
+    N, _, D, H, W = x.shape
+    assert p["units"] == N * p["n_bands"] * D and p["ksteps"] * 16 == W and p["R"] == 3 * (p["LH"] + 2) + 1
+    assert p["Lp"] == (W + 2) * 16 and p["smem"] <= 227 * 1024
+    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * 2 * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] + p["NR"] * 2 * p["Lp"]
+    assert p["smem"] <= 227 * 1024 - 12 * 1024, "leave shared memory for the co-resident memory-bound kernels"
+    assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 6 + 2) * p["Lp"] and p["LH"] + 2 <= p["ND"]
+    Y, X = padded(dy), padded(x)
+    rng = random.Random(seed)
+    partial = np.stack([replay_cta(p, segments(p, cta, N, D, H), Y, X, W, rng) for cta in range(p["grid"])])
+    # wgrad_line_reduce_kernel: dW[co][ci][kd][kh][kw] = sum_cta P[cta][kw*16 + co][kh*48 + kd*16 + ci]
+    tot = partial.sum(0)
+    dW = np.zeros((16, 16, 3, 3, 3))
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                dW[:, :, kd, kh, kw] = tot[kw * 16:(kw + 1) * 16, kh * 48 + kd * 16:kh * 48 + kd * 16 + 16]
+    return dW
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 5, 16), (2, 9, 8, 16), (1, 5, 19, 32), (2, 2, 2, 16), (1, 1, 7, 48)])
+def test_replay_matches_autograd(shape):
+    N, D, H, W = shape
+    p = line_plan(N, D, H, W)
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, 16, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(16, 16, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(N, 16, D, H, W, generator=g, dtype=torch.float64)
+    (ref,) = torch.autograd.grad(F.conv3d(x, w, padding=1), w, dy)
+    got = replay(dy, x, p, seed=sum(shape))
+    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_schedule_survives_many_interleavings_at_the_benchmark_shape():
+    """Config-3 geometry (2 x 128^3): only the ring / barrier bookkeeping is replayed (operands skipped)."""
+    p = line_plan(2, 128, 128, 128)
+    assert p["LH"] == 8 and p["grid"] == 148 and p["Ny"] == 3 and p["NR"] >= 3
+    segs = segments(p, 17, 2, 128, 128) + segments(p, 18, 2, 128, 128)      # a CTA-sized run crossing a band boundary
+
+    class NoData:                                                           # index-only stand-in for the activations
+        def __getitem__(self, k):
+            return np.zeros((130, 16))
+
+    for seed in range(3):
+        replay_cta(p, segs, NoData(), NoData(), 128, random.Random(seed))
+
+
+def test_does_not_apply_outside_its_domain():
+    for desc in (WgradDesc(0, 1, 8, 8, 24, 16, 16), WgradDesc(0, 1, 8, 8, 32, 32, 32), WgradDesc(1, 1, 8, 8, 32, 16, 16)):
+        out = (C.c_int * 32)()
+        assert _lib.lib().b200_wgrad_line_plan_debug(C.byref(desc), out, 32) != 0

@@ -54,10 +54,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, const uint8_t* a_i
     tc_fence_after();
     const uint32_t tm = tslot;
     if (threadIdx.x == 0) {
-        const int Mmma = c.a_mn_major == 2 ? c.base_mode : 128;       // MN-major timing variant: M passed in base_mode
-        const uint32_t idesc = c.a_mn_major == 2 ? make_idesc(Mmma, c.N, 1, 1) : make_idesc(128, c.N, c.a_mn_major, 0);
+        const int Mmma = c.a_mn_major >= 2 ? c.base_mode : 128;       // MN-major timing variant: M passed in base_mode
+        const uint32_t idesc = c.a_mn_major >= 2 ? make_idesc(Mmma, c.N, 1, 1) : make_idesc(128, c.N, c.a_mn_major, 0);
         uint32_t a_addr, b_addr, lbo_a, sbo_a, lbo_b, sbo_b;
-        if (c.a_mn_major == 2) {
+        if (c.a_mn_major == 3) {
+            // line-marching weight gradient (wgrad_line.cuh): block stride = one line plane (rowbytes field), start
+            // address shifted by shift_rows rows of 16 B
+            a_addr = smem_u32(sa) + c.shift_rows * 16; lbo_a = 128; sbo_a = c.rowbytes;
+            b_addr = smem_u32(sb) + c.shift_rows * 16; lbo_b = 128; sbo_b = c.rowbytes;
+        } else if (c.a_mn_major == 2) {
             // both operands MN-major, SWIZZLE_NONE, as the weight-gradient GEMM reads them: planes [8-ch block][row][16 B],
             // LBO = 128 B between 8-row K groups, SBO = plane stride between 8-channel blocks (64-row planes)
             a_addr = smem_u32(sa); lbo_a = 128; sbo_a = 64 * 16;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, const uint8_t* a_i
             b_addr = smem_u32(sb) + c.k0 * 2;
             lbo_b = 16; sbo_b = 8 * c.rowbytes;
         }
-        const uint32_t boff = (c.base_mode && c.a_mn_major != 2) ? ((a_addr >> 7) & 7) : 0;
+        const uint32_t boff = (c.base_mode && c.a_mn_major < 2) ? ((a_addr >> 7) & 7) : 0;
         const uint64_t ad = desc_full(a_addr, lbo_a, sbo_a, c.layout, boff);
         const uint64_t bd = desc_full(b_addr, lbo_b, sbo_b, c.layout, 0);
         long long t0 = clock64();
@@ -188,6 +193,17 @@ int main() {
             long long cyc;
             cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
             printf("MN/MN M=%3d N=%3d : %7.1f cycles/MMA  (N/2 = %d)\n", M, N, (double)cyc / 2000, N / 2);
+        }
+    printf("== MN/MN M=64 N=144 (wgrad_line.cuh operands): block stride x start-row shift, cycles per MMA ==\n");
+    for (int sbo : {1024, 2048, 2080, 2176, 2304})
+        for (int shift : {0, 1, 4, 7, 8}) {
+            Cfg c{0, sbo, 144, 2000, shift, 64, 0, 3};
+            probe_kernel<<<148, 128, 200 * 1024>>>(c, d_a, d_b, 96 * 1024, 64 * 1024, nullptr, d_cyc);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("line form sbo=%d shift=%d: CUDA error %s\n", sbo, shift, cudaGetErrorString(e)); return 1; }
+            long long cyc;
+            cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+            printf("line form SBO=%4d B start shift=%d rows : %7.1f cycles/MMA\n", sbo, shift, (double)cyc / 2000);
         }
     printf("== shifted start (3 rows) timing, N=16/64 ==\n");
     for (auto& L : layouts)
