@@ -46,7 +46,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -101,17 +101,37 @@ def init_weights(model, seed):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle restatement of the reference arithmetic on host cores
 # ------------------------------------------------------------------------------------------------
+class CpuReferenceStep:
+    """One training step of the reference arithmetic on host cores: the oracle restatement of model.py + loss.py
+    (fp32 torch CPU ops, autograd backward) followed by the optimizer of main.py:133-138 (torch.optim.Adam, amsgrad,
+    weight decay) - the same work the CUDA arm's step does.  The checker, timed as a baseline only."""
+
+    def __init__(self, batch, size):
+        import torch
+        from oracle import resunet_oracle as O
+        self.O, self.torch = O, torch
+        self.sd = O.init_params(1337)
+        dead = set(O.dead_param_names())
+        self.leaves = {k: v.clone().requires_grad_(True) for k, v in self.sd.items() if k not in dead}
+        self.opt = torch.optim.Adam(list(self.leaves.values()), lr=2e-5, weight_decay=1e-6, amsgrad=True)
+        g = torch.Generator().manual_seed(0)
+        self.x = torch.randn(batch, 4, size, size, size, generator=g)
+        self.t = (torch.rand(batch, 3, size, size, size, generator=g) > 0.7).float()
+
+    def __call__(self):
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.O.dice_loss_joint(self.O.unet_forward(self.leaves, [self.x]), [self.t])
+        loss.backward()
+        self.opt.step()
+        return float(loss.detach())
+
+
 def cpu_train_step_seconds(size, reps, batch=1):
-    import torch
-    from oracle import resunet_oracle as O      # the checker, timed as the CPU baseline only
-    sd = O.init_params(1337)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 4, size, size, size, generator=g)
-    t = (torch.rand(batch, 3, size, size, size, generator=g) > 0.7).float()
+    step = CpuReferenceStep(batch, size)
     best = 1e30
     for _ in range(reps):
         t0 = time.perf_counter()
-        O.train_step(sd, x, t)
+        step()
         best = min(best, time.perf_counter() - t0)
     return best
 
@@ -130,37 +150,33 @@ def run_reference(args, rank):
         torch.set_num_threads(avail)
     cores = torch.get_num_threads()
     steps, warm = args.steps, args.warmup
-    # bounded sample: pick the largest cube whose (K+W) steps fit ~150 s, from a 32^3 calibration
-    t32 = cpu_train_step_seconds(32, 1)
-    t32 = min(t32, cpu_train_step_seconds(32, 1))
-    budget = 150.0 / max(1, steps + warm)
-    size = 32
-    for s in (128, 96, 64, 48):
-        if t32 * (s / 32.0) ** 3 * 1.3 <= budget:
-            size = s
-            break
-    from oracle import resunet_oracle as O
-    sd = O.init_params(1337)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 4, size, size, size, generator=g)
-    t = (torch.rand(1, 3, size, size, size, generator=g) > 0.7).float()
+    # The CUDA arm's workload is `--batch` volumes of 4 x `--size`^3 per step.  Run exactly that when the whole
+    # (K + W)-step run fits ~4 minutes on this host (calibrated on a 32^3 crop); otherwise one volume per step.
+    t32 = min(cpu_train_step_seconds(32, 1), cpu_train_step_seconds(32, 1))
+    per_volume = t32 * (args.size / 32.0) ** 3 * 1.3
+    batch = args.batch if per_volume * args.batch * (steps + warm) <= 240.0 else 1
+    size = args.size
+    step = CpuReferenceStep(batch, size)
     for _ in range(warm):
-        O.train_step(sd, x, t)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.train_step(sd, x, t)
+        step()
     dt = (time.perf_counter() - t0) / max(1, steps)
-    v = size ** 3 / dt
-    sample = "1 x 4x%d^3 crop per step: fwd + Dice_loss_joint + autograd backward, fp32, torch CPU (oneDNN)" % size
+    v = batch * size ** 3 / dt
+    sample = ("%d x 4x%d^3 volumes per step: fwd + Dice_loss_joint + autograd backward + Adam(amsgrad) step, fp32, torch CPU "
+              "(oneDNN), %d threads" % (batch, size, cores))
     emit({
         "impl": "reference", "metric": "voxels/sec fwd+bwd (ResUNet train step, 4x128^3 volumes)", "value": v,
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "train step fwd+Dice+bwd, 4x128^3 volumes (bounded sample: %s)" % sample},
+        "config": {"workload": "train step: fwd + Dice_loss_joint + bwd + Adam(amsgrad), batch %d x 4x%d^3 per step "
+                               "(BASELINE config 3%s)" % (batch, size, "" if batch == args.batch else "; one volume per step: bounded sample"),
+                   "per_gpu_batch": batch, "volume": [4, size, size, size]},
         "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "oracle port of /root/reference model.py+loss.py (reference is Python and does not travel to the "
-                "GPU box); excludes the reference's gc.collect() per forward and the optimizer step",
+        "note": "oracle port of /root/reference model.py + loss.py (the reference is Python and does not travel to the GPU "
+                "box); excludes only the reference's gc.collect() per forward (model.py:409, ~0.1 s, no numerical effect)",
     })
 
 
@@ -197,6 +213,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=2, help="volumes per GPU per step (config 3: 2)")
     ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="BASELINE config 4 as written: this many volumes per step over ALL ranks (strong scaling; "
+                         "per-GPU batch = global / N).  Default 0: --batch volumes per GPU (weak scaling)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock PyTorch/cuDNN bf16-autocast line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of one CUDA graph per step")
     ap.add_argument("--torch-adam", action="store_true", help="stock torch.optim.Adam(fused=True) instead of brats2019_b200.optim.FusedAdam")
@@ -204,6 +224,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.global_batch:
+        if args.global_batch % max(1, world):
+            raise SystemExit("--global-batch %d is not divisible by %d ranks" % (args.global_batch, world))
+        args.batch = args.global_batch // max(1, world)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -350,61 +374,69 @@ def run(args, rank, world, local_rank, dev):
     model.train()
     fwd_value = vox_step / (ms_fwd / args.steps * 1e-3)
 
-    # dominant conv kernel, timed alone: level-0 3x3x3 16->16 implicit GEMM (5 per forward, 5 data gradients per
-    # backward; 44 % of the model's FLOPs)
-    roof = None
+    # ---- roofline of EVERY kernel family of the step (and the time-dominant one as `roofline`) ----------------------
+    # Algorithmic work per family: the ledger of brats2019_b200.ops filled by one eager step (2*M*N*K per conv with
+    # padding taps counted, bytes at the logical interface for the memory-bound kernels).
+    # Device time per family: CUPTI activity records of graph replays of the same step, taken right after the timed
+    # region (CUDA events cannot bracket a kernel inside a graph replay; the event-timed number is `ms_per_step`).
+    roof, roof_all = None, None
+    if rank == 0 or world > 1:
+        ops.LEDGER = []
+        if use_graph:
+            GraphedTrainStep._eager(gstep)
+        else:
+            step_resident()
+        ledger, ops.LEDGER = ops.LEDGER, None
+        torch.cuda.synchronize()
+        roof_all = kernel_rooflines(step_resident, ledger, peaks, ms_step)      # every rank replays (collectives inside)
     if rank == 0:
-        desc = ops.conv_desc(ops.MODE_K3, Bsz, S, S, S, 16, 16)
-        xa = ops.act_zeros(Bsz, S, S, S, 16, dev)
-        xa.interior().copy_(torch.randn(2, Bsz, S, S, S, 8, device=dev).to(torch.bfloat16))
-        w = torch.randn(16, 16, 3, 3, 3, device=dev) * 0.05
-        pk = ops.conv_pack_weight(desc, ops.W_FWD, w)
-        out = ops.act_zeros(Bsz, S, S, S, 16, dev)
-        st = torch.empty(ops.conv_ctas(desc) * Bsz * 16, device=dev)
-        for _ in range(3):
-            ops.conv_run(desc, xa, pk, out, stats=st)
-        reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            ops.conv_run(desc, xa, pk, out, stats=st)
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        flops = 2.0 * Bsz * S ** 3 * 16 * 432
-        ach = flops / (k_ms * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_burst"], "traffic": traffic,
-                "kernel": "conv_band_kernel<BF16> (3x3x3 16->16 implicit GEMM, kd+kh folded, +GN stats) @ %dx%d^3" % (Bsz, S),
-                "ms_per_launch": k_ms,
-                "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
+        if roof_all:
+            top = roof_all[0]
+            traffic = None
+            tp = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get(top["kernel"], {}).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            roof = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                    "frac": top["frac"], "traffic": traffic, "kernel": top["kernel"], "launches_per_step": top["launches"],
+                    "time_share": top["time_share"], "ms_per_launch": top["ms_per_step"] / max(1, top["launches"]),
+                    "algorithmic_work_per_launch": top["work_per_step"] / max(1, top["launches"]),
+                    "peak_source": peaks["source"] + ", sustained (kernel timed inside the step)" if top["bound"] == "tensor"
+                    else peaks["source"]}
+
+    # ---- stock PyTorch / cuDNN on the same GPU in the same run: the reference arithmetic
+    # (the oracle restatement: F.conv3d, F.group_norm, F.interpolate, autograd) under bf16 autocast + fused Adam ----
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        gpu_base = torch_gpu_baseline(Bsz, S, dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import torch as _t
-        secs = cpu_train_step_seconds(128, 2)
-        cpu = {"value": 128 ** 3 / secs, "unit": "voxels/s", "cores": _t.get_num_threads(), "kind": "port",
-               "sample": "1 x 4x128^3 train step (fwd + Dice + autograd bwd), fp32 torch CPU, best of 2, %.1f s" % secs}
+        secs = cpu_train_step_seconds(S, 2, batch=1)
+        cpu = {"value": S ** 3 / secs, "unit": "voxels/s", "cores": _t.get_num_threads(), "kind": "port",
+               "sample": "1 x 4x%d^3 train step (fwd + Dice + autograd bwd + Adam), fp32 torch CPU, best of 2, %.1f s" % (S, secs)}
+
+    # ---- multi-GPU correctness in the same run: N ranks == one process on the concatenated batch ----
+    ddp = ddp_parity(model, net, crit, rank, world, dev) if world > 1 else None
 
     if rank == 0:
         flops_step = FLOP_PER_VOXEL_FWD_BWD * vox_step
+        strong = bool(args.global_batch)
         out = {
             "metric": "voxels/sec fwd+bwd (ResUNet train step, 4x128^3 volumes)", "value": value, "unit": "voxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
             "config": {"workload": "train step: fwd + Dice_loss_joint + bwd%s + Adam(amsgrad), batch %d x 4x%d^3 per GPU "
-                                   "(BASELINE config 3%s)" % (" + NCCL grad all-reduce" if world > 1 else "", Bsz, S,
-                                                              "/4" if world > 1 else ""),
+                                   "(BASELINE config %s)" % (" + NCCL grad all-reduce" if world > 1 else "", Bsz, S,
+                                                             "4: global batch %d" % args.global_batch if strong else
+                                                             ("3 per GPU" if world > 1 else "3")),
                        "per_gpu_batch": Bsz, "global_batch": Bsz * world, "volume": [4, S, S, S],
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
+                       "optimizer": "torch.optim.Adam(fused)" if args.torch_adam else "brats2019_b200.optim.FusedAdam",
                        "l2": "no flush needed: per-step working set (>2 GB of activations) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -413,9 +445,135 @@ def run(args, rank, world, local_rank, dev):
                         "tensor_frac_of_sustained": fwd_value / world * FLOP_PER_VOXEL_FWD / 1e12 / peaks["tf_sust"]},
             "model_tflops": flops_step / (ms_step * 1e-3) / 1e12 / world,
             "model_tensor_frac_of_sustained": flops_step / (ms_step * 1e-3) / 1e12 / world / peaks["tf_sust"],
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "ddp_parity": ddp,
+            "clocks": clocks,
         }
         emit(out)
+
+
+def kernel_rooflines(step_fn, ledger, peaks, ms_step):
+    """[{kernel, launches, ms_per_step, time_share, bound, work_per_step, achieved, peak, unit, frac}], by time."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    reps = 3
+    try:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(reps):
+                step_fn()
+            torch.cuda.synchronize()
+        kern = {}
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                name = ev.name.replace("void ", "").replace("b200::", "")
+                us = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+                c = kern.setdefault(name, [0, 0.0])
+                c[0] += 1
+                c[1] += us
+    except Exception as e:                                   # CUPTI unavailable: no per-kernel table, the headline stands
+        sys.stderr.write("kernel_rooflines: profiler failed (%r)\n" % (e,))
+        return None
+    work = {}
+    for name, bound, w in ledger:
+        d = work.setdefault(name, [bound, 0.0, 0])
+        d[1] += w
+        d[2] += 1
+    fam = {}
+    total_us = sum(v[1] for v in kern.values()) / reps
+    for name, (cnt, us) in kern.items():
+        key = next((k for k in work if name.startswith(k)), None)
+        if key is None:
+            key = name.split("(")[0][:60]
+        f = fam.setdefault(key, [0, 0.0])
+        f[0] += cnt / reps
+        f[1] += us / reps
+    rows = []
+    for key, (cnt, us) in fam.items():
+        bound, w, _ = work.get(key, ("hbm", 0.0, 0))
+        secs = us * 1e-6
+        if bound == "tensor":
+            ach, peak, unit = w / secs / 1e12, peaks["tf_sust"], "TFLOP/s"
+        else:
+            ach, peak, unit = w / secs / 1e9, peaks["hbm"], "GB/s"
+        rows.append({"kernel": key, "launches": int(round(cnt)), "ms_per_step": us / 1e3, "time_share": us / total_us,
+                     "bound": bound, "work_per_step": w, "achieved": ach, "peak": peak, "unit": unit,
+                     "frac": ach / peak if w else None})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows[:24]
+
+
+def torch_gpu_baseline(Bsz, S, dev):
+    """The same training step as stock PyTorch ops (cuDNN / ATen) under bf16 autocast on this GPU."""
+    import torch
+    from oracle import resunet_oracle as O      # the reference arithmetic, timed as a baseline only
+    try:
+        sd = {k: v.to(dev) for k, v in O.init_params(1337).items()}
+        dead = set(O.dead_param_names())
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k not in dead}
+        opt = torch.optim.Adam(list(leaves.values()), lr=2e-5, weight_decay=1e-6, amsgrad=True, fused=True)
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(Bsz, 4, S, S, S, generator=g).to(dev)
+        t = (torch.rand(Bsz, 3, S, S, S, generator=g) > 0.7).float().to(dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                probs = O.unet_forward(leaves, [x])
+            loss = O.dice_loss_joint([probs[0].float()], [t])
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 5
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        del leaves, opt, x, t
+        torch.cuda.empty_cache()
+        return {"value": Bsz * S ** 3 / (ms * 1e-3), "unit": "voxels/s", "ms_per_step": ms, "kind": "stock PyTorch %s / cuDNN, "
+                "bf16 autocast, fused Adam, eager; the reference arithmetic (oracle restatement of model.py + loss.py)" % torch.__version__}
+    except Exception as e:
+        return {"unavailable": repr(e)[:200]}
+
+
+def ddp_parity(model, net, crit, rank, world, dev):
+    """N ranks (one small volume each) against ONE process on the concatenated batch, same weights: the loss every rank
+    reports and the 86 gradients after the bucketed all-reduce (tools/ddp_parity.py is the long form)."""
+    import torch
+    import torch.distributed as dist
+    S = 32
+    g = torch.Generator().manual_seed(4242)
+    X = torch.randn(world, 4, S, S, S, generator=g).to(dev)
+    T = (torch.rand(world, 3, S, S, S, generator=g) > 0.7).float().to(dev)
+    model.zero_grad(set_to_none=True)
+    loss = crit(net([X[rank:rank + 1].contiguous()]), [T[rank:rank + 1].contiguous()])
+    loss.backward()
+    torch.cuda.synchronize()
+    losses = [torch.zeros(1, device=dev) for _ in range(world)]
+    dist.all_gather(losses, loss.detach().reshape(1))
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    out = None
+    if rank == 0:
+        group, crit.process_group = crit.process_group, None
+        factory, model._grad_store_factory = model._grad_store_factory, None
+        model.zero_grad(set_to_none=True)
+        l1 = crit(model([X]), [T])
+        l1.backward()
+        torch.cuda.synchronize()
+        rel = [((grads[n] - p.grad).norm() / p.grad.norm().clamp_min(1e-20)).item() for n, p in model.named_parameters()
+               if p.grad is not None]
+        crit.process_group, model._grad_store_factory = group, factory
+        ls = [float(v) for v in losses]
+        out = {"shape": "%d ranks x 1 x 4x%d^3 vs 1 process on the concatenated batch" % (world, S),
+               "loss_identical_across_ranks": max(ls) == min(ls), "loss_ddp": ls[0], "loss_single": float(l1),
+               "grad_tensors": len(rel), "grad_rel_l2_max": max(rel), "grad_rel_l2_median": sorted(rel)[len(rel) // 2]}
+    model.zero_grad(set_to_none=True)
+    dist.barrier()
+    return out
 
 
 if __name__ == "__main__":

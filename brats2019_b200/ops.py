@@ -26,6 +26,33 @@ def _count(n):
     LAUNCHES[0] += n
 
 
+# Work ledger (bench.py `roofline_all`): when LEDGER is a list, every wrapper appends
+# (kernel-name prefix as CUPTI reports it, "tensor" | "hbm", algorithmic FLOPs or bytes of that launch) - the
+# algorithmic work of SURVEY.md 8(d): 2*M*N*K per conv with padding taps counted as full taps, and
+# (elements read + written) * element size at the kernel's logical interface for the memory-bound kernels.
+LEDGER = None
+
+
+def _ledger(name, bound, work):
+    if LEDGER is not None:
+        LEDGER.append((name, bound, float(work)))
+
+
+def _act_bytes(a):
+    return 2.0 * a.N * a.D * a.H * a.W * a.C
+
+
+def _conv_kernel_name(desc):
+    """Which kernel b200_conv_run dispatches this descriptor to (same planners, no launch)."""
+    L = _lib.lib()
+    buf = (C.c_int * 64)()
+    if desc.mode == MODE_K3 and L.b200_band_plan_debug(C.byref(desc), buf, 64) == 0:
+        return "conv_band_kernel"
+    if desc.mode == MODE_K3 and L.b200_march_plan_debug(C.byref(desc), buf, 64) == 0:
+        return "conv_march_kernel"
+    return "conv_gemm_kernel<%d," % desc.mode
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -123,6 +150,7 @@ def pack_input(x, Cpad=16, out=None):
     assert Cc <= 8 and out.C == Cpad
     check(_lib.lib().b200_pack_input(_p(x), _p(out), N, D, H, W, Cc, Cpad, _stream()), "b200_pack_input")
     _count(1)
+    _ledger("pack_input", "hbm", x.numel() * 4 + N * D * H * W * 16)
     return out
 
 
@@ -228,6 +256,7 @@ class PackTable:
         check(_lib.lib().b200_pack_table_run(_p(self.table), len(self.jobs), self.total_blocks, _stream()),
               "b200_pack_table_run")
         _count(1)
+        _ledger("pack_weights_batched_kernel", "hbm", sum(j[2].numel() * 4 + j[6].numel() for j in self.jobs))
 
 
 def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=False, stats=None, bias=None,
@@ -236,6 +265,10 @@ def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=Fal
                                    1 if lrelu else 0, _p(stats), _p(bias), _p(probs), _p(logits), n_out_real,
                                    _stream()), "b200_conv_run")
     _count(1)
+    if LEDGER is not None:
+        taps = 27 if desc.mode == MODE_K3 else 1
+        _ledger(_conv_kernel_name(desc), "tensor",
+                2.0 * desc.N * desc.D * desc.H * desc.W * (desc.Cin_a + desc.Cin_b) * desc.Cout * taps)
     return out
 
 
@@ -262,6 +295,16 @@ def wgrad_run(desc, dy, x, grad, kind, ci_off=0, accumulate=False, workspace=Non
                                     grad.shape[1], taps, ci_off, 1 if accumulate else 0, _stream()),
           "b200_wgrad_run")
     _count(2)
+    if LEDGER is not None:
+        import os
+        buf = (C.c_int * 64)()
+        line = (kind == G_K3 and os.environ.get("B200_NO_WGRAD_LINE", "0") in ("", "0") and
+                os.environ.get("B200_WGRAD_MARCH", "0") in ("", "0") and
+                _lib.lib().b200_wgrad_line_plan_debug(C.byref(desc), buf, 64) == 0)
+        t = 27 if desc.mode == 0 else 1
+        _ledger("wgrad_line_kernel" if line else "wgrad_gemm_kernel", "tensor",
+                2.0 * desc.N * desc.D * desc.H * desc.W * desc.Cout * desc.Cin * t)
+        _ledger("wgrad_line_reduce_kernel" if line else "wgrad_reduce_kernel", "hbm", grad.numel() * 4)
     return grad
 
 
@@ -272,6 +315,7 @@ def gn_finalize(stats, ctas, N, Cc, D, H, W, mean, rstd):
     check(_lib.lib().b200_gn_finalize(_p(stats), ctas, N, Cc, D, H, W, GN_EPS, _p(mean), _p(rstd), _stream()),
           "b200_gn_finalize")
     _count(1)
+    _ledger("gn_finalize_kernel", "hbm", ctas * N * 16 * 4)
 
 
 def gn_apply(x, mean, rstd, gamma, beta, out, residual=None, lrelu=True):
@@ -279,6 +323,7 @@ def gn_apply(x, mean, rstd, gamma, beta, out, residual=None, lrelu=True):
     check(_lib.lib().b200_gn_apply(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(out), N, D, H, W,
                                    Cc, 1 if lrelu else 0, _stream()), "b200_gn_apply")
     _count(1)
+    _ledger("gn_apply_kernel", "hbm", (3 if residual is not None else 2) * _act_bytes(x))
     return out
 
 
@@ -293,6 +338,9 @@ def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lr
                                       _p(dbeta), _p(workspace), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
           "b200_gn_backward")
     _count(3)
+    _ledger("gn_bwd_reduce2_kernel", "hbm", 2 * _act_bytes(x))
+    _ledger("gn_bwd_finalize2_kernel", "hbm", 0)
+    _ledger("gn_bwd_apply2_kernel", "hbm", 3 * _act_bytes(x))
     return dx
 
 
@@ -304,6 +352,7 @@ def upsample2x(coarse, fine, lrelu=True):
     check(_lib.lib().b200_upsample2x(_p(coarse), _p(fine), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
           "b200_upsample2x")
     _count(1)
+    _ledger("upsample2x_fwd3_kernel", "hbm", 9 * _act_bytes(coarse))
     return fine
 
 
@@ -329,6 +378,8 @@ def upsample2x_backward(dfine, fine_out, dcoarse, lrelu=True, workspace=None):
     check(L.b200_upsample2x_backward(_p(dfine), _p(fine_out), _p(dcoarse), _p(workspace), N, D, H, W, Cc,
                                      1 if lrelu else 0, _stream()), "b200_upsample2x_backward")
     _count(2)
+    _ledger("upsample2x_bwd_w3_kernel", "hbm", (8 + 8 + 4) * _act_bytes(dcoarse))
+    _ledger("upsample2x_bwd_dh3_kernel", "hbm", (4 + 1) * _act_bytes(dcoarse))
     return dcoarse
 
 
@@ -336,6 +387,7 @@ def space_to_depth(fine, coarse):
     N, D, H, W, C8 = act_dims(coarse)
     check(_lib.lib().b200_space_to_depth(_p(fine), _p(coarse), N, D, H, W, C8 // 8, _stream()), "b200_space_to_depth")
     _count(1)
+    _ledger("s2d_kernel", "hbm", 2 * _act_bytes(coarse))
     return coarse
 
 
@@ -344,6 +396,7 @@ def depth_to_space(coarse, fine, residual=None):
     check(_lib.lib().b200_depth_to_space(_p(coarse), _p(residual), _p(fine), N, D, H, W, C8 // 8, _stream()),
           "b200_depth_to_space")
     _count(1)
+    _ledger("d2s_kernel", "hbm", (3 if residual is not None else 2) * _act_bytes(coarse))
     return fine
 
 
@@ -366,6 +419,7 @@ def sigmoid_backward(grad_probs, probs, dlogit_act, dbias, workspace=None):
     check(_lib.lib().b200_sigmoid_backward(_p(grad_probs), _p(probs), _p(dlogit_act), _p(dbias), _p(workspace), N, D,
                                            H, W, Cr, Cpad, _stream()), "b200_sigmoid_backward")
     _count(2)
+    _ledger("sigmoid_bwd_pack", "hbm", 2 * probs.numel() * 4 + N * D * H * W * 16)
     return dlogit_act
 
 
@@ -379,6 +433,7 @@ def dice_sums(probs, target, sums=None, workspace=None):
     check(_lib.lib().b200_dice_sums(_p(probs), _p(target), _p(sums), _p(workspace), B, Cc, S, _stream()),
           "b200_dice_sums")
     _count(2)
+    _ledger("dice_partial_kernel", "hbm", 2 * probs.numel() * 4)
     return sums
 
 
@@ -398,6 +453,7 @@ def dice_backward(probs, target, sums, grad_out, priority, grad_probs=None):
     check(_lib.lib().b200_dice_backward(_p(probs), _p(target), _p(sums), _p(grad_out), float(priority),
                                         _p(grad_probs), B, Cc, S, _stream()), "b200_dice_backward")
     _count(1)
+    _ledger("dice_bwd_kernel", "hbm", 3 * probs.numel() * 4)
     return grad_probs
 
 

@@ -178,6 +178,7 @@ class FusedAdam(torch.optim.Optimizer):
                 float(group["weight_decay"]), self.lr_step_size, self.lr_gamma,
                 torch.cuda.current_stream().cuda_stream), "b200_adam_step")
         ops._count(1)
+        ops._ledger("adam_step_kernel", "hbm", L["total"] * 4 * (9 if L["X"] is not None else 7))
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that the engine
         # re-packs its bf16 weight images (and anything else that caches by version notices)
         for p in L["params"]:
