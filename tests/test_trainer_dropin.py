@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import resunet_oracle as O
-from tests import trainer_harness as TH
+import trainer_harness as TH
 
 
 def _net():
