@@ -49,12 +49,17 @@ _PROTOS = {
     "b200_pack_table_build": (c_int, [C.POINTER(PackJob), c_int, P, c_size_t, C.POINTER(c_int)]),
     "b200_pack_table_run": (c_int, [P, c_int, c_int, P]),
     "b200_conv_run": (c_int, [C.POINTER(ConvDesc), P, P, P, P, P, c_int, P, P, P, P, c_int, P]),
+    "b200_conv_supports_gnbwd": (c_int, [C.POINTER(ConvDesc)]),
+    "b200_conv_run_gnbwd": (c_int, [C.POINTER(ConvDesc), P, P, P, P, P, c_int, P, P, P, P, c_int, P, P, P]),
     "b200_wgrad_workspace_bytes": (c_size_t, [C.POINTER(WgradDesc)]),
     "b200_wgrad_run": (c_int, [C.POINTER(WgradDesc), P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_gn_finalize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P]),
+    "b200_gn_finalize_coef": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, c_int, P, P, P, P]),
     "b200_gn_apply": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_gn_backward_workspace_floats": (c_size_t, [c_int, c_int]),
     "b200_gn_backward": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200_gn_backward_folded_workspace_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "b200_gn_backward_folded": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_upsample2x": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_upsample2x_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "b200_upsample2x_backward": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),

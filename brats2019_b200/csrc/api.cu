@@ -516,7 +516,7 @@ static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStrea
 
 static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a, const void* packed, void* out,
                      const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
-                     float* logits, int n_out_real, cudaStream_t st) {
+                     float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, cudaStream_t st) {
     if (!src_a || !packed) return fail("conv: null operand");
     if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
     if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
@@ -538,6 +538,10 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
     p.src = make_act(src_a, vol);
     p.out = make_act(out, vol);
     p.residual = make_act(residual, vol);
+    if (gnb_x && (!stats_partial || !gnb_coef || check_ptr16(gnb_x, "gnb_x") || check_ptr16(gnb_coef, "gnb_coef")))
+        return fail("conv: GroupNorm-backward fold needs stats_partial, gnb_coef and 16-byte aligned pointers");
+    p.gnb_x = make_act(gnb_x, vol);
+    p.gnb_coef = gnb_coef;
     const unsigned smem = p.smem_bar_off + kMarchTailBytes;
     if (d->epi == EPI_SIGMOID) return launch_march<16, EPI_SIGMOID>(p, smem, grid, st);
     if (d->Cout == 16) return launch_march<16, EPI_BF16>(p, smem, grid, st);
@@ -554,7 +558,7 @@ static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_
 
 static int run_band(const b200_conv_desc* d, BandParams& p, const void* src_a, const void* packed, void* out,
                     const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
-                    float* logits, int n_out_real, cudaStream_t st) {
+                    float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, cudaStream_t st) {
     if (!src_a || !packed) return fail("conv: null operand");
     if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
     if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
@@ -576,27 +580,49 @@ static int run_band(const b200_conv_desc* d, BandParams& p, const void* src_a, c
     p.src = make_act(src_a, vol);
     p.out = make_act(out, vol);
     p.residual = make_act(residual, vol);
+    if (gnb_x && (!stats_partial || !gnb_coef || check_ptr16(gnb_x, "gnb_x") || check_ptr16(gnb_coef, "gnb_coef")))
+        return fail("conv: GroupNorm-backward fold needs stats_partial, gnb_coef and 16-byte aligned pointers");
+    p.gnb_x = make_act(gnb_x, vol);
+    p.gnb_coef = gnb_coef;
     const unsigned smem = p.smem_bar_off + kBandTailBytes;
     if (d->epi == EPI_SIGMOID) return launch_band<EPI_SIGMOID>(p, smem, grid, st);
     return launch_band<EPI_BF16>(p, smem, grid, st);
 }
 
+extern "C" int b200_conv_supports_gnbwd(const b200_conv_desc* d) {
+    if (check_conv_desc(d) || d->epi != EPI_BF16) return 0;
+    BandParams bp;
+    if (plan_band(d, bp) == 0) return 1;
+    MarchParams mp;
+    if (plan_march(d, mp) == 0) return 1;
+    return 0;
+}
+
 extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
                              void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
                              float* probs, float* logits, int n_out_real, void* stream) {
+    return b200_conv_run_gnbwd(d, src_a, src_b, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
+                               n_out_real, nullptr, nullptr, stream);
+}
+
+extern "C" int b200_conv_run_gnbwd(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
+                                   void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
+                                   float* probs, float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef,
+                                   void* stream) {
     if (check_conv_desc(d)) return 1;
     {
         BandParams bp;
         if (plan_band(d, bp) == 0)
             return run_band(d, bp, src_a, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
-                            n_out_real, (cudaStream_t)stream);
+                            n_out_real, gnb_x, gnb_coef, (cudaStream_t)stream);
     }
     {
         MarchParams mp;
         if (plan_march(d, mp) == 0)
             return run_march(d, mp, src_a, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
-                             n_out_real, (cudaStream_t)stream);
+                             n_out_real, gnb_x, gnb_coef, (cudaStream_t)stream);
     }
+    if (gnb_x) return fail("conv: the GroupNorm-backward fold exists for the band / marching 3x3x3 kernels only (b200_conv_supports_gnbwd)");
     ConvKParams p;
     if (plan_conv(d, p)) return 1;
     if (!src_a || !packed) return fail("conv: null operand");
@@ -1025,7 +1051,20 @@ extern "C" int b200_gn_finalize(const float* stats_partial, int ctas, int N, int
                                 float* mean, float* rstd, void* stream) {
     if (C % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
     const double count = (double)(C / 8) * D * H * W;
-    gn_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd);
+    gn_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd, nullptr, nullptr,
+                                                            nullptr, C, 1);
+    LAUNCH_OK("gn_finalize_kernel");
+    return 0;
+}
+extern "C" int b200_gn_finalize_coef(const float* stats_partial, int ctas, int N, int C, int D, int H, int W, float eps,
+                                     const float* gamma, const float* beta, int do_lrelu, float* mean, float* rstd,
+                                     float* coef, void* stream) {
+    if (C % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
+    if (!gamma || !beta || !coef) return fail("gn_finalize_coef: null argument");
+    if (check_ptr16(coef, "coef")) return 1;
+    const double count = (double)(C / 8) * D * H * W;
+    gn_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd, gamma, beta, coef,
+                                                            C, do_lrelu);
     LAUNCH_OK("gn_finalize_kernel");
     return 0;
 }
@@ -1162,8 +1201,41 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     LAUNCH_OK("gn_bwd_finalize2_kernel");
     const int lpb = lines_per_block(N, D, H, W, C);
     gn_bwd_apply2_kernel<<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                         coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb);
+                                                         coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr);
     LAUNCH_OK("gn_bwd_apply2_kernel");
+    return 0;
+}
+
+// GroupNorm backward when the group sums came from the producing conv's epilogue (b200_conv_run_gnbwd): no reduce pass.
+//   fold-finalize (gpart -> coef)  ->  apply (dx, + per-CTA per-channel sums)  ->  finalize2 (dgamma, dbeta)
+// workspace: coef[N][C][2] | scratch coef[N][C][2] | aff_partial[N][blocks][C][2], blocks = D*H / lines-per-CTA of the apply
+extern "C" size_t b200_gn_backward_folded_workspace_floats(int N, int D, int H, int W, int C) {
+    const int lpb = lines_per_block(N, D, H, W, C);
+    return (size_t)N * C * 4 + (size_t)N * (D * H / lpb) * C * 2;
+}
+extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const float* mean, const float* rstd,
+                                       const float* gamma, const float* beta, const float* gpart, int ctas, void* dx,
+                                       float* dgamma, float* dbeta, float* workspace, int N, int D, int H, int W, int C,
+                                       int do_lrelu, void* stream) {
+    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8) || C < 16) return fail("gn_backward_folded: C=%d unsupported", C);
+    if (!gpart || ctas < 1 || !workspace) return fail("gn_backward_folded: null argument");
+    Vol v{N, D, H, W};
+    cudaStream_t st = (cudaStream_t)stream;
+    const double m = (double)(C / 8) * D * H * W;
+    float* coef = workspace;
+    float* coef_scratch = workspace + (size_t)N * C * 2;
+    float* aff = workspace + (size_t)N * C * 4;
+    gn_bwd_fold_finalize_kernel<<<N, 256, 0, st>>>(gpart, ctas, N, C, m, mean, rstd, coef);
+    LAUNCH_OK("gn_bwd_fold_finalize_kernel");
+    const FastDiv by_W = make_fastdiv((unsigned)W);
+    const int lpb = lines_per_block(N, D, H, W, C);
+    const int bps = D * H / lpb;
+    gn_bwd_apply2_kernel<<<N * bps, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
+                                                 make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff);
+    LAUNCH_OK("gn_bwd_apply2_kernel");
+    const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
+    gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(aff, bps, N, C, m, gamma, coef_scratch, dgamma, dbeta);
+    LAUNCH_OK("gn_bwd_finalize2_kernel");
     return 0;
 }
 

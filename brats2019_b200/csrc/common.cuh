@@ -275,6 +275,43 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
 }
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
 
+// ---------------------------------------------------------------------------------------
+// GroupNorm-backward statistics folded into the epilogue of the data-gradient conv that PRODUCES the gradient
+// (replaces the gn_bwd_reduce2 pass over two tensors; model.py:105-112 backward).  For the GroupNorm y = lrelu(z),
+// z = c * p1 + p2 (p1 = rstd * gamma, p2 = beta - mean * rstd * gamma), whose input gradient is needed next, the
+// closed form needs per (sample, group)   A = sum gamma * dz,   U = sum gamma * dz * c   with dz = dy * lrelu'(z):
+// `dy` are the CO values this thread is about to store (already rounded to bf16, exactly what the apply kernel will
+// read back), `cq` the CO/8 vectors of the saved conv output c at the same voxel, coef = [3][C] (p1 | p2 | gamma) of
+// the sample.  a[g], u[g] accumulate the eight groups (CO / 8 channels each).
+// ---------------------------------------------------------------------------------------
+template <int CO>
+__device__ __forceinline__ void gnb_accumulate(const uint4* dyq, const uint4* cq, const float* __restrict__ coef, int C,
+                                               float* a, float* u) {
+    constexpr int GS = CO / 8;
+#pragma unroll
+    for (int k = 0; k < CO / 8; ++k) {
+        float dy[8], c[8];
+        unpack_bf16x8(dyq[k], dy);
+        unpack_bf16x8(cq[k], c);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(coef + k * 8 + h * 4));
+            const float4 p2 = __ldg(reinterpret_cast<const float4*>(coef + C + k * 8 + h * 4));
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + k * 8 + h * 4));
+            const float P1[4] = {p1.x, p1.y, p1.z, p1.w}, P2[4] = {p2.x, p2.y, p2.z, p2.w}, G[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = k * 8 + h * 4 + e;
+                const float z = fmaf(c[h * 4 + e], P1[e], P2[e]);
+                const float w = z > 0.f ? G[e] : 0.01f * G[e];
+                const float t = dy[h * 4 + e] * w;
+                a[i / GS] += t;
+                u[i / GS] = fmaf(t, c[h * 4 + e], u[i / GS]);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -46,6 +46,8 @@ struct BandParams {
     int lrelu_out;
     ActRef out, residual;
     float* stats_partial;
+    ActRef gnb_x;                     // != null: stats_partial receives GroupNorm-BACKWARD sums (common.cuh gnb_accumulate) of
+    const float* gnb_coef;            //          the GroupNorm whose conv output is gnb_x; coef = [N][3][16]
     const float* bias;
     float* probs;
     float* logits;
@@ -257,6 +259,7 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         int cur_n = -1;
         const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr);
+        const bool do_gnb = do_stats && p.gnb_x.base != nullptr;
         const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
 
         auto flush_stats = [&](int n) {
@@ -304,18 +307,27 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
                     // The residual operand (the identity path of a Residual block's data gradient) is requested
                     // BEFORE the wait for the accumulator, so its L2/HBM latency hides behind the MMAs of this line;
                     // loaded after the TMEM read it serialised ~1 us per line and cost the kernel +50 us.
-                    uint4 rq[CO / 8];
+                    uint4 rq[CO / 8], gq[CO / 8];
                     bool have_res = false;
-                    if (EPI == EPI_BF16 && p.residual.base) {
+                    if (EPI == EPI_BF16 && (p.residual.base || do_gnb)) {
                         const int hp_r = hp0 + jo - 1;
-                        have_res = out_valid && w_ok && hp_r <= p.H;
+                        const bool vox_ok = out_valid && w_ok && hp_r <= p.H;
+                        have_res = vox_ok && p.residual.base != nullptr;
+                        const long long rrow = (((long long)sg.n * (p.D + 2) + dpo) * (p.H + 2) + hp_r) * p.Wp + wp;
                         if (have_res) {
-                            const long long rrow = (((long long)sg.n * (p.D + 2) + dpo) * (p.H + 2) + hp_r) * p.Wp + wp;
 #pragma unroll
                             for (int c = 0; c < CO / 8; ++c) {
                                 const void* rp = p.residual.at(c, rrow);
                                 asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                                              : "=r"(rq[c].x), "=r"(rq[c].y), "=r"(rq[c].z), "=r"(rq[c].w) : "l"(rp));
+                            }
+                        }
+                        if (do_gnb && vox_ok) {           // the saved conv output of the GroupNorm differentiated next
+#pragma unroll
+                            for (int c = 0; c < CO / 8; ++c) {
+                                const void* gp = p.gnb_x.at(c, rrow);
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(gq[c].x), "=r"(gq[c].y), "=r"(gq[c].z), "=r"(gq[c].w) : "l"(gp));
                             }
                         }
                     }
@@ -347,7 +359,7 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
 #pragma unroll
                     for (int i = 0; i < CO; ++i) v[i] = __uint_as_float(r[i]);
                     if (EPI == EPI_BF16) {
-                        if (do_stats) {
+                        if (do_stats && !do_gnb) {
 #pragma unroll
                             for (int i = 0; i < CO; ++i) {
                                 ssum[i / GS] += v[i];
@@ -367,9 +379,13 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
 #pragma unroll
                             for (int i = 0; i < CO; ++i) v[i] = lrelu(v[i]);
                         }
+                        uint4 oq[CO / 8];
 #pragma unroll
-                        for (int c = 0; c < CO / 8; ++c)
-                            *reinterpret_cast<uint4*>(p.out.at(c, orow)) = pack_bf16x8(v + c * 8);
+                        for (int c = 0; c < CO / 8; ++c) {
+                            oq[c] = pack_bf16x8(v + c * 8);
+                            *reinterpret_cast<uint4*>(p.out.at(c, orow)) = oq[c];
+                        }
+                        if (do_gnb) gnb_accumulate<CO>(oq, gq, p.gnb_coef + (size_t)sg.n * 3 * CO, CO, ssum, ssq);
                     } else {   // EPI_SIGMOID
                         const size_t plane = (size_t)p.D * p.H * p.W;
                         const size_t vox = ((size_t)(dpo - 1) * p.H + (hp - 1)) * p.W + (wp - 1);

@@ -57,6 +57,8 @@ struct MarchParams {
     int lrelu_out;
     ActRef out, residual;
     float* stats_partial;             // optional [ctas][N][16]
+    ActRef gnb_x;                     // != null: stats_partial receives GroupNorm-BACKWARD sums (common.cuh gnb_accumulate) of
+    const float* gnb_coef;            //          the GroupNorm whose conv output is gnb_x; coef = [N][3][CO]
     const float* bias;                // EPI_SIGMOID
     float* probs;
     float* logits;
@@ -265,6 +267,7 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         int cur_n = -1;
         const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr);
+        const bool do_gnb = do_stats && p.gnb_x.base != nullptr;
         const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
 
         auto flush_stats = [&](int n) {
@@ -346,11 +349,20 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
 #pragma unroll
                     for (int i = 0; i < CO; ++i) v[i] = __uint_as_float(r[i]);
                     if (EPI == EPI_BF16) {
-                        if (do_stats) {
+                        if (do_stats && !do_gnb) {
 #pragma unroll
                             for (int i = 0; i < CO; ++i) {
                                 ssum[i / GS] += v[i];
                                 ssq[i / GS] += v[i] * v[i];
+                            }
+                        }
+                        uint4 gq[CO / 8];
+                        if (do_gnb) {                    // the saved conv output of the GroupNorm differentiated next
+#pragma unroll
+                            for (int c = 0; c < CO / 8; ++c) {
+                                const void* gp = p.gnb_x.at(c, orow);
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(gq[c].x), "=r"(gq[c].y), "=r"(gq[c].z), "=r"(gq[c].w) : "l"(gp));
                             }
                         }
                         if (p.residual.base) {
@@ -366,9 +378,13 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
 #pragma unroll
                             for (int i = 0; i < CO; ++i) v[i] = lrelu(v[i]);
                         }
+                        uint4 oq[CO / 8];
 #pragma unroll
-                        for (int c = 0; c < CO / 8; ++c)
-                            *reinterpret_cast<uint4*>(p.out.at(c, orow)) = pack_bf16x8(v + c * 8);
+                        for (int c = 0; c < CO / 8; ++c) {
+                            oq[c] = pack_bf16x8(v + c * 8);
+                            *reinterpret_cast<uint4*>(p.out.at(c, orow)) = oq[c];
+                        }
+                        if (do_gnb) gnb_accumulate<CO>(oq, gq, p.gnb_coef + (size_t)sg.n * 3 * CO, CO, ssum, ssq);
                     } else {   // EPI_SIGMOID: first n_out_real columns are real; fp32 NCDHW output
                         const int q = qbase + b * 128 + p.Q0;
                         const int hp = p.by_Wp.div(q);

@@ -78,8 +78,12 @@ __global__ void pack_input_kernel(const float* __restrict__ x, ActRef out, Vol v
 // ---------------------------------------------------------------------------------------
 // grid = N, block = 256: each of the 16 sums is split over 16 threads (strided over CTAs, fixed
 // order) and combined in a fixed order -> deterministic, ~ctas/16 dependent loads of latency.
+// coef (optional, with gamma/beta): [N][3][C] = (p1 | p2 | gamma), z = x * p1 + p2 the normalised value whose sign the
+// LeakyReLU backward needs - read by the data-gradient conv that folds this GroupNorm's backward sums into its epilogue
+// (common.cuh gnb_accumulate).  do_lrelu == 0 (norm_input): p1 = 0, p2 = 1, i.e. the mask is always 1.
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, int N, double count, float eps,
-                                   float* __restrict__ mean, float* __restrict__ rstd) {
+                                   float* __restrict__ mean, float* __restrict__ rstd, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ coef, int C, int do_lrelu) {
     __shared__ double s_part[256];
     __shared__ double s_sum[16];
     const int n = blockIdx.x, t = threadIdx.x;
@@ -94,12 +98,26 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, 
         s_sum[t] = acc;
     }
     __syncthreads();
+    __shared__ float s_m[8], s_r[8];
     if (t < 8) {
         const double m = s_sum[t] / count;
         double var = s_sum[8 + t] / count - m * m;
         if (var < 0.0) var = 0.0;
         mean[n * 8 + t] = (float)m;
         rstd[n * 8 + t] = (float)(1.0 / sqrt(var + (double)eps));
+        s_m[t] = (float)m;
+        s_r[t] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    if (coef == nullptr) return;
+    __syncthreads();
+    const int gs = C >> 3;
+    for (int c = t; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        const float sc = s_r[g] * gamma[c];                       // the same scale / shift gn_apply_kernel forms
+        float* o = coef + (size_t)n * 3 * C;
+        o[c] = do_lrelu ? sc : 0.f;
+        o[C + c] = do_lrelu ? beta[c] - s_m[g] * sc : 1.f;
+        o[2 * C + c] = gamma[c];
     }
 }
 

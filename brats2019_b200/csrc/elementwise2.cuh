@@ -210,11 +210,15 @@ gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, in
 
 // pass 3: dx = rstd * (dz*gamma - A_g - xhat*B_g) = dz*p1 + x*c1 + c0 with per-channel constants
 //   p1 = rstd*gamma, c1 = -rstd^2 B, c0 = -rstd (A + b B), b = -mean*rstd;  z = x*p1 + (b*gamma + beta).
+// aff_partial (optional): this CTA's per-channel sums S1 = sum dz, S2 = sum dz * xhat over its voxels, layout
+// [n][blocks per sample][C][2] like gn_bwd_reduce2's - the input of gn_bwd_finalize2 for dgamma / dbeta when the
+// group sums that dx needs came from the producing conv's epilogue (common.cuh gnb_accumulate) and no reduce pass ran.
 __global__ void __launch_bounds__(256, 2)
 gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
-                     ActRef dx, Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
+                     ActRef dx, Vol v, int C, int do_lrelu, FastDiv by_W, int lpb, float* __restrict__ aff_partial) {
     __shared__ long long s_rows[16];
+    __shared__ float s_red[8][16];
     const int line0 = blockIdx.x * lpb;
     fill_line_rows(v, line0, lpb, s_rows);
     __syncthreads();
@@ -226,10 +230,10 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
     const int stride = wc.wpc * 32;
     for (int pass = 0; pass < wc.npass; ++pass) {
         const int cv = wc.cvb + 8 * pass;
-        float2 p1[4], p2[4], c1[4], c0[4];
+        float2 p1[4], p2[4], c1[4], c0[4], a2[4], b2[4], s1[4], s2[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float k1[2], k2[2], k3[2], k4[2];
+            float k1[2], k2[2], k3[2], k4[2], ka[2], kb[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = cv * 8 + 2 * j + e;
@@ -238,9 +242,12 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
                 const float A = coef[((size_t)n * C + c) * 2 + 0], B = coef[((size_t)n * C + c) * 2 + 1];
                 k1[e] = r * gamma[c]; k2[e] = b * gamma[c] + beta[c];
                 k3[e] = -r * r * B; k4[e] = -r * (A + b * B);
+                ka[e] = r; kb[e] = b;
             }
             p1[j] = f2(k1[0], k1[1]); p2[j] = f2(k2[0], k2[1]);
             c1[j] = f2(k3[0], k3[1]); c0[j] = f2(k4[0], k4[1]);
+            a2[j] = f2(ka[0], ka[1]); b2[j] = f2(kb[0], kb[1]);
+            s1[j] = f2(0.f, 0.f); s2[j] = f2(0.f, 0.f);
         }
         constexpr int U = 4;
         for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
@@ -268,11 +275,72 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
                 for (int j = 0; j < 4; ++j) {
                     float2 dz = fd[j];
                     if (do_lrelu) dz = __fmul2_rn(dz, lrelu_mask(__ffma2_rn(fx[j], p1[j], p2[j])));
+                    if (aff_partial) {
+                        s1[j] = __fadd2_rn(s1[j], dz);
+                        s2[j] = __ffma2_rn(dz, __ffma2_rn(fx[j], a2[j], b2[j]), s2[j]);
+                    }
                     fx[j] = __ffma2_rn(dz, p1[j], __ffma2_rn(fx[j], c1[j], c0[j]));
                 }
                 st16(dx.at(cv, rr[u]), pack4(fx));
             }
         }
+        if (aff_partial) {          // same fixed-order combination as gn_bwd_reduce2_kernel
+            const int warp = threadIdx.x >> 5;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s1[j].x = warp_sum(s1[j].x); s1[j].y = warp_sum(s1[j].y);
+                s2[j].x = warp_sum(s2[j].x); s2[j].y = warp_sum(s2[j].y);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s_red[warp][2 * j] = s1[j].x; s_red[warp][2 * j + 1] = s1[j].y;
+                    s_red[warp][8 + 2 * j] = s2[j].x; s_red[warp][8 + 2 * j + 1] = s2[j].y;
+                }
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < wc.nb * 16) {
+                const int cb = threadIdx.x >> 4, k = threadIdx.x & 15;
+                float acc = 0.f;
+                for (int q = 0; q < wc.wpc; ++q) acc += s_red[cb + q * wc.nb][k];       // fixed order
+                const int c = (cb + 8 * pass) * 8 + (k & 7);
+                const int bps = v.D * v.H / lpb;                                         // CTAs per sample
+                const int b = blockIdx.x - n * bps;
+                aff_partial[(((size_t)n * bps + b) * C + c) * 2 + (k >> 3)] = acc;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Group sums from the producing conv's epilogue (common.cuh gnb_accumulate: per CTA a_g = sum gamma dz, u_g = sum gamma dz c)
+// -> coef[n][C][2] = (A_g, B_g) / m of the channel's group, the two constants gn_bwd_apply2 needs:
+//   A = sum_g gamma S1 = sum a,   B = sum_g gamma S2 = rstd * sum u + (-mean * rstd) * sum a      (xhat = c * rstd - mean * rstd)
+// grid = N, block = 256: each of the 16 sums is split over 16 threads (strided over CTAs, fixed order) - deterministic.
+__global__ void gn_bwd_fold_finalize_kernel(const float* __restrict__ gpart, int ctas, int N, int C, double m,
+                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                            float* __restrict__ coef) {
+    __shared__ double s_part[256];
+    __shared__ double s_sum[16];
+    const int n = blockIdx.x, t = threadIdx.x;
+    const int o = t >> 4, j = t & 15;
+    double a = 0.0;
+    for (int c = j; c < ctas; c += 16) a += (double)gpart[((size_t)c * N + n) * 16 + o];
+    s_part[t] = a;
+    __syncthreads();
+    if (t < 16) {
+        double acc = 0.0;
+        for (int q = 0; q < 16; ++q) acc += s_part[t * 16 + q];
+        s_sum[t] = acc;
+    }
+    __syncthreads();
+    const int gs = C >> 3;
+    for (int c = t; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        const double r = (double)rstd[n * 8 + g], b = -(double)mean[n * 8 + g] * r;
+        const double A = s_sum[g], U = s_sum[8 + g];
+        coef[((size_t)n * C + c) * 2 + 0] = (float)(A / m);
+        coef[((size_t)n * C + c) * 2 + 1] = (float)((r * U + b * A) / m);
     }
 }
 

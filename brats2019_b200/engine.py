@@ -105,6 +105,12 @@ class Engine:
         # data-gradient chain (GroupNorm backward etc.): a wgrad GEMM at 16/32 channels is bound by MMA issue
         # latency and leaves HBM and most issue slots idle, and it is off the critical path of backward.
         self.overlap_wgrad = os.environ.get("B200_NO_WGRAD_OVERLAP", "0") in ("", "0")
+        # GroupNorm-backward sums folded into the epilogue of the conv that produces the gradient (no reduce pass).
+        # OPT-IN (B200_GN_FOLD=1): parity-green (tests/test_layer_parity_gpu.py runs it), but measured a wash on the
+        # training step (5.80 vs 5.79 ms, profiles/r02_ab_gn_fold.txt): the ~150 instructions per voxel it adds to the
+        # band conv's epilogue (+50 us per launch) and the per-channel sums it moves into the apply kernel cost what
+        # the dropped reduce pass saved - the level-0 backward is bound by total issue/SM occupancy, not by one kernel.
+        self.fold_gn_bwd = os.environ.get("B200_GN_FOLD", "0") not in ("", "0")
         self._side_stream = None
         self._side_busy = False
         self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
@@ -200,8 +206,9 @@ class Engine:
     # ---------------------------------------------------------------------------------
     # building blocks
     # ---------------------------------------------------------------------------------
-    def _conv3_gn(self, P, lvl, wname, w, src, cname, Cin_real=None):
-        """c = conv3(src) with fused GroupNorm statistics; returns (c, mean, rstd)."""
+    def _conv3_gn(self, P, lvl, wname, w, src, cname, Cin_real=None, gamma=None, beta=None, lrelu=True):
+        """c = conv3(src) with fused GroupNorm statistics; returns (c, mean, rstd).  With gamma / beta (training) the
+        finalize kernel also writes the coefficient table the backward fold reads (ops.gn_finalize)."""
         D, H, W = P.dims[lvl]
         Cout = w.shape[0]
         Cin = src.C
@@ -213,18 +220,20 @@ class Engine:
         ops.conv_run(desc, src, pk, c, stats=stats)
         mean = P.f32("mean:" + cname, P.N * 8)
         rstd = P.f32("rstd:" + cname, P.N * 8)
-        ops.gn_finalize(stats, ctas, P.N, Cout, D, H, W, mean, rstd)
+        coef = P.f32("gnc:" + cname, P.N * 3 * Cout) if (gamma is not None and self.fold_gn_bwd) else None
+        ops.gn_finalize(stats, ctas, P.N, Cout, D, H, W, mean, rstd, gamma=gamma, beta=beta, coef=coef, lrelu=lrelu)
         return c, mean, rstd
 
-    def _residual_fwd(self, P, lvl, prefix, x_in, prm):
+    def _residual_fwd(self, P, lvl, prefix, x_in, prm, training=False):
         """model.py:99-117 (after the optional downsample): x + lrelu(gn2(conv2(lrelu(gn1(conv1(x))))))."""
         Cc = x_in.C
+        aff = (lambda n: dict(gamma=prm[prefix + n + ".weight"], beta=prm[prefix + n + ".bias"])) if training else (lambda n: {})
         c1, m1, r1 = self._conv3_gn(P, lvl, prefix + "conv1.conv1.weight", prm[prefix + "conv1.conv1.weight"], x_in,
-                                    prefix + "c1")
+                                    prefix + "c1", **aff("norm1"))
         a1 = ops.gn_apply(c1, m1, r1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
                           P.act(prefix + "a1", lvl, Cc), lrelu=True)
         c2, m2, r2 = self._conv3_gn(P, lvl, prefix + "conv2.conv1.weight", prm[prefix + "conv2.conv1.weight"], a1,
-                                    prefix + "c2")
+                                    prefix + "c2", **aff("norm2"))
         out = ops.gn_apply(c2, m2, r2, prm[prefix + "norm2.weight"], prm[prefix + "norm2.bias"],
                            P.act(prefix + "out", lvl, Cc), residual=x_in, lrelu=True)
         return out
@@ -263,11 +272,12 @@ class Engine:
                 P.alias("g.skip", i, gcat.chunks(0, nc))
                 P.alias("g.dup", i, gcat.chunks(nc, 2 * nc))
         x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
-        c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c")
+        c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c", lrelu=False,
+                                 **(dict(gamma=prm["norm_input.weight"], beta=prm["norm_input.bias"]) if training else {}))
         h = ops.gn_apply(c, m, r, prm["norm_input.weight"], prm["norm_input.bias"], P.act("in.a", 0, ch[0]),
                          lrelu=False)                                                     # model.py:412-413
         for j in range(self.enc[0]):                                                      # model.py:414
-            h = self._residual_fwd(P, 0, "conv_first.%d." % j, h, prm)
+            h = self._residual_fwd(P, 0, "conv_first.%d." % j, h, prm, training)
         skips = []
         for i in range(self.depth - 1):                                                   # model.py:416-418
             skips.append(h)
@@ -276,7 +286,7 @@ class Engine:
             wname = "encoder_convs.%d.0.downsample.0.weight" % i
             h = self._conv1(P, i + 1, wname, prm[wname], ops.W_FWD_S2D, s2d, P.act("enc%d.down" % i, i + 1, ch[i + 1]))
             for j in range(self.enc[i + 1]):
-                h = self._residual_fwd(P, i + 1, "encoder_convs.%d.%d." % (i, j), h, prm)
+                h = self._residual_fwd(P, i + 1, "encoder_convs.%d.%d." % (i, j), h, prm, training)
         for i in reversed(range(self.depth - 1)):                                         # model.py:420-426
             wname = "upsampling.%d.1.weight" % i
             ulo = self._conv1(P, i + 1, wname, prm[wname], ops.W_FWD, h, P.act("dec%d.ulo" % i, i + 1, ch[i]))
@@ -286,7 +296,7 @@ class Engine:
             h = self._conv1(P, i, wname, prm[wname], ops.W_FWD, P.act("dec%d.cat" % i, i, 2 * ch[i]),
                             P.act("dec%d.cc" % i, i, ch[i]))
             for j in range(self.dec[i]):
-                h = self._residual_fwd(P, i, "decoder_convs.%d.%d." % (i, j), h, prm)
+                h = self._residual_fwd(P, i, "decoder_convs.%d.%d." % (i, j), h, prm, training)
         D, H, W = P.dims[0]
         desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, ch[0], 16, epi=ops.EPI_SIGMOID)
         w = prm["conv_output.weight"]
@@ -352,23 +362,39 @@ class Engine:
             self._side_busy = False
             self._readers.clear()
 
-    def _dgrad3(self, P, lvl, wname, w, dy, out, residual=None):
+    def _dgrad3(self, P, lvl, wname, w, dy, out, residual=None, fold=None):
+        """Data gradient of a 3x3x3 conv.  fold = name of the conv buffer (e.g. "<prefix>c1") whose GroupNorm takes `out`
+        as its dy next: its backward sums are accumulated in this conv's epilogue and returned as (gpart, ctas) for
+        `_gn_bwd(folded=...)`; None is returned when the kernel this conv runs on has no such epilogue."""
         D, H, W = P.dims[lvl]
         desc = ops.conv_desc(ops.MODE_K3, P.N, D, H, W, dy.C, out.C)
         pk = self._pack(desc, ops.W_DGRAD, wname, w, K_real=w.shape[0], N_real=w.shape[1])
-        return ops.conv_run(desc, dy, pk, out, residual=residual)
+        coef = P.misc.get("gnc:" + fold) if (fold is not None and self.fold_gn_bwd) else None
+        if coef is None or not ops.conv_supports_gnbwd(desc):
+            ops.conv_run(desc, dy, pk, out, residual=residual)
+            return None
+        ctas = ops.conv_ctas(desc)
+        gpart = P.f32("gnb:" + fold, ctas * P.N * 16)
+        ops.conv_run(desc, dy, pk, out, residual=residual, stats=gpart, gnb_x=P.act(fold, lvl, out.C), gnb_coef=coef)
+        return gpart, ctas
 
-    def _gn_bwd(self, P, lvl, cname, x, dy, gamma, beta, dx, grads, gname, bname, lrelu=True):
+    def _gn_bwd(self, P, lvl, cname, x, dy, gamma, beta, dx, grads, gname, bname, lrelu=True, folded=None):
         Cc = x.C
+        D, H, W = P.dims[lvl]
+        L = ops._lib.lib()
+        need = max(L.b200_gn_backward_workspace_floats(P.N, Cc), L.b200_gn_backward_folded_workspace_floats(P.N, D, H, W, Cc))
         ws = P.misc.get("gn_ws")
-        need = ops._lib.lib().b200_gn_backward_workspace_floats(P.N, Cc)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.float32, device=P.device)
             P.misc["gn_ws"] = ws
         dg = grads.new(gname, gamma)
         db = grads.new(bname, beta)
-        ops.gn_backward(x, dy, P.misc["mean:" + cname], P.misc["rstd:" + cname], gamma, beta, dx, dg, db, ws,
-                        lrelu=lrelu)
+        if folded is not None:
+            ops.gn_backward_folded(x, dy, P.misc["mean:" + cname], P.misc["rstd:" + cname], gamma, beta, folded[0],
+                                   folded[1], dx, dg, db, ws, lrelu=lrelu)
+        else:
+            ops.gn_backward(x, dy, P.misc["mean:" + cname], P.misc["rstd:" + cname], gamma, beta, dx, dg, db, ws,
+                            lrelu=lrelu)
         return dx
 
     def _dc_buf(self, P, lvl, Cc):
@@ -385,9 +411,11 @@ class Engine:
             self._join_side()
             self.tap(name, value)
 
-    def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads):
-        """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns grad w.r.t. x_in
-        (written into d_in_buf), which includes the identity path (model.py:115)."""
+    def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads, d_out_folded=None, fold_next=None):
+        """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns (grad w.r.t. x_in written into
+        d_in_buf - it includes the identity path, model.py:115 -, folded sums for `fold_next` or None).
+        d_out_folded: the (gpart, ctas) the producer of d_out left for this block's norm2 (see _dgrad3);
+        fold_next: conv buffer name whose GroupNorm consumes the returned gradient as its dy."""
         Cc = x_in.C
         c1 = P.act(prefix + "c1", lvl, Cc)
         a1 = P.act(prefix + "a1", lvl, Cc)
@@ -395,24 +423,27 @@ class Engine:
         t1 = P.act("tmp.g1", lvl, Cc)
         w1n, w2n = prefix + "conv1.conv1.weight", prefix + "conv2.conv1.weight"
         dc2 = self._gn_bwd(P, lvl, prefix + "c2", c2, d_out, prm[prefix + "norm2.weight"], prm[prefix + "norm2.bias"],
-                           self._dc_buf(P, lvl, Cc), grads, prefix + "norm2.weight", prefix + "norm2.bias")
+                           self._dc_buf(P, lvl, Cc), grads, prefix + "norm2.weight", prefix + "norm2.bias",
+                           folded=d_out_folded)
         # Each weight gradient is queued on the side stream AFTER the data-gradient conv that shares its input:
         # it then runs next to the memory-bound GroupNorm-backward kernels that follow (the two tensor-core
         # kernels cannot share an SM: both need more than half of its shared memory).
         self._tap("g:" + prefix + "d_out", d_out)
         self._tap("g:" + prefix + "dc2", dc2)
         g2 = grads.new(w2n, prm[w2n])
-        da1 = self._dgrad3(P, lvl, w2n, prm[w2n], dc2, t1)
+        f1 = self._dgrad3(P, lvl, w2n, prm[w2n], dc2, t1, fold=prefix + "c1")
+        da1 = t1
         self._tap("g:" + prefix + "da1", da1)
         self._wgrad(P, lvl, 0, dc2, a1, g2, ops.G_K3, overlap=True)
         dc1 = self._gn_bwd(P, lvl, prefix + "c1", c1, da1, prm[prefix + "norm1.weight"], prm[prefix + "norm1.bias"],
-                           self._dc_buf(P, lvl, Cc), grads, prefix + "norm1.weight", prefix + "norm1.bias")
+                           self._dc_buf(P, lvl, Cc), grads, prefix + "norm1.weight", prefix + "norm1.bias", folded=f1)
         self._tap("g:" + prefix + "dc1", dc1)
         g1 = grads.new(w1n, prm[w1n])
-        dx = self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out)
+        fn = self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out, fold=fold_next)
+        dx = d_in_buf
         self._tap("g:" + prefix + "dx", dx)
         self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3, overlap=True)
-        return dx
+        return dx, fn
 
     def _mark(self, grads):
         """Level boundary: a store that ships gradients (BucketedAllReduce) needs them complete, so the side
@@ -458,7 +489,11 @@ class Engine:
             return P.act("g." + name, lvl, Cc)
 
         self._tap("g:dlogit", dlog)
-        cur = self._dgrad3(P, 0, "conv_output.weight", prm["conv_output.weight"], dlog, gbuf("A", 0, ch[0]))
+        # the producer of every block's output gradient leaves the sums of that block's norm2 when it is a k3 data-gradient
+        # conv with the folding epilogue (`folded`), else the reduce kernel runs
+        first_dec = "decoder_convs.0.%d.c2" % (self.dec[0] - 1) if self.dec[0] > 0 else None
+        cur = gbuf("A", 0, ch[0])
+        folded = self._dgrad3(P, 0, "conv_output.weight", prm["conv_output.weight"], dlog, cur, fold=first_dec)
         self._tap("g:final_h", cur)
         cur_name = "A"
         self._wgrad(P, 0, 0, dlog, h_last, g_out, ops.G_K3, overlap=True)
@@ -473,8 +508,11 @@ class Engine:
                 prefix = "decoder_convs.%d.%d." % (i, j)
                 x_in = P.act("dec%d.cc" % i, i, ch[i]) if j == 0 else P.act("decoder_convs.%d.%d.out" % (i, j - 1), i, ch[i])
                 nxt = other(cur_name)
-                cur = self._residual_bwd(P, i, prefix, x_in, cur, gbuf(nxt, i, ch[i]), prm, grads)
+                fold_next = "decoder_convs.%d.%d.c2" % (i, j - 1) if j > 0 else None
+                cur, folded = self._residual_bwd(P, i, prefix, x_in, cur, gbuf(nxt, i, ch[i]), prm, grads,
+                                                 d_out_folded=folded, fold_next=fold_next)
                 cur_name = nxt
+            folded = None
             # cat conv (model.py:424-425): cc = W[:, :C] skip + W[:, C:] up
             wname = "decoder_convs1x1.%d.weight" % i
             w = prm[wname]
@@ -504,8 +542,11 @@ class Engine:
                 prefix = "encoder_convs.%d.%d." % (i, j)
                 x_in = P.act("enc%d.down" % i, lvl, ch[lvl]) if j == 0 else P.act("encoder_convs.%d.%d.out" % (i, j - 1), lvl, ch[lvl])
                 nxt = other(cur_name)
-                cur = self._residual_bwd(P, lvl, prefix, x_in, cur, gbuf(nxt, lvl, ch[lvl]), prm, grads)
+                fold_next = "encoder_convs.%d.%d.c2" % (i, j - 1) if j > 0 else None
+                cur, folded = self._residual_bwd(P, lvl, prefix, x_in, cur, gbuf(nxt, lvl, ch[lvl]), prm, grads,
+                                                 d_out_folded=folded, fold_next=fold_next)
                 cur_name = nxt
+            folded = None
             wname = "encoder_convs.%d.0.downsample.0.weight" % i
             w = prm[wname]
             s2d = P.act("enc%d.s2d" % i, lvl, 8 * ch[i])
@@ -523,10 +564,13 @@ class Engine:
             prefix = "conv_first.%d." % j
             x_in = P.act("in.a", 0, ch[0]) if j == 0 else P.act("conv_first.%d.out" % (j - 1), 0, ch[0])
             nxt = other(cur_name)
-            cur = self._residual_bwd(P, 0, prefix, x_in, cur, gbuf(nxt, 0, ch[0]), prm, grads)
+            fold_next = "conv_first.%d.c2" % (j - 1) if j > 0 else "in.c"
+            cur, folded = self._residual_bwd(P, 0, prefix, x_in, cur, gbuf(nxt, 0, ch[0]), prm, grads,
+                                             d_out_folded=folded, fold_next=fold_next)
             cur_name = nxt
         dcin = self._gn_bwd(P, 0, "in.c", P.act("in.c", 0, ch[0]), cur, prm["norm_input.weight"], prm["norm_input.bias"],
-                            gbuf(other(cur_name), 0, ch[0]), grads, "norm_input.weight", "norm_input.bias", lrelu=False)
+                            gbuf(other(cur_name), 0, ch[0]), grads, "norm_input.weight", "norm_input.bias", lrelu=False,
+                            folded=folded if self.enc[0] > 0 else None)
         self._tap("g:in.a", cur)
         self._tap("g:in.c", dcin)
         self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), grads.new("conv_input.weight", prm["conv_input.weight"]),

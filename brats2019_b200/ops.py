@@ -259,11 +259,17 @@ class PackTable:
         _ledger("pack_weights_batched_kernel", "hbm", sum(j[2].numel() * 4 + j[6].numel() for j in self.jobs))
 
 
+def conv_supports_gnbwd(desc):
+    return _lib.lib().b200_conv_supports_gnbwd(C.byref(desc)) != 0
+
+
 def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=False, stats=None, bias=None,
-             probs=None, logits=None, n_out_real=0):
-    check(_lib.lib().b200_conv_run(C.byref(desc), _p(src_a), _p(src_b), _p(packed), _p(out), _p(residual),
-                                   1 if lrelu else 0, _p(stats), _p(bias), _p(probs), _p(logits), n_out_real,
-                                   _stream()), "b200_conv_run")
+             probs=None, logits=None, n_out_real=0, gnb_x=None, gnb_coef=None):
+    """gnb_x / gnb_coef: fold the backward sums of the GroupNorm that consumes `out` as its dy into the epilogue
+    (b200_conv_run_gnbwd); `stats` then receives those sums."""
+    check(_lib.lib().b200_conv_run_gnbwd(C.byref(desc), _p(src_a), _p(src_b), _p(packed), _p(out), _p(residual),
+                                         1 if lrelu else 0, _p(stats), _p(bias), _p(probs), _p(logits), n_out_real,
+                                         _p(gnb_x), _p(gnb_coef), _stream()), "b200_conv_run")
     _count(1)
     if LEDGER is not None:
         taps = 27 if desc.mode == MODE_K3 else 1
@@ -311,9 +317,15 @@ def wgrad_run(desc, dy, x, grad, kind, ci_off=0, accumulate=False, workspace=Non
 # ------------------------------------------------------------------------------------------
 # GroupNorm / activation / residual
 # ------------------------------------------------------------------------------------------
-def gn_finalize(stats, ctas, N, Cc, D, H, W, mean, rstd):
-    check(_lib.lib().b200_gn_finalize(_p(stats), ctas, N, Cc, D, H, W, GN_EPS, _p(mean), _p(rstd), _stream()),
-          "b200_gn_finalize")
+def gn_finalize(stats, ctas, N, Cc, D, H, W, mean, rstd, gamma=None, beta=None, coef=None, lrelu=True):
+    """coef (with gamma, beta): also write the [N][3][C] table the backward fold reads (b200_gn_finalize_coef)."""
+    if coef is not None:
+        check(_lib.lib().b200_gn_finalize_coef(_p(stats), ctas, N, Cc, D, H, W, GN_EPS, _p(gamma), _p(beta),
+                                               1 if lrelu else 0, _p(mean), _p(rstd), _p(coef), _stream()),
+              "b200_gn_finalize_coef")
+    else:
+        check(_lib.lib().b200_gn_finalize(_p(stats), ctas, N, Cc, D, H, W, GN_EPS, _p(mean), _p(rstd), _stream()),
+              "b200_gn_finalize")
     _count(1)
     _ledger("gn_finalize_kernel", "hbm", ctas * N * 16 * 4)
 
@@ -341,6 +353,19 @@ def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lr
     _ledger("gn_bwd_reduce2_kernel", "hbm", 2 * _act_bytes(x))
     _ledger("gn_bwd_finalize2_kernel", "hbm", 0)
     _ledger("gn_bwd_apply2_kernel", "hbm", 3 * _act_bytes(x))
+    return dx
+
+
+def gn_backward_folded(x, dy, mean, rstd, gamma, beta, gpart, ctas, dx, dgamma, dbeta, workspace, lrelu=True):
+    """GroupNorm backward whose group sums `gpart` were left by the conv that produced dy (conv_run(gnb_x=...))."""
+    N, D, H, W, Cc = act_dims(x)
+    check(_lib.lib().b200_gn_backward_folded(_p(x), _p(dy), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(gpart), ctas,
+                                             _p(dx), _p(dgamma), _p(dbeta), _p(workspace), N, D, H, W, Cc,
+                                             1 if lrelu else 0, _stream()), "b200_gn_backward_folded")
+    _count(3)
+    _ledger("gn_bwd_fold_finalize_kernel", "hbm", 0)
+    _ledger("gn_bwd_apply2_kernel", "hbm", 3 * _act_bytes(x))
+    _ledger("gn_bwd_finalize2_kernel", "hbm", 0)
     return dx
 
 

@@ -84,6 +84,17 @@ int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b,
                   const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
                   float* logits, int n_out_real, void* stream);
 
+/* The same convolution with the NEXT GroupNorm's backward sums folded into the epilogue (replaces the reduction pass of
+ * native_group_norm_backward, model.py:105-112 backward): when this conv PRODUCES the gradient dy of y = lrelu(GN(c)),
+ * pass gnb_x = the saved conv output c (act, same volume and channels as `out`) and gnb_coef = the [N][3][C] table
+ * b200_gn_finalize_coef wrote in the forward pass; stats_partial ([b200_conv_ctas][N][16]) then receives, per group,
+ * sum gamma*dz and sum gamma*dz*c (dz = dy * lrelu'), the input of b200_gn_backward_folded.  Only the band / marching
+ * 3x3x3 kernels have this epilogue: b200_conv_supports_gnbwd(desc) != 0. */
+int b200_conv_supports_gnbwd(const b200_conv_desc* d);
+int b200_conv_run_gnbwd(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed, void* out,
+                        const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
+                        float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, void* stream);
+
 /* ---- convolution weight gradient (weight half of convolution_backward, train.py:210) ---- */
 typedef struct b200_wgrad_desc {
     int mode;          /* 0: 3x3x3;  1: 1x1x1 */
@@ -101,6 +112,11 @@ int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const void* x, void
  *      add; model.py:95-96, 105-115, 338, 413) ------------------------------------------- */
 int b200_gn_finalize(const float* stats_partial, int ctas, int N, int C, int D, int H, int W, float eps, float* mean,
                      float* rstd, void* stream);
+/* b200_gn_finalize + the coefficient table [N][3][C] = (rstd*gamma | beta - mean*rstd*gamma | gamma) that
+ * b200_conv_run_gnbwd reads in the backward pass (do_lrelu == 0: the table encodes "no activation"). */
+int b200_gn_finalize_coef(const float* stats_partial, int ctas, int N, int C, int D, int H, int W, float eps,
+                          const float* gamma, const float* beta, int do_lrelu, float* mean, float* rstd, float* coef,
+                          void* stream);
 int b200_gn_apply(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   const void* residual, void* out, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
 size_t b200_gn_backward_workspace_floats(int N, int C);
@@ -108,6 +124,13 @@ size_t b200_gn_backward_workspace_floats(int N, int C);
 int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd, const float* gamma,
                      const float* beta, void* dx, float* dgamma, float* dbeta, float* workspace, int N, int D, int H,
                      int W, int C, int do_lrelu, void* stream);
+
+/* GroupNorm backward from the group sums a producing conv left in `gpart` ([ctas][N][16], b200_conv_run_gnbwd): no pass
+ * over x and dy for the reduction; dgamma / dbeta come from per-CTA sums the apply kernel writes on its way. */
+size_t b200_gn_backward_folded_workspace_floats(int N, int D, int H, int W, int C);
+int b200_gn_backward_folded(const void* x, const void* dy, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const float* gpart, int ctas, void* dx, float* dgamma, float* dbeta,
+                            float* workspace, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
 
 /* ---- trilinear x2 (aten::upsample_trilinear3d, model.py:7-14) fused with LeakyReLU
  *      (model.py:422); (N,D,H,W) is the COARSE volume -------------------------------------- */

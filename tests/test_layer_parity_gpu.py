@@ -256,3 +256,12 @@ def _run(shape, with_bce, seed=11):
                                             ((2, 128, 128, 128), False)])
 def test_every_stage_matches_the_oracle_on_the_engines_own_inputs(shape, with_bce):
     _run(shape, with_bce)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 24, 32), (1, 24, 40, 72), (2, 64, 64, 128)])
+def test_every_stage_with_the_groupnorm_backward_fold(shape, monkeypatch):
+    """The opt-in path (B200_GN_FOLD=1): GroupNorm-backward sums accumulated in the epilogue of the data-gradient conv
+    that produces the gradient (band kernel at 16 channels, marching kernel at 32), dgamma / dbeta from sums the apply
+    kernel writes.  Same per-stage bar."""
+    monkeypatch.setenv("B200_GN_FOLD", "1")
+    _run(shape, False)
