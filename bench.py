@@ -334,11 +334,24 @@ def run(args, rank, world, local_rank, dev):
 
         gstep.prefetch(x_host, t_host)               # prime the input pipeline (outside the timed region)
 
-        def step_e2e():               # noqa: F811
+        def step_e2e_fp32():
             # every step: one H2D copy of a full host batch (issued on the copy stream so that it
             # overlaps the previous step's kernels), the graph, and a D2H read of the loss
             loss = gstep.step_prefetched()
             gstep.prefetch(x_host, t_host)
+            return loss.item()
+
+        # The same step fed from COMPACT host staging buffers: bf16 images and uint8 binary targets (46 MB instead of
+        # 117 MB per step); the packing kernel and the loss kernels convert in registers (b200_pack_input_t,
+        # b200_dice_*_t), so the arithmetic is bit-identical to fp32 inputs (the first kernel rounds to bf16 anyway).
+        xc_host = x_host.to(torch.bfloat16).pin_memory()
+        tc_host = t_host.to(torch.uint8).pin_memory()
+        gstep_c = GraphedTrainStep(net, crit, opt, xc_host.to(dev), tc_host.to(dev), warmup=1)
+        gstep_c.prefetch(xc_host, tc_host)
+
+        def step_e2e():               # noqa: F811
+            loss = gstep_c.step_prefetched()
+            gstep_c.prefetch(xc_host, tc_host)
             return loss.item()
         l0 = ops.LAUNCHES[0]
         GraphedTrainStep._eager(gstep)                # count kernels of one eager step (same as the graph's)
@@ -360,6 +373,16 @@ def run(args, rank, world, local_rank, dev):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
     e2e_value = vox_step / (ms_e2e / args.steps * 1e-3)
+    e2e_bytes = int(x_host.numel() * 4 + t_host.numel() * 4)
+    e2e_fp32 = None
+    if use_graph:
+        e2e_bytes = int(xc_host.numel() * 2 + tc_host.numel())
+        for _ in range(2):
+            step_e2e_fp32()
+        ms_f, _ = timed(step_e2e_fp32, args.steps)
+        e2e_fp32 = {"value": vox_step / (ms_f / args.steps * 1e-3), "unit": "voxels/s", "ms_per_step": ms_f / args.steps,
+                    "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4), "d2h_bytes_per_step": 4,
+                    "staging": "fp32 images + fp32 targets in pinned host memory (what the reference's loaders produce)"}
 
     # forward-only (eval, no_grad) on the same resident batch
     model.eval()
@@ -438,8 +461,11 @@ def run(args, rank, world, local_rank, dev):
                        "parallelism": "dp%d" % world, "cuda_graph": bool(use_graph),
                        "optimizer": "torch.optim.Adam(fused)" if args.torch_adam else "brats2019_b200.optim.FusedAdam",
                        "l2": "no flush needed: per-step working set (>2 GB of activations) >> 126 MB L2"},
-            "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": e2e_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "staging": ("bf16 images + uint8 targets in pinned host memory, converted inside the first kernels"
+                                if use_graph else "fp32 images + fp32 targets in pinned host memory")},
+            "e2e_fp32_staging": e2e_fp32,
             "gpu_launches": launches,
             "forward": {"value": fwd_value, "unit": "voxels/s", "ms_per_step": ms_fwd / args.steps,
                         "tensor_frac_of_sustained": fwd_value / world * FLOP_PER_VOXEL_FWD / 1e12 / peaks["tf_sust"]},

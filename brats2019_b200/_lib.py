@@ -42,6 +42,7 @@ _PROTOS = {
     "b200_act_guard_rows": (c_ll, [c_int, c_int, c_int]),
     "b200_act_plane_rows": (c_ll, [c_int, c_int, c_int, c_int]),
     "b200_pack_input": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "b200_pack_input_t": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_conv_packed_weight_bytes": (c_size_t, [C.POINTER(ConvDesc)]),
     "b200_conv_ctas": (c_int, [C.POINTER(ConvDesc)]),
     "b200_conv_pack_weight": (c_int, [C.POINTER(ConvDesc), c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -70,6 +71,10 @@ _PROTOS = {
     "b200_sigmoid_backward": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_dice_workspace_floats": (c_size_t, [c_int, c_int]),
     "b200_dice_sums": (c_int, [P, P, P, P, c_int, c_int, c_ll, P]),
+    "b200_dice_sums_t": (c_int, [P, P, c_int, P, P, c_int, c_int, c_ll, P]),
+    "b200_dice_backward_t": (c_int, [P, P, c_int, P, P, c_float, P, c_int, c_int, c_ll, P]),
+    "b200_bce_sum_t": (c_int, [P, P, c_int, c_float, P, P, c_ll, P]),
+    "b200_bce_backward_t": (c_int, [P, P, c_int, P, c_float, C.c_double, P, c_ll, P]),
     "b200_dice_loss": (c_int, [P, c_int, c_float, P, P]),
     "b200_dice_backward": (c_int, [P, P, P, P, c_float, P, c_int, c_int, c_ll, P]),
     "b200_bce_workspace_floats": (c_size_t, []),

@@ -1030,21 +1030,31 @@ static int quad_lpb(int N, int D, int H) {
     return lpb;
 }
 
-extern "C" int b200_pack_input(const float* x, void* act_out, int N, int D, int H, int W, int Creal, int Cpad,
-                               void* stream) {
-    if (check_act(N, D, H, W, Cpad) || Creal > Cpad) return fail("pack_input: bad channels %d -> %d", Creal, Cpad);
+template <typename T>
+static int pack_input_t(const T* x, void* act_out, int N, int D, int H, int W, int Creal, cudaStream_t st) {
     Vol v{N, D, H, W};
-    if (Creal > 8) return fail("pack_input: at most 8 real channels");
-    if (W % 4 == 0 && ((uintptr_t)x & 15) == 0) {
+    if (W % 4 == 0 && ((uintptr_t)x & (4 * sizeof(T) - 1)) == 0) {
         const int lpb = quad_lpb(N, D, H);
-        pack_input4_kernel<<<(N * D * H + lpb - 1) / lpb, 256, 0, (cudaStream_t)stream>>>(x, make_act(act_out, v), v, Creal, lpb,
-                                                                                         make_fastdiv((unsigned)(W / 4)));
+        pack_input4_kernel<T><<<(N * D * H + lpb - 1) / lpb, 256, 0, st>>>(x, make_act(act_out, v), v, Creal, lpb,
+                                                                          make_fastdiv((unsigned)(W / 4)));
         LAUNCH_OK("pack_input4_kernel");
         return 0;
     }
-    pack_input_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(x, make_act(act_out, v), v, Creal);
+    pack_input_kernel<T><<<N * D * H, 128, 0, st>>>(x, make_act(act_out, v), v, Creal);
     LAUNCH_OK("pack_input_kernel");
     return 0;
+}
+extern "C" int b200_pack_input_t(const void* x, int x_dtype, void* act_out, int N, int D, int H, int W, int Creal, int Cpad,
+                                 void* stream) {
+    if (check_act(N, D, H, W, Cpad) || Creal > Cpad) return fail("pack_input: bad channels %d -> %d", Creal, Cpad);
+    if (Creal > 8) return fail("pack_input: at most 8 real channels");
+    if (x_dtype == B200_F32) return pack_input_t((const float*)x, act_out, N, D, H, W, Creal, (cudaStream_t)stream);
+    if (x_dtype == B200_BF16) return pack_input_t((const __nv_bfloat16*)x, act_out, N, D, H, W, Creal, (cudaStream_t)stream);
+    return fail("pack_input: input dtype %d unsupported (fp32 or bf16)", x_dtype);
+}
+extern "C" int b200_pack_input(const float* x, void* act_out, int N, int D, int H, int W, int Creal, int Cpad,
+                               void* stream) {
+    return b200_pack_input_t(x, B200_F32, act_out, N, D, H, W, Creal, Cpad, stream);
 }
 
 extern "C" int b200_gn_finalize(const float* stats_partial, int ctas, int N, int C, int D, int H, int W, float eps,
@@ -1332,54 +1342,95 @@ extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs
 
 static int dice_blocks() { return 2 * num_sms(); }
 extern "C" size_t b200_dice_workspace_floats(int B, int C) { return (size_t)B * C * dice_blocks() * 2; }
-extern "C" int b200_dice_sums(const float* probs, const float* target, float* sums, float* workspace, int B, int C,
-                              long long S, void* stream) {
+// `target_dtype`: B200_F32 (the reference's float targets, loss.py:105-111) or B200_U8 (binary masks staged as bytes)
+extern "C" int b200_dice_sums_t(const float* probs, const void* target, int target_dtype, float* sums, float* workspace,
+                                int B, int C, long long S, void* stream) {
     if (C < 1 || C > 4) return fail("dice: C=%d unsupported (1..4)", C);
     cudaStream_t st = (cudaStream_t)stream;
     const int bx = dice_blocks();
-    dice_partial_kernel<<<dim3(bx, B * C), kEwThreads, 0, st>>>(probs, target, workspace, B, C, S);
+    if (target_dtype == B200_F32)
+        dice_partial_kernel<float><<<dim3(bx, B * C), kEwThreads, 0, st>>>(probs, (const float*)target, workspace, B, C, S);
+    else if (target_dtype == B200_U8)
+        dice_partial_kernel<uint8_t><<<dim3(bx, B * C), kEwThreads, 0, st>>>(probs, (const uint8_t*)target, workspace, B, C, S);
+    else
+        return fail("dice: target dtype %d unsupported (fp32 or uint8)", target_dtype);
     LAUNCH_OK("dice_partial_kernel");
     dice_sums2_kernel<<<1, 256, 0, st>>>(workspace, B, C, bx, sums);
     LAUNCH_OK("dice_sums2_kernel");
     return 0;
+}
+extern "C" int b200_dice_sums(const float* probs, const float* target, float* sums, float* workspace, int B, int C,
+                              long long S, void* stream) {
+    return b200_dice_sums_t(probs, target, B200_F32, sums, workspace, B, C, S, stream);
 }
 extern "C" int b200_dice_loss(const float* sums, int C, float priority, float* loss, void* stream) {
     dice_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, C, priority, loss);
     LAUNCH_OK("dice_loss_kernel");
     return 0;
 }
-extern "C" int b200_dice_backward(const float* probs, const float* target, const float* sums, const float* grad_out,
-                                  float priority, float* grad_probs, int B, int C, long long S, void* stream) {
+extern "C" int b200_dice_backward_t(const float* probs, const void* target, int target_dtype, const float* sums,
+                                    const float* grad_out, float priority, float* grad_probs, int B, int C, long long S,
+                                    void* stream) {
     if (C < 1 || C > 4) return fail("dice: C=%d unsupported (1..4)", C);
-    dice_bwd_kernel<<<dim3(dice_blocks(), B * C), kEwThreads, 0, (cudaStream_t)stream>>>(probs, target, sums, grad_out,
-                                                                                        priority, grad_probs, B, C, S);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(dice_blocks(), B * C);
+    if (target_dtype == B200_F32)
+        dice_bwd_kernel<float><<<grid, kEwThreads, 0, st>>>(probs, (const float*)target, sums, grad_out, priority, grad_probs, B, C, S);
+    else if (target_dtype == B200_U8)
+        dice_bwd_kernel<uint8_t><<<grid, kEwThreads, 0, st>>>(probs, (const uint8_t*)target, sums, grad_out, priority, grad_probs, B, C, S);
+    else
+        return fail("dice: target dtype %d unsupported (fp32 or uint8)", target_dtype);
     LAUNCH_OK("dice_bwd_kernel");
     return 0;
+}
+extern "C" int b200_dice_backward(const float* probs, const float* target, const float* sums, const float* grad_out,
+                                  float priority, float* grad_probs, int B, int C, long long S, void* stream) {
+    return b200_dice_backward_t(probs, target, B200_F32, sums, grad_out, priority, grad_probs, B, C, S, stream);
 }
 
 // BCE_Loss (loss.py:64-79) -------------------------------------------------------------------
 extern "C" size_t b200_bce_workspace_floats(void) { return (size_t)dice_blocks(); }
-extern "C" int b200_bce_sum(const float* probs, const float* target, float bg_weight, float* sum, float* workspace,
-                            long long numel, void* stream) {
+extern "C" int b200_bce_sum_t(const float* probs, const void* target, int target_dtype, float bg_weight, float* sum,
+                              float* workspace, long long numel, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int bx = dice_blocks();
-    bce_partial_kernel<<<bx, kEwThreads, 0, st>>>(probs, target, bg_weight, workspace, numel);
+    if (target_dtype == B200_F32)
+        bce_partial_kernel<float><<<bx, kEwThreads, 0, st>>>(probs, (const float*)target, bg_weight, workspace, numel);
+    else if (target_dtype == B200_U8)
+        bce_partial_kernel<uint8_t><<<bx, kEwThreads, 0, st>>>(probs, (const uint8_t*)target, bg_weight, workspace, numel);
+    else
+        return fail("bce: target dtype %d unsupported (fp32 or uint8)", target_dtype);
     LAUNCH_OK("bce_partial_kernel");
     reduce_partials_kernel<<<1, 256, 0, st>>>(workspace, bx, 1, 1, sum);
     LAUNCH_OK("reduce_partials_kernel");
     return 0;
+}
+extern "C" int b200_bce_sum(const float* probs, const float* target, float bg_weight, float* sum, float* workspace,
+                            long long numel, void* stream) {
+    return b200_bce_sum_t(probs, target, B200_F32, bg_weight, sum, workspace, numel, stream);
 }
 extern "C" int b200_bce_loss(const float* sum, double global_numel, float* loss, void* stream) {
     bce_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sum, global_numel, loss);
     LAUNCH_OK("bce_loss_kernel");
     return 0;
 }
-extern "C" int b200_bce_backward(const float* probs, const float* target, const float* grad_out, float bg_weight,
-                                 double global_numel, float* grad_probs, long long numel, void* stream) {
-    bce_bwd_kernel<<<dice_blocks() * 2, kEwThreads, 0, (cudaStream_t)stream>>>(probs, target, grad_out, bg_weight,
-                                                                              (float)(1.0 / global_numel), grad_probs, numel);
+extern "C" int b200_bce_backward_t(const float* probs, const void* target, int target_dtype, const float* grad_out,
+                                   float bg_weight, double global_numel, float* grad_probs, long long numel, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bx = dice_blocks() * 2;
+    const float inv = (float)(1.0 / global_numel);
+    if (target_dtype == B200_F32)
+        bce_bwd_kernel<float><<<bx, kEwThreads, 0, st>>>(probs, (const float*)target, grad_out, bg_weight, inv, grad_probs, numel);
+    else if (target_dtype == B200_U8)
+        bce_bwd_kernel<uint8_t><<<bx, kEwThreads, 0, st>>>(probs, (const uint8_t*)target, grad_out, bg_weight, inv, grad_probs, numel);
+    else
+        return fail("bce: target dtype %d unsupported (fp32 or uint8)", target_dtype);
     LAUNCH_OK("bce_bwd_kernel");
     return 0;
+}
+extern "C" int b200_bce_backward(const float* probs, const float* target, const float* grad_out, float bg_weight,
+                                 double global_numel, float* grad_probs, long long numel, void* stream) {
+    return b200_bce_backward_t(probs, target, B200_F32, grad_out, bg_weight, global_numel, grad_probs, numel, stream);
 }
 
 // ---------------------------------------------------------------------------------------

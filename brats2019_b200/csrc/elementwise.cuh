@@ -58,7 +58,24 @@ __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& q) { *reinte
 // (B,Creal,D,H,W) fp32 NCDHW  ->  act; only chunk 0 is written (Creal <= 8), higher chunks of the
 // destination stay zero.  Entry layout conversion for model.py:407-412 (`input = x[0]`).
 // ---------------------------------------------------------------------------------------
-__global__ void pack_input_kernel(const float* __restrict__ x, ActRef out, Vol v, int Creal) {
+// element loads of the model's external tensors: the reference's fp32, or the compact staging formats a host pipeline
+// may use to cut host->device traffic (bf16 images, uint8 targets); converted to fp32 in registers
+__device__ __forceinline__ float ld_f(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float ld_f(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ld_f(const uint8_t* p, size_t i) { return (float)p[i]; }
+__device__ __forceinline__ float4 ld_f4(const float* p, size_t i4) { return reinterpret_cast<const float4*>(p)[i4]; }
+__device__ __forceinline__ float4 ld_f4(const __nv_bfloat16* p, size_t i4) {
+    const uint2 q = reinterpret_cast<const uint2*>(p)[i4];
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 ld_f4(const uint8_t* p, size_t i4) {
+    const uchar4 q = reinterpret_cast<const uchar4*>(p)[i4];
+    return make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+}
+
+template <typename T>
+__global__ void pack_input_kernel(const T* __restrict__ x, ActRef out, Vol v, int Creal) {
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
     const size_t plane = (size_t)v.D * v.H * v.W;
@@ -67,7 +84,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, ActRef out, Vol v
     for (int w = threadIdx.x; w < v.W; w += blockDim.x) {
         float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = (i < Creal) ? x[src0 + (size_t)i * plane + w] : 0.f;
+        for (int i = 0; i < 8; ++i) f[i] = (i < Creal) ? ld_f(x, src0 + (size_t)i * plane + w) : 0.f;
         st16(out.at(0, row0 + w), pack_bf16x8(f));
     }
 }
@@ -289,27 +306,30 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int co
 // Dice_loss_joint (loss.py:98-122).  probs/target fp32 (B,C,S) contiguous, C <= 4.
 //   sums[c] = sum p*g, sums[4+c] = sum (p^2 + g)          (per-CTA partials [blocks][8])
 // ---------------------------------------------------------------------------------------
+template <typename TG>
 __global__ void __launch_bounds__(kEwThreads)
-dice_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ partial, int B,
+dice_partial_kernel(const float* __restrict__ p, const TG* __restrict__ g, float* __restrict__ partial, int B,
                     int C, long long S) {
     // grid = (blocks_x, B*C)
     const int bc = blockIdx.y;
     const int c = bc % C;
     const float* pp = p + (size_t)bc * S;
-    const float* gg = g + (size_t)bc * S;
+    const TG* gg = g + (size_t)bc * S;
     float si = 0.f, su = 0.f;
-    // 16-byte loads only when both rows really are 16-byte aligned (a sliced batch is contiguous but may start anywhere)
-    const bool vec = (S % 4 == 0) && (((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(gg)) & 15) == 0);
+    // vector loads only when both rows really are aligned for them (a sliced batch is contiguous but may start anywhere)
+    const bool vec = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gg) & (4 * sizeof(TG) - 1)) == 0);
     const long long nv = vec ? S / 4 : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         const float4 a = reinterpret_cast<const float4*>(pp)[i];
-        const float4 b = reinterpret_cast<const float4*>(gg)[i];
+        const float4 b = ld_f4(gg, (size_t)i);
         si += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
         su += (a.x * a.x + b.x) + (a.y * a.y + b.y) + (a.z * a.z + b.z) + (a.w * a.w + b.w);
     }
     for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x) {
-        si += pp[i] * gg[i];
-        su += pp[i] * pp[i] + gg[i];
+        const float gv = ld_f(gg, (size_t)i);
+        si += pp[i] * gv;
+        su += pp[i] * pp[i] + gv;
     }
     __shared__ float s_i[kEwThreads / 32], s_u[kEwThreads / 32];
     si = warp_sum(si);
@@ -336,18 +356,19 @@ __global__ void dice_loss_kernel(const float* __restrict__ sums, int C, float pr
 }
 
 // dL/dp = gout * priority * -(2/C) (g U_c - 2 p I_c) / U_c^2     
+template <typename TG>
 __global__ void __launch_bounds__(kEwThreads)
-dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ sums,
+dice_bwd_kernel(const float* __restrict__ p, const TG* __restrict__ g, const float* __restrict__ sums,
                 const float* __restrict__ gout, float priority, float* __restrict__ dp, int B, int C, long long S) {
     const int bc = blockIdx.y;
     const int c = bc % C;
     const float I = sums[c] + 1e-6f, U = sums[4 + c] + 2e-6f;
     const float k = -gout[0] * priority * (2.f / C) / (U * U);
     const float* pp = p + (size_t)bc * S;
-    const float* gg = g + (size_t)bc * S;
+    const TG* gg = g + (size_t)bc * S;
     float* dd = dp + (size_t)bc * S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x)
-        dd[i] = k * (gg[i] * U - 2.f * pp[i] * I);
+        dd[i] = k * (ld_f(gg, (size_t)i) * U - 2.f * pp[i] * I);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -355,22 +376,26 @@ dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const 
 //   forward: per-CTA partial sums of the bracket  (partial[blocks])
 //   backward: dL/dp = -gout/numel * ( g/(p+1e-6) - w (1-g)/((1+1e-6) - p) )
 // ---------------------------------------------------------------------------------------
+template <typename TG>
 __global__ void __launch_bounds__(kEwThreads)
-bce_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, float w, float* __restrict__ partial,
+bce_partial_kernel(const float* __restrict__ p, const TG* __restrict__ g, float w, float* __restrict__ partial,
                    long long n) {
     float acc = 0.f;
-    const bool vec = ((n & 3) == 0) && (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) & 15) == 0);
+    const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(g) & (4 * sizeof(TG) - 1)) == 0);
     const long long nv = vec ? n / 4 : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
         const float4 a = reinterpret_cast<const float4*>(p)[i];
-        const float4 b = reinterpret_cast<const float4*>(g)[i];
+        const float4 b = ld_f4(g, (size_t)i);
         acc += b.x * logf(a.x + 1e-6f) + w * (1.f - b.x) * logf((1.f + 1e-6f) - a.x);
         acc += b.y * logf(a.y + 1e-6f) + w * (1.f - b.y) * logf((1.f + 1e-6f) - a.y);
         acc += b.z * logf(a.z + 1e-6f) + w * (1.f - b.z) * logf((1.f + 1e-6f) - a.z);
         acc += b.w * logf(a.w + 1e-6f) + w * (1.f - b.w) * logf((1.f + 1e-6f) - a.w);
     }
-    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        acc += g[i] * logf(p[i] + 1e-6f) + w * (1.f - g[i]) * logf((1.f + 1e-6f) - p[i]);
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gv = ld_f(g, (size_t)i);
+        acc += gv * logf(p[i] + 1e-6f) + w * (1.f - gv) * logf((1.f + 1e-6f) - p[i]);
+    }
     __shared__ float s_red[kEwThreads / 32];
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -385,12 +410,15 @@ bce_partial_kernel(const float* __restrict__ p, const float* __restrict__ g, flo
 __global__ void bce_loss_kernel(const float* __restrict__ sum, double numel, float* __restrict__ loss) {
     if (threadIdx.x == 0) loss[0] = (float)(-(double)sum[0] / numel);
 }
+template <typename TG>
 __global__ void __launch_bounds__(kEwThreads)
-bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ gout, float w,
+bce_bwd_kernel(const float* __restrict__ p, const TG* __restrict__ g, const float* __restrict__ gout, float w,
                float inv_numel, float* __restrict__ dp, long long n) {
     const float k = -gout[0] * inv_numel;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dp[i] = k * (g[i] / (p[i] + 1e-6f) - w * (1.f - g[i]) / ((1.f + 1e-6f) - p[i]));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gv = ld_f(g, (size_t)i);
+        dp[i] = k * (gv / (p[i] + 1e-6f) - w * (1.f - gv) / ((1.f + 1e-6f) - p[i]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------

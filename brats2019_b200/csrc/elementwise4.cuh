@@ -211,8 +211,9 @@ upsample2x_bwd_dh3_kernel(ActRef T, ActRef dcoarse, Vol vc, int C, FastDiv by_Wc
 // fp32 tensors are required (the entry points fall back to the scalar kernels otherwise).
 // ---------------------------------------------------------------------------------------
 // (B,Creal,D,H,W) fp32 NCDHW -> chunk 0 of an act tensor (model.py:407-412), Creal <= 8.
+template <typename T>
 __global__ void __launch_bounds__(256)
-pack_input4_kernel(const float* __restrict__ x, ActRef out, Vol v, int Creal, int lpb, FastDiv by_Q) {
+pack_input4_kernel(const T* __restrict__ x, ActRef out, Vol v, int Creal, int lpb, FastDiv by_Q) {
     __shared__ long long s_src[16], s_row[16];
     const int line0 = blockIdx.x * lpb;
     const int nl = min(lpb, v.N * v.D * v.H - line0);
@@ -227,11 +228,11 @@ pack_input4_kernel(const float* __restrict__ x, ActRef out, Vol v, int Creal, in
     const int Q = v.W >> 2;
     for (int idx = threadIdx.x; idx < nl * Q; idx += blockDim.x) {
         const int li = by_Q.div(idx), q = idx - li * Q;
-        const float* src = x + s_src[li] + 4 * q;
+        const size_t src4 = (size_t)(s_src[li] >> 2) + q;        // in units of four elements (W % 4 == 0, aligned base)
         float4 c[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            c[i] = (i < Creal) ? *reinterpret_cast<const float4*>(src + (size_t)i * plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            c[i] = (i < Creal) ? ld_f4(x, src4 + (size_t)i * (plane >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
         __nv_bfloat16* dst = out.at(0, s_row[li] + 4 * q);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

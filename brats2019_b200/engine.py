@@ -257,7 +257,7 @@ class Engine:
         prm = self._params()
         ch = self.ch
         x = x.contiguous()
-        if x.dtype != torch.float32:
+        if x.dtype not in (torch.float32, torch.bfloat16):     # bf16 images are converted by the packing kernel itself
             x = x.float()
         # cat([skip, up]) of model.py:424 is ONE 2C-channel buffer per level: the encoder writes the skip
         # tensor into its first half and the up-sampling its second half (chunk-planar layout: a half is a
@@ -446,10 +446,18 @@ class Engine:
         return dx, fn
 
     def _mark(self, grads):
-        """Level boundary: a store that ships gradients (BucketedAllReduce) needs them complete, so the side
-        stream is joined first; the default store does nothing here and the side stream keeps running."""
-        if type(grads).mark is not GradStore.mark:
-            self._join_side()
+        """Level boundary: a store that ships gradients (BucketedAllReduce) may launch a bucket here.  The bucket's
+        weight gradients are still being produced on the side stream, so the collective is issued FROM the side stream
+        (after it has been ordered behind the main stream's work so far): the NCCL stream then waits for both, and the
+        main stream - the critical path of backward - is never stalled (round 1 joined the side stream here, six times
+        per backward, and lost part of the wgrad / GroupNorm-backward overlap)."""
+        if type(grads).mark is not GradStore.mark and self._side_busy:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._side_stream.wait_event(ev)
+            with torch.cuda.stream(self._side_stream):
+                grads.mark()
+            return
         grads.mark()
 
     def backward(self, gprobs, store=None, state=None):

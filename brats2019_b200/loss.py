@@ -14,11 +14,20 @@ import torch.nn as nn
 from . import ops
 
 
+def _as_target(t):
+    """fp32 targets as the reference passes them (soft values allowed, loss.py:105-111), or binary masks staged as
+    uint8 / bool, which the kernels convert on the fly (a quarter of the host->device bytes)."""
+    t = t.contiguous()
+    if t.dtype == torch.bool:
+        t = t.view(torch.uint8)
+    return t if t.dtype in (torch.float32, torch.uint8) else t.float()
+
+
 class _DiceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, probs, target, priority, group):
         probs = probs.contiguous()
-        target = target.contiguous().float()
+        target = _as_target(target)
         sums = ops.dice_sums(probs, target)
         if group is not None:
             import torch.distributed as dist
@@ -62,7 +71,7 @@ class _BCEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, probs, target, bg_weight, group):
         probs = probs.contiguous()
-        target = target.contiguous().float()
+        target = _as_target(target)
         s = ops.bce_sum(probs, target, bg_weight)
         numel = probs.numel()
         if group is not None:

@@ -142,15 +142,19 @@ def act_outside_absmax(a):
     return c.float().abs().max()
 
 
+F32, BF16, U8 = 0, 1, 2          # include/brats_b200.h: B200_F32 / B200_BF16 / B200_U8
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8, torch.bool: U8}
+
+
 def pack_input(x, Cpad=16, out=None):
     N, Cc, D, H, W = x.shape
-    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous() and x.is_cuda
     if out is None:
         out = act_zeros(N, D, H, W, Cpad, x.device)
     assert Cc <= 8 and out.C == Cpad
-    check(_lib.lib().b200_pack_input(_p(x), _p(out), N, D, H, W, Cc, Cpad, _stream()), "b200_pack_input")
+    check(_lib.lib().b200_pack_input_t(_p(x), _DT[x.dtype], _p(out), N, D, H, W, Cc, Cpad, _stream()), "b200_pack_input")
     _count(1)
-    _ledger("pack_input", "hbm", x.numel() * 4 + N * D * H * W * 16)
+    _ledger("pack_input", "hbm", x.numel() * x.element_size() + N * D * H * W * 16)
     return out
 
 
@@ -455,10 +459,10 @@ def dice_sums(probs, target, sums=None, workspace=None):
         sums = torch.zeros(8, dtype=torch.float32, device=probs.device)
     if workspace is None:
         workspace = torch.empty(_lib.lib().b200_dice_workspace_floats(B, Cc), dtype=torch.float32, device=probs.device)
-    check(_lib.lib().b200_dice_sums(_p(probs), _p(target), _p(sums), _p(workspace), B, Cc, S, _stream()),
-          "b200_dice_sums")
+    check(_lib.lib().b200_dice_sums_t(_p(probs), _p(target), _DT[target.dtype], _p(sums), _p(workspace), B, Cc, S,
+                                      _stream()), "b200_dice_sums")
     _count(2)
-    _ledger("dice_partial_kernel", "hbm", 2 * probs.numel() * 4)
+    _ledger("dice_partial_kernel", "hbm", probs.numel() * (4 + target.element_size()))
     return sums
 
 
@@ -475,10 +479,10 @@ def dice_backward(probs, target, sums, grad_out, priority, grad_probs=None):
     S = probs[0, 0].numel()
     if grad_probs is None:
         grad_probs = torch.empty_like(probs)
-    check(_lib.lib().b200_dice_backward(_p(probs), _p(target), _p(sums), _p(grad_out), float(priority),
-                                        _p(grad_probs), B, Cc, S, _stream()), "b200_dice_backward")
+    check(_lib.lib().b200_dice_backward_t(_p(probs), _p(target), _DT[target.dtype], _p(sums), _p(grad_out),
+                                          float(priority), _p(grad_probs), B, Cc, S, _stream()), "b200_dice_backward")
     _count(1)
-    _ledger("dice_bwd_kernel", "hbm", 3 * probs.numel() * 4)
+    _ledger("dice_bwd_kernel", "hbm", probs.numel() * (8 + target.element_size()))
     return grad_probs
 
 
@@ -487,8 +491,8 @@ def bce_sum(probs, target, bg_weight, workspace=None):
     s = torch.empty(1, dtype=torch.float32, device=probs.device)
     if workspace is None:
         workspace = torch.empty(L.b200_bce_workspace_floats(), dtype=torch.float32, device=probs.device)
-    check(L.b200_bce_sum(_p(probs), _p(target), float(bg_weight), _p(s), _p(workspace), probs.numel(), _stream()),
-          "b200_bce_sum")
+    check(L.b200_bce_sum_t(_p(probs), _p(target), _DT[target.dtype], float(bg_weight), _p(s), _p(workspace),
+                           probs.numel(), _stream()), "b200_bce_sum")
     _count(2)
     return s
 
@@ -502,7 +506,7 @@ def bce_loss(s, global_numel):
 
 def bce_backward(probs, target, grad_out, bg_weight, global_numel):
     gp = torch.empty_like(probs)
-    check(_lib.lib().b200_bce_backward(_p(probs), _p(target), _p(grad_out), float(bg_weight), float(global_numel),
-                                       _p(gp), probs.numel(), _stream()), "b200_bce_backward")
+    check(_lib.lib().b200_bce_backward_t(_p(probs), _p(target), _DT[target.dtype], _p(grad_out), float(bg_weight),
+                                         float(global_numel), _p(gp), probs.numel(), _stream()), "b200_bce_backward")
     _count(1)
     return gp

@@ -28,6 +28,11 @@
 extern "C" {
 #endif
 
+/* element types of the model's EXTERNAL tensors (everything inside the library is bf16 activations / fp32 sums):
+ * fp32 is what the reference's loaders and trainer pass (train.py:194-199); bf16 images and uint8 binary targets are
+ * compact staging formats a host pipeline may use instead - converted in registers by the first kernel that reads them */
+enum { B200_F32 = 0, B200_BF16 = 1, B200_U8 = 2 };
+
 const char* b200_last_error(void);
 /* 0 if device `dev` is compute capability 10.x with tcgen05/TMA available. */
 int b200_device_check(int dev);
@@ -40,6 +45,9 @@ long long b200_act_plane_rows(int N, int D, int H, int W);   /* rows per chunk p
 /* ---- layout (model.py:410-412 `input = x[0]`) -------------------------------------------- */
 /* x: fp32 (N,Creal,D,H,W) contiguous  ->  act with Cpad channels (channels >= Creal are 0). */
 int b200_pack_input(const float* x, void* act_out, int N, int D, int H, int W, int Creal, int Cpad, void* stream);
+/* same with x_dtype = B200_F32 or B200_BF16 */
+int b200_pack_input_t(const void* x, int x_dtype, void* act_out, int N, int D, int H, int W, int Creal, int Cpad,
+                      void* stream);
 
 /* ---- convolution, forward and data-gradient (aten::convolution, model.py:72-73, 336, 348,
  *      362, 393, 401; data half of convolution_backward, train.py:210) ------------------- */
@@ -158,9 +166,14 @@ size_t b200_dice_workspace_floats(int B, int C);
 /* sums[8]: I_c = sum p*g at [c], U_c = sum (p^2+g) at [4+c] (no epsilons; all-reducible). */
 int b200_dice_sums(const float* probs, const float* target, float* sums, float* workspace, int B, int C, long long S,
                    void* stream);
+int b200_dice_sums_t(const float* probs, const void* target, int target_dtype, float* sums, float* workspace, int B,
+                     int C, long long S, void* stream);                 /* target_dtype = B200_F32 or B200_U8 */
 int b200_dice_loss(const float* sums, int C, float priority, float* loss, void* stream);
 int b200_dice_backward(const float* probs, const float* target, const float* sums, const float* grad_out,
                        float priority, float* grad_probs, int B, int C, long long S, void* stream);
+
+int b200_dice_backward_t(const float* probs, const void* target, int target_dtype, const float* sums,
+                         const float* grad_out, float priority, float* grad_probs, int B, int C, long long S, void* stream);
 
 /* ---- BCE_Loss (loss.py:64-79) ------------------------------------------------
  * sum[1] = sum over elements of g log(p+1e-6) + bg_weight (1-g) log(1+1e-6-p)  (all-reducible);
@@ -168,6 +181,8 @@ int b200_dice_backward(const float* probs, const float* target, const float* sum
 size_t b200_bce_workspace_floats(void);
 int b200_bce_sum(const float* probs, const float* target, float bg_weight, float* sum, float* workspace,
                  long long numel, void* stream);
+int b200_bce_sum_t(const float* probs, const void* target, int target_dtype, float bg_weight, float* sum,
+                   float* workspace, long long numel, void* stream);
 int b200_bce_loss(const float* sum, double global_numel, float* loss, void* stream);
 int b200_bce_backward(const float* probs, const float* target, const float* grad_out, float bg_weight,
                       double global_numel, float* grad_probs, long long numel, void* stream);
@@ -184,6 +199,9 @@ int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                    const long long* seg_begin, const long long* seg_len, int n_segs, const float* lr, float* step,
                    unsigned* ticket, double beta1, double beta2, float eps, float weight_decay, int lr_step_size,
                    float lr_gamma, void* stream);
+
+int b200_bce_backward_t(const float* probs, const void* target, int target_dtype, const float* grad_out, float bg_weight,
+                        double global_numel, float* grad_probs, long long numel, void* stream);
 
 /* ---- plan introspection (tests): integer dump of the launch plan ---------------- */
 int b200_conv_plan_debug(const b200_conv_desc* d, int* out, int n_out);

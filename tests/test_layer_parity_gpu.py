@@ -40,14 +40,15 @@ class _Report:
     def __init__(self, tag):
         self.tag, self.rows, self.fail = tag, [], []
 
-    def stored(self, name, got, exp32, cap_l2=5e-4, cap_neq=0.01):
-        """`got`: engine's stored bf16 tensor (as fp32); `exp32`: oracle value BEFORE the bf16 store."""
+    def stored(self, name, got, exp32, cap_l2=5e-4, cap_neq=0.01, ulps=1):
+        """`got`: engine's stored bf16 tensor (as fp32); `exp32`: oracle value BEFORE the bf16 store.  ulps = 2 for a stage
+        whose expected value is itself the sum of two rounded tensors (the skip-gradient add)."""
         exp = _bf(exp32)
         d = (got - exp).abs()
         rms = exp.pow(2).mean().sqrt().item()
         l2 = (d.norm() / exp.norm().clamp_min(1e-30)).item()
         neq = (got != exp).float().mean().item()
-        over = (d > ULP * exp.abs() + 1e-4 * rms).float().mean().item()
+        over = (d > ulps * ULP * exp.abs() + 1e-4 * rms).float().mean().item()
         self.rows.append("%-44s rel-L2 %.2e  differ %.5f  >1ulp %.2e" % (name, l2, neq, over))
         if not (l2 <= cap_l2 and neq <= cap_neq and over <= 1e-5):
             self.fail.append(self.rows[-1])
@@ -233,7 +234,7 @@ def _run(shape, with_bce, seed=11):
         wn = "encoder_convs.%d.0.downsample.0.weight" % i
         dh, dw = _conv_grads(skips[i], wr[wn], ddown, stride=2)
         R.f32("bwd " + wn, grad[wn], dw)
-        R.stored("bwd enc%d skip total" % i, taps["g:enc%d.skip_total" % i], _bf(dh) + dskip[i])
+        R.stored("bwd enc%d skip total" % i, taps["g:enc%d.skip_total" % i], _bf(dh) + dskip[i], ulps=2)
     for j in reversed(range(enc[0])):
         check_block_bwd("conv_first.%d." % j, 0, ch[0])
     mi, ri = stat("in.c")

