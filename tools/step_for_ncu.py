@@ -18,7 +18,8 @@ fwd_only = len(sys.argv) > 3 and sys.argv[3] == "fwd"
 torch.manual_seed(0)
 m = B.UNet(**B.DEFAULT_CFG).cuda().train()
 crit = B.Dice_loss_joint()
-opt = torch.optim.Adam(m.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True)
+from brats2019_b200.optim import FusedAdam  # noqa: E402
+opt = FusedAdam(m.parameters(), lr=2e-5, weight_decay=1e-6, amsgrad=True, lr_step_size=16000, lr_gamma=0.5, model=m)
 x = torch.randn(Bsz, 4, S, S, S, device="cuda")
 t = (torch.rand(Bsz, 3, S, S, S, device="cuda") > 0.7).float()
 
