@@ -177,11 +177,14 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
         p.w_stage_bytes = (unsigned)(p.TG * p.KC * Nm * 2);
         double best_cost = 1e300;
         int bBD = 0, bMB = 0, bWhole = 0;
+        int fBD = 0, fMB = 0, fWhole = -1;                // diagnostics: B200_CONV_TILE="BD MB whole" forces a tile shape
+        if (const char* e = getenv("B200_CONV_TILE")) sscanf(e, "%d %d %d", &fBD, &fMB, &fWhole);
         for (int whole = 0; whole < 2; ++whole)
             for (int BD : {1, 2, 4}) {
                 if (whole && BD != 1) continue;
                 if (BD > d->D || d->D % BD) continue;     // no ragged slice groups
                 for (int MB : {1, 2, 4}) {
+                    if (fBD && (BD != fBD || MB != fMB || (fWhole >= 0 && whole != fWhole))) continue;
                     const int R = BD * MB;
                     if (2 * R * Nm > 512) continue;
                     const int TR = RB * MB;
