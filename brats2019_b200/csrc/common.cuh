@@ -6,6 +6,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Perf probes (skip-a-stage switches, in-kernel cycle accounting) exist only in the probes build
+// (`python -m brats2019_b200.build --probes`, -DB200_PROBES): in the default library B200_DBG() is a compile-time
+// false and every probe branch is dead code.
+#ifdef B200_PROBES
+#define B200_DBG(p, bits) (((p).debug & (bits)) != 0)
+#else
+#define B200_DBG(p, bits) false
+#endif
+
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------

@@ -128,7 +128,7 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
             for (int dpi = sg.d0; dpi <= sg.d1 + 2; ++dpi) {
                 mbar_wait(&x_empty[xs], xph ^ 1);
                 if (elect_one()) {
-                    if (p.debug & 1) {
+                    if (B200_DBG(p, 1)) {
                         mbar_arrive(&x_full[xs]);
                     } else {
                         mbar_arrive_expect_tx(&x_full[xs], seg_bytes * 2 * kBandLines);
@@ -168,8 +168,8 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
         const uint64_t b_hi = ((uint64_t)144 << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);   // LBO = 144 rows * 16 B
         const uint32_t xbase16 = smem_u32(smem_x) >> 4, wbase16 = smem_u32(smem_w) >> 4;
         const uint32_t slot16 = p.slot_bytes >> 4, wimg16 = p.wimg_bytes >> 4;
-        const bool skip_mma = (p.debug & 2) != 0;
-        const bool prof = (p.debug & 256) != 0;
+        const bool skip_mma = B200_DBG(p, 2);
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_x = 0, w_acc = 0, t_issue = 0, tb = 0, nsteps = 0;
         unsigned long long gt0 = 0;
         MARCH_PROF_T(tb);
@@ -282,7 +282,7 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
             for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         };
 
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_done = 0, t_ld = 0, t_st = 0, t_rest = 0, tb = 0;
         MARCH_PROF_T(tb);
         uint32_t k = 0;

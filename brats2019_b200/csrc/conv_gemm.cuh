@@ -145,7 +145,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             for (int g = 0; g < p.KG; ++g) {
                 mbar_wait(&x_empty[xs], xph ^ 1);
                 if (elect_one()) {
-                    if (p.debug & 1) {
+                    if (B200_DBG(p, 1)) {
                         mbar_arrive(&x_full[xs]);
                     } else {
                         mbar_arrive_expect_tx(&x_full[xs], p.x_stage_bytes);
@@ -208,7 +208,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
         const uint32_t xstage16 = p.x_stage_bytes >> 4, wstage16 = p.w_stage_bytes >> 4;
         const int ksteps = p.KC / 16;
         const uint32_t wtap16 = (uint32_t)(p.KC / 8) * NMMA;     // 16B units per tap in a weight stage
-        const bool skip_mma = (p.debug & 2) != 0;
+        const bool skip_mma = B200_DBG(p, 2);
         int xs = 0, ws = 0; uint32_t xph = 0, wph = 0;
         int it = 0;
         for (int t = cta; t < p.num_tiles; t += ctas, ++it) {
@@ -292,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         int cur_n = -1;
-        const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr) && !(p.debug & 64);
+        const bool do_stats = (EPI == EPI_BF16) && (p.stats_partial != nullptr) && !B200_DBG(p, 64);
         float* xch = xch_smem + grp * (2 * 4 * 2 * 16);
         int xbuf = 0;
 
@@ -357,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                         float a0[16], a2[16];
                         {
                             uint32_t r0[16], r1[16], r2[16];
-                            if (!(p.debug & 16)) {
+                            if (!B200_DBG(p, 16)) {
                                 tmem_ld16_nowait(trow + c0, r0);
                                 tmem_ld16_nowait(trow + CO + c0, r1);
                                 tmem_ld16_nowait(trow + 2 * CO + c0, r2);
@@ -377,7 +377,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                         // come through shared memory (lane 31's P_0 row and lane 0's P_2 row per warp).
                         float* xb = xch + xbuf * (4 * 2 * 16);
                         float bnd[16];      // read only by lanes 0/31; rows 0 and 127 of a block are never stored
-                        if (!(p.debug & 4)) {
+                        if (!B200_DBG(p, 4)) {
                             if (lane == 31) {
                                 float4* d4 = reinterpret_cast<float4*>(xb + (ew * 2 + 0) * 16);
 #pragma unroll
@@ -400,7 +400,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                                 }
                             }
                         }
-                        if (!(p.debug & 8)) {
+                        if (!B200_DBG(p, 8)) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 const float up = __shfl_up_sync(0xffffffffu, a0[i], 1);
@@ -436,7 +436,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i]);
                             }
-                            if (!(p.debug & 32) || v[0] == 123.456f) {
+                            if (!B200_DBG(p, 32) || v[0] == 123.456f) {
                                 *reinterpret_cast<uint4*>(p.out.at(ch, orow)) = pack_bf16x8(v);
                                 *reinterpret_cast<uint4*>(p.out.at(ch + 1, orow)) = pack_bf16x8(v + 8);
                             }

@@ -146,7 +146,7 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
         int xs = 0; uint32_t xph = 0;
         const uint32_t bytes = (uint32_t)p.SRp * 16;
         const int chunks = p.KS * 2;
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, w_empty = 0, tb = 0;
         MARCH_PROF_T(tb);
         for (long long u = u_begin; u < u_end;) {
@@ -158,7 +158,7 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
                 MARCH_PROF_T(t1);
                 w_empty += t1 - t0;
                 if (elect_one()) {
-                    if (p.debug & 1) {
+                    if (B200_DBG(p, 1)) {
                         mbar_arrive(&x_full[xs]);
                     } else {
                         mbar_arrive_expect_tx(&x_full[xs], bytes * chunks);
@@ -196,12 +196,12 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
         const uint64_t b_hi = ((uint64_t)((5 * CO * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
         const uint32_t xbase16 = smem_u32(smem_x) >> 4, wbase16 = smem_u32(smem_w) >> 4;
         const uint32_t slot16 = p.slot_bytes >> 4, wtile16 = p.wtile_bytes >> 4;
-        const bool skip_mma = (p.debug & 2) != 0;
+        const bool skip_mma = B200_DBG(p, 2);
         const int MB = p.MB, KS = p.KS;
         uint32_t tof[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) tof[t] = (uint32_t)((t / 3) * p.Wp + (t % 3));
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_x = 0, w_acc = 0, t_issue = 0, tb = 0, nsteps = 0;
         MARCH_PROF_T(tb);
         mbar_wait(w_full, 0);
@@ -290,7 +290,7 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
             for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         };
 
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_done = 0, t_ld = 0, t_st = 0, t_rest = 0, tb = 0;
         MARCH_PROF_T(tb);
         uint32_t k = 0;

@@ -119,7 +119,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
         const uint8_t* ysrc = reinterpret_cast<const uint8_t*>(p.dy.base);
         const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(p.x.base);
         int s = 0; uint32_t ph = 0;
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, tb = 0, w_empty = 0, t_issue = 0;
         MARCH_PROF_T(tb);
         for (int i = 0; i < nst; ++i) {
@@ -161,7 +161,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
         const uint64_t b_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((p.x_plane_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
         const int ksteps = p.KT / 16;
         int s = 0; uint32_t ph = 0;
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, tb = 0, w_full = 0, t_issue = 0;
         MARCH_PROF_T(tb);
         for (int i = 0; i < nst; ++i) {
@@ -209,7 +209,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
         int row; bool row_ok;
         if (p.M == 128) { row = ew * 32 + lane; row_ok = true; }
         else            { row = ew * 16 + lane; row_ok = lane < 16; }   // M=64: lanes 0-15 of each quadrant
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long tb = 0, t1 = 0;
         MARCH_PROF_T(tb);
         if (nst > 0) {

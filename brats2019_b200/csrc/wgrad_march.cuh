@@ -179,7 +179,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams p) {
         const uint32_t ysubring16 = (6u * p.y_sub_bytes) >> 4;      // one half band's ring: 3 slots x 2 chunks
         const uint32_t yline16 = (uint32_t)p.Wp;                    // one line = Wp rows of 16 B
         const uint32_t xline16 = (uint32_t)(2 * p.Wp);              // one line of an X stage = 2 blocks
-        const bool prof = (p.debug & 256) != 0;
+        const bool prof = B200_DBG(p, 256);
         long long t0 = 0, t1 = 0, t2 = 0, tb = 0, w_wait = 0, t_issue = 0, nsteps = 0;
         MARCH_PROF_T(tb);
         long long j = 0, i = 0;                                     // dY refills / X stages consumed so far

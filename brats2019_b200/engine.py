@@ -268,9 +268,6 @@ class Engine:
                 nc = ch[i] // 8
                 P.alias(self._skip_name(i), i, cat.chunks(0, nc))
                 P.alias("dec%d.up" % i, i, cat.chunks(nc, 2 * nc))
-                gcat = P.act("g.cat", i, 2 * ch[i])
-                P.alias("g.skip", i, gcat.chunks(0, nc))
-                P.alias("g.dup", i, gcat.chunks(nc, 2 * nc))
         x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
         c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c", lrelu=False,
                                  **(dict(gamma=prm["norm_input.weight"], beta=prm["norm_input.bias"]) if training else {}))
@@ -482,6 +479,12 @@ class Engine:
                                % (tuple(gprobs.shape), tuple(probs.shape)))
         prm = {k: v.detach() for k, v in self._params().items()}
         ch = self.ch
+        for i in range(self.depth - 1):          # gradient twins of the cat buffers: allocated on the first backward only
+            if ("g.cat", i, 2 * ch[i]) not in P.acts:
+                gcat = P.act("g.cat", i, 2 * ch[i])
+                nc = ch[i] // 8
+                P.alias("g.skip", i, gcat.chunks(0, nc))
+                P.alias("g.dup", i, gcat.chunks(nc, 2 * nc))
         grads = store if store is not None else GradStore()
         gprobs = gprobs.contiguous().float()
         D, H, W = P.dims[0]

@@ -1,0 +1,18 @@
+# Round-2 multi-GPU evidence on N GPUs of one box: bash tools/gpu_r02_scale.sh N
+N=${1:-8}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29533 bench.py --gpus $N --steps 40 --warmup 3 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "weak rc=$?"
+timeout 600 $TR --master-port 29534 bench.py --gpus $N --global-batch 16 --steps 40 --warmup 3 > gpurun_out/r02_bench_n${N}_global16.json 2> gpurun_out/bench_g16_n$N.err; echo "global16 rc=$?"
+timeout 900 $TR --master-port 29535 tools/bench_inference.py --volumes 8 --tiled-volumes 8 --reps 2 > gpurun_out/r02_inference_config5_n$N.jsonl 2> gpurun_out/inf_n$N.err; echo "inference rc=$?"
+timeout 600 $TR --master-port 29536 tools/ddp_parity.py > gpurun_out/r02_ddp_parity_n$N.log 2>&1; echo "ddp_parity rc=$?"
+python - <<PY
+import json
+for f in ("gpurun_out/r02_bench_n$N.json", "gpurun_out/r02_bench_n${N}_global16.json"):
+    try:
+        d = json.loads(open(f).read())
+        print(f, {k: d[k] for k in ("value", "ms_per_step", "n_gpus", "scaling")}, "e2e %.3f ms" % d["e2e"]["ms_per_step"], d.get("ddp_parity"))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
+cat gpurun_out/r02_inference_config5_n$N.jsonl | cut -c1-400; tail -3 gpurun_out/r02_ddp_parity_n$N.log

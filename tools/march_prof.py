@@ -6,6 +6,13 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the skip-a-stage / cycle-accounting code exists only in the probes build: python -m brats2019_b200.build --probes
+_PROBES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "brats2019_b200", "libbrats_b200_probes.so")
+if True:
+    if not os.path.exists(_PROBES):
+        raise SystemExit("build the probes library first: python -m brats2019_b200.build --probes")
+    os.environ["B200_LIB_PATH"] = _PROBES
+
 flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 os.environ["B200_CONV_DEBUG"] = str(256 | flags)
 import torch  # noqa: E402

@@ -12,6 +12,13 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
+# the skip-a-stage / cycle-accounting code exists only in the probes build: python -m brats2019_b200.build --probes
+_PROBES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "brats2019_b200", "libbrats_b200_probes.so")
+if "--probes" in sys.argv:
+    if not os.path.exists(_PROBES):
+        raise SystemExit("build the probes library first: python -m brats2019_b200.build --probes")
+    os.environ["B200_LIB_PATH"] = _PROBES
+
 
 import torch  # noqa: E402
 
@@ -51,8 +58,8 @@ def line(name, ms, flops=None, bytes_=None):
 
 def main():
     from brats2019_b200 import ops
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
+    S = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 128
     dev = "cuda"
     ch = [16, 32, 64, 128]
     only = os.environ.get("PROBE_ONLY", "")
@@ -69,7 +76,7 @@ def main():
         fl = 2.0 * vox * Cc * Cc * 27
         if not only or "conv3" in only:
             line("conv3 %d->%d @ %dx%d^3 (+GN stats)" % (Cc, Cc, B, s), timeit(lambda: ops.conv_run(desc, x, pk, y, stats=st)), flops=fl)
-        if lvl == 0 and (not only or "conv3" in only) and os.environ.get("B200_CONV_DEBUG") is None:
+        if lvl == 0 and (not only or "conv3" in only) and os.environ.get("B200_CONV_DEBUG") is None and "--probes" in sys.argv:
             for flag, what in ((1, "no activation loads"), (2, "no MMAs"), (3, "neither (epilogue + weights only)"),
                                (7, "neither, no fold exchange/barrier"), (15, "neither, no exchange, no shuffles"),
                                (3 + 16, "neither, no tmem ld"), (3 + 32, "neither, no stores"), (3 + 64, "neither, no stats"),
