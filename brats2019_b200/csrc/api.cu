@@ -1213,8 +1213,8 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
     LAUNCH_OK("gn_bwd_finalize2_kernel");
     const int lpb = lines_per_block(N, D, H, W, C);
-    gn_bwd_apply2_kernel<<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                         coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr);
+    gn_bwd_apply2_kernel<false><<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                                coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr);
     LAUNCH_OK("gn_bwd_apply2_kernel");
     return 0;
 }
@@ -1243,8 +1243,8 @@ extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const floa
     const FastDiv by_W = make_fastdiv((unsigned)W);
     const int lpb = lines_per_block(N, D, H, W, C);
     const int bps = D * H / lpb;
-    gn_bwd_apply2_kernel<<<N * bps, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
-                                                 make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff);
+    gn_bwd_apply2_kernel<true><<<N * bps, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
+                                                       make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff);
     LAUNCH_OK("gn_bwd_apply2_kernel");
     const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
     gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(aff, bps, N, C, m, gamma, coef_scratch, dgamma, dbeta);

@@ -14,6 +14,19 @@
 namespace b200 {
 
 constexpr int kRedLines = 128;      // lines one gn_bwd_reduce2 CTA may own
+// Register budget of the two GroupNorm-backward kernels.  In the training step they run beside a weight-gradient CTA
+// (12 K registers, ~217 KB of shared memory per SM): at 128 registers per thread only ONE of their CTAs fits next to it
+// (8 warps per SM for a memory-bound kernel), at 64 three do.  kGnBwdMinCtas / kGnBwdUnroll trade per-thread loads in
+// flight for resident warps.  Measured on the training step (min CTAs, unroll): (2,4) 5.66 ms, (3,2) 5.68, (3,4) 5.87,
+// (4,2) 5.95, (4,1) 6.02 - loads in flight per thread beat resident warps; (2,4) stays.
+#ifndef B200_GNBWD_MINCTAS
+#define B200_GNBWD_MINCTAS 2
+#endif
+#ifndef B200_GNBWD_UNROLL
+#define B200_GNBWD_UNROLL 4
+#endif
+constexpr int kGnBwdMinCtas = B200_GNBWD_MINCTAS;
+constexpr int kGnBwdUnroll = B200_GNBWD_UNROLL;
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 // bf16x2 word -> two floats (low half first)
@@ -57,7 +70,7 @@ __device__ __forceinline__ WarpChunk warp_chunk(int C) {
 //   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
 // grid = (blocks, N); CTA b owns lines [b*lpb, b*lpb+lpb) of sample n; partial[n][blocks][C][2].
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, kGnBwdMinCtas)
 gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
                       Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
@@ -96,7 +109,7 @@ gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const
             p1[j] = f2(k1[0], k1[1]); p2[j] = f2(k2[0], k2[1]);
             s1[j] = f2(0.f, 0.f); s2[j] = f2(0.f, 0.f);
         }
-        constexpr int U = 4;
+        constexpr int U = kGnBwdUnroll;
         for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
             uint4 qx[U], qd[U];
             bool ok[U];
@@ -213,7 +226,8 @@ gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, in
 // aff_partial (optional): this CTA's per-channel sums S1 = sum dz, S2 = sum dz * xhat over its voxels, layout
 // [n][blocks per sample][C][2] like gn_bwd_reduce2's - the input of gn_bwd_finalize2 for dgamma / dbeta when the
 // group sums that dx needs came from the producing conv's epilogue (common.cuh gnb_accumulate) and no reduce pass ran.
-__global__ void __launch_bounds__(256, 2)
+template <bool AFF>
+__global__ void __launch_bounds__(256, AFF ? 2 : kGnBwdMinCtas)
 gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
                      ActRef dx, Vol v, int C, int do_lrelu, FastDiv by_W, int lpb, float* __restrict__ aff_partial) {
@@ -249,7 +263,7 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
             a2[j] = f2(ka[0], ka[1]); b2[j] = f2(kb[0], kb[1]);
             s1[j] = f2(0.f, 0.f); s2[j] = f2(0.f, 0.f);
         }
-        constexpr int U = 4;
+        constexpr int U = kGnBwdUnroll;
         for (int i0 = wc.ws * 32 + lane; i0 < total; i0 += stride * U) {
             uint4 qx[U], qd[U];
             long long rr[U];
@@ -275,7 +289,7 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
                 for (int j = 0; j < 4; ++j) {
                     float2 dz = fd[j];
                     if (do_lrelu) dz = __fmul2_rn(dz, lrelu_mask(__ffma2_rn(fx[j], p1[j], p2[j])));
-                    if (aff_partial) {
+                    if (AFF) {
                         s1[j] = __fadd2_rn(s1[j], dz);
                         s2[j] = __ffma2_rn(dz, __ffma2_rn(fx[j], a2[j], b2[j]), s2[j]);
                     }
@@ -284,7 +298,7 @@ gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const 
                 st16(dx.at(cv, rr[u]), pack4(fx));
             }
         }
-        if (aff_partial) {          // same fixed-order combination as gn_bwd_reduce2_kernel
+        if (AFF) {          // same fixed-order combination as gn_bwd_reduce2_kernel
             const int warp = threadIdx.x >> 5;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
