@@ -114,6 +114,8 @@ class Engine:
         self._side_stream = None
         self._side_busy = False
         self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
+        self._deferred = []       # side-stream weight-gradient jobs held back until the chain's next conv is enqueued
+        self.sched = os.environ.get("B200_BWD_SCHED", "1") not in ("", "0")   # A/B: 0 = round-2a launch order
         self.last = None          # (plan, generation) of the most recent training forward
         self.tap = None           # tests only: callable(name, Act | tensor) invoked after every backward stage, while
                                   # the (reused) gradient buffer still holds that stage's result
@@ -315,9 +317,14 @@ class Engine:
     # ---------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------
-    def _wgrad(self, P, lvl, mode, dy, x, grad, kind, ci_off=0, accumulate=False, overlap=False):
+    def _wgrad(self, P, lvl, mode, dy, x, grad, kind, ci_off=0, accumulate=False, overlap=False, defer=False):
         """Weight gradient of one conv.  overlap=True: enqueue on the side stream (after everything already on
-        the current stream); the caller must not overwrite `dy` before `_wait_readers(dy)`."""
+        the current stream); the caller must not overwrite `dy` before `_wait_readers(dy)`.
+        defer=True (with overlap): do not enqueue yet - `_flush_deferred()` does, after the caller has put the NEXT
+        tensor-core kernel of the data-gradient chain on the main stream.  A weight-gradient CTA takes a whole SM for the
+        length of the kernel (persistent, ~217 KB of shared memory), so a weight gradient that becomes runnable at the
+        same moment as the chain's next conv delays that conv by up to its whole duration; behind it, it runs beside the
+        memory-bound kernels that follow (trilinear adjoint, depth-to-space, GroupNorm backward)."""
         D, H, W = P.dims[lvl]
         desc = ops.wgrad_desc(mode, P.N, D, H, W, dy.C, x.C)
         overlap = overlap and self.overlap_wgrad
@@ -334,6 +341,17 @@ class Engine:
         if not overlap:
             ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=ws)
             return
+        job = (desc, dy, x, grad, kind, ci_off, accumulate, wsname, P)
+        if defer:
+            self._deferred.append(job)
+        else:
+            self._side_launch([job])
+
+    def _side_launch(self, jobs):
+        """Enqueue weight-gradient jobs on the side stream, ordered behind everything already on the current stream."""
+        if not jobs:
+            return
+        P = jobs[0][8]
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=P.device)
         main, side = torch.cuda.current_stream(), self._side_stream
@@ -341,11 +359,17 @@ class Engine:
         ready.record(main)
         side.wait_event(ready)
         with torch.cuda.stream(side):
-            ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=ws)
+            for desc, dy, x, grad, kind, ci_off, accumulate, wsname, Pj in jobs:
+                ops.wgrad_run(desc, dy, x, grad, kind, ci_off=ci_off, accumulate=accumulate, workspace=Pj.misc[wsname])
             done = torch.cuda.Event()
             done.record(side)
-        self._readers[id(dy.t)] = done
+        for job in jobs:
+            self._readers[id(job[1].t)] = done
         self._side_busy = True
+
+    def _flush_deferred(self):
+        jobs, self._deferred = self._deferred, []
+        self._side_launch(jobs)
 
     def _wait_readers(self, buf):
         """Order the current stream after the last side-stream kernel that reads `buf` (before overwriting it)."""
@@ -408,11 +432,13 @@ class Engine:
             self._join_side()
             self.tap(name, value)
 
-    def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads, d_out_folded=None, fold_next=None):
+    def _residual_bwd(self, P, lvl, prefix, x_in, d_out, d_in_buf, prm, grads, d_out_folded=None, fold_next=None,
+                      defer_last=False):
         """Backward of _residual_fwd.  d_out: grad w.r.t. the block output.  Returns (grad w.r.t. x_in written into
         d_in_buf - it includes the identity path, model.py:115 -, folded sums for `fold_next` or None).
         d_out_folded: the (gpart, ctas) the producer of d_out left for this block's norm2 (see _dgrad3);
-        fold_next: conv buffer name whose GroupNorm consumes the returned gradient as its dy."""
+        fold_next: conv buffer name whose GroupNorm consumes the returned gradient as its dy.
+        defer_last: hold conv1's weight gradient back (`_wgrad(defer=True)`) - the caller enqueues a conv next."""
         Cc = x_in.C
         c1 = P.act(prefix + "c1", lvl, Cc)
         a1 = P.act(prefix + "a1", lvl, Cc)
@@ -439,7 +465,7 @@ class Engine:
         fn = self._dgrad3(P, lvl, w1n, prm[w1n], dc1, d_in_buf, residual=d_out, fold=fold_next)
         dx = d_in_buf
         self._tap("g:" + prefix + "dx", dx)
-        self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3, overlap=True)
+        self._wgrad(P, lvl, 0, dc1, x_in, g1, ops.G_K3, overlap=True, defer=defer_last)
         return dx, fn
 
     def _mark(self, grads):
@@ -497,7 +523,9 @@ class Engine:
         g_out = grads.new("conv_output.weight", prm["conv_output.weight"])
         # ping-pong gradient buffers per level: "g.A"/"g.B"
         def gbuf(name, lvl, Cc):
-            return P.act("g." + name, lvl, Cc)
+            buf = P.act("g." + name, lvl, Cc)
+            self._wait_readers(buf)           # a side-stream weight gradient may still be reading its previous contents
+            return buf
 
         self._tap("g:dlogit", dlog)
         # the producer of every block's output gradient leaves the sums of that block's norm2 when it is a k3 data-gradient
@@ -521,16 +549,24 @@ class Engine:
                 nxt = other(cur_name)
                 fold_next = "decoder_convs.%d.%d.c2" % (i, j - 1) if j > 0 else None
                 cur, folded = self._residual_bwd(P, i, prefix, x_in, cur, gbuf(nxt, i, ch[i]), prm, grads,
-                                                 d_out_folded=folded, fold_next=fold_next)
+                                                 d_out_folded=folded, fold_next=fold_next,
+                                                 defer_last=self.sched and j == 0)
                 cur_name = nxt
             folded = None
             # cat conv (model.py:424-425): cc = W[:, :C] skip + W[:, C:] up
+            # Launch order (self.sched): the chain's convs go first, every weight gradient of the level boundary goes to
+            # the side stream behind them, next to the memory-bound trilinear adjoint / GroupNorm backward that follow.
             wname = "decoder_convs1x1.%d.weight" % i
             w = prm[wname]
             up = P.act("dec%d.up" % i, i, ch[i])
             self._tap("g:dec%d.cc" % i, cur)
-            self._wgrad(P, i, 1, cur, P.act("dec%d.cat" % i, i, 2 * ch[i]), grads.new(wname, w), ops.G_K1)
+            gcatw = grads.new(wname, w)
+            if not self.sched:
+                self._wgrad(P, i, 1, cur, P.act("dec%d.cat" % i, i, 2 * ch[i]), gcatw, ops.G_K1)
             self._conv1(P, i, wname, w, ops.W_DGRAD, cur, gbuf("cat", i, 2 * ch[i]))       # [dskip | dup] in one GEMM
+            if self.sched:
+                self._flush_deferred()
+                self._wgrad(P, i, 1, cur, P.act("dec%d.cat" % i, i, 2 * ch[i]), gcatw, ops.G_K1, overlap=True)
             self._tap("g:dec%d.cat" % i, gbuf("cat", i, 2 * ch[i]))
             dskip[i] = gbuf("skip", i, ch[i])
             dup = gbuf("dup", i, ch[i])
@@ -540,9 +576,14 @@ class Engine:
             wname = "upsampling.%d.1.weight" % i
             w = prm[wname]
             h_lo = self._level_output(P, i + 1)
-            self._wgrad(P, i + 1, 1, dulo, h_lo, grads.new(wname, w), ops.G_K1)
-            self._mark(grads)
+            gupw = grads.new(wname, w)
+            if not self.sched:
+                self._wgrad(P, i + 1, 1, dulo, h_lo, gupw, ops.G_K1)
+                self._mark(grads)
             cur = self._conv1(P, i + 1, wname, w, ops.W_DGRAD, dulo, gbuf("A", i + 1, ch[i + 1]))
+            if self.sched:
+                self._wgrad(P, i + 1, 1, dulo, h_lo, gupw, ops.G_K1, overlap=True)
+                self._mark(grads)
             self._tap("g:dec%d.h_lo" % i, cur)
             cur_name = "A"
         # At this point `cur` is the gradient w.r.t. the bottleneck output (encoder level depth-1).
@@ -555,16 +596,23 @@ class Engine:
                 nxt = other(cur_name)
                 fold_next = "encoder_convs.%d.%d.c2" % (i, j - 1) if j > 0 else None
                 cur, folded = self._residual_bwd(P, lvl, prefix, x_in, cur, gbuf(nxt, lvl, ch[lvl]), prm, grads,
-                                                 d_out_folded=folded, fold_next=fold_next)
+                                                 d_out_folded=folded, fold_next=fold_next,
+                                                 defer_last=self.sched and j == 0)
                 cur_name = nxt
             folded = None
             wname = "encoder_convs.%d.0.downsample.0.weight" % i
             w = prm[wname]
             s2d = P.act("enc%d.s2d" % i, lvl, 8 * ch[i])
             self._tap("g:enc%d.down" % i, cur)
-            self._wgrad(P, lvl, 1, cur, s2d, grads.new(wname, w), ops.G_S2D)
-            self._mark(grads)
+            gdw = grads.new(wname, w)
+            if not self.sched:
+                self._wgrad(P, lvl, 1, cur, s2d, gdw, ops.G_S2D)
+                self._mark(grads)
             ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
+            if self.sched:
+                self._flush_deferred()
+                self._wgrad(P, lvl, 1, cur, s2d, gdw, ops.G_S2D, overlap=True)
+                self._mark(grads)
             # back to the fine grid, adding the skip-connection gradient from the decoder
             self._tap("g:enc%d.s2d" % i, ds2d)
             cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
@@ -586,6 +634,7 @@ class Engine:
         self._tap("g:in.c", dcin)
         self._wgrad(P, 0, 0, dcin, P.act("x16", 0, 16), grads.new("conv_input.weight", prm["conv_input.weight"]),
                     ops.G_K3)
+        self._flush_deferred()
         self._join_side()
         grads.finish()
         self.grad_order = list(grads.grads.keys())
