@@ -52,6 +52,7 @@ _PROTOS = {
     "b200_conv_run": (c_int, [C.POINTER(ConvDesc), P, P, P, P, P, c_int, P, P, P, P, c_int, P]),
     "b200_conv_supports_gnbwd": (c_int, [C.POINTER(ConvDesc)]),
     "b200_conv_run_gnbwd": (c_int, [C.POINTER(ConvDesc), P, P, P, P, P, c_int, P, P, P, P, c_int, P, P, P]),
+    "b200_conv_run_gn": (c_int, [C.POINTER(ConvDesc), P, P, P, P, P, P, P, c_float, P]),
     "b200_wgrad_workspace_bytes": (c_size_t, [C.POINTER(WgradDesc)]),
     "b200_wgrad_run": (c_int, [C.POINTER(WgradDesc), P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_gn_finalize": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P]),

@@ -70,6 +70,45 @@ static int num_sms() {
     }
     return cache[dev];
 }
+// Launch with a per-kernel scheduling priority (cudaLaunchAttributePriority; kept by CUDA-graph kernel nodes).  The
+// block scheduler hands a freed SM slot to the pending CTA of the highest-priority kernel; running CTAs are never
+// preempted.  In the training step's backward pass three classes of kernels are pending at once:
+//   convs of the data-gradient chain  (critical path)                 -> kPrioConv   (highest)
+//   weight-gradient GEMMs + their reduces (side stream)               -> kPrioWgrad
+//   memory-bound kernels (GroupNorm backward, trilinear adjoint, ...) -> default (0, lowest)
+// Without priorities a 2-CTA weight-gradient reduce queues behind the ~2000 not-yet-resident CTAs of a GroupNorm kernel
+// launched a microsecond earlier (measured: 50 us of side-stream idle per level boundary).  B200_PRIO="conv wgrad"
+// (e.g. "-2 -1") turns it on.  Measured: the priorities do move the weight-gradient kernels forward in the timeline, and
+// the memory-bound kernels they then overlap slow down by the same amount - the backward pass is bound by the sum of the
+// work, not by the launch order (5.504 vs 5.503 ms per step) - so the default is off.
+static void launch_priorities(int& conv, int& wgrad) {
+    static int c = 1, w = 1, init = 0;
+    if (!init) {
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); least = greatest = 0; }
+        c = 0; w = 0;            // measured (profiles/r02_ab_priorities.txt): no effect on the step, off by default
+        if (const char* e = getenv("B200_PRIO")) sscanf(e, "%d %d", &c, &w);
+        c = std::max(c, greatest); w = std::max(w, greatest);
+        c = std::min(c, least); w = std::min(w, least);
+        init = 1;
+    }
+    conv = c; wgrad = w;
+}
+static int prio_conv() { int c, w; launch_priorities(c, w); return c; }
+static int prio_wgrad() { int c, w; launch_priorities(c, w); return w; }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio,
+                               Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = prio;
+    cfg.attrs = attr;
+    cfg.numAttrs = prio != 0 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
 #define SET_MAX_SMEM_ONCE(...)                                                                                     \
     do {                                                                                                           \
@@ -504,7 +543,7 @@ extern "C" int b200_pack_table_run(const void* table_device, int n_jobs, int tot
 template <int MODE, int EPI, int NM, int FOLD>
 static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_gemm_kernel<MODE, EPI, NM, FOLD>);
-    conv_gemm_kernel<MODE, EPI, NM, FOLD><<<grid, kConvThreads, smem, st>>>(p);
+    CUDA_OK(launch_prio(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), p));
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
 }
@@ -512,14 +551,15 @@ static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream
 template <int CO, int EPI>
 static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_march_kernel<CO, EPI>);
-    conv_march_kernel<CO, EPI><<<grid, kMarchThreads, smem, st>>>(p);
+    CUDA_OK(launch_prio(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), p));
     LAUNCH_OK("conv_march_kernel");
     return 0;
 }
 
 static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a, const void* packed, void* out,
                      const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
-                     float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, cudaStream_t st) {
+                     float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, const GnFin* fin,
+                     cudaStream_t st) {
     if (!src_a || !packed) return fail("conv: null operand");
     if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
     if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
@@ -545,6 +585,10 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
         return fail("conv: GroupNorm-backward fold needs stats_partial, gnb_coef and 16-byte aligned pointers");
     p.gnb_x = make_act(gnb_x, vol);
     p.gnb_coef = gnb_coef;
+    if (fin) {
+        if (!stats_partial || gnb_x) return fail("conv: fused GroupNorm finalize needs forward statistics (stats_partial, no backward fold)");
+        p.gn_fin = *fin;
+    }
     const unsigned smem = p.smem_bar_off + kMarchTailBytes;
     if (d->epi == EPI_SIGMOID) return launch_march<16, EPI_SIGMOID>(p, smem, grid, st);
     if (d->Cout == 16) return launch_march<16, EPI_BF16>(p, smem, grid, st);
@@ -554,14 +598,15 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
 template <int EPI>
 static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_band_kernel<EPI>);
-    conv_band_kernel<EPI><<<grid, kBandThreads, smem, st>>>(p);
+    CUDA_OK(launch_prio(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), p));
     LAUNCH_OK("conv_band_kernel");
     return 0;
 }
 
 static int run_band(const b200_conv_desc* d, BandParams& p, const void* src_a, const void* packed, void* out,
                     const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
-                    float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, cudaStream_t st) {
+                    float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, const GnFin* fin,
+                    cudaStream_t st) {
     if (!src_a || !packed) return fail("conv: null operand");
     if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
     if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
@@ -587,6 +632,10 @@ static int run_band(const b200_conv_desc* d, BandParams& p, const void* src_a, c
         return fail("conv: GroupNorm-backward fold needs stats_partial, gnb_coef and 16-byte aligned pointers");
     p.gnb_x = make_act(gnb_x, vol);
     p.gnb_coef = gnb_coef;
+    if (fin) {
+        if (!stats_partial || gnb_x) return fail("conv: fused GroupNorm finalize needs forward statistics (stats_partial, no backward fold)");
+        p.gn_fin = *fin;
+    }
     const unsigned smem = p.smem_bar_off + kBandTailBytes;
     if (d->epi == EPI_SIGMOID) return launch_band<EPI_SIGMOID>(p, smem, grid, st);
     return launch_band<EPI_BF16>(p, smem, grid, st);
@@ -601,29 +650,59 @@ extern "C" int b200_conv_supports_gnbwd(const b200_conv_desc* d) {
     return 0;
 }
 
+static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed, void* out,
+                         const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
+                         float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, const GnFin* fin,
+                         void* stream);
+
 extern "C" int b200_conv_run(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
                              void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
                              float* probs, float* logits, int n_out_real, void* stream) {
-    return b200_conv_run_gnbwd(d, src_a, src_b, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
-                               n_out_real, nullptr, nullptr, stream);
+    return conv_run_impl(d, src_a, src_b, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits, n_out_real,
+                         nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int b200_conv_run_gnbwd(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed,
                                    void* out, const void* residual, int lrelu_out, float* stats_partial, const float* bias,
                                    float* probs, float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef,
                                    void* stream) {
+    return conv_run_impl(d, src_a, src_b, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits, n_out_real,
+                         gnb_x, gnb_coef, nullptr, stream);
+}
+
+// 3x3x3 conv + GroupNorm statistics in ONE launch: the epilogue leaves per-CTA partial sums in stats_partial and the
+// last CTA to finish reduces them to mean / rstd ([N][8] each) - what b200_conv_run(stats_partial) followed by
+// b200_gn_finalize computes, bit for bit, without the second launch.  ticket: one zero-initialised 32-bit word of device
+// memory, left zero again (reusable by the next launch on the same stream).
+extern "C" int b200_conv_run_gn(const b200_conv_desc* d, const void* src_a, const void* packed, void* out,
+                                float* stats_partial, float* mean, float* rstd, unsigned int* ticket, float eps,
+                                void* stream) {
+    if (check_conv_desc(d)) return 1;
+    if (!stats_partial || !mean || !rstd || !ticket) return fail("conv_run_gn: null argument");
+    if (d->Cout % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
+    GnFin fin;
+    fin.mean = mean; fin.rstd = rstd; fin.ticket = ticket; fin.eps = eps;
+    fin.count = (double)(d->Cout / 8) * d->D * d->H * d->W;
+    return conv_run_impl(d, src_a, nullptr, packed, out, nullptr, 0, stats_partial, nullptr, nullptr, nullptr, 0, nullptr,
+                         nullptr, &fin, stream);
+}
+
+static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void* src_b, const void* packed, void* out,
+                         const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
+                         float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, const GnFin* fin,
+                         void* stream) {
     if (check_conv_desc(d)) return 1;
     {
         BandParams bp;
         if (plan_band(d, bp) == 0)
             return run_band(d, bp, src_a, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
-                            n_out_real, gnb_x, gnb_coef, (cudaStream_t)stream);
+                            n_out_real, gnb_x, gnb_coef, fin, (cudaStream_t)stream);
     }
     {
         MarchParams mp;
         if (plan_march(d, mp) == 0)
             return run_march(d, mp, src_a, packed, out, residual, lrelu_out, stats_partial, bias, probs, logits,
-                             n_out_real, gnb_x, gnb_coef, (cudaStream_t)stream);
+                             n_out_real, gnb_x, gnb_coef, fin, (cudaStream_t)stream);
     }
     if (gnb_x) return fail("conv: the GroupNorm-backward fold exists for the band / marching 3x3x3 kernels only (b200_conv_supports_gnbwd)");
     ConvKParams p;
@@ -639,6 +718,10 @@ extern "C" int b200_conv_run_gnbwd(const b200_conv_desc* d, const void* src_a, c
     p.wpacked = (const __nv_bfloat16*)packed;
     p.lrelu_out = lrelu_out;
     p.stats_partial = stats_partial;
+    if (fin) {
+        if (!stats_partial) return fail("conv: fused GroupNorm finalize needs stats_partial");
+        p.gn_fin = *fin;
+    }
     p.bias = bias; p.probs = probs; p.logits = logits; p.n_out_real = n_out_real;
     {
         const char* dbg = getenv("B200_CONV_DEBUG");     // perf probes only (tools/perf_probe.py)
@@ -945,12 +1028,13 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
 #ifdef B200_PROBES
             { const char* e2 = getenv("B200_WGL_DEBUG"); LP.k.debug = e2 ? atoi(e2) : 0; }
 #endif
-            wgrad_line_kernel<<<LP.grid, kWglThreads, LP.smem, st>>>(LP.k);
+            CUDA_OK(launch_prio(wgrad_line_kernel, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k));
             LAUNCH_OK("wgrad_line_kernel");
             WglReduceParams rq;
             rq.ctas = LP.grid; rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
             constexpr int qpb = 256 / kWglReduceGroups;
-            wgrad_line_reduce_kernel<<<(27 * 16 * 4 + qpb - 1) / qpb, 256, 0, st>>>((const float*)workspace, grad, rq);
+            CUDA_OK(launch_prio(wgrad_line_reduce_kernel, dim3((27 * 16 * 4 + qpb - 1) / qpb), dim3(256), 0, st, prio_wgrad(),
+                                (const float*)workspace, grad, rq));
             LAUNCH_OK("wgrad_line_reduce_kernel");
             return 0;
         }
@@ -972,7 +1056,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     }
     if (P.k.stage_tx_bytes >= (1u << 20)) return fail("wgrad: stage exceeds the mbarrier tx-count range");
     P.k.debug = wdbg;
-    wgrad_gemm_kernel<<<P.grid, kWgradThreads, P.smem, st>>>(P.k);
+    CUDA_OK(launch_prio(wgrad_gemm_kernel, dim3(P.grid), dim3(kWgradThreads), P.smem, st, prio_wgrad(), P.k));
     LAUNCH_OK("wgrad_gemm_kernel");
     WgradReduceParams q;
     q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
@@ -985,7 +1069,8 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     int SG = 1;
     while (SG < 32 && SG * 2 <= q.splits && (long long)quads * SG < 2LL * 256 * num_sms()) SG *= 2;
     const int qpc = 256 / SG;
-    wgrad_reduce_kernel<<<(quads + qpc - 1) / qpc, 256, 0, st>>>(P.k.partial, grad, q, SG);
+    CUDA_OK(launch_prio(wgrad_reduce_kernel, dim3((quads + qpc - 1) / qpc), dim3(256), 0, st, prio_wgrad(),
+                        (const float*)P.k.partial, grad, q, SG));
     LAUNCH_OK("wgrad_reduce_kernel");
     return 0;
 }
@@ -1164,9 +1249,11 @@ static bool plan_gn_cluster(const Vol& v, int C, GnClusterParams& q, unsigned& s
     smem = (unsigned)bytes;
     return true;
 }      // >= blocks for any volume up to 1M lines
+// workspace: tickets[N + 1] (32-bit words, padded to 64) | partial[N][blocks][C][2] | coef[N][C][2] | tot[N][C][2] (double)
+// The ticket words must be ZERO when the workspace is first used (allocate it zero-filled); every launch leaves them zero.
+static size_t gn_bwd_ticket_floats(int N) { return ((size_t)N + 1 + 63) / 64 * 64; }
 extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
-    // partial[N][blocks][C][2] + coef[N][C][2]
-    return (size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2;
+    return gn_bwd_ticket_floats(N) + (size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2 + (size_t)N * C * 4 + 2;
 }
 extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta,
@@ -1200,18 +1287,35 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     }
     int blocks, rlpb;
     gn_bwd_grid(N, D, H, W, C, blocks, rlpb);
-    float* partial = workspace;
+    if (!workspace || ((uintptr_t)workspace & 7)) return fail("gn_backward: workspace must be 8-byte aligned");
+    float* partial = workspace + gn_bwd_ticket_floats(N);
     if (blocks > gn_bwd_max_blocks()) return fail("gn_backward: volume too large");
-    float* coef = workspace + (size_t)N * gn_bwd_max_blocks() * C * 2;
+    float* coef = partial + (size_t)N * gn_bwd_max_blocks() * C * 2;
     const FastDiv by_W = make_fastdiv((unsigned)W);
-    gn_bwd_reduce2_kernel<<<dim3(blocks, N), 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                          partial, v, C, do_lrelu, by_W, rlpb);
-    LAUNCH_OK("gn_bwd_reduce2_kernel");
     const double m = (double)(C / 8) * D * H * W;
-    // one warp per (sample, channel, S1|S2) sum, up to 32 warps: min(8, N) * (C/8) * 2 sums per CTA
-    const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
-    gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
-    LAUNCH_OK("gn_bwd_finalize2_kernel");
+    // B200_GN_BWD_FUSED_FIN=1: pass 2 (partial -> coef, dgamma, dbeta) runs inside the reduction kernel, in its last CTAs
+    // (C <= 128: one thread per (channel, S1|S2) column).  Opt-in: parity-green, one launch fewer, +0.06 ms per step
+    // (profiles/r02_ab_last_cta_finalize.txt) - one CTA reading 75-150 KB of partials is slower than the 8-CTA kernel.
+    int fused = 0;
+    if (const char* e = getenv("B200_GN_BWD_FUSED_FIN")) fused = atoi(e) != 0;
+    GnBwdFin fin;
+    memset(&fin, 0, sizeof(fin));
+    if (fused && C <= 128) {
+        fin.coef = coef;
+        fin.tot = reinterpret_cast<double*>(coef + (size_t)N * C * 2 + (((size_t)N * C * 2) & 1));
+        fin.dgamma = dgamma; fin.dbeta = dbeta;
+        fin.tickets = reinterpret_cast<unsigned int*>(workspace);
+        fin.m = m;
+    }
+    gn_bwd_reduce2_kernel<<<dim3(blocks, N), 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                          partial, v, C, do_lrelu, by_W, rlpb, fin);
+    LAUNCH_OK("gn_bwd_reduce2_kernel");
+    if (fin.coef == nullptr) {
+        // one warp per (sample, channel, S1|S2) sum, up to 32 warps: min(8, N) * (C/8) * 2 sums per CTA
+        const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
+        gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
+        LAUNCH_OK("gn_bwd_finalize2_kernel");
+    }
     const int lpb = lines_per_block(N, D, H, W, C);
     gn_bwd_apply2_kernel<false><<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
                                                                 coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr);
@@ -1224,7 +1328,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
 // workspace: coef[N][C][2] | scratch coef[N][C][2] | aff_partial[N][blocks][C][2], blocks = D*H / lines-per-CTA of the apply
 extern "C" size_t b200_gn_backward_folded_workspace_floats(int N, int D, int H, int W, int C) {
     const int lpb = lines_per_block(N, D, H, W, C);
-    return (size_t)N * C * 4 + (size_t)N * (D * H / lpb) * C * 2;
+    return gn_bwd_ticket_floats(N) + (size_t)N * C * 4 + (size_t)N * (D * H / lpb) * C * 2;
 }
 extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const float* mean, const float* rstd,
                                        const float* gamma, const float* beta, const float* gpart, int ctas, void* dx,
@@ -1235,6 +1339,7 @@ extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const floa
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     const double m = (double)(C / 8) * D * H * W;
+    workspace += gn_bwd_ticket_floats(N);      // the ticket words of b200_gn_backward (the two share one workspace)
     float* coef = workspace;
     float* coef_scratch = workspace + (size_t)N * C * 2;
     float* aff = workspace + (size_t)N * C * 4;

@@ -327,4 +327,66 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// "The last CTA finishes the reduction": instead of a separate tiny kernel that sums per-CTA partial results (a
+// 4-9 us link in a dependent chain of launches, 50 of them per training step), every CTA takes a ticket after its
+// partials are written and the one that draws the last ticket does the finalize pass, reading the other CTAs' partials
+// through L2 (ld.cg).  `ticket` is a zero-initialised word in global memory; the last CTA leaves it zero again, so
+// the same word serves every launch on a stream (and every CUDA-graph replay).
+// Call from ALL threads of the CTA, after the partials have been stored; returns true in every thread of the last CTA.
+// Memory ordering: bar.sync orders the CTA's stores before thread 0's fence, the fence (cumulative, gpu scope) before
+// the ticket; the last CTA fences again after reading the ticket before it loads the partials.
+// ---------------------------------------------------------------------------------------
+// s_ticket: one word of shared memory (the tensor-core kernels have no static shared memory to spare: they pass a
+// word of their - by then idle - dynamic allocation).
+__device__ __forceinline__ bool cta_draws_last_ticket(unsigned int* ticket, unsigned int total, unsigned int* s_ticket) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *s_ticket = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    const bool last = (*s_ticket == total - 1u);
+    if (last) __threadfence();
+    return last;
+}
+
+// GroupNorm statistics finished by the last CTA of the conv whose epilogue produced the partial sums
+// (replaces gn_finalize_kernel; same summation order, bit-identical mean / rstd).
+struct GnFin {
+    float* mean;              // [N][8]; nullptr: no fused finalize (the caller runs b200_gn_finalize)
+    float* rstd;              // [N][8]
+    unsigned int* ticket;     // one zero-initialised word
+    double count;             // elements per (sample, group)
+    float eps;
+};
+// partial: [ctas][N][16] (sum[8] | sumsq[8]); scratch: >= 256 doubles of shared memory; all threads of a CTA with
+// blockDim.x >= 256.
+__device__ __noinline__ void gn_stats_finalize_cta(const float* partial, int ctas, int N, const GnFin& f, double* scratch) {
+    const int t = threadIdx.x;
+    for (int n = 0; n < N; ++n) {
+        if (t < 256) {
+            const int o = t >> 4, j = t & 15;
+            double a = 0.0;
+#pragma unroll 4
+            for (int c = j; c < ctas; c += 16) a += (double)__ldcg(partial + ((size_t)c * N + n) * 16 + o);
+            scratch[t] = a;
+        }
+        __syncthreads();
+        if (t < 8) {
+            double s = 0.0, q = 0.0;
+            for (int k = 0; k < 16; ++k) s += scratch[t * 16 + k];
+            for (int k = 0; k < 16; ++k) q += scratch[(8 + t) * 16 + k];
+            const double m = s / f.count;
+            double var = q / f.count - m * m;
+            if (var < 0.0) var = 0.0;
+            f.mean[n * 8 + t] = (float)m;
+            f.rstd[n * 8 + t] = (float)(1.0 / sqrt(var + (double)f.eps));
+        }
+        __syncthreads();
+    }
+    if (t == 0) *f.ticket = 0u;
+}
+
 }  // namespace b200

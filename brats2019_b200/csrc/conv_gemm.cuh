@@ -70,6 +70,7 @@ struct ConvKParams {
     ActRef out;
     ActRef residual;       // optional (base == nullptr if unused), same layout as out, added before activation
     float* stats_partial;            // optional [ctas][N][16] (sum[8], sumsq[8])
+    GnFin gn_fin;                     // mean != nullptr: the last CTA turns stats_partial into mean / rstd (common.cuh)
     const float* bias;               // EPI_SIGMOID
     float* probs;                    // EPI_SIGMOID: fp32 NCDHW (unpadded)
     float* logits;                   // EPI_SIGMOID: optional fp32 NCDHW
@@ -467,6 +468,11 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 3) tmem_dealloc(tmem_base, p.tmem_cols);
+    // GroupNorm statistics: the CTA that finishes last sums every CTA's partial row (the pipeline's shared memory is idle
+    // by now: every bulk copy has been consumed) - no separate finalize launch between this conv and gn_apply.
+    if (p.gn_fin.mean != nullptr &&
+        cta_draws_last_ticket(p.gn_fin.ticket, gridDim.x, reinterpret_cast<unsigned int*>(smem + 2048)))
+        gn_stats_finalize_cta(p.stats_partial, ctas, p.N, p.gn_fin, reinterpret_cast<double*>(smem));
 }
 
 }  // namespace b200

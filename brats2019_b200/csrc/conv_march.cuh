@@ -57,6 +57,7 @@ struct MarchParams {
     int lrelu_out;
     ActRef out, residual;
     float* stats_partial;             // optional [ctas][N][16]
+    GnFin gn_fin;                     // mean != nullptr: the last CTA turns stats_partial into mean / rstd (common.cuh)
     ActRef gnb_x;                     // != null: stats_partial receives GroupNorm-BACKWARD sums (common.cuh gnb_accumulate) of
     const float* gnb_coef;            //          the GroupNorm whose conv output is gnb_x; coef = [N][3][CO]
     const float* bias;                // EPI_SIGMOID
@@ -418,6 +419,11 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 3) tmem_dealloc(tmem_base, p.tmem_cols);
+    // GroupNorm statistics: the CTA that finishes last sums every CTA's partial row (the pipeline's shared memory is idle
+    // by now: every bulk copy has been consumed) - no separate finalize launch between this conv and gn_apply.
+    if (p.gn_fin.mean != nullptr &&
+        cta_draws_last_ticket(p.gn_fin.ticket, gridDim.x, reinterpret_cast<unsigned int*>(smem + 2048)))
+        gn_stats_finalize_cta(p.stats_partial, ctas, p.N, p.gn_fin, reinterpret_cast<double*>(smem));
 }
 
 }  // namespace b200

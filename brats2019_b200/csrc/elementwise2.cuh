@@ -70,10 +70,25 @@ __device__ __forceinline__ WarpChunk warp_chunk(int C) {
 //   dz = dy * lrelu'(z), z = xhat*gamma + beta, xhat = (x - mean) * rstd.
 // grid = (blocks, N); CTA b owns lines [b*lpb, b*lpb+lpb) of sample n; partial[n][blocks][C][2].
 // ---------------------------------------------------------------------------------------
+// fin.coef != nullptr: the last CTA of each sample also does pass 2 (below) for that sample, and the last of those the
+// sum over samples for dgamma / dbeta - no finalize launch between the reduction and the apply kernel.
+struct GnBwdFin {
+    float* coef;              // [N][C][2]; nullptr: pass 2 is a separate launch (gn_bwd_finalize2_kernel)
+    double* tot;              // [N][C][2] scratch: per-sample (S1, S2) in double, for the sum over samples
+    float* dgamma;            // [C]
+    float* dbeta;             // [C]
+    unsigned int* tickets;    // [N + 1] zero-initialised words (one per sample + one for the samples), left zero
+    double m;                 // elements per (sample, group)
+};
+
+__device__ __forceinline__ void gn_bwd_finalize_sample(const float* __restrict__ partial, int blocks, int n, int N, int C,
+                                                       const float* __restrict__ gamma, const GnBwdFin& f,
+                                                       unsigned int* s_ticket);
+
 __global__ void __launch_bounds__(256, kGnBwdMinCtas)
 gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
-                      Vol v, int C, int do_lrelu, FastDiv by_W, int lpb) {
+                      Vol v, int C, int do_lrelu, FastDiv by_W, int lpb, GnBwdFin fin) {
     __shared__ long long s_rows[kRedLines];
     __shared__ float s_red[8][16];
     const int n = blockIdx.y;
@@ -161,6 +176,69 @@ gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const
             partial[(((size_t)n * gridDim.x + blockIdx.x) * C + c) * 2 + (k >> 3)] = acc;
         }
         __syncthreads();
+    }
+    __shared__ unsigned int s_ticket;
+    if (fin.coef != nullptr && cta_draws_last_ticket(fin.tickets + n, gridDim.x, &s_ticket))
+        gn_bwd_finalize_sample(partial, (int)gridDim.x, n, v.N, C, gamma, fin, &s_ticket);
+}
+
+// Pass 2 inside the reduction kernel: ONE CTA (the last of sample n to finish) sums that sample's partial[blocks][C][2]
+// - a [blocks][2C] matrix whose rows are contiguous: thread = (column, row group), coalesced ld.cg loads, double
+// accumulation, row groups combined in a fixed order (deterministic) -, writes coef[n] and the per-sample sums; the
+// last sample to get there adds the samples up for dgamma / dbeta.
+__device__ __forceinline__ void gn_bwd_finalize_sample(const float* __restrict__ partial, int blocks, int n, int N, int C,
+                                                       const float* __restrict__ gamma, const GnBwdFin& f,
+                                                       unsigned int* s_ticket) {
+    __shared__ double s_acc[256];
+    __shared__ double s_col[256];       // [c * 2 + which], C <= 128
+    const int t = threadIdx.x;
+    const int cols = 2 * C;                                 // 32 .. 256
+    const int R = 256 / cols;                               // row groups
+    const int col = t % cols, rg = t / cols;
+    {
+        const float* src = partial + (size_t)n * blocks * cols + col;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int b = rg;
+        for (; b + 3 * R < blocks; b += 4 * R) {
+            const float v0 = __ldcg(src + (size_t)b * cols), v1 = __ldcg(src + (size_t)(b + R) * cols);
+            const float v2 = __ldcg(src + (size_t)(b + 2 * R) * cols), v3 = __ldcg(src + (size_t)(b + 3 * R) * cols);
+            a0 += (double)v0; a1 += (double)v1; a2 += (double)v2; a3 += (double)v3;
+        }
+        for (; b < blocks; b += R) a0 += (double)__ldcg(src + (size_t)b * cols);
+        s_acc[t] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (t < cols) {
+        double a = 0.0;
+        for (int q = 0; q < R; ++q) a += s_acc[q * cols + t];
+        s_col[t] = a;
+        f.tot[(size_t)n * cols + t] = a;
+    }
+    __syncthreads();
+    const int gs = C >> 3;
+    if (t < C) {
+        const int g = t / gs;
+        double A = 0.0, B = 0.0;
+        for (int k = 0; k < gs; ++k) {
+            const double gm = (double)gamma[g * gs + k];
+            A += s_col[2 * (g * gs + k)] * gm;
+            B += s_col[2 * (g * gs + k) + 1] * gm;
+        }
+        f.coef[((size_t)n * C + t) * 2 + 0] = (float)(A / f.m);
+        f.coef[((size_t)n * C + t) * 2 + 1] = (float)(B / f.m);
+    }
+    if (t == 0) f.tickets[n] = 0u;
+    if (cta_draws_last_ticket(f.tickets + N, (unsigned)N, s_ticket)) {
+        if (t < C) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int q = 0; q < N; ++q) {                    // fixed order over the samples
+                s1 += __ldcg(f.tot + ((size_t)q * C + t) * 2);
+                s2 += __ldcg(f.tot + ((size_t)q * C + t) * 2 + 1);
+            }
+            f.dbeta[t] = (float)s1;
+            f.dgamma[t] = (float)s2;
+        }
+        if (t == 0) f.tickets[N] = 0u;
     }
 }
 

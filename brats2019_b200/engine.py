@@ -111,6 +111,11 @@ class Engine:
         # band conv's epilogue (+50 us per launch) and the per-channel sums it moves into the apply kernel cost what
         # the dropped reduce pass saved - the level-0 backward is bound by total issue/SM occupancy, not by one kernel.
         self.fold_gn_bwd = os.environ.get("B200_GN_FOLD", "0") not in ("", "0")
+        # GroupNorm statistics finished by the last CTA of the producing conv (b200_conv_run_gn) instead of a finalize
+        # launch.  OPT-IN (B200_GN_FUSED_STATS=1): bit-identical, 25 launches fewer, and 0.05-0.1 ms SLOWER per forward
+        # (profiles/r02_ab_last_cta_finalize.txt): every CTA pays a fence + ticket at its tail and the one CTA that
+        # finishes the sums takes longer than the 4 us kernel it replaces - launches inside a CUDA graph are cheap.
+        self.fused_gn_stats = os.environ.get("B200_GN_FUSED_STATS", "0") not in ("", "0")
         self._side_stream = None
         self._side_busy = False
         self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
@@ -219,10 +224,17 @@ class Engine:
         c = P.act(cname, lvl, Cout)
         ctas = ops.conv_ctas(desc)
         stats = P.f32("stats:" + cname, ctas * P.N * 16)
-        ops.conv_run(desc, src, pk, c, stats=stats)
         mean = P.f32("mean:" + cname, P.N * 8)
         rstd = P.f32("rstd:" + cname, P.N * 8)
         coef = P.f32("gnc:" + cname, P.N * 3 * Cout) if (gamma is not None and self.fold_gn_bwd) else None
+        if coef is None and self.fused_gn_stats:
+            # the conv's last CTA reduces the partial sums to mean / rstd: no finalize launch
+            ticket = P.misc.get("gn_ticket")
+            if ticket is None:
+                ticket = P.misc["gn_ticket"] = torch.zeros(16, dtype=torch.int32, device=P.device)
+            ops.conv_run_gn(desc, src, pk, c, stats, mean, rstd, ticket)
+            return c, mean, rstd
+        ops.conv_run(desc, src, pk, c, stats=stats)
         ops.gn_finalize(stats, ctas, P.N, Cout, D, H, W, mean, rstd, gamma=gamma, beta=beta, coef=coef, lrelu=lrelu)
         return c, mean, rstd
 
@@ -406,7 +418,7 @@ class Engine:
         need = max(L.b200_gn_backward_workspace_floats(P.N, Cc), L.b200_gn_backward_folded_workspace_floats(P.N, D, H, W, Cc))
         ws = P.misc.get("gn_ws")
         if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.float32, device=P.device)
+            ws = torch.zeros(need, dtype=torch.float32, device=P.device)    # leading ticket words start at zero
             P.misc["gn_ws"] = ws
         dg = grads.new(gname, gamma)
         db = grads.new(bname, beta)

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -282,6 +284,17 @@ def conv_run(desc, src_a, packed, out=None, src_b=None, residual=None, lrelu=Fal
     return out
 
 
+def conv_run_gn(desc, src, packed, out, stats, mean, rstd, ticket):
+    """3x3x3 conv + GroupNorm statistics in one launch (b200_conv_run_gn): the last CTA reduces `stats` to mean / rstd.
+    ticket: zero-initialised int32 tensor (one word is used and left zero)."""
+    check(_lib.lib().b200_conv_run_gn(C.byref(desc), _p(src), _p(packed), _p(out), _p(stats), _p(mean), _p(rstd),
+                                      _p(ticket), GN_EPS, _stream()), "b200_conv_run_gn")
+    _count(1)
+    if LEDGER is not None:
+        _ledger(_conv_kernel_name(desc), "tensor", 2.0 * desc.N * desc.D * desc.H * desc.W * desc.Cin_a * desc.Cout * 27)
+    return out
+
+
 def wgrad_desc(mode, N, D, H, W, Cout, Cin):
     return WgradDesc(mode, N, D, H, W, Cout, Cin)
 
@@ -345,7 +358,7 @@ def gn_apply(x, mean, rstd, gamma, beta, out, residual=None, lrelu=True):
 
 def gn_backward_workspace(N, Cc, device):
     n = _lib.lib().b200_gn_backward_workspace_floats(N, Cc)
-    return torch.empty(n, dtype=torch.float32, device=device)
+    return torch.zeros(n, dtype=torch.float32, device=device)     # its leading ticket words must start at zero
 
 
 def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lrelu=True):
@@ -353,9 +366,12 @@ def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lr
     check(_lib.lib().b200_gn_backward(_p(x), _p(dy), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma),
                                       _p(dbeta), _p(workspace), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
           "b200_gn_backward")
-    _count(3)
+    fused = Cc <= 128 and os.environ.get("B200_GN_BWD_FUSED_FIN", "0") not in ("", "0") and \
+        os.environ.get("B200_GN_BWD_CLUSTER", "0") in ("", "0")
+    _count(2 if fused else 3)
     _ledger("gn_bwd_reduce2_kernel", "hbm", 2 * _act_bytes(x))
-    _ledger("gn_bwd_finalize2_kernel", "hbm", 0)
+    if not fused:
+        _ledger("gn_bwd_finalize2_kernel", "hbm", 0)
     _ledger("gn_bwd_apply2_kernel", "hbm", 3 * _act_bytes(x))
     return dx
 

@@ -103,6 +103,15 @@ int b200_conv_run_gnbwd(const b200_conv_desc* d, const void* src_a, const void* 
                         const void* residual, int lrelu_out, float* stats_partial, const float* bias, float* probs,
                         float* logits, int n_out_real, const void* gnb_x, const float* gnb_coef, void* stream);
 
+/* 3x3x3 conv (epi 0, one source) + the statistics of the GroupNorm that follows it (aten::native_group_norm's mean /
+ * rstd, model.py:95-96, 105-106, 338) in ONE launch: the epilogue leaves per-CTA partial sums in stats_partial
+ * ([b200_conv_ctas][N][16]) and the last CTA to finish reduces them to mean / rstd ([N][8] each) - bit for bit what
+ * b200_conv_run(stats_partial) followed by b200_gn_finalize writes, without the second launch.
+ * ticket: one 32-bit word of device memory that is ZERO before the first launch; every launch leaves it zero again
+ * (one word serves all launches on a stream and all replays of a CUDA graph). */
+int b200_conv_run_gn(const b200_conv_desc* d, const void* src_a, const void* packed, void* out, float* stats_partial,
+                     float* mean, float* rstd, unsigned int* ticket, float eps, void* stream);
+
 /* ---- convolution weight gradient (weight half of convolution_backward, train.py:210) ---- */
 typedef struct b200_wgrad_desc {
     int mode;          /* 0: 3x3x3;  1: 1x1x1 */
@@ -128,7 +137,10 @@ int b200_gn_finalize_coef(const float* stats_partial, int ctas, int N, int C, in
 int b200_gn_apply(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   const void* residual, void* out, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
 size_t b200_gn_backward_workspace_floats(int N, int C);
-/* dx, dgamma, dbeta of y = lrelu?(GN(x)); dy is the gradient w.r.t. y. */
+/* dx, dgamma, dbeta of y = lrelu?(GN(x)); dy is the gradient w.r.t. y.  Two launches: reduction (whose last CTAs also
+ * turn the partial sums into the per-group coefficients and dgamma / dbeta) and apply.
+ * workspace: 8-byte aligned, b200_gn_backward_workspace_floats floats, ZERO-FILLED when allocated (its first words are
+ * the tickets of the last-CTA pass; every call leaves them zero, so the buffer is reusable call after call). */
 int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd, const float* gamma,
                      const float* beta, void* dx, float* dgamma, float* dbeta, float* workspace, int N, int D, int H,
                      int W, int C, int do_lrelu, void* stream);

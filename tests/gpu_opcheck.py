@@ -110,6 +110,37 @@ def group_ew():
                 report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
                 report("gn_backward halo untouched " + tag, ops.act_outside_absmax(dx).view(1), torch.zeros(1, device=dev), tol_abs=0)
             os.environ.pop("B200_GN_BWD_CLUSTER", None)
+        # many reduction CTAs per sample, odd batch: the last-CTA finalize inside the reduction kernel (default) against
+        # the separate finalize launch (B200_GN_BWD_FUSED_FIN=0) and against autograd; repeated calls reuse the tickets
+        for (N2, D2, H2, W2) in (((3, 32, 32, 32) if Cc == 16 else (2, 16, 16, 16)),):
+            x2 = bf(torch.randn(N2, Cc, D2, H2, W2, device=dev) * 2 + 0.5)
+            g2 = x2.view(N2, 8, -1)
+            mean2 = g2.mean(-1).reshape(-1).contiguous()
+            rstd2 = (1 / torch.sqrt(g2.var(-1, unbiased=False) + 1e-5)).reshape(-1).contiguous()
+            xr = x2.clone().requires_grad_(True)
+            gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+            y = F.leaky_relu(F.group_norm(xr, 8, gr, br, 1e-5), 0.01)
+            dy2 = bf(torch.randn_like(y))
+            y.backward(dy2)
+            xa2, dya2 = ops.act_from_ncdhw(x2), ops.act_from_ncdhw(dy2)
+            ws = ops.gn_backward_workspace(N2, Cc, dev)
+            res = {}
+            for form in ("fused", "fused again", "separate"):
+                os.environ["B200_GN_BWD_FUSED_FIN"] = "0" if form == "separate" else "1"
+                dx = ops.act_zeros(N2, D2, H2, W2, Cc, dev)
+                dgam = torch.full((Cc,), 5.0, device=dev); dbet = torch.full((Cc,), 5.0, device=dev)
+                ops.gn_backward(xa2, dya2, mean2, rstd2, gamma, beta, dx, dgam, dbet, ws, lrelu=True)
+                torch.cuda.synchronize()
+                res[form] = (ops.act_to_ncdhw(dx), dgam, dbet)
+                tag = "C=%d %dx(%d,%d,%d) %s" % (Cc, N2, D2, H2, W2, form)
+                report("gn_backward dx " + tag, res[form][0], xr.grad, tol_rel=2e-2)
+                report("gn_backward dgamma " + tag, dgam, gr.grad, tol_rel=2e-3)
+                report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
+            os.environ.pop("B200_GN_BWD_FUSED_FIN", None)
+            report("gn_backward fused == separate dx C=%d" % Cc, res["fused"][0], res["separate"][0], tol_abs=0)
+            report("gn_backward fused twice dx C=%d" % Cc, res["fused again"][0], res["fused"][0], tol_abs=0)
+            report("gn_backward fused == separate dgamma C=%d" % Cc, res["fused"][1], res["separate"][1], tol_rel=1e-6)
+            report("gn_backward fused == separate dbeta C=%d" % Cc, res["fused"][2], res["separate"][2], tol_rel=1e-6)
         # upsample
         xr = xc.clone().requires_grad_(True)
         up = F.leaky_relu(F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=False), 0.01)
@@ -201,6 +232,22 @@ def _conv3_case(name, N, D, H, W, Cin, Cout, residual=False, lrelu=False, stats=
         s = st.sum(0)
         report("conv3 %s GN sum" % name, s[:, :8], g.sum(-1), tol_abs=2e-3 * g.abs().sum(-1).max().item())
         report("conv3 %s GN sumsq" % name, s[:, 8:], (g * g).sum(-1), tol_rel=5e-3)
+        if Cout % 16 == 0:
+            # one-launch form (b200_conv_run_gn: the conv's last CTA finishes the statistics) == conv + gn_finalize,
+            # bit for bit; three launches in a row reuse the same ticket word
+            mean = torch.empty(N * 8, device=dev); rstd = torch.empty(N * 8, device=dev)
+            ops.gn_finalize(st.view(-1), ctas, N, Cout, D, H, W, mean, rstd)
+            ticket = torch.zeros(16, dtype=torch.int32, device=dev)
+            for rep in range(3):
+                out2 = ops.act_zeros(N, D, H, W, Cout, dev)
+                st2 = torch.full((ctas, N, 16), -3.0, device=dev)
+                m2 = torch.full((N * 8,), 9.0, device=dev); r2 = torch.full((N * 8,), 9.0, device=dev)
+                ops.conv_run_gn(desc, xa, packed, out2, st2.view(-1), m2, r2, ticket)
+                torch.cuda.synchronize()
+            report("conv3 %s fused GN mean (bit-exact)" % name, m2, mean, tol_abs=0)
+            report("conv3 %s fused GN rstd (bit-exact)" % name, r2, rstd, tol_abs=0)
+            report("conv3 %s fused GN output" % name, out2.t, out.t, tol_abs=0)
+            report("conv3 %s fused GN ticket left zero" % name, ticket.float(), torch.zeros(16, device=dev), tol_abs=0)
     return ok
 
 
