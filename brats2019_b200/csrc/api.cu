@@ -12,6 +12,7 @@
 
 #include "../../include/brats_b200.h"
 #include "conv_gemm.cuh"
+#include "conv_pair.cuh"
 #include "conv_march.cuh"
 #include "conv_band.cuh"
 #include "elementwise.cuh"
@@ -166,6 +167,17 @@ static int conv_nmma(const b200_conv_desc* d) {
     if (conv_fold(d)) return 3 * d->Cout;
     return d->Cout > 256 ? 256 : d->Cout;
 }
+// CTA-pair kernel (conv_pair.cuh, tcgen05.mma.cta_group::2): 3x3x3, 128 output channels, bf16 epilogue.
+// OPT-IN (B200_CONV_PAIR=1).  Bit-identical to conv_gemm and SLOWER (profiles/r02_conv_pair_ab.txt: 128 -> 128 at
+// 2 x 16^3 23.6 vs 20.0 us, at 8 x 16^3 60.8 vs 49.0 us): the deep-level conv is not bound by the weight stream the pair
+// halves.  tools/conv_deep_probe.py: weight stream alone 8.5 us, MMAs alone 7.2 us (64 cycles each, tools/umma_probe),
+// together 20.4 us - the two do not overlap: at M = N = 128 the operand fetch of the MMA (8 KB per 64 cycles) takes the
+// whole shared-memory bandwidth and the incoming bulk copies take their turn on the same port.
+static bool conv_pair(const b200_conv_desc* d) {
+    int on = 0;
+    if (const char* e = getenv("B200_CONV_PAIR")) on = atoi(e);
+    return on && d->mode == MODE_K3 && d->epi == EPI_BF16 && d->Cout == 128 && d->Cin_b == 0 && !conv_fold(d);
+}
 static int conv_kc(const b200_conv_desc* d) {
     if (d->mode == MODE_K3) return 16;
     for (int kc : {64, 32, 16})
@@ -191,7 +203,11 @@ static int check_conv_desc(const b200_conv_desc* d) {
 static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     if (check_conv_desc(d)) return 1;
     memset(&p, 0, sizeof(p));
-    const int Nm = conv_nmma(d);
+    const bool pair = conv_pair(d);
+    const int Nfull = conv_nmma(d);                    // GEMM N of one MMA (accumulator columns per run)
+    const int Nm = pair ? Nfull / 2 : Nfull;           // columns of one CTA's B operand = one packed-weight job
+    p.pair = pair ? 1 : 0;
+    p.Nm_pack = Nm;
     p.N = d->N; p.D = d->D; p.H = d->H; p.W = d->W;
     p.Wp = d->W + 2;
     p.SS = (d->H + 2) * p.Wp;
@@ -225,7 +241,7 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
                 for (int MB : {1, 2, 4}) {
                     if (fBD && (BD != fBD || MB != fMB || (fWhole >= 0 && whole != fWhole))) continue;
                     const int R = BD * MB;
-                    if (2 * R * Nm > 512) continue;
+                    if (2 * R * Nfull > 512) continue;
                     const int TR = RB * MB;
                     const int SR = (MB - 1) * RB + 128 + 2 * p.Wp + (fold ? 0 : 2);
                     const int SRp = (SR + 7) / 8 * 8;
@@ -302,15 +318,17 @@ static int plan_conv(const b200_conv_desc* d, ConvKParams& p) {
     auto used = [&]() { return align_up(p.x_stages * p.x_stage_bytes, 128) + p.w_stages * p.w_stage_bytes; };
     if (used() > budget) return fail("conv: shared memory plan does not fit (%u bytes)", used());
     // k3: up to 4 stages; k1 (HBM-bound, small stages): up to 8 so that >= ~100 KB are in flight per SM
-    const int rounds = (d->mode == MODE_K1) ? 6 : 2;
+    // pair: half-size weight stages, up to 8 of them (the ring must cover the L2 round trip at the MMA rate)
+    const int rounds = (d->mode == MODE_K1 || pair) ? 6 : 2;
     for (int round = 0; round < rounds; ++round) {
-        if (!p.w_resident && round < 2) { ++p.w_stages; if (used() > budget) --p.w_stages; }
+        if (!p.w_resident && (round < 2 || pair)) { ++p.w_stages; if (used() > budget) --p.w_stages; }
+        if (pair && round >= 2) continue;              // activations: 4 stages
         ++p.x_stages; if (used() > budget) --p.x_stages;
     }
     p.smem_x_off = 0;
     p.smem_w_off = align_up(p.x_stages * p.x_stage_bytes, 128);
     p.smem_bar_off = align_up(p.smem_w_off + p.w_stages * p.w_stage_bytes, 16);
-    p.tmem_cols = pow2_cols(2u * p.BD * p.MB * Nm);
+    p.tmem_cols = pow2_cols(2u * p.BD * p.MB * Nfull);
     if (p.tmem_cols > 512) return fail("conv: TMEM plan does not fit");
     return 0;
 }
@@ -418,6 +436,7 @@ static int plan_band(const b200_conv_desc* d, BandParams& p) {
 static int band_ctas(const BandParams& p) { return (int)std::min<long long>(num_sms(), p.units); }
 
 static int conv_grid_ctas(const ConvKParams& p) {
+    if (p.pair) return 2 * std::min(std::max(1, num_sms() / 2), (p.num_tiles + 1) / 2);    // whole CTA pairs
     int per_job = std::max(1, num_sms() / p.n_jobs);
     return std::min(per_job, p.num_tiles);
 }
@@ -483,7 +502,7 @@ static int make_pack_job(const b200_conv_desc* d, int kind, int Cout_w, int Cin_
     PackParams& q = J.q;
     q.kind = kind; q.Cout_w = Cout_w; q.Cin_w = Cin_w; q.taps_w = taps_w; q.ci_off = ci_off;
     q.K_real = K_real; q.N_real = N_real;
-    q.n_jobs = p.n_jobs; q.KG = p.KG; q.NTG = p.NTG; q.TG = p.TG; q.KC = p.KC; q.Nmma = conv_nmma(d);
+    q.n_jobs = p.n_jobs; q.KG = p.KG; q.NTG = p.NTG; q.TG = p.TG; q.KC = p.KC; q.Nmma = p.Nm_pack;
     q.fold = conv_fold(d) ? 1 : 0;
     if (q.fold && kind > B200_W_DGRAD) return fail("fold applies to 3x3x3 weights only");
     J.layout = 0;
@@ -712,7 +731,7 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
     if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
     if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
         return fail("conv: sigmoid epilogue needs bias, probs and 1..4 real outputs");
-    if (stats_partial && (d->mode != MODE_K3 || d->epi != EPI_BF16 || p.n_jobs != 1))
+    if (stats_partial && (d->mode != MODE_K3 || d->epi != EPI_BF16 || (p.n_jobs != 1 && !p.pair)))
         return fail("conv: GroupNorm statistics only for the k3 bf16 path");
     cudaStream_t st = (cudaStream_t)stream;
     p.wpacked = (const __nv_bfloat16*)packed;
@@ -728,7 +747,7 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
         p.debug = dbg ? atoi(dbg) : 0;
     }
     const int ctas = conv_grid_ctas(p);
-    const int grid = ctas * p.n_jobs;
+    const int grid = p.pair ? ctas : ctas * p.n_jobs;
     if (check_ptr16(src_a, "src_a") || check_ptr16(src_b, "src_b") || check_ptr16(out, "out") ||
         check_ptr16(residual, "residual") || check_ptr16(packed, "packed weights"))
         return 1;
@@ -740,6 +759,12 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
     if (p.x_stage_bytes >= (1u << 20) || p.w_stage_bytes >= (1u << 20)) return fail("conv: stage exceeds the mbarrier tx-count range");
     const unsigned smem = p.smem_bar_off + kConvTailBytes;
     const int Nm = conv_nmma(d);
+    if (p.pair) {
+        SET_MAX_SMEM_ONCE(conv_pair_kernel<128>);
+        CUDA_OK(launch_prio(conv_pair_kernel<128>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), p));
+        LAUNCH_OK("conv_pair_kernel");
+        return 0;
+    }
 #define CONV_CASE(MODE, EPI, NM, FOLD) return launch_conv<MODE, EPI, NM, FOLD>(p, smem, grid, st)
     if (d->epi == EPI_SIGMOID) CONV_CASE(MODE_K3, EPI_SIGMOID, 16, 0);
     if (d->mode == MODE_K3) {

@@ -51,6 +51,8 @@ struct ConvKParams {
     int tiles_q, tiles_d, num_tiles;
     int whole;             // 1: q runs over the whole sample (BD == 1), 0: per slice
     int n_jobs;            // column blocks (each its own packed weights); grid = ctas * n_jobs
+    int pair;              // 1: conv_pair.cuh (cta_group::2); the two column jobs are the two CTAs' halves of B, grid = 2 * pairs
+    int Nm_pack;           // columns per packed-weight job (GEMM N of one CTA's B operand)
     // K loop
     int KG, KGa, KC, NTG, TG;
     // shared-memory plan

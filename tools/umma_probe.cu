@@ -215,5 +215,15 @@ int main() {
             cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
             printf("%s N=%3d shift3: %7.1f cycles/MMA\n", L.name, N, (double)cyc / 2000);
         }
+    printf("== K-major SWIZZLE_NONE chunk planes, A start shifted by s rows (conv_gemm.cuh taps), N = 64 / 128 ==\n");
+    for (int N : {64, 128})
+        for (int shift : {0, 1, 2, 3, 4, 8, 19, 36}) {
+            Cfg c{0, 16, N, 2000, shift, 0, 0, 0};
+            probe_kernel<<<148, 128, 200 * 1024>>>(c, d_a, d_b, 96 * 1024, 64 * 1024, nullptr, d_cyc);
+            cudaDeviceSynchronize();
+            long long cyc;
+            cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+            printf("NONE  N=%3d shift=%2d: %7.1f cycles/MMA\n", N, shift, (double)cyc / 2000);
+        }
     return 0;
 }
