@@ -59,6 +59,7 @@ _PROTOS = {
     "b200_gn_finalize_coef": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, c_int, P, P, P, P]),
     "b200_gn_apply": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_gn_backward_workspace_floats": (c_size_t, [c_int, c_int]),
+    "b200_gn_backward_form": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "b200_gn_backward": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "b200_gn_backward_folded_workspace_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "b200_gn_backward_folded": (c_int, [P, P, P, P, P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),

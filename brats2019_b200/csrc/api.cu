@@ -196,6 +196,10 @@ static int check_conv_desc(const b200_conv_desc* d) {
         return fail("Cout=%d unsupported (16/32/64/128/256 or a multiple of 256)", d->Cout);
     if (d->mode == MODE_K3 && (d->Cout > 128 || d->Cin_b != 0)) return fail("k3 conv: Cout<=128 and one source only");
     if (d->epi == EPI_SIGMOID && (d->mode != MODE_K3 || d->Cout != 16)) return fail("sigmoid epilogue needs k3, Cout=16");
+    if (d->epi == EPI_D2S && (d->mode != MODE_K1 || d->Cout % 128 || d->Cin_b != 0 ||
+                              ((d->Cout / 64) & (d->Cout / 64 - 1)) != 0))
+        return fail("depth-to-space epilogue needs a 1x1x1 GEMM with Cout = 8 * Cf, Cf a power of two >= 16");
+    if (d->epi < EPI_BF16 || d->epi > EPI_D2S) return fail("conv epilogue %d unsupported", d->epi);
     if (d->W + 2 > 4000) return fail("W too large");
     return 0;
 }
@@ -728,7 +732,7 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
     if (plan_conv(d, p)) return 1;
     if (!src_a || !packed) return fail("conv: null operand");
     if (d->Cin_b > 0 && !src_b) return fail("conv: second source missing");
-    if (d->epi == EPI_BF16 && !out) return fail("conv: null output");
+    if (d->epi != EPI_SIGMOID && !out) return fail("conv: null output");
     if (d->epi == EPI_SIGMOID && (!probs || !bias || n_out_real < 1 || n_out_real > 4))
         return fail("conv: sigmoid epilogue needs bias, probs and 1..4 real outputs");
     if (stats_partial && (d->mode != MODE_K3 || d->epi != EPI_BF16 || (p.n_jobs != 1 && !p.pair)))
@@ -756,6 +760,16 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
     p.src_b = make_act(d->Cin_b > 0 ? src_b : src_a, vol);
     p.out = make_act(out, vol);
     p.residual = make_act(residual, vol);
+    if (d->epi == EPI_D2S) {
+        // the output and the residual are FINE tensors of Cout / 8 channels (conv_gemm.cuh ConvKParams::d2s)
+        Vol fine{d->N, 2 * d->D, 2 * d->H, 2 * d->W};
+        p.out = make_act(out, fine);
+        p.residual = make_act(residual, fine);
+        p.d2s = 1;
+        p.d2s_sh = 0;
+        while ((8 << p.d2s_sh) < d->Cout / 8) ++p.d2s_sh;
+        if (lrelu_out) return fail("conv: no activation with the depth-to-space epilogue");
+    }
     if (p.x_stage_bytes >= (1u << 20) || p.w_stage_bytes >= (1u << 20)) return fail("conv: stage exceeds the mbarrier tx-count range");
     const unsigned smem = p.smem_bar_off + kConvTailBytes;
     const int Nm = conv_nmma(d);
@@ -1273,12 +1287,83 @@ static bool plan_gn_cluster(const Vol& v, int C, GnClusterParams& q, unsigned& s
     q.m = (double)gs * v.D * v.H * v.W;
     smem = (unsigned)bytes;
     return true;
-}      // >= blocks for any volume up to 1M lines
+}
+// Register-resident one-launch form (elementwise3.cuh gn_bwd_creg_kernel): usable when 8 or 16 CTAs per unit can hold
+// one sample's slice of the unit in registers (UCS chunks x VPT vectors per thread, UCS * VPT <= 8): the 16^3 and 32^3
+// levels of the U-Net at any batch size.  B200_GN_BWD_CREG=0 turns it off.
+typedef void (*GnCregKernel)(GnClusterParams);
+static const int kGnCregMaxUnits = 32;
+static GnCregKernel gn_creg_kernel(int ucs, int vpt) {
+    switch (ucs * 16 + vpt) {
+        case 1 * 16 + 1: return gn_bwd_creg_kernel<1, 1>;
+        case 1 * 16 + 2: return gn_bwd_creg_kernel<1, 2>;
+        case 1 * 16 + 4: return gn_bwd_creg_kernel<1, 4>;
+        case 1 * 16 + 8: return gn_bwd_creg_kernel<1, 8>;
+        case 2 * 16 + 1: return gn_bwd_creg_kernel<2, 1>;
+        case 2 * 16 + 2: return gn_bwd_creg_kernel<2, 2>;
+        case 2 * 16 + 4: return gn_bwd_creg_kernel<2, 4>;
+        case 4 * 16 + 1: return gn_bwd_creg_kernel<4, 1>;
+        case 4 * 16 + 2: return gn_bwd_creg_kernel<4, 2>;
+    }
+    return nullptr;
+}
+static bool plan_gn_creg(const Vol& v, int C, GnClusterParams& q, int& csize, int& vpt) {
+    // OPT-IN (B200_GN_BWD_CREG=1): parity-green, 28 launches fewer, and no faster inside the training step
+    // (profiles/r02_ab_gn_creg.txt: 5.575 vs 5.570 ms): beside a weight-gradient GEMM the one-launch kernel - a chain of
+    // load -> shuffle -> barrier -> exchange -> apply latencies, twice (two samples) - stretches to the length of the three
+    // small kernels it replaces.
+    {
+        const char* e = getenv("B200_GN_BWD_CREG");
+        if (!e || atoi(e) == 0) return false;
+    }
+    const int gs = C / 8;
+    if (gs < 2 || (gs < 8 && 8 % gs) || (gs >= 8 && gs % 8)) return false;
+    const int ucs = gs >= 8 ? gs / 8 : 1;
+    if (ucs > kGnClusterMaxUcs) return false;
+    const int lines = v.D * v.H;
+    for (int cs : {8, 16}) {
+        const int lpc = (lines + cs - 1) / cs;
+        if (lpc > kGnClusterMaxLines) continue;
+        const long long nv = (long long)lpc * v.W;
+        int vp = 1;
+        while (vp < 8 && (long long)vp * kGnClusterThreads < nv) vp *= 2;
+        if ((long long)vp * kGnClusterThreads < nv || ucs * vp > 8) continue;
+        GnCregKernel k = gn_creg_kernel(ucs, vp);
+        if (!k) continue;
+        // every CTA of a unit spins on the others: all of them must be resident at once
+        const int units = (C / 8) / ucs;
+        if (units * cs > num_sms() || units > kGnCregMaxUnits) continue;
+        memset(&q, 0, sizeof(q));
+        q.v = v; q.C = C;
+        q.by_W = make_fastdiv((unsigned)v.W);
+        q.lpc = lpc; q.nv = (int)nv; q.ucs = ucs;
+        q.m = (double)gs * v.D * v.H * v.W;
+        csize = cs; vpt = vp;
+        return nv < (1 << 24);
+    }
+    return false;
+}
 // workspace: tickets[N + 1] (32-bit words, padded to 64) | partial[N][blocks][C][2] | coef[N][C][2] | tot[N][C][2] (double)
 // The ticket words must be ZERO when the workspace is first used (allocate it zero-filled); every launch leaves them zero.
-static size_t gn_bwd_ticket_floats(int N) { return ((size_t)N + 1 + 63) / 64 * 64; }
+// (words [0, N]: last-CTA tickets of the fused finalize; the last 64 words: arrive / exit counters of the
+// register-resident form, two per unit)
+static size_t gn_bwd_ticket_floats(int N) { return std::max<size_t>(256, ((size_t)N + 1 + 63) / 64 * 64 + 128); }
+static size_t gn_bwd_xchg_floats() { return (size_t)kGnCregMaxUnits * 16 * 128 * 2; }     // doubles: [units][csize <= 16][2][64]
 extern "C" size_t b200_gn_backward_workspace_floats(int N, int C) {
-    return gn_bwd_ticket_floats(N) + (size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2 + (size_t)N * C * 4 + 2;
+    return gn_bwd_ticket_floats(N) + std::max((size_t)N * gn_bwd_max_blocks() * C * 2 + (size_t)N * C * 2 + (size_t)N * C * 4 + 2,
+                                              gn_bwd_xchg_floats());
+}
+// which form b200_gn_backward takes for this tensor: 0 = reduce -> finalize -> apply, 1 = shared-memory cluster kernel
+// (opt-in), 2 = register-resident cluster kernel (one launch)
+extern "C" int b200_gn_backward_form(int N, int D, int H, int W, int C) {
+    if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8) || C < 16) return -1;
+    Vol v{N, D, H, W};
+    GnClusterParams q;
+    int csize = 0, vpt = 0;
+    unsigned smem = 0;
+    if (plan_gn_creg(v, C, q, csize, vpt)) return 2;
+    if (plan_gn_cluster(v, C, q, smem)) return 1;
+    return 0;
 }
 extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean, const float* rstd,
                                 const float* gamma, const float* beta, void* dx, float* dgamma, float* dbeta,
@@ -1287,7 +1372,24 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     Vol v{N, D, H, W};
     cudaStream_t st = (cudaStream_t)stream;
     {
-        // small tensors: one cluster launch that keeps x and dy in shared memory (elementwise3.cuh)
+        // small tensors: one cluster launch that keeps x and dy in registers between the two passes (elementwise3.cuh)
+        GnClusterParams q;
+        int csize = 0, vpt = 0;
+        if (plan_gn_creg(v, C, q, csize, vpt)) {
+            q.x = make_act(x, v); q.dy = make_act(dy, v); q.dx = make_act(dx, v);
+            q.mean = mean; q.rstd = rstd; q.gamma = gamma; q.beta = beta; q.dgamma = dgamma; q.dbeta = dbeta;
+            q.do_lrelu = do_lrelu;
+            if (!workspace || ((uintptr_t)workspace & 7)) return fail("gn_backward: workspace must be 8-byte aligned");
+            q.csize = csize;
+            q.counters = reinterpret_cast<unsigned int*>(workspace) + gn_bwd_ticket_floats(N) - 64;
+            q.xchg = reinterpret_cast<double*>(workspace + gn_bwd_ticket_floats(N));
+            gn_creg_kernel(q.ucs, vpt)<<<(unsigned)((C / 8) / q.ucs * csize), kGnClusterThreads, 0, st>>>(q);
+            LAUNCH_OK("gn_bwd_creg_kernel");
+            return 0;
+        }
+    }
+    {
+        // (opt-in, B200_GN_BWD_CLUSTER=1) the shared-memory form of the same kernel
         GnClusterParams q;
         unsigned smem = 0;
         if (plan_gn_cluster(v, C, q, smem)) {

@@ -32,7 +32,7 @@
 namespace b200 {
 
 enum { MODE_K3 = 0, MODE_K1 = 1 };
-enum { EPI_BF16 = 0, EPI_SIGMOID = 1 };
+enum { EPI_BF16 = 0, EPI_SIGMOID = 1, EPI_D2S = 2 };   // EPI_D2S: host-side name of the bf16 epilogue with ConvKParams::d2s set
 
 constexpr int kMaxTaps = 27;
 constexpr int kEpiGroups = 3;                       // epilogue warp groups (4 warps each)
@@ -71,6 +71,12 @@ struct ConvKParams {
     int lrelu_out;         // apply LeakyReLU(0.01) before storing
     ActRef out;
     ActRef residual;       // optional (base == nullptr if unused), same layout as out, added before activation
+    // depth-to-space store (MODE_K1, data gradient of the k2 s2 conv, model.py:360-363 backward): the GEMM's Cout = 8 * Cf
+    // columns of coarse voxel (d, h, w) are the Cf channels of the eight fine voxels (2d+kd, 2h+kh, 2w+kw), column block
+    // ((kd*2+kh)*2+kw) * Cf (elementwise.cuh s2d layout); `out` / `residual` are then FINE tensors (2D, 2H, 2W, Cf) and the
+    // epilogue scatters its 16-byte vectors there (+ the skip gradient as residual) - no coarse tensor, no d2s pass.
+    int d2s;               // 1: scatter
+    int d2s_sh;            // log2(Cf / 8): coarse chunk q -> tap q >> sh, fine chunk q & ((1 << sh) - 1)
     float* stats_partial;            // optional [ctas][N][16] (sum[8], sumsq[8])
     GnFin gn_fin;                     // mean != nullptr: the last CTA turns stats_partial into mean / rstd (common.cuh)
     const float* bias;               // EPI_SIGMOID
@@ -335,6 +341,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 // ---- which voxel is this row? ----
                 bool valid;
                 long long orow;      // output row in the padded tensor
+                long long frow0 = 0; // d2s: row of the fine voxel (2d, 2h, 2w)
                 int vd = 0, vh = 0, vw = 0;
                 if (MODE == MODE_K3) {
                     const int q = tc.q0 + mb * RB + m - (FOLD ? 1 : 0);
@@ -351,6 +358,16 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 } else {
                     orow = (long long)t * p.TR + mb * 128 + m;
                     valid = orow < p.total_rows;
+                    if (p.d2s) {
+                        // coarse padded row -> (n, dp, hp, wp); halo rows hold nothing; fine row of the voxel's (0,0,0) corner
+                        const long long dpf = orow / p.SS;
+                        const int r2 = (int)(orow - dpf * p.SS);
+                        const int hp = p.by_Wp.div(r2), wp = r2 - hp * p.Wp;
+                        const int nn = (int)(dpf / (p.D + 2)), dp = (int)(dpf - (long long)nn * (p.D + 2));
+                        valid = valid && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
+                        frow0 = (((long long)nn * (2 * p.D + 2) + (2 * dp - 1)) * (2 * p.H + 2) + (2 * hp - 1)) * (2 * p.W + 2) +
+                                (2 * wp - 1);
+                    }
                 }
                 const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((as * R + r) * NMMA);
 #pragma unroll
@@ -425,7 +442,13 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                                     ssq[gi] += v[i] * v[i];
                                 }
                             }
-                            const int ch = (job * CO + c0) >> 3;      // first of the two 8-channel chunks
+                            int ch = (job * CO + c0) >> 3;            // first of the two 8-channel chunks
+                            if (MODE == MODE_K1 && p.d2s) {
+                                const int tap8 = ch >> p.d2s_sh;
+                                ch &= (1 << p.d2s_sh) - 1;
+                                orow = frow0 + (long long)(tap8 >> 2) * ((2 * p.H + 2) * (2 * p.W + 2)) +
+                                       ((tap8 >> 1) & 1) * (2 * p.W + 2) + (tap8 & 1);
+                            }
                             if (p.residual.base) {
                                 float f[8];
                                 unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch, orow)), f);

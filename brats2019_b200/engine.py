@@ -116,6 +116,8 @@ class Engine:
         # (profiles/r02_ab_last_cta_finalize.txt): every CTA pays a fence + ticket at its tail and the one CTA that
         # finishes the sums takes longer than the 4 us kernel it replaces - launches inside a CUDA graph are cheap.
         self.fused_gn_stats = os.environ.get("B200_GN_FUSED_STATS", "0") not in ("", "0")
+        # depth-to-space fused into the epilogue of the k2 s2 data-gradient GEMM (EPI_D2S); 0 = separate d2s pass (A/B)
+        self.fused_d2s = os.environ.get("B200_D2S_FUSED", "1") not in ("", "0")
         self._side_stream = None
         self._side_busy = False
         self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
@@ -620,14 +622,25 @@ class Engine:
             if not self.sched:
                 self._wgrad(P, lvl, 1, cur, s2d, gdw, ops.G_S2D)
                 self._mark(grads)
-            ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
+            if self.fused_d2s:
+                # data gradient of the k2 s2 conv written straight to the fine grid, + the skip-connection gradient from
+                # the decoder (depth-to-space epilogue: no coarse 8C-channel gradient tensor, no d2s pass)
+                D, H, W = P.dims[lvl]
+                desc = ops.conv_desc(ops.MODE_K1, P.N, D, H, W, ch[lvl], 8 * ch[i], epi=ops.EPI_D2S)
+                pk = self._pack(desc, ops.W_DGRAD_S2D, wname, w, K_real=ch[lvl], N_real=8 * ch[i])
+                nxt = ops.conv_run(desc, cur, pk, gbuf("A", i, ch[i]), residual=dskip[i])
+            else:
+                ds2d = self._conv1(P, lvl, wname, w, ops.W_DGRAD_S2D, cur, gbuf("s2d", lvl, 8 * ch[i]))
             if self.sched:
                 self._flush_deferred()
                 self._wgrad(P, lvl, 1, cur, s2d, gdw, ops.G_S2D, overlap=True)
                 self._mark(grads)
-            # back to the fine grid, adding the skip-connection gradient from the decoder
-            self._tap("g:enc%d.s2d" % i, ds2d)
-            cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
+            if self.fused_d2s:
+                cur = nxt
+            else:
+                # back to the fine grid, adding the skip-connection gradient from the decoder
+                self._tap("g:enc%d.s2d" % i, ds2d)
+                cur = ops.depth_to_space(ds2d, gbuf("A", i, ch[i]), residual=dskip[i])
             self._tap("g:enc%d.skip_total" % i, cur)
             cur_name = "A"
         # ---- level 0 head ----

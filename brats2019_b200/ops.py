@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import ConvDesc, WgradDesc, check
 
 MODE_K3, MODE_K1 = 0, 1
-EPI_BF16, EPI_SIGMOID = 0, 1
+EPI_BF16, EPI_SIGMOID, EPI_D2S = 0, 1, 2
 W_FWD, W_DGRAD, W_FWD_S2D, W_DGRAD_S2D = 0, 1, 2, 3
 G_K3, G_K1, G_S2D = 0, 1, 2
 GN_EPS = 1e-5
@@ -366,8 +366,16 @@ def gn_backward(x, dy, mean, rstd, gamma, beta, dx, dgamma, dbeta, workspace, lr
     check(_lib.lib().b200_gn_backward(_p(x), _p(dy), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma),
                                       _p(dbeta), _p(workspace), N, D, H, W, Cc, 1 if lrelu else 0, _stream()),
           "b200_gn_backward")
-    fused = Cc <= 128 and os.environ.get("B200_GN_BWD_FUSED_FIN", "0") not in ("", "0") and \
-        os.environ.get("B200_GN_BWD_CLUSTER", "0") in ("", "0")
+    form = _lib.lib().b200_gn_backward_form(N, D, H, W, Cc)
+    if form == 2:
+        _count(1)
+        _ledger("gn_bwd_creg_kernel", "hbm", 3 * _act_bytes(x))
+        return dx
+    if form == 1:
+        _count(1)
+        _ledger("gn_bwd_cluster_kernel", "hbm", 3 * _act_bytes(x))
+        return dx
+    fused = Cc <= 128 and os.environ.get("B200_GN_BWD_FUSED_FIN", "0") not in ("", "0")
     _count(2 if fused else 3)
     _ledger("gn_bwd_reduce2_kernel", "hbm", 2 * _act_bytes(x))
     if not fused:

@@ -53,7 +53,13 @@ int b200_pack_input_t(const void* x, int x_dtype, void* act_out, int N, int D, i
  *      362, 393, 401; data half of convolution_backward, train.py:210) ------------------- */
 typedef struct b200_conv_desc {
     int mode;          /* 0: 3x3x3 stride 1 pad 1;  1: 1x1x1 */
-    int epi;           /* 0: store bf16 act;  1: + bias, sigmoid, store fp32 NCDHW (conv_output) */
+    int epi;           /* 0: store bf16 act;  1: + bias, sigmoid, store fp32 NCDHW (conv_output);
+                        * 2 (mode 1, Cout = 8 * Cf): depth-to-space store - the data gradient of the k2 s2 conv
+                        *   (model.py:360-363 backward) written straight to the FINE tensor: `out` and `residual` of
+                        *   b200_conv_run are (N, 2D, 2H, 2W) activations of Cf channels, column block
+                        *   ((kd*2+kh)*2+kw) * Cf of coarse voxel (d,h,w) lands on fine voxel (2d+kd, 2h+kh, 2w+kw), the
+                        *   residual (the skip-connection gradient) is added in fp32 before the one bf16 rounding;
+                        *   replaces b200_conv_run(epi 0) + b200_depth_to_space and their coarse intermediate */
     int N, D, H, W;    /* output volume (== input volume) */
     int Cin_a, Cin_b;  /* channels of the two K sources (Cin_b = 0 if unused): cat([a,b]) fused */
     int Cout;          /* GEMM N: stored channels per output row (multiple of 16) */
@@ -137,6 +143,10 @@ int b200_gn_finalize_coef(const float* stats_partial, int ctas, int N, int C, in
 int b200_gn_apply(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   const void* residual, void* out, int N, int D, int H, int W, int C, int do_lrelu, void* stream);
 size_t b200_gn_backward_workspace_floats(int N, int C);
+/* which kernels b200_gn_backward launches for this tensor: 0 = reduction, finalize, apply (three launches, x and dy read
+ * twice); 1 / 2 = ONE thread-block-cluster launch that keeps the tensors on chip between the two passes (1: in shared
+ * memory, opt-in; 2: in registers - the 16^3 and 32^3 levels of the U-Net) */
+int b200_gn_backward_form(int N, int D, int H, int W, int C);
 /* dx, dgamma, dbeta of y = lrelu?(GN(x)); dy is the gradient w.r.t. y.  Two launches: reduction (whose last CTAs also
  * turn the partial sums into the per-group coefficients and dgamma / dbeta) and apply.
  * workspace: 8-byte aligned, b200_gn_backward_workspace_floats floats, ZERO-FILLED when allocated (its first words are

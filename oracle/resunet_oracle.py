@@ -554,7 +554,9 @@ def unet_logits_bf16_emulated(p, x, cfg=DEFAULT_CFG, trace=None):
         for j in range(enc[i + 1]):
             prefix = "encoder_convs.%d.%d." % (i, j)
             if j == 0:                                                                        # model.py:101-102
-                h = _Stored.apply(_conv_e(_GradStored.apply(h), p[prefix + "downsample.0.weight"], stride=2))
+                # (the data gradient of this conv is NOT stored on its own: the depth-to-space epilogue adds it to the skip
+                # gradient in fp32 and the sum is rounded where the next stage reads it)
+                h = _Stored.apply(_conv_e(h, p[prefix + "downsample.0.weight"], stride=2))
                 tr["enc%d.down" % i] = h
             h = _residual_block_emulated(p, prefix, h, trace)
     for i in reversed(range(depth - 1)):

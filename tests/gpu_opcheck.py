@@ -98,7 +98,9 @@ def group_ew():
             y.backward(dy)
             # both forms behind b200_gn_backward: the one-launch cluster kernel (small tensors) and the
             # reduce -> finalize -> apply path (B200_GN_BWD_CLUSTER=0 forces it)
-            for form in ("cluster", "3-kernel"):
+            for form in ("creg", "cluster", "3-kernel"):
+                # register-resident cluster kernel (default for small tensors), shared-memory cluster kernel, three launches
+                os.environ["B200_GN_BWD_CREG"] = "1" if form == "creg" else "0"
                 os.environ["B200_GN_BWD_CLUSTER"] = "1" if form == "cluster" else "0"
                 dx = ops.act_zeros(N, D, H, W, Cc, dev)
                 dgam = torch.empty(Cc, device=dev); dbet = torch.empty(Cc, device=dev)
@@ -110,6 +112,7 @@ def group_ew():
                 report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
                 report("gn_backward halo untouched " + tag, ops.act_outside_absmax(dx).view(1), torch.zeros(1, device=dev), tol_abs=0)
             os.environ.pop("B200_GN_BWD_CLUSTER", None)
+            os.environ.pop("B200_GN_BWD_CREG", None)
         # many reduction CTAs per sample, odd batch: the last-CTA finalize inside the reduction kernel (default) against
         # the separate finalize launch (B200_GN_BWD_FUSED_FIN=0) and against autograd; repeated calls reuse the tickets
         for (N2, D2, H2, W2) in (((3, 32, 32, 32) if Cc == 16 else (2, 16, 16, 16)),):
@@ -125,6 +128,7 @@ def group_ew():
             xa2, dya2 = ops.act_from_ncdhw(x2), ops.act_from_ncdhw(dy2)
             ws = ops.gn_backward_workspace(N2, Cc, dev)
             res = {}
+            os.environ["B200_GN_BWD_CREG"] = "0"         # (these shapes would otherwise take the one-launch cluster kernel)
             for form in ("fused", "fused again", "separate"):
                 os.environ["B200_GN_BWD_FUSED_FIN"] = "0" if form == "separate" else "1"
                 dx = ops.act_zeros(N2, D2, H2, W2, Cc, dev)
@@ -137,6 +141,17 @@ def group_ew():
                 report("gn_backward dgamma " + tag, dgam, gr.grad, tol_rel=2e-3)
                 report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
             os.environ.pop("B200_GN_BWD_FUSED_FIN", None)
+            os.environ.pop("B200_GN_BWD_CREG", None)
+            # ... and the register-resident cluster kernel at the same shape (cluster of 16 for the 32^3 volume)
+            dx = ops.act_zeros(N2, D2, H2, W2, Cc, dev)
+            dgam = torch.full((Cc,), 5.0, device=dev); dbet = torch.full((Cc,), 5.0, device=dev)
+            ops.gn_backward(xa2, dya2, mean2, rstd2, gamma, beta, dx, dgam, dbet, ws, lrelu=True)
+            tag = "C=%d %dx(%d,%d,%d) form %d" % (Cc, N2, D2, H2, W2, ops._lib.lib().b200_gn_backward_form(N2, D2, H2, W2, Cc))
+            report("gn_backward dx " + tag, ops.act_to_ncdhw(dx), xr.grad, tol_rel=2e-2)
+            report("gn_backward dx vs 3-kernel " + tag, ops.act_to_ncdhw(dx), res["separate"][0], tol_rel=1e-2)
+            report("gn_backward dgamma " + tag, dgam, gr.grad, tol_rel=2e-3)
+            report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
+            report("gn_backward halo untouched " + tag, ops.act_outside_absmax(dx).view(1), torch.zeros(1, device=dev), tol_abs=0)
             report("gn_backward fused == separate dx C=%d" % Cc, res["fused"][0], res["separate"][0], tol_abs=0)
             report("gn_backward fused twice dx C=%d" % Cc, res["fused again"][0], res["fused"][0], tol_abs=0)
             report("gn_backward fused == separate dgamma C=%d" % Cc, res["fused"][1], res["separate"][1], tol_rel=1e-6)
@@ -344,6 +359,19 @@ def group_conv1():
         ops.depth_to_space(o, fine)
         ref = F.conv_transpose3d(dy, w, stride=2)
         report("down k2s2 dgrad %d<-%d" % (Cf, Cd), ops.act_to_ncdhw(fine), ref, tol_rel=1.5e-2)
+        # the same data gradient through the depth-to-space epilogue (EPI_D2S): one launch, written to the fine grid;
+        # without a residual it must equal conv + depth_to_space bit for bit, with one it adds the skip gradient in fp32
+        d2 = ops.conv_desc(ops.MODE_K1, N, D, H, W, Cd, 8 * Cf, epi=ops.EPI_D2S)
+        pk2 = ops.conv_pack_weight(d2, ops.W_DGRAD_S2D, w)
+        fine2 = ops.act_zeros(N, 2 * D, 2 * H, 2 * W, Cf, dev)
+        ops.conv_run(d2, ops.act_from_ncdhw(dy), pk2, fine2)
+        report("down k2s2 dgrad d2s-epilogue %d<-%d == two-step" % (Cf, Cd), fine2.t, fine.t, tol_abs=0)
+        skip = bf(torch.randn(N, Cf, 2 * D, 2 * H, 2 * W, device=dev))
+        fine3 = ops.act_zeros(N, 2 * D, 2 * H, 2 * W, Cf, dev)
+        ops.conv_run(d2, ops.act_from_ncdhw(dy), pk2, fine3, residual=ops.act_from_ncdhw(skip))
+        report("down k2s2 dgrad d2s-epilogue + skip %d<-%d" % (Cf, Cd), ops.act_to_ncdhw(fine3), ref + skip, tol_rel=1.5e-2)
+        report("down k2s2 dgrad d2s-epilogue halo+guard stay zero %d" % Cf, ops.act_outside_absmax(fine3).view(1),
+               torch.zeros(1, device=dev), tol_abs=0)
 
 
 def group_dgrad():

@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+python - <<'PY'
+import sys; sys.path.insert(0,'.')
+from brats2019_b200 import _lib
+L=_lib.lib()
+print("gn_backward forms:", [(N,s,C,L.b200_gn_backward_form(N,s,s,s,C)) for (N,s,C) in ((2,128,16),(2,64,32),(2,32,64),(2,16,128),(3,32,16),(8,16,128))])
+PY
+timeout 300 python tests/gpu_opcheck.py ew 2>&1 | grep -v "^PASS" | tail -12
+for v in 0 1 0 1; do
+  env B200_GN_BWD_CREG=$v timeout 600 python bench.py --no-cpu-baseline --no-gpu-baseline --steps 40 2> gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('B200_GN_BWD_CREG=$v', 'ms_per_step %.4f' % d['ms_per_step'], 'fwd %.4f' % d['forward']['ms_per_step'], 'e2e %.4f' % d['e2e']['ms_per_step'], 'launches', d['gpu_launches']/d['steps'])" || tail -5 gpurun_out/ab.err
+done
+timeout 300 python tools/step_timeline.py 2 128 gpurun_out/r02d_step_timeline.csv 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_layer_parity_gpu.py tests/test_model_gpu.py -m gpu -x -q 2>&1 | tail -4
