@@ -141,8 +141,8 @@ def group_ew():
                 report("gn_backward dgamma " + tag, dgam, gr.grad, tol_rel=2e-3)
                 report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
             os.environ.pop("B200_GN_BWD_FUSED_FIN", None)
-            os.environ.pop("B200_GN_BWD_CREG", None)
-            # ... and the register-resident cluster kernel at the same shape (cluster of 16 for the 32^3 volume)
+            os.environ["B200_GN_BWD_CREG"] = "1"
+            # ... and the register-resident one-launch kernel at the same shape (16 CTAs per unit for the 32^3 volume)
             dx = ops.act_zeros(N2, D2, H2, W2, Cc, dev)
             dgam = torch.full((Cc,), 5.0, device=dev); dbet = torch.full((Cc,), 5.0, device=dev)
             ops.gn_backward(xa2, dya2, mean2, rstd2, gamma, beta, dx, dgam, dbet, ws, lrelu=True)
@@ -152,6 +152,7 @@ def group_ew():
             report("gn_backward dgamma " + tag, dgam, gr.grad, tol_rel=2e-3)
             report("gn_backward dbeta " + tag, dbet, br.grad, tol_rel=2e-3)
             report("gn_backward halo untouched " + tag, ops.act_outside_absmax(dx).view(1), torch.zeros(1, device=dev), tol_abs=0)
+            os.environ.pop("B200_GN_BWD_CREG", None)
             report("gn_backward fused == separate dx C=%d" % Cc, res["fused"][0], res["separate"][0], tol_abs=0)
             report("gn_backward fused twice dx C=%d" % Cc, res["fused again"][0], res["fused"][0], tol_abs=0)
             report("gn_backward fused == separate dgamma C=%d" % Cc, res["fused"][1], res["separate"][1], tol_rel=1e-6)
