@@ -971,13 +971,25 @@ struct WgradLinePlan {
     WgradLineParams k;
     unsigned smem;
     int grid;
+    int nch;            // chunk planes per line: 2 (16 channels) or 4 (32 channels)
 };
 static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ignore_switch = false) {
     const char* e = getenv("B200_NO_WGRAD_LINE");        // read per call: tests switch forms in one process
     if (!ignore_switch && e && atoi(e)) return false;
-    if (d->mode != 0 || d->Cout != 16 || d->Cin != 16 || d->W % 16 || d->W < 16) return false;
+    if (d->mode != 0 || d->Cout != d->Cin || (d->Cout != 16 && d->Cout != 32) || d->W % 16 || d->W < 16) return false;
+    if (d->Cout == 32 && !ignore_switch) {
+        // 32 <-> 32 channels: OPT-IN (B200_WGRAD_LINE32=1).  Correct (CPU replay + op checks) and slower than the linear-row
+        // kernel (profiles/r02_ab_wgrad_line32.txt: 58.6 vs 48.3 us at 2 x 64^3): N = 288 needs three MMAs per K step, the
+        // same tensor time as the linear form, and the shared->shared kw copies of dY plus twice as many (half as long)
+        // bulk copies per line cost more shared-memory bandwidth and issue slots than the 3.4x L2 re-ingest they remove.
+        const char* e32 = getenv("B200_WGRAD_LINE32");
+        if (!e32 || !atoi(e32)) return false;
+    }
     memset(&P, 0, sizeof(P));
     WgradLineParams& k = P.k;
+    const unsigned nch = (unsigned)d->Cout / 8u;          // chunk planes per line (2: 16 channels, 4: 32 channels)
+    const unsigned slack = (nch == 2 ? 64u : 128u) / 8u - 3u * nch;
+    P.nch = (int)nch;
     k.N = d->N; k.D = d->D; k.H = d->H; k.W = d->W; k.Wp = d->W + 2;
     k.ksteps = d->W / 16;
     k.Lp = (unsigned)k.Wp * 16u;
@@ -990,8 +1002,8 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     const unsigned budget = kMaxSmem - 12 * 1024;
     auto need = [&](int LH, int NR, int Ny) {
         const unsigned R = 3u * (LH + 2) + 1u;
-        return (unsigned long long)(R + kWglMirror) * 2u * k.Lp + 128u + (unsigned long long)NR * 2u * k.Lp +
-               ((unsigned long long)Ny * 6u + 2u) * k.Lp + bar_bytes;
+        return (unsigned long long)(R + kWglMirror) * nch * k.Lp + 128u + (unsigned long long)NR * nch * k.Lp +
+               ((unsigned long long)Ny * 3u * nch + slack) * k.Lp + bar_bytes;
     };
     k.LH = 0;
     {   // diagnostics: B200_WGL_LH / B200_WGL_NR / B200_WGL_NY force the plan (tools/wgrad_ab.py sweeps them)
@@ -1018,9 +1030,9 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     k.n_bands = ceil_div(d->H, k.LH);
     k.units = (long long)d->N * k.n_bands * d->D;
     k.smem_x_off = 0;
-    k.smem_raw_off = align_up((unsigned)(k.R + kWglMirror) * 2u * k.Lp, 128);
-    k.smem_y_off = k.smem_raw_off + (unsigned)k.NR * 2u * k.Lp;
-    k.smem_bar_off = align_up(k.smem_y_off + ((unsigned)k.Ny * 6u + 2u) * k.Lp, 16);
+    k.smem_raw_off = align_up((unsigned)(k.R + kWglMirror) * nch * k.Lp, 128);
+    k.smem_y_off = k.smem_raw_off + (unsigned)k.NR * nch * k.Lp;
+    k.smem_bar_off = align_up(k.smem_y_off + ((unsigned)k.Ny * 3u * nch + slack) * k.Lp, 16);
     P.smem = k.smem_bar_off + bar_bytes;
     if (P.smem > kMaxSmem) return false;
     P.grid = (int)std::min<long long>(num_sms(), k.units);
@@ -1033,7 +1045,7 @@ extern "C" size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d) {
     size_t bytes = (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
     WgradLinePlan LP;
     if (plan_wgrad_line(d, LP, true))
-        bytes = std::max(bytes, (size_t)LP.grid * kWglRows * kWglN * sizeof(float));
+        bytes = std::max(bytes, (size_t)LP.grid * (3 * 8 * LP.nch) * (9 * 8 * LP.nch) * sizeof(float));
     WgradMarchPlan MP;
     if (plan_wgrad_march(d, MP))
         bytes = std::max(bytes, (size_t)MP.grid * kWgmAccs * kWgmM * kWgmN * sizeof(float));
@@ -1062,17 +1074,24 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
         WgradLinePlan LP;
         const char* em = getenv("B200_WGRAD_MARCH");
         if (kind == B200_G_K3 && !(em && atoi(em)) && plan_wgrad_line(d, LP)) {
-            SET_MAX_SMEM_ONCE(wgrad_line_kernel);
             LP.k.dy = P.k.dy; LP.k.x = P.k.x; LP.k.partial = (float*)workspace;
 #ifdef B200_PROBES
             { const char* e2 = getenv("B200_WGL_DEBUG"); LP.k.debug = e2 ? atoi(e2) : 0; }
 #endif
-            CUDA_OK(launch_prio(wgrad_line_kernel, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k));
+            if (LP.nch == 2) {
+                SET_MAX_SMEM_ONCE(wgrad_line_kernel<2>);
+                CUDA_OK(launch_prio(wgrad_line_kernel<2>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k));
+            } else {
+                SET_MAX_SMEM_ONCE(wgrad_line_kernel<4>);
+                CUDA_OK(launch_prio(wgrad_line_kernel<4>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k));
+            }
             LAUNCH_OK("wgrad_line_kernel");
             WglReduceParams rq;
             rq.ctas = LP.grid; rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
+            rq.C = 8 * LP.nch;
             constexpr int qpb = 256 / kWglReduceGroups;
-            CUDA_OK(launch_prio(wgrad_line_reduce_kernel, dim3((27 * 16 * 4 + qpb - 1) / qpb), dim3(256), 0, st, prio_wgrad(),
+            const int quads = 27 * rq.C * rq.C / 4;
+            CUDA_OK(launch_prio(wgrad_line_reduce_kernel, dim3((quads + qpb - 1) / qpb), dim3(256), 0, st, prio_wgrad(),
                                 (const float*)workspace, grad, rq));
             LAUNCH_OK("wgrad_line_reduce_kernel");
             return 0;
@@ -1778,11 +1797,11 @@ extern "C" int b200_wgrad_march_plan_debug(const b200_wgrad_desc* d, int* out, i
 
 extern "C" int b200_wgrad_line_plan_debug(const b200_wgrad_desc* d, int* out, int n_out) {
     WgradLinePlan P;
-    if (!plan_wgrad_line(d, P, true)) return fail("wgrad_line: does not apply (needs mode 0, 16 x 16 channels, W %% 16 == 0)");
+    if (!plan_wgrad_line(d, P, true)) return fail("wgrad_line: does not apply (needs mode 0, 16 x 16 or 32 x 32 channels, W %% 16 == 0)");
     const WgradLineParams& k = P.k;
     const int vals[] = {k.LH, k.n_bands, (int)k.units, k.ksteps, k.R, k.Ny, k.Wp, (int)k.Lp, (int)k.smem_x_off,
                         (int)k.smem_y_off, (int)k.smem_bar_off, (int)P.smem, P.grid, kWglMirror, kWglNB, kWglND, k.NR,
-                        (int)k.smem_raw_off};
+                        (int)k.smem_raw_off, P.nch};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv) return fail("wgrad_line_plan_debug: need %d ints", nv);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];

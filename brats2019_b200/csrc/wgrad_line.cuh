@@ -35,9 +35,25 @@
 namespace b200 {
 
 constexpr int kWglThreads = 256;
-constexpr int kWglM = 64;             // (kw 3) x 16 co, padded to the 64-row MMA
-constexpr int kWglN = 144;            // (kh 3) x (kd 3) x 16 ci
-constexpr int kWglRows = 48;          // rows of the partial that carry data
+// Channel count C = 8 * NCH (NCH chunk planes per line), the same on both sides:
+//   NCH = 2 (16 <-> 16, level 0): M = 64 (48 used), ONE MMA of N = 144 per 16 voxels (as described above);
+//   NCH = 4 (32 <-> 32, level 1): M = 128 (96 used = (kw 3) x 32 co), N = 9 * 32 = 288 exceeds one MMA, so the window is
+//            walked as THREE MMAs of N = 96 = (kd 3) x 32 ci, one per kh (three consecutive ring slots each), into three
+//            column blocks of a 128 x 288 accumulator.  Same tensor time as the linear-row kernel (3 x 56 cycles per 16
+//            voxels) - what changes is that every operand byte crosses L2 -> shared memory ~1.5 times instead of 3.4.
+template <int NCH> struct WglShape {
+    static constexpr int C = 8 * NCH;
+    static constexpr int M = NCH == 2 ? 64 : 128;         // MMA rows: (kw 3) x C, padded
+    static constexpr int Rows = 3 * C;                    // rows of the partial that carry data
+    static constexpr int Ntot = 9 * C;                    // (kh 3) x (kd 3) x C accumulator columns
+    static constexpr int Nmma = NCH == 2 ? Ntot : 3 * C;  // columns of one MMA
+    static constexpr int NM = Ntot / Nmma;                // MMAs per K step (1 or 3, one per kh)
+    static constexpr int Slack = M / 8 - 3 * NCH;         // planes past the last expanded dY line that an A operand touches
+    static constexpr int TmemCols = NCH == 2 ? 256 : 512;
+};
+constexpr int kWglM = 64;             // NCH = 2 values, kept for the host code and the tests
+constexpr int kWglN = 144;
+constexpr int kWglRows = 48;
 constexpr int kWglMirror = 8;         // ring slots mirrored behind the ring (window of 9 slots)
 constexpr int kWglNB = 64;            // X-load barriers (ring)
 constexpr int kWglND = 16;            // step-done barriers (ring, power of two), >= LH + 2
@@ -84,8 +100,10 @@ __device__ __forceinline__ int wgl_segment(const WgradLineParams& p, long long u
     return (int)len;
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(kWglThreads, 1)
 wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
+    using S = WglShape<NCH>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -113,20 +131,20 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
         *ready = 0;
         fence_barrier_init();
     }
-    if (warp == 3) tmem_alloc(tmem_slot, 256);
+    if (warp == 3) tmem_alloc(tmem_slot, S::TmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const long long SS = (long long)(p.H + 2) * p.Wp;      // rows per padded slice
-    const unsigned slot_bytes = 2u * p.Lp;                 // one ring slot: two chunk planes
-    const unsigned yline_bytes = 6u * p.Lp;                // one dY line: (kw 3) x (chunk 2) planes
+    const unsigned slot_bytes = (unsigned)NCH * p.Lp;      // one ring slot: NCH chunk planes
+    const unsigned yline_bytes = 3u * NCH * p.Lp;          // one dY line: (kw 3) x (chunk NCH) planes
 
     if (warp == 0) {
         // ============ X producer: line pairs in (slice, line) order into ring slot (3 * line + slice) mod R ============
         const uint8_t* x0 = reinterpret_cast<const uint8_t*>(p.x.at(0, 0));
-        const uint8_t* x1 = reinterpret_cast<const uint8_t*>(p.x.at(1, 0));
+        const size_t xplane = (size_t)p.x.plane_rows * 16;     // bytes between the chunk planes of the tensor in HBM
         // All counters are 32-bit and advance incrementally (a 64-bit division costs ~100 cycles, and every cycle of this
         // loop delays the prefetch): kx = loads issued, t_base = steps before this segment, t_known = highest step known done.
         int kx = 0, t_base = 0, t_known = -1;
@@ -143,7 +161,6 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
             int qs = 0;                                    // s mod R
             for (int s = 0; s < sg.len + 2; ++s) {
                 const uint8_t* src0 = x0 + (row00 + (long long)s * SS) * 16;
-                const uint8_t* src1 = x1 + (row00 + (long long)s * SS) * 16;
                 const int tn0 = t_base + (s - 3) * nl;
                 int q = qs;                                // (3 * lam + s) mod R
                 for (int lam = 0; lam < nl + 2; ++lam, ++kx) {
@@ -163,17 +180,17 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                         } else {
                             mbar_arrive_expect_tx(bar, (mirror ? 2u : 1u) * slot_bytes);
                             uint8_t* dst = smem_x + (size_t)q * slot_bytes;
-                            bulk_load_1d(dst, src0, p.Lp, bar);
-                            bulk_load_1d(dst + p.Lp, src1, p.Lp, bar);
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * xplane, p.Lp, bar);
                             if (mirror) {
                                 uint8_t* dm = dst + (size_t)p.R * slot_bytes;
-                                bulk_load_1d(dm, src0, p.Lp, bar);
-                                bulk_load_1d(dm + p.Lp, src1, p.Lp, bar);
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) bulk_load_1d(dm + c * p.Lp, src0 + c * xplane, p.Lp, bar);
                             }
                         }
                     }
                     __syncwarp();
-                    src0 += p.Lp; src1 += p.Lp;            // next line of the slice: Wp rows of 16 B further
+                    src0 += p.Lp;                          // next line of the slice: Wp rows of 16 B further
                     q += 3; if (q >= p.R) q -= p.R;
                 }
                 if (++qs == p.R) qs = 0;
@@ -183,7 +200,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     } else if (warp == 1) {
         // ============ dY producer: one interior line per step into the centre (kw = 1) planes of its slot ============
         const uint8_t* y0 = reinterpret_cast<const uint8_t*>(p.dy.at(0, 0));
-        const uint8_t* y1 = reinterpret_cast<const uint8_t*>(p.dy.at(1, 0));
+        const size_t yplane = (size_t)p.dy.plane_rows * 16;
         // The raw ring decouples the prefetch depth from the (three times larger) expanded lines: a raw slot is free as
         // soon as the copy warps have read it, NR + Ny lines ahead of the MMA that consumes the line.
         int t = 0, slot = 0, ph = 0;                       // lines issued; t mod NR; parity of the slot's current use
@@ -193,28 +210,27 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
             for (int sd = 0; sd < sg.len; ++sd) {
                 const long long row0 = ((long long)sg.n * (p.D + 2) + sg.d0 + 1 + sd) * SS + (long long)(sg.band * p.LH + 1) * p.Wp;
                 const uint8_t* src0 = y0 + row0 * 16;
-                const uint8_t* src1 = y1 + row0 * 16;
                 for (int l = 0; l < sg.nl; ++l, ++t) {
                     if (t >= p.NR) mbar_wait(&raw_free[slot], (uint32_t)(ph ^ 1));      // the previous use of the slot was read
                     if (elect_one()) {
                         if (WGL_DEBUG(8)) {
                             mbar_arrive(&y_raw[slot]);
                         } else {
-                            mbar_arrive_expect_tx(&y_raw[slot], 2u * p.Lp);
+                            mbar_arrive_expect_tx(&y_raw[slot], slot_bytes);
                             uint8_t* dst = smem_raw + (size_t)slot * slot_bytes;
-                            bulk_load_1d(dst, src0, p.Lp, &y_raw[slot]);
-                            bulk_load_1d(dst + p.Lp, src1, p.Lp, &y_raw[slot]);
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * yplane, p.Lp, &y_raw[slot]);
                         }
                     }
                     __syncwarp();
-                    src0 += p.Lp; src1 += p.Lp;
+                    src0 += p.Lp;
                     if (++slot == p.NR) { slot = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 2) {
-        // ============ MMA issuer: 8 x (M=64, N=144, K=16) per line ============
-        constexpr uint32_t idesc = make_idesc(kWglM, kWglN, 1, 1);
+        // ============ MMA issuer: W/16 x NM x (M, Nmma, K=16) per line ============
+        constexpr uint32_t idesc = make_idesc(S::M, S::Nmma, 1, 1);
         // MN-major SWIZZLE_NONE: LBO = 128 B between 8-row K groups, SBO = Lp between consecutive 8-channel blocks
         const uint64_t hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((p.Lp >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
         const uint32_t xbase16 = smem_u32(smem_x) >> 4, ybase16 = smem_u32(smem_y) >> 4;
@@ -255,15 +271,34 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                                 const uint32_t a16 = ybase16 + (uint32_t)sl * yline16 + 1u;     // row wp = 1 of the kw = 0 copy
                                 const uint32_t b16 = xbase16 + (uint32_t)q0 * slot16 + 1u;      // row wp = 1 of the window's first slot
                                 const uint32_t acc = (t + j) != 0;
-                                if (p.ksteps == 8) {                                  // W = 128: the level-0 lines of the benchmark
+                                if (NCH == 2) {
+                                    if (p.ksteps == 8) {                              // W = 128: the level-0 lines of the benchmark
 #pragma unroll
-                                    for (int ks = 0; ks < 8; ++ks)
-                                        umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
-                                                  hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        for (int ks = 0; ks < 8; ++ks)
+                                            umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                      hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                    } else {
+                                        for (int ks = 0; ks < p.ksteps; ++ks)             // 16 rows of 16 B per K step
+                                            umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                      hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                    }
                                 } else {
-                                    for (int ks = 0; ks < p.ksteps; ++ks)                 // 16 rows of 16 B per K step
-                                        umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
-                                                  hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                    // one MMA per kh: the three slots (kd 0..2) of window row kh, column block kh
+                                    const uint32_t kh16 = 3u * slot16;
+                                    if (p.ksteps == 4) {                              // W = 64: the level-1 lines of the benchmark
+#pragma unroll
+                                        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                                            for (int kh = 0; kh < S::NM; ++kh)
+                                                umma_bf16(tmem_base + (uint32_t)(kh * S::Nmma), hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                          hi | (uint64_t)((b16 + kh * kh16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                    } else {
+                                        for (int ks = 0; ks < p.ksteps; ++ks)
+#pragma unroll
+                                            for (int kh = 0; kh < S::NM; ++kh)
+                                                umma_bf16(tmem_base + (uint32_t)(kh * S::Nmma), hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                          hi | (uint64_t)((b16 + kh * kh16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                    }
                                 }
                                 umma_commit(&step_done[(dslot + j) & (kWglND - 1)]);
                             }
@@ -321,7 +356,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
         // ============ copy warps: the kw = 0 / kw = 2 copies of every dY line ============
         //   A_kw[r] = dY[r - kw + 1] for the rows r = 1 .. W the MMAs read (source rows 0 .. W+1 exist: the halo)
         const int f = threadIdx.x - 128;
-        const int items = 2 * p.W;
+        const int items = NCH * p.W;
         int t = 0, rslot = 0, rph = 0, slot = 0;           // lines expanded; raw slot and its parity; expanded slot
         for (long long u = u_begin; u < u_end;) {
             WglSeg sg;
@@ -337,15 +372,15 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 uint8_t* base = smem_y + (size_t)slot * yline_bytes;
                 if (!WGL_DEBUG(4))
                 for (int it = f; it < items; it += 128) {
-                    const int c = it >= p.W ? 1 : 0;
+                    const int c = it / p.W;
                     const int r = 1 + it - c * p.W;
                     const uint8_t* src = raw + (size_t)c * p.Lp + (size_t)r * 16;
                     const uint4 vm = *reinterpret_cast<const uint4*>(src - 16);
                     const uint4 v0 = *reinterpret_cast<const uint4*>(src);
                     const uint4 vp = *reinterpret_cast<const uint4*>(src + 16);
                     *reinterpret_cast<uint4*>(base + (size_t)c * p.Lp + (size_t)r * 16) = vp;            // kw = 0: dY[r + 1]
-                    *reinterpret_cast<uint4*>(base + (size_t)(2 + c) * p.Lp + (size_t)r * 16) = v0;      // kw = 1: dY[r]
-                    *reinterpret_cast<uint4*>(base + (size_t)(4 + c) * p.Lp + (size_t)r * 16) = vm;      // kw = 2: dY[r - 1]
+                    *reinterpret_cast<uint4*>(base + (size_t)(NCH + c) * p.Lp + (size_t)r * 16) = v0;    // kw = 1: dY[r]
+                    *reinterpret_cast<uint4*>(base + (size_t)(2 * NCH + c) * p.Lp + (size_t)r * 16) = vm; // kw = 2: dY[r - 1]
                 }
                 fence_proxy_async_smem();               // generic writes -> visible to the tensor core
                 __syncwarp();
@@ -354,18 +389,19 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 if (++slot == p.Ny) slot = 0;
             }
         }
-        // ============ epilogue: TMEM -> fp32 partial [48][144] ============
+        // ============ epilogue: TMEM -> fp32 partial [Rows][Ntot] ============
         const int ew = warp - 4;
-        float* dst = p.partial + (size_t)cta * kWglRows * kWglN;
-        const int row = ew * 16 + lane;                   // M = 64: rows 16*ew .. +15 live in lanes 0-15 of quadrant ew
-        const bool row_ok = lane < 16 && row < kWglRows;
+        float* dst = p.partial + (size_t)cta * S::Rows * S::Ntot;
+        // M = 64: rows 16*ew .. +15 live in lanes 0-15 of quadrant ew;  M = 128: row = TMEM lane
+        const int row = S::M == 64 ? ew * 16 + lane : ew * 32 + lane;
+        const bool row_ok = (S::M == 64 ? lane < 16 : true) && row < S::Rows;
         const bool any = u_end > u_begin;
         if (any) {
             mbar_wait(done, 0);
             tc_fence_after();
         }
 #pragma unroll
-        for (int c0 = 0; c0 < kWglN; c0 += 16) {
+        for (int c0 = 0; c0 < S::Ntot; c0 += 16) {
             float v[16];
             if (any) {
                 tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
@@ -374,7 +410,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
             if (row_ok) {
-                float4* o = reinterpret_cast<float4*>(dst + (size_t)row * kWglN + c0);
+                float4* o = reinterpret_cast<float4*>(dst + (size_t)row * S::Ntot + c0);
                 o[0] = make_float4(v[0], v[1], v[2], v[3]);
                 o[1] = make_float4(v[4], v[5], v[6], v[7]);
                 o[2] = make_float4(v[8], v[9], v[10], v[11]);
@@ -384,13 +420,14 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) tmem_dealloc(tmem_base, 256);
+    if (warp == 3) tmem_dealloc(tmem_base, S::TmemCols);
 }
 
-// dW[co][ci][kd][kh][kw] = sum over CTAs of P[cta][kw*16 + co][kh*48 + kd*16 + ci].
+// dW[co][ci][kd][kh][kw] = sum over CTAs of P[cta][kw*C + co][kh*3C + kd*C + ci]   (C = 16 or 32).
 // One thread per (output float4 over ci, CTA group); groups are combined in a fixed order in shared memory.
 struct WglReduceParams {
     int ctas, Cout_w, Cin_w, accumulate;
+    int C;                                                // padded channels of the GEMM (16 or 32)
 };
 constexpr int kWglReduceGroups = 32;
 __global__ void __launch_bounds__(256)
@@ -398,15 +435,17 @@ wgrad_line_reduce_kernel(const float* __restrict__ partial, float* __restrict__ 
     __shared__ double s_acc[256][4];
     constexpr int QPB = 256 / kWglReduceGroups;           // output quads per CTA
     const int g = threadIdx.x / QPB, ql = threadIdx.x % QPB;
-    const int quad = blockIdx.x * QPB + ql;               // (tap, co, ci/4): 27 * 16 * 4 quads
-    const bool active = quad < 27 * 16 * 4;
+    const int quad = blockIdx.x * QPB + ql;               // (tap, co, ci/4): 27 * C * C/4 quads
+    const int Cg = q.C, qpr = Cg / 4;                     // quads per (tap, co) row
+    const bool active = quad < 27 * Cg * qpr;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int tap = 0, co = 0, ci0 = 0;
     if (active) {
-        ci0 = (quad & 3) * 4; co = (quad >> 2) & 15; tap = quad >> 6;
+        ci0 = (quad % qpr) * 4; co = (quad / qpr) % Cg; tap = quad / (qpr * Cg);
         const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        const float* src = partial + (size_t)(kw * 16 + co) * kWglN + kh * 48 + kd * 16 + ci0;
-        const size_t cs = (size_t)kWglRows * kWglN;
+        const int Ntot = 9 * Cg;
+        const float* src = partial + (size_t)(kw * Cg + co) * Ntot + kh * 3 * Cg + kd * Cg + ci0;
+        const size_t cs = (size_t)(3 * Cg) * Ntot;
         // every thread's loads are issued together (the kernel is a chain of L2 latencies otherwise): groups of five
         int c = g;
         for (; c + 4 * kWglReduceGroups < q.ctas; c += 5 * kWglReduceGroups) {

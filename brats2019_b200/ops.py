@@ -323,6 +323,7 @@ def wgrad_run(desc, dy, x, grad, kind, ci_off=0, accumulate=False, workspace=Non
         buf = (C.c_int * 64)()
         line = (kind == G_K3 and os.environ.get("B200_NO_WGRAD_LINE", "0") in ("", "0") and
                 os.environ.get("B200_WGRAD_MARCH", "0") in ("", "0") and
+                (desc.Cout != 32 or os.environ.get("B200_WGRAD_LINE32", "0") not in ("", "0")) and
                 _lib.lib().b200_wgrad_line_plan_debug(C.byref(desc), buf, 64) == 0)
         t = 27 if desc.mode == 0 else 1
         _ledger("wgrad_line_kernel" if line else "wgrad_gemm_kernel", "tensor",

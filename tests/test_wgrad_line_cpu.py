@@ -22,11 +22,11 @@ import torch.nn.functional as F
 from brats2019_b200 import _lib
 from brats2019_b200._lib import WgradDesc
 
-FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off".split()
+FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off nch".split()
 
 
-def line_plan(N, D, H, W):
-    d = WgradDesc(0, N, D, H, W, 16, 16)
+def line_plan(N, D, H, W, Cc=16):
+    d = WgradDesc(0, N, D, H, W, Cc, Cc)
     out = (C.c_int * 32)()
     assert _lib.lib().b200_wgrad_line_plan_debug(C.byref(d), out, 32) == 0, _lib.lib().b200_last_error()
     return {k: out[i] for i, k in enumerate(FIELDS)}
@@ -53,12 +53,15 @@ def segments(p, cta, N, D, H):
 
 
 def replay_cta(p, segs, Y, X, W, rng):
-    """One CTA.  Returns its 64 x 144 accumulator."""
+    """One CTA.  Returns its (3C padded to 64 / 128) x 9C accumulator (C = 16: one N = 144 MMA per K step; C = 32: three
+    N = 96 MMAs, one per kh, into the column blocks kh * 96)."""
     R, Ny, NR, NB, ND, MIR, LH = p["R"], p["Ny"], p["NR"], p["NB"], p["ND"], p["mirror"], p["LH"]
+    Cc = 8 * p["nch"]
+    Mm = 64 if Cc == 16 else 128
     ring = [None] * (R + MIR)                    # slot -> (seg index, slice s, line lam) currently stored
     rawslot = [None] * NR                        # raw dY ring: slot -> line index it holds
     yslot = [None] * Ny                          # slot -> step index whose expanded line it holds
-    acc = np.zeros((64, 144))
+    acc = np.zeros((Mm, 9 * Cc))
     # ---- static schedules of the three actors (exactly the kernel's loops) ----
     xloads, steps = [], []                       # (seg, s, lam, wait_step or None) ; (seg, sd, l, k_need)
     t_base, seg_k0 = 0, 0
@@ -131,16 +134,20 @@ def replay_cta(p, segs, Y, X, W, rng):
                 n, band, d0 = sg["n"], sg["band"], sg["d0"]
                 dp = d0 + sd                                     # padded slice of the dY line (sd = 1 <-> interior slice d0)
                 hp = band * LH + 1 + l
-                yl = Y[n, dp, hp]                                # (W+2, 16)
-                A = np.zeros((64, W))                            # rows kw*16 + co, K = X rows 1 .. W
+                yl = Y[n, dp, hp]                                # (W+2, C)
+                A = np.zeros((Mm, W))                            # rows kw*C + co, K = X rows 1 .. W
                 for kw in range(3):
-                    A[kw * 16:(kw + 1) * 16] = yl[1 - kw + 1:1 - kw + 1 + W].T      # A_kw[r] = dY[r - kw + 1]
-                B = np.zeros((144, W))
+                    A[kw * Cc:(kw + 1) * Cc] = yl[1 - kw + 1:1 - kw + 1 + W].T      # A_kw[r] = dY[r - kw + 1]
+                B = np.zeros((9 * Cc, W))
                 for kh in range(3):
                     for kd in range(3):
                         xl = X[n, d0 + sd - 1 + kd, band * LH + l + kh]              # slice s = sd-1+kd <-> padded d0+s
-                        B[(3 * kh + kd) * 16:(3 * kh + kd + 1) * 16] = xl[1:1 + W].T
-                acc += A @ B.T
+                        B[(3 * kh + kd) * Cc:(3 * kh + kd + 1) * Cc] = xl[1:1 + W].T
+                if Cc == 16:
+                    acc += A @ B.T
+                else:                                            # one MMA per kh: ring slots q0 + 3*kh .. + 2, column block kh
+                    for kh in range(3):
+                        acc[:, kh * 3 * Cc:(kh + 1) * 3 * Cc] += A @ B[kh * 3 * Cc:(kh + 1) * 3 * Cc].T
                 t += 1
     assert max_ahead_x < NB
     return acc
@@ -150,30 +157,36 @@ def replay(dy, x, p, seed=0):
     N, _, D, H, W = x.shape
     assert p["units"] == N * p["n_bands"] * D and p["ksteps"] * 16 == W and p["R"] == 3 * (p["LH"] + 2) + 1
     assert p["Lp"] == (W + 2) * 16 and p["smem"] <= 227 * 1024
-    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * 2 * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] + p["NR"] * 2 * p["Lp"]
+    nch = p["nch"]
+    Cc = 8 * nch
+    assert Cc == x.shape[1] == dy.shape[1]
+    slack = (64 if Cc == 16 else 128) // 8 - 3 * nch             # planes an A operand reads past the last expanded line
+    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * nch * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] + p["NR"] * nch * p["Lp"]
     assert p["smem"] <= 227 * 1024 - 12 * 1024, "leave shared memory for the co-resident memory-bound kernels"
-    assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 6 + 2) * p["Lp"] and p["LH"] + 2 <= p["ND"]
+    assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 3 * nch + slack) * p["Lp"] and p["LH"] + 2 <= p["ND"]
     Y, X = padded(dy), padded(x)
     rng = random.Random(seed)
     partial = np.stack([replay_cta(p, segments(p, cta, N, D, H), Y, X, W, rng) for cta in range(p["grid"])])
-    # wgrad_line_reduce_kernel: dW[co][ci][kd][kh][kw] = sum_cta P[cta][kw*16 + co][kh*48 + kd*16 + ci]
+    # wgrad_line_reduce_kernel: dW[co][ci][kd][kh][kw] = sum_cta P[cta][kw*C + co][kh*3C + kd*C + ci]
     tot = partial.sum(0)
-    dW = np.zeros((16, 16, 3, 3, 3))
+    dW = np.zeros((Cc, Cc, 3, 3, 3))
     for kd in range(3):
         for kh in range(3):
             for kw in range(3):
-                dW[:, :, kd, kh, kw] = tot[kw * 16:(kw + 1) * 16, kh * 48 + kd * 16:kh * 48 + kd * 16 + 16]
+                dW[:, :, kd, kh, kw] = tot[kw * Cc:(kw + 1) * Cc, kh * 3 * Cc + kd * Cc:kh * 3 * Cc + kd * Cc + Cc]
     return dW
 
 
+@pytest.mark.parametrize("Cc", [16, 32])
 @pytest.mark.parametrize("shape", [(1, 3, 5, 16), (2, 9, 8, 16), (1, 5, 19, 32), (2, 2, 2, 16), (1, 1, 7, 48)])
-def test_replay_matches_autograd(shape):
+def test_replay_matches_autograd(shape, Cc):
     N, D, H, W = shape
-    p = line_plan(N, D, H, W)
+    p = line_plan(N, D, H, W, Cc)
+    assert p["nch"] == Cc // 8
     g = torch.Generator().manual_seed(sum(shape))
-    x = torch.randn(N, 16, D, H, W, generator=g, dtype=torch.float64)
-    w = torch.randn(16, 16, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
-    dy = torch.randn(N, 16, D, H, W, generator=g, dtype=torch.float64)
+    x = torch.randn(N, Cc, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Cc, Cc, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(N, Cc, D, H, W, generator=g, dtype=torch.float64)
     (ref,) = torch.autograd.grad(F.conv3d(x, w, padding=1), w, dy)
     got = replay(dy, x, p, seed=sum(shape))
     np.testing.assert_allclose(got, ref.numpy(), rtol=1e-9, atol=1e-9)
@@ -193,7 +206,22 @@ def test_schedule_survives_many_interleavings_at_the_benchmark_shape():
         replay_cta(p, segs, NoData(), NoData(), 128, random.Random(seed))
 
 
+def test_schedule_at_the_level_1_shape():
+    """32 <-> 32 channels at 2 x 64^3 (level 1 of config 3): plan + ring / barrier bookkeeping."""
+    p = line_plan(2, 64, 64, 64, 32)
+    assert p["nch"] == 4 and p["grid"] == 148 and p["ksteps"] == 4 and p["LH"] >= 4 and 64 % p["LH"] == 0
+    segs = segments(p, 11, 2, 64, 64) + segments(p, 12, 2, 64, 64)
+
+    class NoData:
+        def __getitem__(self, k):
+            return np.zeros((66, 32))
+
+    for seed in range(3):
+        replay_cta(p, segs, NoData(), NoData(), 64, random.Random(seed))
+
+
 def test_does_not_apply_outside_its_domain():
-    for desc in (WgradDesc(0, 1, 8, 8, 24, 16, 16), WgradDesc(0, 1, 8, 8, 32, 32, 32), WgradDesc(1, 1, 8, 8, 32, 16, 16)):
+    for desc in (WgradDesc(0, 1, 8, 8, 24, 16, 16), WgradDesc(0, 1, 8, 8, 32, 64, 64), WgradDesc(0, 1, 8, 8, 32, 32, 16),
+                 WgradDesc(1, 1, 8, 8, 32, 16, 16)):
         out = (C.c_int * 32)()
         assert _lib.lib().b200_wgrad_line_plan_debug(C.byref(desc), out, 32) != 0
