@@ -88,6 +88,7 @@ _PROTOS = {
     "b200_conv_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_wgrad_line_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
+    "b200_wgrad_line_plan_debug2": (c_int, [C.POINTER(WgradDesc), c_int, c_int, C.POINTER(c_int), c_int]),
     "b200_wgrad_march_plan_debug": (c_int, [C.POINTER(WgradDesc), C.POINTER(c_int), c_int]),
     "b200_march_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),
     "b200_band_plan_debug": (c_int, [C.POINTER(ConvDesc), C.POINTER(c_int), c_int]),

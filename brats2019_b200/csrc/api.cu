@@ -971,9 +971,13 @@ struct WgradLinePlan {
     WgradLineParams k;
     unsigned smem;
     int grid;
-    int nch;            // chunk planes per line: 2 (16 channels) or 4 (32 channels)
+    int nchy, nchx;     // chunk planes per line of dY / X: 2 (16 channels), 4 (32 channels), 1 (upper chunk known zero)
 };
-static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ignore_switch = false) {
+// real_out / real_in: PyTorch channel counts of the gradient being computed (0 = unknown): with <= 8 of them the upper
+// 8-channel chunk of the 16-channel tensor is zero by layout contract (b200_pack_input, b200_sigmoid_backward write zeros
+// there) and is neither loaded nor multiplied.
+static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ignore_switch = false, int real_out = 0,
+                            int real_in = 0) {
     const char* e = getenv("B200_NO_WGRAD_LINE");        // read per call: tests switch forms in one process
     if (!ignore_switch && e && atoi(e)) return false;
     if (d->mode != 0 || d->Cout != d->Cin || (d->Cout != 16 && d->Cout != 32) || d->W % 16 || d->W < 16) return false;
@@ -987,9 +991,17 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     }
     memset(&P, 0, sizeof(P));
     WgradLineParams& k = P.k;
-    const unsigned nch = (unsigned)d->Cout / 8u;          // chunk planes per line (2: 16 channels, 4: 32 channels)
-    const unsigned slack = (nch == 2 ? 64u : 128u) / 8u - 3u * nch;
-    P.nch = (int)nch;
+    // chunk planes per line of dY / X (2: 16 channels, 4: 32 channels, 1: 16-channel tensor whose upper chunk is zero)
+    unsigned nchy = (unsigned)d->Cout / 8u, nchx = (unsigned)d->Cin / 8u;
+    {
+        const char* eh = getenv("B200_WGL_NO_HALF");        // A/B: always load both chunks
+        const bool half = !(eh && atoi(eh));
+        if (half && d->Cout == 16 && real_out > 0 && real_out <= 8 && !(real_in > 0 && real_in <= 8)) nchy = 1;
+        else if (half && d->Cin == 16 && real_in > 0 && real_in <= 8) nchx = 1;
+    }
+    const unsigned Mmma = 3u * 8u * nchy <= 64u ? 64u : 128u;
+    const unsigned slack = Mmma / 8u - 3u * nchy;
+    P.nchy = (int)nchy; P.nchx = (int)nchx;
     k.N = d->N; k.D = d->D; k.H = d->H; k.W = d->W; k.Wp = d->W + 2;
     k.ksteps = d->W / 16;
     k.Lp = (unsigned)k.Wp * 16u;
@@ -1002,8 +1014,8 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     const unsigned budget = kMaxSmem - 12 * 1024;
     auto need = [&](int LH, int NR, int Ny) {
         const unsigned R = 3u * (LH + 2) + 1u;
-        return (unsigned long long)(R + kWglMirror) * nch * k.Lp + 128u + (unsigned long long)NR * nch * k.Lp +
-               ((unsigned long long)Ny * 3u * nch + slack) * k.Lp + bar_bytes;
+        return (unsigned long long)(R + kWglMirror) * nchx * k.Lp + 128u + (unsigned long long)NR * nchy * k.Lp +
+               ((unsigned long long)Ny * 3u * nchy + slack) * k.Lp + bar_bytes;
     };
     k.LH = 0;
     {   // diagnostics: B200_WGL_LH / B200_WGL_NR / B200_WGL_NY force the plan (tools/wgrad_ab.py sweeps them)
@@ -1030,9 +1042,9 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     k.n_bands = ceil_div(d->H, k.LH);
     k.units = (long long)d->N * k.n_bands * d->D;
     k.smem_x_off = 0;
-    k.smem_raw_off = align_up((unsigned)(k.R + kWglMirror) * nch * k.Lp, 128);
-    k.smem_y_off = k.smem_raw_off + (unsigned)k.NR * nch * k.Lp;
-    k.smem_bar_off = align_up(k.smem_y_off + ((unsigned)k.Ny * 3u * nch + slack) * k.Lp, 16);
+    k.smem_raw_off = align_up((unsigned)(k.R + kWglMirror) * nchx * k.Lp, 128);
+    k.smem_y_off = k.smem_raw_off + (unsigned)k.NR * nchy * k.Lp;
+    k.smem_bar_off = align_up(k.smem_y_off + ((unsigned)k.Ny * 3u * nchy + slack) * k.Lp, 16);
     P.smem = k.smem_bar_off + bar_bytes;
     if (P.smem > kMaxSmem) return false;
     P.grid = (int)std::min<long long>(num_sms(), k.units);
@@ -1045,7 +1057,7 @@ extern "C" size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d) {
     size_t bytes = (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
     WgradLinePlan LP;
     if (plan_wgrad_line(d, LP, true))
-        bytes = std::max(bytes, (size_t)LP.grid * (3 * 8 * LP.nch) * (9 * 8 * LP.nch) * sizeof(float));
+        bytes = std::max(bytes, (size_t)LP.grid * (3 * 8 * LP.nchy) * (9 * 8 * LP.nchx) * sizeof(float));
     WgradMarchPlan MP;
     if (plan_wgrad_march(d, MP))
         bytes = std::max(bytes, (size_t)MP.grid * kWgmAccs * kWgmM * kWgmN * sizeof(float));
@@ -1073,24 +1085,24 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     {
         WgradLinePlan LP;
         const char* em = getenv("B200_WGRAD_MARCH");
-        if (kind == B200_G_K3 && !(em && atoi(em)) && plan_wgrad_line(d, LP)) {
+        if (kind == B200_G_K3 && !(em && atoi(em)) && plan_wgrad_line(d, LP, false, Cout_w, Cin_w + ci_off)) {
             LP.k.dy = P.k.dy; LP.k.x = P.k.x; LP.k.partial = (float*)workspace;
 #ifdef B200_PROBES
             { const char* e2 = getenv("B200_WGL_DEBUG"); LP.k.debug = e2 ? atoi(e2) : 0; }
 #endif
-            if (LP.nch == 2) {
-                SET_MAX_SMEM_ONCE(wgrad_line_kernel<2>);
-                CUDA_OK(launch_prio(wgrad_line_kernel<2>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k));
-            } else {
-                SET_MAX_SMEM_ONCE(wgrad_line_kernel<4>);
-                CUDA_OK(launch_prio(wgrad_line_kernel<4>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k));
-            }
+#define WGL_CASE(Y, X)                                                                                                   \
+    if (LP.nchy == Y && LP.nchx == X) {                                                                                  \
+        SET_MAX_SMEM_ONCE(wgrad_line_kernel<Y, X>);                                                                      \
+        CUDA_OK(launch_prio(wgrad_line_kernel<Y, X>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k)); \
+    }
+            WGL_CASE(2, 2) else WGL_CASE(2, 1) else WGL_CASE(1, 2) else WGL_CASE(4, 4) else return fail("wgrad_line: no kernel");
+#undef WGL_CASE
             LAUNCH_OK("wgrad_line_kernel");
             WglReduceParams rq;
             rq.ctas = LP.grid; rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
-            rq.C = 8 * LP.nch;
+            rq.CY = 8 * LP.nchy; rq.CX = 8 * LP.nchx;
             constexpr int qpb = 256 / kWglReduceGroups;
-            const int quads = 27 * rq.C * rq.C / 4;
+            const int quads = 27 * rq.CY * rq.CX / 4;
             CUDA_OK(launch_prio(wgrad_line_reduce_kernel, dim3((quads + qpb - 1) / qpb), dim3(256), 0, st, prio_wgrad(),
                                 (const float*)workspace, grad, rq));
             LAUNCH_OK("wgrad_line_reduce_kernel");
@@ -1795,13 +1807,22 @@ extern "C" int b200_wgrad_march_plan_debug(const b200_wgrad_desc* d, int* out, i
     return 0;
 }
 
+static int wgrad_line_plan_debug(const b200_wgrad_desc* d, int real_out, int real_in, int* out, int n_out);
 extern "C" int b200_wgrad_line_plan_debug(const b200_wgrad_desc* d, int* out, int n_out) {
+    return wgrad_line_plan_debug(d, 0, 0, out, n_out);
+}
+// the plan b200_wgrad_run takes for a gradient with `real_out` x `real_in` PyTorch channels (<= 8 on one side of a
+// 16-channel GEMM: that side's upper chunk is skipped)
+extern "C" int b200_wgrad_line_plan_debug2(const b200_wgrad_desc* d, int real_out, int real_in, int* out, int n_out) {
+    return wgrad_line_plan_debug(d, real_out, real_in, out, n_out);
+}
+static int wgrad_line_plan_debug(const b200_wgrad_desc* d, int real_out, int real_in, int* out, int n_out) {
     WgradLinePlan P;
-    if (!plan_wgrad_line(d, P, true)) return fail("wgrad_line: does not apply (needs mode 0, 16 x 16 or 32 x 32 channels, W %% 16 == 0)");
+    if (!plan_wgrad_line(d, P, true, real_out, real_in)) return fail("wgrad_line: does not apply (needs mode 0, 16 x 16 or 32 x 32 channels, W %% 16 == 0)");
     const WgradLineParams& k = P.k;
     const int vals[] = {k.LH, k.n_bands, (int)k.units, k.ksteps, k.R, k.Ny, k.Wp, (int)k.Lp, (int)k.smem_x_off,
                         (int)k.smem_y_off, (int)k.smem_bar_off, (int)P.smem, P.grid, kWglMirror, kWglNB, kWglND, k.NR,
-                        (int)k.smem_raw_off, P.nch};
+                        (int)k.smem_raw_off, P.nchy, P.nchx};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv) return fail("wgrad_line_plan_debug: need %d ints", nv);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];

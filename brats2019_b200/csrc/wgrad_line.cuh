@@ -35,23 +35,26 @@
 namespace b200 {
 
 constexpr int kWglThreads = 256;
-// Channel count C = 8 * NCH (NCH chunk planes per line), the same on both sides:
-//   NCH = 2 (16 <-> 16, level 0): M = 64 (48 used), ONE MMA of N = 144 per 16 voxels (as described above);
-//   NCH = 4 (32 <-> 32, level 1): M = 128 (96 used = (kw 3) x 32 co), N = 9 * 32 = 288 exceeds one MMA, so the window is
-//            walked as THREE MMAs of N = 96 = (kd 3) x 32 ci, one per kh (three consecutive ring slots each), into three
-//            column blocks of a 128 x 288 accumulator.  Same tensor time as the linear-row kernel (3 x 56 cycles per 16
-//            voxels) - what changes is that every operand byte crosses L2 -> shared memory ~1.5 times instead of 3.4.
-template <int NCH> struct WglShape {
-    static constexpr int C = 8 * NCH;
-    static constexpr int M = NCH == 2 ? 64 : 128;         // MMA rows: (kw 3) x C, padded
-    static constexpr int Rows = 3 * C;                    // rows of the partial that carry data
-    static constexpr int Ntot = 9 * C;                    // (kh 3) x (kd 3) x C accumulator columns
-    static constexpr int Nmma = NCH == 2 ? Ntot : 3 * C;  // columns of one MMA
-    static constexpr int NM = Ntot / Nmma;                // MMAs per K step (1 or 3, one per kh)
-    static constexpr int Slack = M / 8 - 3 * NCH;         // planes past the last expanded dY line that an A operand touches
-    static constexpr int TmemCols = NCH == 2 ? 256 : 512;
+// Channel counts: dY has CY = 8 * NCHY channels (NCHY chunk planes per line), X has CX = 8 * NCHX:
+//   <2, 2> (16 <-> 16, level 0): M = 64 (48 used), ONE MMA of N = 144 per 16 voxels (as described above);
+//   <2, 1> (conv_input, model.py:336: 4 real input channels, the upper chunk of the packed input is zero by layout
+//            contract): only chunk 0 of X is loaded, N = 72 - the MMA drops from 72 to the 46-cycle floor.  This launch is
+//            the LAST kernel of the backward pass (nothing left to overlap it with): its time is step time;
+//   <1, 2> (conv_output, model.py:348: 3 real output channels): only chunk 0 of dY is loaded and expanded (M = 24 of 64);
+//   <4, 4> (32 <-> 32, level 1; opt-in): M = 128 (96 used), N = 288 exceeds one MMA, so the window is walked as THREE MMAs
+//            of N = 96 = (kd 3) x 32 ci, one per kh (three consecutive ring slots each), into three column blocks of a
+//            128 x 288 accumulator.  Same tensor time as the linear-row kernel (3 x 56 cycles per 16 voxels).
+template <int NCHY, int NCHX> struct WglShape {
+    static constexpr int CY = 8 * NCHY, CX = 8 * NCHX;
+    static constexpr int M = 3 * CY <= 64 ? 64 : 128;     // MMA rows: (kw 3) x CY, padded
+    static constexpr int Rows = 3 * CY;                   // rows of the partial that carry data
+    static constexpr int Ntot = 9 * CX;                   // (kh 3) x (kd 3) x CX accumulator columns
+    static constexpr int Nmma = Ntot <= 256 ? Ntot : 3 * CX;   // columns of one MMA
+    static constexpr int NM = Ntot / Nmma;                // MMAs per K step (1, or 3: one per kh)
+    static constexpr int Slack = M / 8 - 3 * NCHY;        // planes past the last expanded dY line that an A operand touches
+    static constexpr int TmemCols = Ntot <= 128 ? 128 : (Ntot <= 256 ? 256 : 512);
 };
-constexpr int kWglM = 64;             // NCH = 2 values, kept for the host code and the tests
+constexpr int kWglM = 64;             // <2, 2> values, kept for the host code and the tests
 constexpr int kWglN = 144;
 constexpr int kWglRows = 48;
 constexpr int kWglMirror = 8;         // ring slots mirrored behind the ring (window of 9 slots)
@@ -100,10 +103,10 @@ __device__ __forceinline__ int wgl_segment(const WgradLineParams& p, long long u
     return (int)len;
 }
 
-template <int NCH>
+template <int NCHY, int NCHX>
 __global__ void __launch_bounds__(kWglThreads, 1)
 wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
-    using S = WglShape<NCH>;
+    using S = WglShape<NCHY, NCHX>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -138,8 +141,9 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     const long long SS = (long long)(p.H + 2) * p.Wp;      // rows per padded slice
-    const unsigned slot_bytes = (unsigned)NCH * p.Lp;      // one ring slot: NCH chunk planes
-    const unsigned yline_bytes = 3u * NCH * p.Lp;          // one dY line: (kw 3) x (chunk NCH) planes
+    const unsigned slot_bytes = (unsigned)NCHX * p.Lp;     // one X ring slot: NCHX chunk planes
+    const unsigned raw_bytes = (unsigned)NCHY * p.Lp;      // one raw dY line: NCHY chunk planes
+    const unsigned yline_bytes = 3u * NCHY * p.Lp;         // one expanded dY line: (kw 3) x (chunk NCHY) planes
 
     if (warp == 0) {
         // ============ X producer: line pairs in (slice, line) order into ring slot (3 * line + slice) mod R ============
@@ -181,11 +185,11 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                             mbar_arrive_expect_tx(bar, (mirror ? 2u : 1u) * slot_bytes);
                             uint8_t* dst = smem_x + (size_t)q * slot_bytes;
 #pragma unroll
-                            for (int c = 0; c < NCH; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * xplane, p.Lp, bar);
+                            for (int c = 0; c < NCHX; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * xplane, p.Lp, bar);
                             if (mirror) {
                                 uint8_t* dm = dst + (size_t)p.R * slot_bytes;
 #pragma unroll
-                                for (int c = 0; c < NCH; ++c) bulk_load_1d(dm + c * p.Lp, src0 + c * xplane, p.Lp, bar);
+                                for (int c = 0; c < NCHX; ++c) bulk_load_1d(dm + c * p.Lp, src0 + c * xplane, p.Lp, bar);
                             }
                         }
                     }
@@ -216,10 +220,10 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                         if (WGL_DEBUG(8)) {
                             mbar_arrive(&y_raw[slot]);
                         } else {
-                            mbar_arrive_expect_tx(&y_raw[slot], slot_bytes);
-                            uint8_t* dst = smem_raw + (size_t)slot * slot_bytes;
+                            mbar_arrive_expect_tx(&y_raw[slot], raw_bytes);
+                            uint8_t* dst = smem_raw + (size_t)slot * raw_bytes;
 #pragma unroll
-                            for (int c = 0; c < NCH; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * yplane, p.Lp, &y_raw[slot]);
+                            for (int c = 0; c < NCHY; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * yplane, p.Lp, &y_raw[slot]);
                         }
                     }
                     __syncwarp();
@@ -271,7 +275,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                                 const uint32_t a16 = ybase16 + (uint32_t)sl * yline16 + 1u;     // row wp = 1 of the kw = 0 copy
                                 const uint32_t b16 = xbase16 + (uint32_t)q0 * slot16 + 1u;      // row wp = 1 of the window's first slot
                                 const uint32_t acc = (t + j) != 0;
-                                if (NCH == 2) {
+                                if (S::NM == 1) {
                                     if (p.ksteps == 8) {                              // W = 128: the level-0 lines of the benchmark
 #pragma unroll
                                         for (int ks = 0; ks < 8; ++ks)
@@ -356,7 +360,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
         // ============ copy warps: the kw = 0 / kw = 2 copies of every dY line ============
         //   A_kw[r] = dY[r - kw + 1] for the rows r = 1 .. W the MMAs read (source rows 0 .. W+1 exist: the halo)
         const int f = threadIdx.x - 128;
-        const int items = NCH * p.W;
+        const int items = NCHY * p.W;
         int t = 0, rslot = 0, rph = 0, slot = 0;           // lines expanded; raw slot and its parity; expanded slot
         for (long long u = u_begin; u < u_end;) {
             WglSeg sg;
@@ -368,7 +372,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                     const int tn = t - p.Ny;
                     mbar_wait(&step_done[tn & (kWglND - 1)], (uint32_t)((tn / kWglND) & 1));
                 }
-                const uint8_t* raw = smem_raw + (size_t)rslot * slot_bytes;
+                const uint8_t* raw = smem_raw + (size_t)rslot * raw_bytes;
                 uint8_t* base = smem_y + (size_t)slot * yline_bytes;
                 if (!WGL_DEBUG(4))
                 for (int it = f; it < items; it += 128) {
@@ -379,8 +383,8 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                     const uint4 v0 = *reinterpret_cast<const uint4*>(src);
                     const uint4 vp = *reinterpret_cast<const uint4*>(src + 16);
                     *reinterpret_cast<uint4*>(base + (size_t)c * p.Lp + (size_t)r * 16) = vp;            // kw = 0: dY[r + 1]
-                    *reinterpret_cast<uint4*>(base + (size_t)(NCH + c) * p.Lp + (size_t)r * 16) = v0;    // kw = 1: dY[r]
-                    *reinterpret_cast<uint4*>(base + (size_t)(2 * NCH + c) * p.Lp + (size_t)r * 16) = vm; // kw = 2: dY[r - 1]
+                    *reinterpret_cast<uint4*>(base + (size_t)(NCHY + c) * p.Lp + (size_t)r * 16) = v0;    // kw = 1: dY[r]
+                    *reinterpret_cast<uint4*>(base + (size_t)(2 * NCHY + c) * p.Lp + (size_t)r * 16) = vm; // kw = 2: dY[r - 1]
                 }
                 fence_proxy_async_smem();               // generic writes -> visible to the tensor core
                 __syncwarp();
@@ -413,8 +417,10 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 float4* o = reinterpret_cast<float4*>(dst + (size_t)row * S::Ntot + c0);
                 o[0] = make_float4(v[0], v[1], v[2], v[3]);
                 o[1] = make_float4(v[4], v[5], v[6], v[7]);
-                o[2] = make_float4(v[8], v[9], v[10], v[11]);
-                o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                if (c0 + 8 < S::Ntot) {                   // Ntot = 72: the last group carries 8 columns
+                    o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                }
             }
         }
     }
@@ -423,11 +429,11 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     if (warp == 3) tmem_dealloc(tmem_base, S::TmemCols);
 }
 
-// dW[co][ci][kd][kh][kw] = sum over CTAs of P[cta][kw*C + co][kh*3C + kd*C + ci]   (C = 16 or 32).
+// dW[co][ci][kd][kh][kw] = sum over CTAs of P[cta][kw*CY + co][kh*3*CX + kd*CX + ci].
 // One thread per (output float4 over ci, CTA group); groups are combined in a fixed order in shared memory.
 struct WglReduceParams {
     int ctas, Cout_w, Cin_w, accumulate;
-    int C;                                                // padded channels of the GEMM (16 or 32)
+    int CY, CX;                                           // channels of the GEMM's two sides (8, 16 or 32 each)
 };
 constexpr int kWglReduceGroups = 32;
 __global__ void __launch_bounds__(256)
@@ -436,16 +442,16 @@ wgrad_line_reduce_kernel(const float* __restrict__ partial, float* __restrict__ 
     constexpr int QPB = 256 / kWglReduceGroups;           // output quads per CTA
     const int g = threadIdx.x / QPB, ql = threadIdx.x % QPB;
     const int quad = blockIdx.x * QPB + ql;               // (tap, co, ci/4): 27 * C * C/4 quads
-    const int Cg = q.C, qpr = Cg / 4;                     // quads per (tap, co) row
-    const bool active = quad < 27 * Cg * qpr;
+    const int CYg = q.CY, CXg = q.CX, qpr = CXg / 4;      // quads per (tap, co) row
+    const bool active = quad < 27 * CYg * qpr;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int tap = 0, co = 0, ci0 = 0;
     if (active) {
-        ci0 = (quad % qpr) * 4; co = (quad / qpr) % Cg; tap = quad / (qpr * Cg);
+        ci0 = (quad % qpr) * 4; co = (quad / qpr) % CYg; tap = quad / (qpr * CYg);
         const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        const int Ntot = 9 * Cg;
-        const float* src = partial + (size_t)(kw * Cg + co) * Ntot + kh * 3 * Cg + kd * Cg + ci0;
-        const size_t cs = (size_t)(3 * Cg) * Ntot;
+        const int Ntot = 9 * CXg;
+        const float* src = partial + (size_t)(kw * CYg + co) * Ntot + kh * 3 * CXg + kd * CXg + ci0;
+        const size_t cs = (size_t)(3 * CYg) * Ntot;
         // every thread's loads are issued together (the kernel is a chain of L2 latencies otherwise): groups of five
         int c = g;
         for (; c + 4 * kWglReduceGroups < q.ctas; c += 5 * kWglReduceGroups) {

@@ -231,6 +231,7 @@ int b200_wgrad_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
 /* plan of the line-marching weight-gradient kernel (3x3x3, 16 x 16 channels, W % 16 == 0; the default form for
  * those convs); error if it does not apply */
 int b200_wgrad_line_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
+int b200_wgrad_line_plan_debug2(const b200_wgrad_desc* d, int real_out, int real_in, int* out, int n_out);
 /* plan of the marching weight-gradient kernel (3x3x3, 16 x 16 channels, W % 16 == 0); error if it does not apply */
 int b200_wgrad_march_plan_debug(const b200_wgrad_desc* d, int* out, int n_out);
 /* plan of the marching 3x3x3 kernel (Cin, Cout <= 32); error if it does not apply to `d` */

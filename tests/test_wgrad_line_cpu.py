@@ -22,13 +22,14 @@ import torch.nn.functional as F
 from brats2019_b200 import _lib
 from brats2019_b200._lib import WgradDesc
 
-FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off nch".split()
+FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off nchy nchx".split()
 
 
-def line_plan(N, D, H, W, Cc=16):
+def line_plan(N, D, H, W, Cc=16, real_out=0, real_in=0):
+    """real_out / real_in: PyTorch channel counts of the gradient (<= 8 on one side: that side's upper chunk is skipped)."""
     d = WgradDesc(0, N, D, H, W, Cc, Cc)
     out = (C.c_int * 32)()
-    assert _lib.lib().b200_wgrad_line_plan_debug(C.byref(d), out, 32) == 0, _lib.lib().b200_last_error()
+    assert _lib.lib().b200_wgrad_line_plan_debug2(C.byref(d), real_out, real_in, out, 32) == 0, _lib.lib().b200_last_error()
     return {k: out[i] for i, k in enumerate(FIELDS)}
 
 
@@ -56,12 +57,12 @@ def replay_cta(p, segs, Y, X, W, rng):
     """One CTA.  Returns its (3C padded to 64 / 128) x 9C accumulator (C = 16: one N = 144 MMA per K step; C = 32: three
     N = 96 MMAs, one per kh, into the column blocks kh * 96)."""
     R, Ny, NR, NB, ND, MIR, LH = p["R"], p["Ny"], p["NR"], p["NB"], p["ND"], p["mirror"], p["LH"]
-    Cc = 8 * p["nch"]
-    Mm = 64 if Cc == 16 else 128
+    Cy, Cx = 8 * p["nchy"], 8 * p["nchx"]                 # channels of dY / X the kernel loads
+    Mm = 64 if 3 * Cy <= 64 else 128
     ring = [None] * (R + MIR)                    # slot -> (seg index, slice s, line lam) currently stored
     rawslot = [None] * NR                        # raw dY ring: slot -> line index it holds
     yslot = [None] * Ny                          # slot -> step index whose expanded line it holds
-    acc = np.zeros((Mm, 9 * Cc))
+    acc = np.zeros((Mm, 9 * Cx))
     # ---- static schedules of the three actors (exactly the kernel's loops) ----
     xloads, steps = [], []                       # (seg, s, lam, wait_step or None) ; (seg, sd, l, k_need)
     t_base, seg_k0 = 0, 0
@@ -134,20 +135,20 @@ def replay_cta(p, segs, Y, X, W, rng):
                 n, band, d0 = sg["n"], sg["band"], sg["d0"]
                 dp = d0 + sd                                     # padded slice of the dY line (sd = 1 <-> interior slice d0)
                 hp = band * LH + 1 + l
-                yl = Y[n, dp, hp]                                # (W+2, C)
-                A = np.zeros((Mm, W))                            # rows kw*C + co, K = X rows 1 .. W
+                yl = Y[n, dp, hp][:, :Cy]                        # (W+2, Cy): the chunk planes the kernel loads
+                A = np.zeros((Mm, W))                            # rows kw*Cy + co, K = X rows 1 .. W
                 for kw in range(3):
-                    A[kw * Cc:(kw + 1) * Cc] = yl[1 - kw + 1:1 - kw + 1 + W].T      # A_kw[r] = dY[r - kw + 1]
-                B = np.zeros((9 * Cc, W))
+                    A[kw * Cy:(kw + 1) * Cy] = yl[1 - kw + 1:1 - kw + 1 + W].T      # A_kw[r] = dY[r - kw + 1]
+                B = np.zeros((9 * Cx, W))
                 for kh in range(3):
                     for kd in range(3):
-                        xl = X[n, d0 + sd - 1 + kd, band * LH + l + kh]              # slice s = sd-1+kd <-> padded d0+s
-                        B[(3 * kh + kd) * Cc:(3 * kh + kd + 1) * Cc] = xl[1:1 + W].T
-                if Cc == 16:
+                        xl = X[n, d0 + sd - 1 + kd, band * LH + l + kh][:, :Cx]      # slice s = sd-1+kd <-> padded d0+s
+                        B[(3 * kh + kd) * Cx:(3 * kh + kd + 1) * Cx] = xl[1:1 + W].T
+                if 9 * Cx <= 256:
                     acc += A @ B.T
                 else:                                            # one MMA per kh: ring slots q0 + 3*kh .. + 2, column block kh
                     for kh in range(3):
-                        acc[:, kh * 3 * Cc:(kh + 1) * 3 * Cc] += A @ B[kh * 3 * Cc:(kh + 1) * 3 * Cc].T
+                        acc[:, kh * 3 * Cx:(kh + 1) * 3 * Cx] += A @ B[kh * 3 * Cx:(kh + 1) * 3 * Cx].T
                 t += 1
     assert max_ahead_x < NB
     return acc
@@ -157,39 +158,43 @@ def replay(dy, x, p, seed=0):
     N, _, D, H, W = x.shape
     assert p["units"] == N * p["n_bands"] * D and p["ksteps"] * 16 == W and p["R"] == 3 * (p["LH"] + 2) + 1
     assert p["Lp"] == (W + 2) * 16 and p["smem"] <= 227 * 1024
-    nch = p["nch"]
-    Cc = 8 * nch
-    assert Cc == x.shape[1] == dy.shape[1]
-    slack = (64 if Cc == 16 else 128) // 8 - 3 * nch             # planes an A operand reads past the last expanded line
-    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * nch * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] + p["NR"] * nch * p["Lp"]
+    nchy, nchx = p["nchy"], p["nchx"]
+    Cy, Cx = 8 * nchy, 8 * nchx
+    assert Cy <= dy.shape[1] and Cx <= x.shape[1]
+    slack = (64 if 3 * Cy <= 64 else 128) // 8 - 3 * nchy        # planes an A operand reads past the last expanded line
+    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * nchx * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] + p["NR"] * nchy * p["Lp"]
     assert p["smem"] <= 227 * 1024 - 12 * 1024, "leave shared memory for the co-resident memory-bound kernels"
-    assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 3 * nch + slack) * p["Lp"] and p["LH"] + 2 <= p["ND"]
+    assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 3 * nchy + slack) * p["Lp"] and p["LH"] + 2 <= p["ND"]
     Y, X = padded(dy), padded(x)
     rng = random.Random(seed)
     partial = np.stack([replay_cta(p, segments(p, cta, N, D, H), Y, X, W, rng) for cta in range(p["grid"])])
-    # wgrad_line_reduce_kernel: dW[co][ci][kd][kh][kw] = sum_cta P[cta][kw*C + co][kh*3C + kd*C + ci]
+    # wgrad_line_reduce_kernel: dW[co][ci][kd][kh][kw] = sum_cta P[cta][kw*Cy + co][kh*3*Cx + kd*Cx + ci]
     tot = partial.sum(0)
-    dW = np.zeros((Cc, Cc, 3, 3, 3))
+    dW = np.zeros((Cy, Cx, 3, 3, 3))
     for kd in range(3):
         for kh in range(3):
             for kw in range(3):
-                dW[:, :, kd, kh, kw] = tot[kw * Cc:(kw + 1) * Cc, kh * 3 * Cc + kd * Cc:kh * 3 * Cc + kd * Cc + Cc]
+                dW[:, :, kd, kh, kw] = tot[kw * Cy:(kw + 1) * Cy, kh * 3 * Cx + kd * Cx:kh * 3 * Cx + kd * Cx + Cx]
     return dW
 
 
-@pytest.mark.parametrize("Cc", [16, 32])
+# (padded channels, real output channels, real input channels): 16 <-> 16, 32 <-> 32 (three MMAs per K step), conv_input
+# (4 real input channels: X's upper chunk is skipped, N = 72), conv_output (3 real output channels: dY's upper chunk skipped)
+@pytest.mark.parametrize("chans", [(16, 16, 16), (32, 32, 32), (16, 16, 4), (16, 3, 16)])
 @pytest.mark.parametrize("shape", [(1, 3, 5, 16), (2, 9, 8, 16), (1, 5, 19, 32), (2, 2, 2, 16), (1, 1, 7, 48)])
-def test_replay_matches_autograd(shape, Cc):
+def test_replay_matches_autograd(shape, chans):
     N, D, H, W = shape
-    p = line_plan(N, D, H, W, Cc)
-    assert p["nch"] == Cc // 8
+    Cc, ro, ri = chans
+    p = line_plan(N, D, H, W, Cc, ro, ri)
+    assert (p["nchy"], p["nchx"]) == (1 if ro <= 8 else Cc // 8, 1 if ri <= 8 else Cc // 8)
     g = torch.Generator().manual_seed(sum(shape))
-    x = torch.randn(N, Cc, D, H, W, generator=g, dtype=torch.float64)
-    w = torch.randn(Cc, Cc, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
-    dy = torch.randn(N, Cc, D, H, W, generator=g, dtype=torch.float64)
+    x = torch.randn(N, ri, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(ro, ri, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(N, ro, D, H, W, generator=g, dtype=torch.float64)
     (ref,) = torch.autograd.grad(F.conv3d(x, w, padding=1), w, dy)
-    got = replay(dy, x, p, seed=sum(shape))
-    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-9, atol=1e-9)
+    pad = lambda t: F.pad(t, (0, 0, 0, 0, 0, 0, 0, Cc - t.shape[1]))          # channels padded with zeros, as in HBM
+    got = replay(pad(dy), pad(x), p, seed=sum(shape))
+    np.testing.assert_allclose(got[:ro, :ri], ref.numpy(), rtol=1e-9, atol=1e-9)
 
 
 def test_schedule_survives_many_interleavings_at_the_benchmark_shape():
@@ -209,7 +214,7 @@ def test_schedule_survives_many_interleavings_at_the_benchmark_shape():
 def test_schedule_at_the_level_1_shape():
     """32 <-> 32 channels at 2 x 64^3 (level 1 of config 3): plan + ring / barrier bookkeeping."""
     p = line_plan(2, 64, 64, 64, 32)
-    assert p["nch"] == 4 and p["grid"] == 148 and p["ksteps"] == 4 and p["LH"] >= 4 and 64 % p["LH"] == 0
+    assert p["nchy"] == 4 and p["nchx"] == 4 and p["grid"] == 148 and p["ksteps"] == 4 and p["LH"] >= 4 and 64 % p["LH"] == 0
     segs = segments(p, 11, 2, 64, 64) + segments(p, 12, 2, 64, 64)
 
     class NoData:

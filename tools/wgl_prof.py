@@ -1,5 +1,5 @@
 """Where the line-marching weight-gradient kernel spends its time (perf diagnostic, GPU box, probes build):
-    python -m brats2019_b200.build --probes && python tools/wgl_prof.py [B] [S]
+    python -m brats2019_b200.build --probes && python tools/wgl_prof.py [B] [S] [Cout_w] [Cin_w]
 Times the kernel with one stage switched off at a time (B200_WGL_DEBUG bits: 1 no X copies, 2 no MMAs, 4 no shift
 copies, 8 no dY copies) and prints the MMA warp's cycle accounting (bit 256)."""
 import ctypes as C
@@ -24,7 +24,10 @@ def main():
     dy.interior().copy_(torch.randn(2, B, S, S, S, 8, device=dev).to(torch.bfloat16))
     desc = ops.wgrad_desc(0, B, S, S, S, 16, 16)
     ws = ops.wgrad_workspace(desc, dev)
-    g = torch.zeros(16, 16, 3, 3, 3, device=dev)
+    co_w = int(sys.argv[3]) if len(sys.argv) > 3 else 16       # PyTorch channel counts of the gradient: <= 8 on one side
+    ci_w = int(sys.argv[4]) if len(sys.argv) > 4 else 16       # skips that side's upper chunk (conv_input: 16 4, conv_output: 3 16)
+    g = torch.zeros(co_w, ci_w, 3, 3, 3, device=dev)
+    print("gradient %d x %d" % (co_w, ci_w))
     L = _lib.lib()
     L.b200_wgl_prof_read.restype = C.c_int
     L.b200_wgl_prof_read.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
