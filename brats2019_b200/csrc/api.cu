@@ -1007,7 +1007,7 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     k.Lp = (unsigned)k.Wp * 16u;
     if (k.Lp >= (1u << 18)) return false;               // descriptor stride field
     const unsigned bar_bytes = 1024;
-    // Shared memory: the X ring, NR raw dY lines, Ny expanded dY lines.  ~12 KB per SM stay free on purpose: in the training
+    // Shared memory: the X ring and Ny expanded dY lines (NR: the raw dY ring of the first version of the kernel, now 0).  ~12 KB per SM stay free on purpose: in the training
     // step this kernel runs beside the memory-bound GroupNorm-backward kernels (engine.py, side stream), whose CTAs need a
     // few KB each to be co-resident - with the whole 227 KB taken they queue behind this kernel and the overlap is lost
     // (measured: step 5.89 ms vs 5.81 ms).
@@ -1024,18 +1024,18 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
         const char* en = getenv("B200_WGL_NY");
         if (el && er && en) {
             const int LH = atoi(el), NR = atoi(er), Ny = atoi(en);
-            if (LH >= 1 && LH <= d->H && LH + 2 <= kWglND && NR >= 2 && NR <= kWglMaxNy && Ny >= 2 && Ny <= kWglMaxNy &&
+            if (LH >= 1 && LH <= d->H && LH + 2 <= kWglND && NR >= 0 && NR <= kWglMaxNy && Ny >= 2 && Ny <= kWglMaxNy &&
                 need(LH, NR, Ny) <= kMaxSmem) { k.LH = LH; k.NR = NR; k.Ny = Ny; }
         }
     }
-    // band height: prefer one that divides H (equal work per band), then the tallest; 3 expanded lines (two steps of
-    // slack for the copy warps), as many raw lines as fit (>= 3)
+    // band height: prefer one that divides H (equal work per band), then the tallest; as many expanded dY lines in flight
+    // as fit (>= 4: a slot's round trip is the MMAs of its line + ~2000 cycles of L2 latency, a line is ~600 cycles)
     for (int pass = 0; pass < 2 && k.LH == 0; ++pass)
         for (int LH = 8; LH >= 2 && k.LH == 0; --LH) {
             if (LH > d->H || LH + 2 > kWglND) continue;     // a producer polls a step_done barrier at most LH steps late
             if (pass == 0 && d->H % LH) continue;
-            for (int NR = kWglMaxNy; NR >= 3; --NR)
-                if (need(LH, NR, 3) <= budget) { k.LH = LH; k.NR = NR; k.Ny = 3; break; }
+            for (int Ny = kWglMaxNy; Ny >= 4; --Ny)
+                if (need(LH, 0, Ny) <= budget) { k.LH = LH; k.NR = 0; k.Ny = Ny; break; }
         }
     if (k.LH == 0) return false;
     k.R = 3 * (k.LH + 2) + 1;

@@ -9,9 +9,12 @@
 // operand byte crosses L2 -> shared memory about once instead of 3.1 times:
 //
 //   * A (M side) = dY line (d, h), three copies shifted by one voxel for the kw taps: blocks (kw, chunk) at one
-//     uniform stride.  The line is landed once by a bulk copy into a small raw ring (prefetch depth); the three
-//     shifted copies are made shared -> shared by four otherwise idle warps into a short ring of expanded lines
-//     (12 KB per line: cheaper than three L2 reads, and no extra L2 traffic).
+//     uniform stride.  The three copies are three bulk copies of the same HBM line whose source / destination differ by
+//     one 16-byte row (kw = 0: src + 16 B, kw = 2: dst + 16 B) into a ring of Ny expanded lines.  (Until round 2b the
+//     line landed once in a raw ring and four warps made the shifted copies shared -> shared: no extra L2 traffic, but
+//     24.6 KB of loads + stores per line on a shared-memory port that the MMA operand fetch already fills to 70 % - the
+//     stage breakdown of profiles/r02_ab_wgrad_line_half.txt showed those copies, not the tensor pipe, bounding the
+//     kernel.  The repeats hit L2.)
 //   * B (N side) = the nine input lines (kd, kh) around (d, h): the band's lines of the slices d-1 .. d+1 live in a
 //     shared-memory ring whose slot index is  q = 3*line + slice  (mod R), two chunk planes per slot, so that the nine
 //     (kh, kd) lines of any output line are NINE CONSECUTIVE slots: blocks (kh, kd, chunk) at one uniform stride -
@@ -27,8 +30,7 @@
 // gradient.
 //
 // Warp roles: w0 X producer, w1 dY producer (cp.async.bulk + mbarrier expect_tx), w2 MMA issuer, w3 TMEM allocator,
-// (then scout: waits for every step's operands and publishes a ready count the MMA warp polls), w4-7 dY shift
-// copies, then the epilogue.
+// (then scout: waits for every step's operands and publishes a ready count the MMA warp polls), w4-7 epilogue.
 #pragma once
 #include "common.cuh"
 
@@ -68,8 +70,8 @@ struct WgradLineParams {
     long long units;                  // N * n_bands * D, slice fastest
     int ksteps;                       // W / 16
     int R;                            // ring slots (without the mirror): 3 * (LH + 2) + 1
-    int NR;                           // raw dY lines in flight (landed by bulk copies, 2 planes each)
-    int Ny;                           // expanded dY lines ((kw 3) x (chunk 2) planes each) between the copy warps and the MMAs
+    int NR;                           // (unused since round 2b: the raw dY ring is gone; kept for the plan-debug layout)
+    int Ny;                           // expanded dY lines ((kw 3) x (chunk) planes each) in flight between L2 and the MMAs
     unsigned Lp;                      // bytes of one (line, chunk) plane: Wp * 16
     unsigned smem_x_off, smem_raw_off, smem_y_off, smem_bar_off;
     ActRef dy, x;
@@ -114,7 +116,6 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     const long long u_begin = p.units * cta / ctas, u_end = p.units * (cta + 1) / ctas;
 
     uint8_t* smem_x = smem + p.smem_x_off;            // ring: [R + mirror slots][chunk 2][Wp rows][16 B]
-    uint8_t* smem_raw = smem + p.smem_raw_off;        // raw dY lines: [NR][chunk 2][Wp rows][16 B]
     uint8_t* smem_y = smem + p.smem_y_off;            // expanded dY lines: [Ny][kw 3][chunk 2][Wp rows][16 B] (+ 2 planes of slack)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
     uint64_t* x_full = bars;                          // [NB]  bulk copies of one X line pair -> MMA
@@ -129,7 +130,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kWglNB; ++i) mbar_init(&x_full[i], 1);
         for (int i = 0; i < kWglND; ++i) mbar_init(&step_done[i], 1);
-        for (int i = 0; i < kWglMaxNy; ++i) { mbar_init(&y_raw[i], 1); mbar_init(&y_exp[i], 4); mbar_init(&raw_free[i], 4); }
+        for (int i = 0; i < kWglMaxNy; ++i) { mbar_init(&y_raw[i], 1); mbar_init(&y_exp[i], 1); mbar_init(&raw_free[i], 1); }
         mbar_init(done, 1);
         *ready = 0;
         fence_barrier_init();
@@ -142,7 +143,6 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
 
     const long long SS = (long long)(p.H + 2) * p.Wp;      // rows per padded slice
     const unsigned slot_bytes = (unsigned)NCHX * p.Lp;     // one X ring slot: NCHX chunk planes
-    const unsigned raw_bytes = (unsigned)NCHY * p.Lp;      // one raw dY line: NCHY chunk planes
     const unsigned yline_bytes = 3u * NCHY * p.Lp;         // one expanded dY line: (kw 3) x (chunk NCHY) planes
 
     if (warp == 0) {
@@ -202,12 +202,12 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
             t_base += sg.len * nl;
         }
     } else if (warp == 1) {
-        // ============ dY producer: one interior line per step into the centre (kw = 1) planes of its slot ============
+        // ============ dY producer: the three kw copies of one interior line per step, straight from L2 ============
+        //   A_kw[r] = dY[r - kw + 1] for the rows r = 1 .. W the MMAs read: kw = 1 is the line itself, kw = 0 the line from
+        //   its second row on, kw = 2 the line landed one row further (rows 0 / Wp-1 of those planes are never read)
         const uint8_t* y0 = reinterpret_cast<const uint8_t*>(p.dy.at(0, 0));
         const size_t yplane = (size_t)p.dy.plane_rows * 16;
-        // The raw ring decouples the prefetch depth from the (three times larger) expanded lines: a raw slot is free as
-        // soon as the copy warps have read it, NR + Ny lines ahead of the MMA that consumes the line.
-        int t = 0, slot = 0, ph = 0;                       // lines issued; t mod NR; parity of the slot's current use
+        int t = 0, slot = 0;                               // lines issued; t mod Ny
         for (long long u = u_begin; u < u_end;) {
             WglSeg sg;
             u += wgl_segment(p, u, u_end, sg);
@@ -215,20 +215,32 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 const long long row0 = ((long long)sg.n * (p.D + 2) + sg.d0 + 1 + sd) * SS + (long long)(sg.band * p.LH + 1) * p.Wp;
                 const uint8_t* src0 = y0 + row0 * 16;
                 for (int l = 0; l < sg.nl; ++l, ++t) {
-                    if (t >= p.NR) mbar_wait(&raw_free[slot], (uint32_t)(ph ^ 1));      // the previous use of the slot was read
+                    if (t >= p.Ny) {                        // the slot is free once the MMAs of line t - Ny are done
+                        const int tn = t - p.Ny;
+                        mbar_wait(&step_done[tn & (kWglND - 1)], (uint32_t)((tn / kWglND) & 1));
+                    }
                     if (elect_one()) {
+                        uint64_t* bar = &y_exp[slot];
                         if (WGL_DEBUG(8)) {
-                            mbar_arrive(&y_raw[slot]);
+                            mbar_arrive(bar);
                         } else {
-                            mbar_arrive_expect_tx(&y_raw[slot], raw_bytes);
-                            uint8_t* dst = smem_raw + (size_t)slot * raw_bytes;
+                            const bool shifts = !WGL_DEBUG(4);
+                            mbar_arrive_expect_tx(bar, (uint32_t)NCHY * (p.Lp + (shifts ? 2u * (p.Lp - 16u) : 0u)));
+                            uint8_t* dst = smem_y + (size_t)slot * yline_bytes;
 #pragma unroll
-                            for (int c = 0; c < NCHY; ++c) bulk_load_1d(dst + c * p.Lp, src0 + c * yplane, p.Lp, &y_raw[slot]);
+                            for (int c = 0; c < NCHY; ++c) {
+                                const uint8_t* sc = src0 + c * yplane;
+                                bulk_load_1d(dst + (size_t)(NCHY + c) * p.Lp, sc, p.Lp, bar);                      // kw = 1: dY[r]
+                                if (shifts) {
+                                    bulk_load_1d(dst + (size_t)c * p.Lp, sc + 16, p.Lp - 16u, bar);                // kw = 0: dY[r + 1]
+                                    bulk_load_1d(dst + (size_t)(2 * NCHY + c) * p.Lp + 16, sc, p.Lp - 16u, bar);   // kw = 2: dY[r - 1]
+                                }
+                            }
                         }
                     }
                     __syncwarp();
                     src0 += p.Lp;
-                    if (++slot == p.NR) { slot = 0; ph ^= 1; }
+                    if (++slot == p.Ny) slot = 0;
                 }
             }
         }
@@ -357,42 +369,6 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
             seg_k0 += (sg.len + 2) * (nl + 2);
         }
     } else if (warp >= 4) {
-        // ============ copy warps: the kw = 0 / kw = 2 copies of every dY line ============
-        //   A_kw[r] = dY[r - kw + 1] for the rows r = 1 .. W the MMAs read (source rows 0 .. W+1 exist: the halo)
-        const int f = threadIdx.x - 128;
-        const int items = NCHY * p.W;
-        int t = 0, rslot = 0, rph = 0, slot = 0;           // lines expanded; raw slot and its parity; expanded slot
-        for (long long u = u_begin; u < u_end;) {
-            WglSeg sg;
-            u += wgl_segment(p, u, u_end, sg);
-            const int nsteps = sg.len * sg.nl;
-            for (int i = 0; i < nsteps; ++i, ++t) {
-                mbar_wait(&y_raw[rslot], (uint32_t)rph);
-                if (t >= p.Ny) {                            // the expanded slot is free once the MMAs of line t - Ny are done
-                    const int tn = t - p.Ny;
-                    mbar_wait(&step_done[tn & (kWglND - 1)], (uint32_t)((tn / kWglND) & 1));
-                }
-                const uint8_t* raw = smem_raw + (size_t)rslot * raw_bytes;
-                uint8_t* base = smem_y + (size_t)slot * yline_bytes;
-                if (!WGL_DEBUG(4))
-                for (int it = f; it < items; it += 128) {
-                    const int c = it / p.W;
-                    const int r = 1 + it - c * p.W;
-                    const uint8_t* src = raw + (size_t)c * p.Lp + (size_t)r * 16;
-                    const uint4 vm = *reinterpret_cast<const uint4*>(src - 16);
-                    const uint4 v0 = *reinterpret_cast<const uint4*>(src);
-                    const uint4 vp = *reinterpret_cast<const uint4*>(src + 16);
-                    *reinterpret_cast<uint4*>(base + (size_t)c * p.Lp + (size_t)r * 16) = vp;            // kw = 0: dY[r + 1]
-                    *reinterpret_cast<uint4*>(base + (size_t)(NCHY + c) * p.Lp + (size_t)r * 16) = v0;    // kw = 1: dY[r]
-                    *reinterpret_cast<uint4*>(base + (size_t)(2 * NCHY + c) * p.Lp + (size_t)r * 16) = vm; // kw = 2: dY[r - 1]
-                }
-                fence_proxy_async_smem();               // generic writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&raw_free[rslot]); mbar_arrive(&y_exp[slot]); }
-                if (++rslot == p.NR) { rslot = 0; rph ^= 1; }
-                if (++slot == p.Ny) slot = 0;
-            }
-        }
         // ============ epilogue: TMEM -> fp32 partial [Rows][Ntot] ============
         const int ew = warp - 4;
         float* dst = p.partial + (size_t)cta * S::Rows * S::Ntot;
@@ -401,7 +377,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
         const bool row_ok = (S::M == 64 ? lane < 16 : true) && row < S::Rows;
         const bool any = u_end > u_begin;
         if (any) {
-            mbar_wait(done, 0);
+            while (!mbar_try_wait(done, 0)) __nanosleep(256);     // idle for the whole main loop: do not take issue slots
             tc_fence_after();
         }
 #pragma unroll

@@ -1,12 +1,13 @@
 """CPU replay of the line-marching weight-gradient kernel (brats2019_b200/csrc/wgrad_line.cuh): the planner's
 numbers (b200_wgrad_line_plan_debug) drive a numpy emulation of what a CTA does, including its asynchronous
-structure - four actors (X producer, dY producer, the copy warps that expand a raw dY line into its three kw copies,
-MMA issuer) that only advance when the kernel's own wait rules allow it, scheduled in random order with the producers as greedy as the rules let them be:
+structure - three actors (X producer, dY producer, MMA issuer) that only advance when the kernel's own wait rules allow
+it, scheduled in random order with the producers as greedy as the rules let them be:
 
   * shared-memory ring: slot (3*line + slice) mod R with the first 8 slots mirrored behind the ring; every 9-slot
     window the MMA reads must hold exactly the lines (kh, kd) of the step, i.e. no load may land in a slot that a
     later step still reads (the reuse rule `step (s-3)*nl + min(line+1, nl-1) done`) and no window may wrap;
-  * mbarrier rings: a waiter is never two phases behind the barrier it polls (x_full[64], step_done[16], y[Ny]);
+  * the ring of Ny expanded dY lines: line t lands (three bulk copies per chunk) only after the MMAs of line t - Ny;
+  * mbarrier rings: a waiter is never two phases behind the barrier it polls (x_full[64], step_done[16], y_exp[Ny]);
   * operands: the (kw, chunk) copies of a dY line and the K range over the interior voxels of a line;
   * the reduce kernel's index map back to the PyTorch (Cout, Cin, 3, 3, 3) gradient, against torch autograd.
 No GPU: what the hardware does with the descriptors is covered by tests/gpu_opcheck.py (wgrad group) and
@@ -60,7 +61,6 @@ def replay_cta(p, segs, Y, X, W, rng):
     Cy, Cx = 8 * p["nchy"], 8 * p["nchx"]                 # channels of dY / X the kernel loads
     Mm = 64 if 3 * Cy <= 64 else 128
     ring = [None] * (R + MIR)                    # slot -> (seg index, slice s, line lam) currently stored
-    rawslot = [None] * NR                        # raw dY ring: slot -> line index it holds
     yslot = [None] * Ny                          # slot -> step index whose expanded line it holds
     acc = np.zeros((Mm, 9 * Cx))
     # ---- static schedules of the three actors (exactly the kernel's loops) ----
@@ -82,13 +82,13 @@ def replay_cta(p, segs, Y, X, W, rng):
         t_base += sg["len"] * nl
         seg_k0 += (sg["len"] + 2) * (nl + 2)
     nsteps = len(steps)
-    kx = ky = kc = t = 0                         # progress of X producer, dY producer, copy warps, MMA
+    kx = ky = t = 0                              # progress of X producer, dY producer, MMA
     max_ahead_x = 0
     guard = 0
     while t < nsteps:
         guard += 1
         assert guard < 50 * (len(xloads) + 2 * nsteps) + 1000, "deadlock: no actor can advance"
-        order = [0, 0, 0, 1, 1, 3, 3, 2]         # producers greedy, MMA lazy: the hardest interleaving for slot reuse
+        order = [0, 0, 0, 1, 1, 1, 2]            # producers greedy, MMA lazy: the hardest interleaving for slot reuse
         rng.shuffle(order)
         for who in order:
             if who == 0 and kx < len(xloads):
@@ -105,23 +105,15 @@ def replay_cta(p, segs, Y, X, W, rng):
                     ring[q + R] = (si, s, lam)
                 kx += 1
             elif who == 1 and ky < nsteps:
-                if ky >= NR and ky - NR >= kc:
-                    continue                                     # raw slot not read yet (raw_free)
-                rawslot[ky % NR] = ky
+                if ky >= Ny and ky - Ny >= t:
+                    continue                                     # the MMAs of line ky - Ny still read the slot (step_done)
+                if ky >= Ny:
+                    assert t - 1 - (ky - Ny) < ND, "step_done phase ambiguity for the dY producer"
+                yslot[ky % Ny] = ky
                 ky += 1
-            elif who == 3 and kc < nsteps:
-                if ky <= kc:
-                    continue                                     # raw line not landed (y_raw)
-                if kc >= Ny and kc - Ny >= t:
-                    continue                                     # expanded slot still read by the MMAs (step_done)
-                if kc >= Ny:
-                    assert t - 1 - (kc - Ny) < ND, "step_done phase ambiguity for the copy warps"
-                assert rawslot[kc % NR] == kc
-                yslot[kc % Ny] = kc
-                kc += 1
             elif who == 2 and t < nsteps:
                 si, sd, l, k_need = steps[t]
-                if kx <= k_need or kc <= t:
+                if kx <= k_need or ky <= t:
                     continue
                 max_ahead_x = max(max_ahead_x, kx - (k_need + 1))
                 sg = segs[si]
@@ -162,7 +154,7 @@ def replay(dy, x, p, seed=0):
     Cy, Cx = 8 * nchy, 8 * nchx
     assert Cy <= dy.shape[1] and Cx <= x.shape[1]
     slack = (64 if 3 * Cy <= 64 else 128) // 8 - 3 * nchy        # planes an A operand reads past the last expanded line
-    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * nchx * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] + p["NR"] * nchy * p["Lp"]
+    assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * nchx * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] and p["NR"] == 0
     assert p["smem"] <= 227 * 1024 - 12 * 1024, "leave shared memory for the co-resident memory-bound kernels"
     assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 3 * nchy + slack) * p["Lp"] and p["LH"] + 2 <= p["ND"]
     Y, X = padded(dy), padded(x)
@@ -200,7 +192,7 @@ def test_replay_matches_autograd(shape, chans):
 def test_schedule_survives_many_interleavings_at_the_benchmark_shape():
     """Config-3 geometry (2 x 128^3): only the ring / barrier bookkeeping is replayed (operands skipped)."""
     p = line_plan(2, 128, 128, 128)
-    assert p["LH"] == 8 and p["grid"] == 148 and p["Ny"] == 3 and p["NR"] >= 3
+    assert p["LH"] == 8 and p["grid"] == 148 and p["Ny"] >= 4 and p["NR"] == 0
     segs = segments(p, 17, 2, 128, 128) + segments(p, 18, 2, 128, 128)      # a CTA-sized run crossing a band boundary
 
     class NoData:                                                           # index-only stand-in for the activations
