@@ -97,18 +97,30 @@ static void launch_priorities(int& conv, int& wgrad) {
 }
 static int prio_conv() { int c, w; launch_priorities(c, w); return c; }
 static int prio_wgrad() { int c, w; launch_priorities(c, w); return w; }
+// Programmatic dependent launch of the conv kernels (common.cuh pdl_wait): B200_PDL=0 turns it off (A/B).
+static bool pdl_enabled() {
+    int on = 1;
+    if (const char* e = getenv("B200_PDL")) on = atoi(e);
+    return on != 0;
+}
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio,
-                               Args&&... args) {
+static cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, bool pdl,
+                             Args&&... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributePriority;
-    attr[0].val.priority = prio;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (prio != 0) { attr[na].id = cudaLaunchAttributePriority; attr[na].val.priority = prio; ++na; }
+    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
     cfg.attrs = attr;
-    cfg.numAttrs = prio != 0 ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio,
+                               Args&&... args) {
+    return launch_ex(kernel, grid, block, smem, st, prio, false, std::forward<Args>(args)...);
 }
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
 #define SET_MAX_SMEM_ONCE(...)                                                                                     \
@@ -566,7 +578,7 @@ extern "C" int b200_pack_table_run(const void* table_device, int n_jobs, int tot
 template <int MODE, int EPI, int NM, int FOLD>
 static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_gemm_kernel<MODE, EPI, NM, FOLD>);
-    CUDA_OK(launch_prio(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), p));
+    CUDA_OK(launch_ex(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), pdl_enabled(), p));
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
 }
@@ -574,7 +586,7 @@ static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream
 template <int CO, int EPI>
 static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_march_kernel<CO, EPI>);
-    CUDA_OK(launch_prio(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), p));
+    CUDA_OK(launch_ex(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), pdl_enabled(), p));
     LAUNCH_OK("conv_march_kernel");
     return 0;
 }
@@ -621,7 +633,7 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
 template <int EPI>
 static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_band_kernel<EPI>);
-    CUDA_OK(launch_prio(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), p));
+    CUDA_OK(launch_ex(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), pdl_enabled(), p));
     LAUNCH_OK("conv_band_kernel");
     return 0;
 }

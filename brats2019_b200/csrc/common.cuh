@@ -103,6 +103,18 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its stream predecessor is still draining;
+// pdl_wait() blocks until that predecessor has completed and its memory is visible - everything that reads or writes a
+// tensor of an earlier kernel goes after it, what comes before (mbarrier init, TMEM allocation, the first weight
+// copies: weights were packed long before) overlaps the predecessor's tail.  pdl_trigger() in the PREDECESSOR lets the
+// dependent grid start launching once every CTA of this grid has started (without it the trigger is the grid's end and
+// nothing overlaps).  Both are no-ops in an ordinary launch.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

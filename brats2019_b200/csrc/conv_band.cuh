@@ -101,10 +101,6 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc(tmem_slot, 512);
-    // GroupNorm partial sums [ctas][N][16]: this CTA's row starts at zero (samples it never touches must contribute
-    // nothing); the epilogue overwrites the entries of the samples it does touch, after the barrier below.
-    if (p.stats_partial)
-        for (int i = threadIdx.x; i < p.N * 16; i += blockDim.x) p.stats_partial[(size_t)cta * p.N * 16 + i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -118,6 +114,17 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
     __syncthreads();
     tc_fence_after();
 
+
+    // Programmatic dependent launch: everything above (and the weight copies of warp 1, which never touch a tensor of an
+    // earlier kernel) may overlap the tail of the stream predecessor; every other warp waits for it here.
+    if (warp != 1) pdl_wait();
+    pdl_trigger();
+    // GroupNorm partial sums [ctas][N][16]: this CTA's row starts at zero (samples it never touches must contribute
+    // nothing); the epilogue (the same warp among others) overwrites the entries of the samples it does touch.
+    if (p.stats_partial && warp == 4) {
+        for (int i = lane; i < p.N * 16; i += 32) p.stats_partial[(size_t)cta * p.N * 16 + i] = 0.f;
+        __syncwarp();
+    }
     if (warp == 0) {
         // ================= activation producer: BH+2 line segments x 2 chunks per step =================
         int xs = 0; uint32_t xph = 0;
