@@ -97,12 +97,18 @@ static void launch_priorities(int& conv, int& wgrad) {
 }
 static int prio_conv() { int c, w; launch_priorities(c, w); return c; }
 static int prio_wgrad() { int c, w; launch_priorities(c, w); return w; }
-// Programmatic dependent launch of the conv kernels (common.cuh pdl_wait): B200_PDL=0 turns it off (A/B).
-static bool pdl_enabled() {
+// Programmatic dependent launch (common.cuh pdl_wait): B200_PDL=0 off, 1 (default) the conv kernels, 2 also the
+// memory-bound kernels.  Measured (profiles/r02_ab_pdl.txt): 0 -> 1 gains 0.11 ms per step (the conv prologues - barrier
+// init, TMEM allocation, first weight copies - run under the predecessor's tail); 1 -> 2 LOSES 0.28 ms: a memory-bound
+// kernel has no prologue worth hiding, and its thousands of early-resident CTAs parked in griddepcontrol.wait sit on the
+// SMs of the conv that is still running.
+static int pdl_level() {
     int on = 1;
     if (const char* e = getenv("B200_PDL")) on = atoi(e);
-    return on != 0;
+    return on;
 }
+static bool pdl_enabled() { return pdl_level() >= 2; }      // memory-bound kernels
+static bool pdl_conv() { return pdl_level() >= 1; }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, bool pdl,
                              Args&&... args) {
@@ -578,7 +584,7 @@ extern "C" int b200_pack_table_run(const void* table_device, int n_jobs, int tot
 template <int MODE, int EPI, int NM, int FOLD>
 static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_gemm_kernel<MODE, EPI, NM, FOLD>);
-    CUDA_OK(launch_ex(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), pdl_enabled(), p));
+    CUDA_OK(launch_ex(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), pdl_conv(), p));
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
 }
@@ -586,7 +592,7 @@ static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream
 template <int CO, int EPI>
 static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_march_kernel<CO, EPI>);
-    CUDA_OK(launch_ex(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), pdl_enabled(), p));
+    CUDA_OK(launch_ex(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), pdl_conv(), p));
     LAUNCH_OK("conv_march_kernel");
     return 0;
 }
@@ -633,7 +639,7 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
 template <int EPI>
 static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_band_kernel<EPI>);
-    CUDA_OK(launch_ex(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), pdl_enabled(), p));
+    CUDA_OK(launch_ex(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), pdl_conv(), p));
     LAUNCH_OK("conv_band_kernel");
     return 0;
 }
@@ -1205,12 +1211,12 @@ static int pack_input_t(const T* x, void* act_out, int N, int D, int H, int W, i
     Vol v{N, D, H, W};
     if (W % 4 == 0 && ((uintptr_t)x & (4 * sizeof(T) - 1)) == 0) {
         const int lpb = quad_lpb(N, D, H);
-        pack_input4_kernel<T><<<(N * D * H + lpb - 1) / lpb, 256, 0, st>>>(x, make_act(act_out, v), v, Creal, lpb,
-                                                                          make_fastdiv((unsigned)(W / 4)));
+        CUDA_OK(launch_ex(pack_input4_kernel<T>, dim3((N * D * H + lpb - 1) / lpb), dim3(256), 0, st, 0, pdl_enabled(), x, make_act(act_out, v), v, Creal, lpb,
+                                                                          make_fastdiv((unsigned)(W / 4))));
         LAUNCH_OK("pack_input4_kernel");
         return 0;
     }
-    pack_input_kernel<T><<<N * D * H, 128, 0, st>>>(x, make_act(act_out, v), v, Creal);
+    CUDA_OK(launch_ex(pack_input_kernel<T>, dim3(N * D * H), dim3(128), 0, st, 0, pdl_enabled(), x, make_act(act_out, v), v, Creal));
     LAUNCH_OK("pack_input_kernel");
     return 0;
 }
@@ -1231,8 +1237,8 @@ extern "C" int b200_gn_finalize(const float* stats_partial, int ctas, int N, int
                                 float* mean, float* rstd, void* stream) {
     if (C % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
     const double count = (double)(C / 8) * D * H * W;
-    gn_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd, nullptr, nullptr,
-                                                            nullptr, C, 1);
+    CUDA_OK(launch_ex(gn_finalize_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, 0, pdl_enabled(), stats_partial, ctas, N, count, eps, mean, rstd, nullptr, nullptr,
+                                                            nullptr, C, 1));
     LAUNCH_OK("gn_finalize_kernel");
     return 0;
 }
@@ -1243,8 +1249,8 @@ extern "C" int b200_gn_finalize_coef(const float* stats_partial, int ctas, int N
     if (!gamma || !beta || !coef) return fail("gn_finalize_coef: null argument");
     if (check_ptr16(coef, "coef")) return 1;
     const double count = (double)(C / 8) * D * H * W;
-    gn_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stats_partial, ctas, N, count, eps, mean, rstd, gamma, beta, coef,
-                                                            C, do_lrelu);
+    CUDA_OK(launch_ex(gn_finalize_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, 0, pdl_enabled(), stats_partial, ctas, N, count, eps, mean, rstd, gamma, beta, coef,
+                                                            C, do_lrelu));
     LAUNCH_OK("gn_finalize_kernel");
     return 0;
 }
@@ -1255,9 +1261,8 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
     if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_apply: C=%d unsupported", C);
     Vol v{N, D, H, W};
     const int lpb = lines_per_block(N, D, H);
-    gn_apply_kernel<<<N * D * H / lpb, kEwThreads, 0, (cudaStream_t)stream>>>(
-        make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu,
-        make_line_geom(W, C, lpb));
+    CUDA_OK(launch_ex(gn_apply_kernel, dim3(N * D * H / lpb), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu,
+        make_line_geom(W, C, lpb)));
     LAUNCH_OK("gn_apply_kernel");
     return 0;
 }
@@ -1477,18 +1482,18 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
         fin.tickets = reinterpret_cast<unsigned int*>(workspace);
         fin.m = m;
     }
-    gn_bwd_reduce2_kernel<<<dim3(blocks, N), 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                          partial, v, C, do_lrelu, by_W, rlpb, fin);
+    CUDA_OK(launch_ex(gn_bwd_reduce2_kernel, dim3(blocks, N), dim3(256), 0, st, 0, pdl_enabled(), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                          partial, v, C, do_lrelu, by_W, rlpb, fin));
     LAUNCH_OK("gn_bwd_reduce2_kernel");
     if (fin.coef == nullptr) {
         // one warp per (sample, channel, S1|S2) sum, up to 32 warps: min(8, N) * (C/8) * 2 sums per CTA
         const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
-        gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(partial, blocks, N, C, m, gamma, coef, dgamma, dbeta);
+        CUDA_OK(launch_ex(gn_bwd_finalize2_kernel, dim3(8), dim3(fin_threads), 0, st, 0, pdl_enabled(), partial, blocks, N, C, m, gamma, coef, dgamma, dbeta));
         LAUNCH_OK("gn_bwd_finalize2_kernel");
     }
     const int lpb = lines_per_block(N, D, H, W, C);
-    gn_bwd_apply2_kernel<false><<<N * D * H / lpb, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
-                                                                coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr);
+    CUDA_OK(launch_ex(gn_bwd_apply2_kernel<false>, dim3(N * D * H / lpb), dim3(256), 0, st, 0, pdl_enabled(), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+                                                                coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr));
     LAUNCH_OK("gn_bwd_apply2_kernel");
     return 0;
 }
@@ -1518,11 +1523,11 @@ extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const floa
     const FastDiv by_W = make_fastdiv((unsigned)W);
     const int lpb = lines_per_block(N, D, H, W, C);
     const int bps = D * H / lpb;
-    gn_bwd_apply2_kernel<true><<<N * bps, 256, 0, st>>>(make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
-                                                       make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff);
+    CUDA_OK(launch_ex(gn_bwd_apply2_kernel<true>, dim3(N * bps), dim3(256), 0, st, 0, pdl_enabled(), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
+                                                       make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff));
     LAUNCH_OK("gn_bwd_apply2_kernel");
     const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
-    gn_bwd_finalize2_kernel<<<8, fin_threads, 0, st>>>(aff, bps, N, C, m, gamma, coef_scratch, dgamma, dbeta);
+    CUDA_OK(launch_ex(gn_bwd_finalize2_kernel, dim3(8), dim3(fin_threads), 0, st, 0, pdl_enabled(), aff, bps, N, C, m, gamma, coef_scratch, dgamma, dbeta));
     LAUNCH_OK("gn_bwd_finalize2_kernel");
     return 0;
 }
@@ -1532,8 +1537,8 @@ extern "C" int b200_upsample2x(const void* coarse, void* fine, int N, int D, int
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    upsample2x_fwd3_kernel<<<N * D * H, 128, 0, (cudaStream_t)stream>>>(make_act(coarse, vc), make_act(fine, vf), vc, C,
-                                                                       do_lrelu, make_fastdiv((unsigned)W));
+    CUDA_OK(launch_ex(upsample2x_fwd3_kernel, dim3(N * D * H), dim3(128), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(coarse, vc), make_act(fine, vf), vc, C,
+                                                                       do_lrelu, make_fastdiv((unsigned)W)));
     LAUNCH_OK("upsample2x_fwd3_kernel");
     return 0;
 }
@@ -1551,10 +1556,10 @@ extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out,
     Vol vt{N, 2 * D, 2 * H, W};
     cudaStream_t st = (cudaStream_t)stream;
     const FastDiv by_W = make_fastdiv((unsigned)W);
-    upsample2x_bwd_w3_kernel<<<N * 2 * D * 2 * H, 128, 0, st>>>(make_act(dfine, vf), make_act(fine_out, vf),
-                                                               make_act(workspace, vt), vc, C, do_lrelu, by_W);
+    CUDA_OK(launch_ex(upsample2x_bwd_w3_kernel, dim3(N * 2 * D * 2 * H), dim3(128), 0, st, 0, pdl_enabled(), make_act(dfine, vf), make_act(fine_out, vf),
+                                                               make_act(workspace, vt), vc, C, do_lrelu, by_W));
     LAUNCH_OK("upsample2x_bwd_w3_kernel");
-    upsample2x_bwd_dh3_kernel<<<N * D * H, 128, 0, st>>>(make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W);
+    CUDA_OK(launch_ex(upsample2x_bwd_dh3_kernel, dim3(N * D * H), dim3(128), 0, st, 0, pdl_enabled(), make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W));
     LAUNCH_OK("upsample2x_bwd_dh3_kernel");
     return 0;
 }
@@ -1563,7 +1568,7 @@ extern "C" int b200_space_to_depth(const void* fine, void* coarse, int N, int D,
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    s2d_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(fine, vf), make_act(coarse, vc), vc, C);
+    CUDA_OK(launch_ex(s2d_kernel, dim3(N * D * H), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(fine, vf), make_act(coarse, vc), vc, C));
     LAUNCH_OK("s2d_kernel");
     return 0;
 }
@@ -1572,8 +1577,8 @@ extern "C" int b200_depth_to_space(const void* coarse, const void* residual, voi
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    d2s_kernel<<<N * D * H, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(coarse, vc), make_act(residual, vf),
-                                                                  make_act(fine, vf), vc, C);
+    CUDA_OK(launch_ex(d2s_kernel, dim3(N * D * H), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(coarse, vc), make_act(residual, vf),
+                                                                  make_act(fine, vf), vc, C));
     LAUNCH_OK("d2s_kernel");
     return 0;
 }
@@ -1581,8 +1586,8 @@ extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, i
     if (check_act(N, D, H, W, C)) return 1;
     Vol v{N, D, H, W};
     const int lpb = lines_per_block(N, D, H);
-    add_kernel<<<N * D * H / lpb, kEwThreads, 0, (cudaStream_t)stream>>>(make_act(a, v), make_act(b, v), make_act(out, v),
-                                                                        v, C, make_line_geom(W, C, lpb));
+    CUDA_OK(launch_ex(add_kernel, dim3(N * D * H / lpb), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(a, v), make_act(b, v), make_act(out, v),
+                                                                        v, C, make_line_geom(W, C, lpb)));
     LAUNCH_OK("add_kernel");
     return 0;
 }
@@ -1603,16 +1608,16 @@ extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs
     const int lpb = sigmoid_lpb(N, D, H);
     const int blocks = (N * D * H + lpb - 1) / lpb;
     if (W % 4 == 0 && (((uintptr_t)grad_probs | (uintptr_t)probs) & 15) == 0) {
-        sigmoid_bwd_pack4_kernel<<<blocks, 256, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
-                                                        make_fastdiv((unsigned)(W / 4)));
+        CUDA_OK(launch_ex(sigmoid_bwd_pack4_kernel, dim3(blocks), dim3(256), 0, st, 0, pdl_enabled(), grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+                                                        make_fastdiv((unsigned)(W / 4))));
         LAUNCH_OK("sigmoid_bwd_pack4_kernel");
     } else {
-        sigmoid_bwd_pack2_kernel<<<blocks, 256, 0, st>>>(grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
-                                                        make_fastdiv((unsigned)W));
+        CUDA_OK(launch_ex(sigmoid_bwd_pack2_kernel, dim3(blocks), dim3(256), 0, st, 0, pdl_enabled(), grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+                                                        make_fastdiv((unsigned)W)));
         LAUNCH_OK("sigmoid_bwd_pack2_kernel");
     }
     if (dbias) {
-        reduce_partials_kernel<<<Creal, 256, 0, st>>>(workspace, blocks, 4, Creal, dbias);
+        CUDA_OK(launch_ex(reduce_partials_kernel, dim3(Creal), dim3(256), 0, st, 0, pdl_enabled(), workspace, blocks, 4, Creal, dbias));
         LAUNCH_OK("reduce_partials_kernel");
     }
     return 0;
@@ -1679,7 +1684,7 @@ extern "C" int b200_bce_sum_t(const float* probs, const void* target, int target
     else
         return fail("bce: target dtype %d unsupported (fp32 or uint8)", target_dtype);
     LAUNCH_OK("bce_partial_kernel");
-    reduce_partials_kernel<<<1, 256, 0, st>>>(workspace, bx, 1, 1, sum);
+    CUDA_OK(launch_ex(reduce_partials_kernel, dim3(1), dim3(256), 0, st, 0, pdl_enabled(), workspace, bx, 1, 1, sum));
     LAUNCH_OK("reduce_partials_kernel");
     return 0;
 }
