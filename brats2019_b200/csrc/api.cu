@@ -109,6 +109,13 @@ static int pdl_level() {
 }
 static bool pdl_enabled() { return pdl_level() >= 2; }      // memory-bound kernels
 static bool pdl_conv() { return pdl_level() >= 1; }
+// the few-CTA finalize kernels between a conv / reduction and its apply pass are dependents too (their handful of parked
+// CTAs cost nothing): -0.02 ms per step; B200_PDL_SMALL=0 turns that off
+static bool pdl_small() {
+    int on = 1;
+    if (const char* e = getenv("B200_PDL_SMALL")) on = atoi(e);
+    return pdl_level() >= 2 || (pdl_level() >= 1 && on);
+}
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, bool pdl,
                              Args&&... args) {
@@ -1237,7 +1244,7 @@ extern "C" int b200_gn_finalize(const float* stats_partial, int ctas, int N, int
                                 float* mean, float* rstd, void* stream) {
     if (C % 8) return fail("GroupNorm(8) needs C %% 8 == 0");
     const double count = (double)(C / 8) * D * H * W;
-    CUDA_OK(launch_ex(gn_finalize_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, 0, pdl_enabled(), stats_partial, ctas, N, count, eps, mean, rstd, nullptr, nullptr,
+    CUDA_OK(launch_ex(gn_finalize_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, 0, pdl_small(), stats_partial, ctas, N, count, eps, mean, rstd, nullptr, nullptr,
                                                             nullptr, C, 1));
     LAUNCH_OK("gn_finalize_kernel");
     return 0;
@@ -1249,7 +1256,7 @@ extern "C" int b200_gn_finalize_coef(const float* stats_partial, int ctas, int N
     if (!gamma || !beta || !coef) return fail("gn_finalize_coef: null argument");
     if (check_ptr16(coef, "coef")) return 1;
     const double count = (double)(C / 8) * D * H * W;
-    CUDA_OK(launch_ex(gn_finalize_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, 0, pdl_enabled(), stats_partial, ctas, N, count, eps, mean, rstd, gamma, beta, coef,
+    CUDA_OK(launch_ex(gn_finalize_kernel, dim3(N), dim3(256), 0, (cudaStream_t)stream, 0, pdl_small(), stats_partial, ctas, N, count, eps, mean, rstd, gamma, beta, coef,
                                                             C, do_lrelu));
     LAUNCH_OK("gn_finalize_kernel");
     return 0;
@@ -1488,7 +1495,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
     if (fin.coef == nullptr) {
         // one warp per (sample, channel, S1|S2) sum, up to 32 warps: min(8, N) * (C/8) * 2 sums per CTA
         const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
-        CUDA_OK(launch_ex(gn_bwd_finalize2_kernel, dim3(8), dim3(fin_threads), 0, st, 0, pdl_enabled(), partial, blocks, N, C, m, gamma, coef, dgamma, dbeta));
+        CUDA_OK(launch_ex(gn_bwd_finalize2_kernel, dim3(8), dim3(fin_threads), 0, st, 0, pdl_small(), partial, blocks, N, C, m, gamma, coef, dgamma, dbeta));
         LAUNCH_OK("gn_bwd_finalize2_kernel");
     }
     const int lpb = lines_per_block(N, D, H, W, C);
@@ -1527,7 +1534,7 @@ extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const floa
                                                        make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff));
     LAUNCH_OK("gn_bwd_apply2_kernel");
     const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
-    CUDA_OK(launch_ex(gn_bwd_finalize2_kernel, dim3(8), dim3(fin_threads), 0, st, 0, pdl_enabled(), aff, bps, N, C, m, gamma, coef_scratch, dgamma, dbeta));
+    CUDA_OK(launch_ex(gn_bwd_finalize2_kernel, dim3(8), dim3(fin_threads), 0, st, 0, pdl_small(), aff, bps, N, C, m, gamma, coef_scratch, dgamma, dbeta));
     LAUNCH_OK("gn_bwd_finalize2_kernel");
     return 0;
 }
@@ -1617,7 +1624,7 @@ extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs
         LAUNCH_OK("sigmoid_bwd_pack2_kernel");
     }
     if (dbias) {
-        CUDA_OK(launch_ex(reduce_partials_kernel, dim3(Creal), dim3(256), 0, st, 0, pdl_enabled(), workspace, blocks, 4, Creal, dbias));
+        CUDA_OK(launch_ex(reduce_partials_kernel, dim3(Creal), dim3(256), 0, st, 0, pdl_small(), workspace, blocks, 4, Creal, dbias));
         LAUNCH_OK("reduce_partials_kernel");
     }
     return 0;
@@ -1684,7 +1691,7 @@ extern "C" int b200_bce_sum_t(const float* probs, const void* target, int target
     else
         return fail("bce: target dtype %d unsupported (fp32 or uint8)", target_dtype);
     LAUNCH_OK("bce_partial_kernel");
-    CUDA_OK(launch_ex(reduce_partials_kernel, dim3(1), dim3(256), 0, st, 0, pdl_enabled(), workspace, bx, 1, 1, sum));
+    CUDA_OK(launch_ex(reduce_partials_kernel, dim3(1), dim3(256), 0, st, 0, pdl_small(), workspace, bx, 1, 1, sum));
     LAUNCH_OK("reduce_partials_kernel");
     return 0;
 }
