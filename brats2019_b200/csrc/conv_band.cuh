@@ -118,7 +118,6 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
     // Programmatic dependent launch: everything above (and the weight copies of warp 1, which never touch a tensor of an
     // earlier kernel) may overlap the tail of the stream predecessor; every other warp waits for it here.
     if (warp != 1) pdl_wait();
-    pdl_trigger();
     // GroupNorm partial sums [ctas][N][16]: this CTA's row starts at zero (samples it never touches must contribute
     // nothing); the epilogue (the same warp among others) overwrites the entries of the samples it does touch.
     if (p.stats_partial && warp == 4) {
@@ -256,6 +255,10 @@ conv_band_kernel(const __grid_constant__ BandParams p) {
             g_march_prof[cta * 16 + 5] = (unsigned long long)t_issue;
             g_march_prof[cta * 16 + 6] = (unsigned long long)nsteps;
         }
+        // every MMA of this CTA is issued: what is left is its last epilogue - the dependent kernel may start launching
+        // (it still waits for this whole grid in its own pdl_wait; triggering at the start would park its CTAs here for
+        // the whole kernel)
+        pdl_trigger();
     } else if (warp >= 4) {
         // ================= epilogue =================
         const int grp = (warp - 4) >> 2;

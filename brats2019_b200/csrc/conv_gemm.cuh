@@ -146,7 +146,6 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
     // Programmatic dependent launch: everything above (and the weight copies of warp 1, which never touch a tensor of an
     // earlier kernel) may overlap the tail of the stream predecessor; every other warp waits for it here.
     if (warp != 1) pdl_wait();
-    pdl_trigger();
     // GroupNorm partial sums [ctas][N][16]: this CTA's row starts at zero (samples it never touches must contribute
     // nothing); the epilogue (the same warp among others) overwrites the entries of the samples it does touch.
     if (p.stats_partial && warp == 4) {
@@ -298,6 +297,10 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             if (elect_one()) umma_commit(&t_full[as]);
             __syncwarp();
         }
+        // every MMA of this CTA is issued: what is left is its last epilogue - the dependent kernel may start launching
+        // (it still waits for this whole grid in its own pdl_wait; triggering at the start would park its CTAs here for
+        // the whole kernel)
+        pdl_trigger();
     } else if (warp >= 4) {
         // ================= epilogue (kEpiGroups groups of 4 warps take runs round-robin) =================
         const int grp = (warp - 4) >> 2;

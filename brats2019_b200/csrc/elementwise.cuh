@@ -76,8 +76,8 @@ __device__ __forceinline__ float4 ld_f4(const uint8_t* p, size_t i4) {
 
 template <typename T>
 __global__ void pack_input_kernel(const T* __restrict__ x, ActRef out, Vol v, int Creal) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     int n, d, h;
     line_coords(v, blockIdx.x, n, d, h);
     const size_t plane = (size_t)v.D * v.H * v.W;
@@ -103,8 +103,8 @@ __global__ void pack_input_kernel(const T* __restrict__ x, ActRef out, Vol v, in
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int ctas, int N, double count, float eps,
                                    float* __restrict__ mean, float* __restrict__ rstd, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ coef, int C, int do_lrelu) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ double s_part[256];
     __shared__ double s_sum[16];
     const int n = blockIdx.x, t = threadIdx.x;
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kEwThreads)
 gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, ActRef residual, ActRef out, Vol v,
                 int C, int do_lrelu, LineGeom lg) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ float s_scale[256], s_shift[256];
     __shared__ long long s_rows[16];
     const int lpb = lg.lpb;
@@ -212,8 +212,8 @@ gn_apply_kernel(ActRef x, const float* __restrict__ mean, const float* __restric
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads)
 s2d_kernel(ActRef fine, ActRef coarse, Vol vc, int C) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vc, blockIdx.x, n, d, h);
@@ -233,8 +233,8 @@ s2d_kernel(ActRef fine, ActRef coarse, Vol vc, int C) {
 
 __global__ void __launch_bounds__(kEwThreads)
 d2s_kernel(ActRef coarse, ActRef residual, ActRef fine, Vol vc, int C) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vc, blockIdx.x, n, d, h);
@@ -265,8 +265,8 @@ d2s_kernel(ActRef coarse, ActRef residual, ActRef fine, Vol vc, int C) {
 // out = a + b over the interior (gradient accumulation where two paths meet)
 __global__ void __launch_bounds__(kEwThreads)
 add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, LineGeom lg) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ long long s_rows[16];
     const int lpb = lg.lpb;
     const int line0 = blockIdx.x * lpb;
@@ -301,8 +301,8 @@ add_kernel(ActRef a, ActRef b, ActRef out, Vol v, int C, LineGeom lg) {
 // out[j] = sum_i partial[i*stride + j], j < n_out, in double, fixed order.
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int count, int stride, int n_out,
                                        float* __restrict__ out) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     const int j = blockIdx.x;
     __shared__ double sh[256];
     double a = 0.0;

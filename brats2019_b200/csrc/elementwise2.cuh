@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256, kGnBwdMinCtas)
 gn_bwd_reduce2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ partial,
                       Vol v, int C, int do_lrelu, FastDiv by_W, int lpb, GnBwdFin fin) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ long long s_rows[kRedLines];
     __shared__ float s_red[8][16];
     const int n = blockIdx.y;
@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(1024)
 gn_bwd_finalize2_kernel(const float* __restrict__ partial, int blocks, int N, int C, double m,
                         const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ dgamma,
                         float* __restrict__ dbeta) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ double s_sum[8][64];     // [n % 8][k*2 + which], k < gs <= 32
     __shared__ double s_tot[64];
     const int g = blockIdx.x, gs = C >> 3;
@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(256, AFF ? 2 : kGnBwdMinCtas)
 gn_bwd_apply2_kernel(ActRef x, ActRef dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ coef,
                      ActRef dx, Vol v, int C, int do_lrelu, FastDiv by_W, int lpb, float* __restrict__ aff_partial) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ long long s_rows[16];
     __shared__ float s_red[8][16];
     const int line0 = blockIdx.x * lpb;
@@ -450,8 +450,8 @@ __global__ void gn_bwd_fold_finalize_kernel(const float* __restrict__ gpart, int
 __global__ void __launch_bounds__(256)
 sigmoid_bwd_pack2_kernel(const float* __restrict__ gp, const float* __restrict__ probs, ActRef dlogit,
                          float* __restrict__ bias_partial, Vol v, int Creal, int lpb, FastDiv by_W) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ float s_red[8][4];
     const int line0 = blockIdx.x * lpb;
     const int nlines = v.N * v.D * v.H;

@@ -24,8 +24,8 @@ __device__ __forceinline__ float2 lrelu2(float2 v) {
 
 __global__ void __launch_bounds__(128)
 upsample2x_fwd3_kernel(ActRef in, ActRef out, Vol vc, int C, int do_lrelu, FastDiv by_Wc) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     int n, d, h;
     line_coords(vc, blockIdx.x, n, d, h);
@@ -107,8 +107,8 @@ __device__ __forceinline__ void up_masked(const __nv_bfloat16* gp, const __nv_bf
 
 __global__ void __launch_bounds__(128)
 upsample2x_bwd_w3_kernel(ActRef dy, ActRef y, ActRef T, Vol vc, int C, int do_lrelu, FastDiv by_Wc) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     Vol vf{vc.N, vc.D * 2, vc.H * 2, vc.W * 2};
     Vol vt{vc.N, vc.D * 2, vc.H * 2, vc.W};
     int n, d, h;
@@ -165,8 +165,8 @@ upsample2x_bwd_w3_kernel(ActRef dy, ActRef y, ActRef T, Vol vc, int C, int do_lr
 // wd * wh * T[n, fd, fh, w].  One CTA per coarse line; the 16 row offsets are computed once per CTA.
 __global__ void __launch_bounds__(128)
 upsample2x_bwd_dh3_kernel(ActRef T, ActRef dcoarse, Vol vc, int C, FastDiv by_Wc) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     Vol vt{vc.N, vc.D * 2, vc.H * 2, vc.W};
     __shared__ long long s_off[16];
     int n, d, h;
@@ -220,8 +220,8 @@ upsample2x_bwd_dh3_kernel(ActRef T, ActRef dcoarse, Vol vc, int C, FastDiv by_Wc
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_input4_kernel(const T* __restrict__ x, ActRef out, Vol v, int Creal, int lpb, FastDiv by_Q) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ long long s_src[16], s_row[16];
     const int line0 = blockIdx.x * lpb;
     const int nl = min(lpb, v.N * v.D * v.H - line0);
@@ -257,8 +257,8 @@ pack_input4_kernel(const T* __restrict__ x, ActRef out, Vol v, int Creal, int lp
 __global__ void __launch_bounds__(256)
 sigmoid_bwd_pack4_kernel(const float* __restrict__ gp, const float* __restrict__ probs, ActRef dlogit,
                          float* __restrict__ bias_partial, Vol v, int Creal, int lpb, FastDiv by_Q) {
-    pdl_trigger();      // the next kernel may become resident while this grid drains (common.cuh) ...
-    pdl_wait();         // ... and this one while its own predecessor does: nothing above touches global memory
+    pdl_wait();         // (launched as a programmatic dependent: nothing above touches global memory, common.cuh)
+    pdl_trigger();      // the next kernel may become resident while this grid drains - never more than one kernel ahead
     __shared__ long long s_src[16], s_row[16];
     __shared__ float s_red[8][4];
     const int line0 = blockIdx.x * lpb;
