@@ -193,9 +193,9 @@ class Engine:
 
     def _refresh_packed(self):
         """One launch re-packs every registered weight image if any parameter changed (always while a CUDA
-        graph is being captured: the weights differ between replays)."""
+        graph is being captured: the weights differ between replays).  Returns True when the packing kernel ran."""
         if not self.packed:
-            return
+            return False
         capturing = torch.cuda.is_current_stream_capturing()
         stale = capturing or self._packed_dirty
         if not stale:
@@ -211,6 +211,7 @@ class Engine:
                 ent[0] = (w._version, w.data_ptr())
             if not capturing:
                 self._packed_dirty = False
+        return stale
 
     # ---------------------------------------------------------------------------------
     # building blocks
@@ -269,12 +270,17 @@ class Engine:
     def forward(self, x, want_logits=False, training=False):
         P = self.plan_for(x)
         P.generation += 1
-        self._refresh_packed()
-        prm = self._params()
-        ch = self.ch
         x = x.contiguous()
         if x.dtype not in (torch.float32, torch.bfloat16):     # bf16 images are converted by the packing kernel itself
             x = x.float()
+        # The weight re-pack (41 us for this model, first kernel of every training step) and the input layout conversion
+        # (27 us) are independent: when the pack runs, the conversion goes to the side stream beside it, ordered behind
+        # everything the main stream held BEFORE the pack was enqueued (the last readers of x16, the producer of x).
+        fwd_start = torch.cuda.Event()
+        fwd_start.record(torch.cuda.current_stream())
+        repacked = self._refresh_packed() and self.overlap_wgrad
+        prm = self._params()
+        ch = self.ch
         # cat([skip, up]) of model.py:424 is ONE 2C-channel buffer per level: the encoder writes the skip
         # tensor into its first half and the up-sampling its second half (chunk-planar layout: a half is a
         # tensor of its own), so the cat conv, its data gradient and its weight gradient are single GEMMs.
@@ -284,7 +290,18 @@ class Engine:
                 nc = ch[i] // 8
                 P.alias(self._skip_name(i), i, cat.chunks(0, nc))
                 P.alias("dec%d.up" % i, i, cat.chunks(nc, 2 * nc))
-        x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
+        if repacked:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=P.device)
+            main, side = torch.cuda.current_stream(), self._side_stream
+            side.wait_event(fwd_start)
+            with torch.cuda.stream(side):
+                x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)        # (x stays alive: the main stream, which owns it, is ordered behind its last use)
+        else:
+            x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
         c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c", lrelu=False,
                                  **(dict(gamma=prm["norm_input.weight"], beta=prm["norm_input.bias"]) if training else {}))
         h = ops.gn_apply(c, m, r, prm["norm_input.weight"], prm["norm_input.bias"], P.act("in.a", 0, ch[0]),
