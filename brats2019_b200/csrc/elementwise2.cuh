@@ -18,7 +18,9 @@ constexpr int kRedLines = 128;      // lines one gn_bwd_reduce2 CTA may own
 // (12 K registers, ~217 KB of shared memory per SM): at 128 registers per thread only ONE of their CTAs fits next to it
 // (8 warps per SM for a memory-bound kernel), at 64 three do.  kGnBwdMinCtas / kGnBwdUnroll trade per-thread loads in
 // flight for resident warps.  Measured on the training step (min CTAs, unroll): (2,4) 5.66 ms, (3,2) 5.68, (3,4) 5.87,
-// (4,2) 5.95, (4,1) 6.02 - loads in flight per thread beat resident warps; (2,4) stays.
+// (4,2) 5.95, (4,1) 6.02 - loads in flight per thread beat resident warps; (2,4) stays.  Round 2b tried the other
+// settings for the SMALL tensors only (levels 1-3, < 48 MB, where one (2,4) CTA fits beside a weight-gradient CTA):
+// (4,2) 5.47 ms and (3,2) 5.38 ms against 5.35 ms - the same answer.
 #ifndef B200_GNBWD_MINCTAS
 #define B200_GNBWD_MINCTAS 2
 #endif
