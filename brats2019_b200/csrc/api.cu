@@ -109,6 +109,13 @@ static int pdl_level() {
 }
 static bool pdl_enabled() { return pdl_level() >= 2; }      // memory-bound kernels
 static bool pdl_conv() { return pdl_level() >= 1; }
+// the reduce kernel behind a weight-gradient GEMM (side stream) as a dependent: measured neutral (5.405 / 5.437 vs
+// 5.410 ms), off by default; B200_PDL_WGRAD=1 turns it on
+static bool pdl_wgrad() {
+    int on = 0;
+    if (const char* e = getenv("B200_PDL_WGRAD")) on = atoi(e);
+    return pdl_level() >= 1 && on;
+}
 // the few-CTA finalize kernels between a conv / reduction and its apply pass are dependents too (their handful of parked
 // CTAs cost nothing): -0.02 ms per step; B200_PDL_SMALL=0 turns that off
 static bool pdl_small() {
@@ -1128,7 +1135,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
             rq.CY = 8 * LP.nchy; rq.CX = 8 * LP.nchx;
             constexpr int qpb = 256 / kWglReduceGroups;
             const int quads = 27 * rq.CY * rq.CX / 4;
-            CUDA_OK(launch_prio(wgrad_line_reduce_kernel, dim3((quads + qpb - 1) / qpb), dim3(256), 0, st, prio_wgrad(),
+            CUDA_OK(launch_ex(wgrad_line_reduce_kernel, dim3((quads + qpb - 1) / qpb), dim3(256), 0, st, prio_wgrad(), pdl_wgrad(),
                                 (const float*)workspace, grad, rq));
             LAUNCH_OK("wgrad_line_reduce_kernel");
             return 0;
@@ -1164,7 +1171,7 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
     int SG = 1;
     while (SG < 32 && SG * 2 <= q.splits && (long long)quads * SG < 2LL * 256 * num_sms()) SG *= 2;
     const int qpc = 256 / SG;
-    CUDA_OK(launch_prio(wgrad_reduce_kernel, dim3((quads + qpc - 1) / qpc), dim3(256), 0, st, prio_wgrad(),
+    CUDA_OK(launch_ex(wgrad_reduce_kernel, dim3((quads + qpc - 1) / qpc), dim3(256), 0, st, prio_wgrad(), pdl_wgrad(),
                         (const float*)P.k.partial, grad, q, SG));
     LAUNCH_OK("wgrad_reduce_kernel");
     return 0;

@@ -660,6 +660,7 @@ __device__ __forceinline__ void wgrad_scatter(float* __restrict__ grad, const Wg
 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WgradReduceParams q, int SG) {
+    pdl_wait();         // (launched as a programmatic dependent of the weight-gradient GEMM, common.cuh)
     __shared__ double s_acc[256][4];
     const int per_job = q.nacc * q.M * q.Nmma;            // multiple of 4
     const int quads = q.n_jobs * (per_job >> 2);

@@ -195,6 +195,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradKParams p) {
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit(done);
+        pdl_trigger();      // every MMA is issued: the reduce kernel may become resident while the epilogues drain
         __syncwarp();
         if (prof && lane == 0 && blockIdx.x < 160) {
             g_march_prof[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - tb);

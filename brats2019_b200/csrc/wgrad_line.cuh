@@ -333,6 +333,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
             }
         }
         if (elect_one()) umma_commit(done);
+        pdl_trigger();      // every MMA is issued: the reduce kernel may become resident while the epilogues drain
         __syncwarp();
 #ifdef B200_PROBES
         if (WGL_DEBUG(256) && lane == 0 && cta < 160) {
@@ -414,6 +415,7 @@ struct WglReduceParams {
 constexpr int kWglReduceGroups = 32;
 __global__ void __launch_bounds__(256)
 wgrad_line_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, WglReduceParams q) {
+    pdl_wait();         // (launched as a programmatic dependent of wgrad_line_kernel, common.cuh)
     __shared__ double s_acc[256][4];
     constexpr int QPB = 256 / kWglReduceGroups;           // output quads per CTA
     const int g = threadIdx.x / QPB, ql = threadIdx.x % QPB;
