@@ -109,6 +109,18 @@ static int pdl_level() {
 }
 static bool pdl_enabled() { return pdl_level() >= 2; }      // memory-bound kernels
 static bool pdl_conv() { return pdl_level() >= 1; }
+// A conv launched as a programmatic dependent copies its weights BEFORE griddepcontrol.wait (they "were packed long
+// before").  That is false for the first conv enqueued on a stream right after a weight-packing kernel: it is launched
+// with full serialization instead.  (Host-side launch order per stream is what counts, also under stream capture.)
+static thread_local void* g_pack_stream = reinterpret_cast<void*>(-1);
+static void note_pack_launch(void* stream) { g_pack_stream = stream; }
+static bool pdl_conv_on(cudaStream_t st) {
+    if (g_pack_stream == (void*)st) {
+        g_pack_stream = reinterpret_cast<void*>(-1);
+        return false;
+    }
+    return pdl_conv();
+}
 // the reduce kernel behind a weight-gradient GEMM (side stream) as a dependent: measured neutral (5.405 / 5.437 vs
 // 5.410 ms), off by default; B200_PDL_WGRAD=1 turns it on
 static bool pdl_wgrad() {
@@ -555,12 +567,15 @@ extern "C" int b200_conv_pack_weight(const b200_conv_desc* d, int kind, const fl
     if (J.layout == 2) {
         pack_weight_band_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.mq);
         LAUNCH_OK("pack_weight_band_kernel");
+        note_pack_launch(stream);
     } else if (J.layout == 1) {
         pack_weight_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.mq);
         LAUNCH_OK("pack_weight_march_kernel");
+        note_pack_launch(stream);
     } else {
         pack_weight_kernel<<<std::min(blocks, 1024), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, J.q);
         LAUNCH_OK("pack_weight_kernel");
+        note_pack_launch(stream);
     }
     return 0;
 }
@@ -592,13 +607,14 @@ extern "C" int b200_pack_table_run(const void* table_device, int n_jobs, int tot
     if (!table_device || n_jobs < 1 || total_blocks < 1) return fail("pack_table_run: bad arguments");
     pack_weights_batched_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const PackJobDev*)table_device, n_jobs);
     LAUNCH_OK("pack_weights_batched_kernel");
+    note_pack_launch(stream);
     return 0;
 }
 
 template <int MODE, int EPI, int NM, int FOLD>
 static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_gemm_kernel<MODE, EPI, NM, FOLD>);
-    CUDA_OK(launch_ex(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), pdl_conv(), p));
+    CUDA_OK(launch_ex(conv_gemm_kernel<MODE, EPI, NM, FOLD>, dim3(grid), dim3(kConvThreads), smem, st, prio_conv(), pdl_conv_on(st), p));
     LAUNCH_OK("conv_gemm_kernel");
     return 0;
 }
@@ -606,7 +622,7 @@ static int launch_conv(const ConvKParams& p, unsigned smem, int grid, cudaStream
 template <int CO, int EPI>
 static int launch_march(const MarchParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_march_kernel<CO, EPI>);
-    CUDA_OK(launch_ex(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), pdl_conv(), p));
+    CUDA_OK(launch_ex(conv_march_kernel<CO, EPI>, dim3(grid), dim3(kMarchThreads), smem, st, prio_conv(), pdl_conv_on(st), p));
     LAUNCH_OK("conv_march_kernel");
     return 0;
 }
@@ -653,7 +669,7 @@ static int run_march(const b200_conv_desc* d, MarchParams& p, const void* src_a,
 template <int EPI>
 static int launch_band(const BandParams& p, unsigned smem, int grid, cudaStream_t st) {
     SET_MAX_SMEM_ONCE(conv_band_kernel<EPI>);
-    CUDA_OK(launch_ex(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), pdl_conv(), p));
+    CUDA_OK(launch_ex(conv_band_kernel<EPI>, dim3(grid), dim3(kBandThreads), smem, st, prio_conv(), pdl_conv_on(st), p));
     LAUNCH_OK("conv_band_kernel");
     return 0;
 }

@@ -521,6 +521,7 @@ class Engine:
         buffer, all-reduced bucket by bucket while the rest of backward still runs).
         `state`: the `saved_state()` of the forward this backward belongs to (default: the latest)."""
         state = state if state is not None else self.last
+        self._deferred = []          # (a backward that raised half-way must not leave jobs for this one)
         if state is None:
             raise RuntimeError("brats2019_b200: backward without a training forward")
         P, gen, probs = state
