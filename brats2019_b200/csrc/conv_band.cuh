@@ -27,7 +27,8 @@
 
 namespace b200 {
 
-constexpr int kBandEpiGroups = 3;
+constexpr int kBandEpiGroups = 3;            // measured round 2b: 4 groups (GroupNorm-backward fold compiled out, 84 registers) and
+                                             // 5 groups change nothing (5.385-5.424 vs 5.408 ms per step; 0.062 ms alone either way)
 constexpr int kBandThreads = 128 + 128 * kBandEpiGroups;
 constexpr int kBandBH = 8;                        // output lines per band
 constexpr int kBandLines = kBandBH + 2;           // input lines per step == line slots in TMEM
