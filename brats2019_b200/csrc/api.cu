@@ -1020,6 +1020,7 @@ struct WgradLinePlan {
     unsigned smem;
     int grid;
     int nchy, nchx;     // chunk planes per line of dY / X: 2 (16 channels), 4 (32 channels), 1 (upper chunk known zero)
+    int pair;           // two dY lines per MMA (wgrad_line.cuh, WglShape<.., PAIR = 1>)
 };
 // real_out / real_in: PyTorch channel counts of the gradient being computed (0 = unknown): with <= 8 of them the upper
 // 8-channel chunk of the 16-channel tensor is zero by layout contract (b200_pack_input, b200_sigmoid_backward write zeros
@@ -1047,9 +1048,24 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
         if (half && d->Cout == 16 && real_out > 0 && real_out <= 8 && !(real_in > 0 && real_in <= 8)) nchy = 1;
         else if (half && d->Cin == 16 && real_in > 0 && real_in <= 8) nchx = 1;
     }
-    const unsigned Mmma = 3u * 8u * nchy <= 64u ? 64u : 128u;
-    const unsigned slack = Mmma / 8u - 3u * nchy;
-    P.nchy = (int)nchy; P.nchx = (int)nchx;
+    // Pair mode (round 2c): two dY lines per MMA, window of 12 ring slots (wgrad_line.cuh).  Needs an even number of lines in
+    // every band (H and LH even) and an even Ny >= 4.  OPT-IN: B200_WGL_PAIR is a mask over the channel variants (1: 16 x 16,
+    // 2: conv_input, 4: conv_output).  Correct (CPU replay + op checks) and SLOWER at 2 x 128^3 (154 vs 108 us,
+    // profiles/r02c_ab_wgrad_pair.txt): the 12-slot window + 11 mirrored slots leave room for bands of only 4 lines, and the
+    // ring's prefetch lead is (band height - 4) lines - zero; DESIGN 4.2.
+    bool pair = false;
+    {
+        const char* ep = getenv("B200_WGL_PAIR");
+        const int mask = ep ? atoi(ep) : 0;
+        const int bit = (nchy == 2 && nchx == 2) ? 1 : (nchy == 2 && nchx == 1) ? 2 : (nchy == 1 && nchx == 2) ? 4 : 0;
+        pair = (mask & bit) != 0 && d->H % 2 == 0 && d->H >= 2;
+    }
+    const unsigned lines = pair ? 2u : 1u;
+    const unsigned mirror = pair ? 11u : (unsigned)kWglMirror;
+    const unsigned Mmma = lines * 3u * 8u * nchy <= 64u ? 64u : 128u;
+    const unsigned slack = Mmma / 8u - lines * 3u * nchy;
+    P.nchy = (int)nchy; P.nchx = (int)nchx; P.pair = pair ? 1 : 0;
+    k.pair = P.pair; k.mirror = (int)mirror;
     k.N = d->N; k.D = d->D; k.H = d->H; k.W = d->W; k.Wp = d->W + 2;
     k.ksteps = d->W / 16;
     k.Lp = (unsigned)k.Wp * 16u;
@@ -1062,7 +1078,7 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     const unsigned budget = kMaxSmem - 12 * 1024;
     auto need = [&](int LH, int NR, int Ny) {
         const unsigned R = 3u * (LH + 2) + 1u;
-        return (unsigned long long)(R + kWglMirror) * nchx * k.Lp + 128u + (unsigned long long)NR * nchy * k.Lp +
+        return (unsigned long long)(R + mirror) * nchx * k.Lp + 128u + (unsigned long long)NR * nchy * k.Lp +
                ((unsigned long long)Ny * 3u * nchy + slack) * k.Lp + bar_bytes;
     };
     k.LH = 0;
@@ -1073,16 +1089,17 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
         if (el && er && en) {
             const int LH = atoi(el), NR = atoi(er), Ny = atoi(en);
             if (LH >= 1 && LH <= d->H && LH + 2 <= kWglND && NR >= 0 && NR <= kWglMaxNy && Ny >= 2 && Ny <= kWglMaxNy &&
-                need(LH, NR, Ny) <= kMaxSmem) { k.LH = LH; k.NR = NR; k.Ny = Ny; }
+                (!pair || (LH % 2 == 0 && Ny % 2 == 0 && Ny >= 4)) && need(LH, NR, Ny) <= kMaxSmem) { k.LH = LH; k.NR = NR; k.Ny = Ny; }
         }
     }
     // band height: prefer one that divides H (equal work per band), then the tallest; as many expanded dY lines in flight
     // as fit (>= 4: a slot's round trip is the MMAs of its line + ~2000 cycles of L2 latency, a line is ~600 cycles)
+    const int lstep = pair ? 2 : 1;
     for (int pass = 0; pass < 2 && k.LH == 0; ++pass)
-        for (int LH = 8; LH >= 2 && k.LH == 0; --LH) {
+        for (int LH = 8; LH >= 2 && k.LH == 0; LH -= lstep) {
             if (LH > d->H || LH + 2 > kWglND) continue;     // a producer polls a step_done barrier at most LH steps late
             if (pass == 0 && d->H % LH) continue;
-            for (int Ny = kWglMaxNy; Ny >= 4; --Ny)
+            for (int Ny = kWglMaxNy; Ny >= 4; Ny -= lstep)
                 if (need(LH, 0, Ny) <= budget) { k.LH = LH; k.NR = 0; k.Ny = Ny; break; }
         }
     if (k.LH == 0) return false;
@@ -1090,7 +1107,7 @@ static bool plan_wgrad_line(const b200_wgrad_desc* d, WgradLinePlan& P, bool ign
     k.n_bands = ceil_div(d->H, k.LH);
     k.units = (long long)d->N * k.n_bands * d->D;
     k.smem_x_off = 0;
-    k.smem_raw_off = align_up((unsigned)(k.R + kWglMirror) * nchx * k.Lp, 128);
+    k.smem_raw_off = align_up((unsigned)(k.R + mirror) * nchx * k.Lp, 128);
     k.smem_y_off = k.smem_raw_off + (unsigned)k.NR * nchy * k.Lp;
     k.smem_bar_off = align_up(k.smem_y_off + ((unsigned)k.Ny * 3u * nchy + slack) * k.Lp, 16);
     P.smem = k.smem_bar_off + bar_bytes;
@@ -1105,7 +1122,7 @@ extern "C" size_t b200_wgrad_workspace_bytes(const b200_wgrad_desc* d) {
     size_t bytes = (size_t)P.k.n_jobs * P.k.splits * P.k.nacc * P.k.M * P.k.Nmma * sizeof(float);
     WgradLinePlan LP;
     if (plan_wgrad_line(d, LP, true))
-        bytes = std::max(bytes, (size_t)LP.grid * (3 * 8 * LP.nchy) * (9 * 8 * LP.nchx) * sizeof(float));
+        bytes = std::max(bytes, (size_t)LP.grid * 2 * (3 * 8 * LP.nchy) * (9 * 8 * LP.nchx) * sizeof(float));   // (x 2: pair mode)
     WgradMarchPlan MP;
     if (plan_wgrad_march(d, MP))
         bytes = std::max(bytes, (size_t)MP.grid * kWgmAccs * kWgmM * kWgmN * sizeof(float));
@@ -1138,16 +1155,18 @@ extern "C" int b200_wgrad_run(const b200_wgrad_desc* d, const void* dy, const vo
 #ifdef B200_PROBES
             { const char* e2 = getenv("B200_WGL_DEBUG"); LP.k.debug = e2 ? atoi(e2) : 0; }
 #endif
-#define WGL_CASE(Y, X)                                                                                                   \
-    if (LP.nchy == Y && LP.nchx == X) {                                                                                  \
-        SET_MAX_SMEM_ONCE(wgrad_line_kernel<Y, X>);                                                                      \
-        CUDA_OK(launch_prio(wgrad_line_kernel<Y, X>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k)); \
+#define WGL_CASE(Y, X, PR)                                                                                                   \
+    if (LP.nchy == Y && LP.nchx == X && LP.pair == PR) {                                                                     \
+        SET_MAX_SMEM_ONCE(wgrad_line_kernel<Y, X, PR>);                                                                      \
+        CUDA_OK(launch_prio(wgrad_line_kernel<Y, X, PR>, dim3(LP.grid), dim3(kWglThreads), LP.smem, st, prio_wgrad(), LP.k)); \
     }
-            WGL_CASE(2, 2) else WGL_CASE(2, 1) else WGL_CASE(1, 2) else WGL_CASE(4, 4) else return fail("wgrad_line: no kernel");
+            WGL_CASE(2, 2, 1) else WGL_CASE(2, 1, 1) else WGL_CASE(1, 2, 1) else
+            WGL_CASE(2, 2, 0) else WGL_CASE(2, 1, 0) else WGL_CASE(1, 2, 0) else WGL_CASE(4, 4, 0) else return fail("wgrad_line: no kernel");
 #undef WGL_CASE
             LAUNCH_OK("wgrad_line_kernel");
             WglReduceParams rq;
-            rq.ctas = LP.grid; rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
+            rq.ctas = LP.grid * (LP.pair ? 2 : 1);      // pair mode: two partial blocks per CTA
+            rq.Cout_w = Cout_w; rq.Cin_w = Cin_w; rq.accumulate = accumulate;
             rq.CY = 8 * LP.nchy; rq.CX = 8 * LP.nchx;
             constexpr int qpb = 256 / kWglReduceGroups;
             const int quads = 27 * rq.CY * rq.CX / 4;
@@ -1868,8 +1887,8 @@ static int wgrad_line_plan_debug(const b200_wgrad_desc* d, int real_out, int rea
     if (!plan_wgrad_line(d, P, true, real_out, real_in)) return fail("wgrad_line: does not apply (needs mode 0, 16 x 16 or 32 x 32 channels, W %% 16 == 0)");
     const WgradLineParams& k = P.k;
     const int vals[] = {k.LH, k.n_bands, (int)k.units, k.ksteps, k.R, k.Ny, k.Wp, (int)k.Lp, (int)k.smem_x_off,
-                        (int)k.smem_y_off, (int)k.smem_bar_off, (int)P.smem, P.grid, kWglMirror, kWglNB, kWglND, k.NR,
-                        (int)k.smem_raw_off, P.nchy, P.nchx};
+                        (int)k.smem_y_off, (int)k.smem_bar_off, (int)P.smem, P.grid, k.mirror, kWglNB, kWglND, k.NR,
+                        (int)k.smem_raw_off, P.nchy, P.nchx, P.pair};
     const int nv = (int)(sizeof(vals) / sizeof(int));
     if (n_out < nv) return fail("wgrad_line_plan_debug: need %d ints", nv);
     for (int i = 0; i < nv; ++i) out[i] = vals[i];

@@ -46,20 +46,33 @@ constexpr int kWglThreads = 256;
 //   <4, 4> (32 <-> 32, level 1; opt-in): M = 128 (96 used), N = 288 exceeds one MMA, so the window is walked as THREE MMAs
 //            of N = 96 = (kd 3) x 32 ci, one per kh (three consecutive ring slots each), into three column blocks of a
 //            128 x 288 accumulator.  Same tensor time as the linear-row kernel (3 x 56 cycles per 16 voxels).
-template <int NCHY, int NCHX> struct WglShape {
+//   PAIR = 1 (round 2c; <2,2>, <2,1>, <1,2>): TWO dY lines (l, l+1) of a band per MMA.  M = (line 2) x (kw 3) x CY (96 of
+//            128 rows at CY = 16), N = the window of the FOUR input lines l .. l+3 x (kd 3) x CX = 12 consecutive ring slots
+//            (192 columns at CX = 16).  Row block j = 0 (line l) uses the column blocks of window lines 0..2, row block j = 1
+//            (line l+1) those of window lines 1..3; the other quarter of the products lands in accumulator columns nobody
+//            reads.  One N = 192 MMA costs 96 cycles for two lines (one N = 144 MMA per line: 72 each), and the
+//            shared-memory port - the bound of the one-line form - carries A 4 KB + B 6 KB per two lines instead of
+//            2 x (2 KB + 4.6 KB).  The epilogue writes the two row blocks as two partials [2][3 CY][9 CX] (columns
+//            shifted back by 3 CX for j = 1), so the reduce kernel just sees twice as many CTAs.
+template <int NCHY, int NCHX, int PAIR = 0> struct WglShape {
     static constexpr int CY = 8 * NCHY, CX = 8 * NCHX;
-    static constexpr int M = 3 * CY <= 64 ? 64 : 128;     // MMA rows: (kw 3) x CY, padded
-    static constexpr int Rows = 3 * CY;                   // rows of the partial that carry data
-    static constexpr int Ntot = 9 * CX;                   // (kh 3) x (kd 3) x CX accumulator columns
-    static constexpr int Nmma = Ntot <= 256 ? Ntot : 3 * CX;   // columns of one MMA
-    static constexpr int NM = Ntot / Nmma;                // MMAs per K step (1, or 3: one per kh)
-    static constexpr int Slack = M / 8 - 3 * NCHY;        // planes past the last expanded dY line that an A operand touches
-    static constexpr int TmemCols = Ntot <= 128 ? 128 : (Ntot <= 256 ? 256 : 512);
+    static constexpr int Lines = PAIR ? 2 : 1;            // dY lines per MMA
+    static constexpr int Win = PAIR ? 12 : 9;             // ring slots one B operand covers
+    static constexpr int M = Lines * 3 * CY <= 64 ? 64 : 128;     // MMA rows: (line) x (kw 3) x CY, padded
+    static constexpr int Rows = 3 * CY;                   // rows of one partial block
+    static constexpr int Ntot = 9 * CX;                   // (kh 3) x (kd 3) x CX columns of one partial block
+    static constexpr int Nacc = Win * CX;                 // accumulator columns
+    static constexpr int Nmma = Nacc <= 256 ? Nacc : 3 * CX;   // columns of one MMA
+    static constexpr int NM = Nacc / Nmma;                // MMAs per K step (1, or 3: one per kh)
+    static constexpr int Slack = M / 8 - Lines * 3 * NCHY;     // planes past the last expanded dY line that an A operand touches
+    static constexpr int Mirror = Win - 1;                // ring slots mirrored behind the ring: a window never wraps
+    static constexpr int TmemCols = Nacc <= 128 ? 128 : (Nacc <= 256 ? 256 : 512);
+    static_assert(!PAIR || (NCHY <= 2 && NCHX <= 2), "pair mode: 16-channel operands only");
 };
 constexpr int kWglM = 64;             // <2, 2> values, kept for the host code and the tests
 constexpr int kWglN = 144;
 constexpr int kWglRows = 48;
-constexpr int kWglMirror = 8;         // ring slots mirrored behind the ring (window of 9 slots)
+constexpr int kWglMirror = 8;         // ring slots mirrored behind the ring (window of 9 slots; pair mode: 11 for its window of 12)
 constexpr int kWglNB = 64;            // X-load barriers (ring)
 constexpr int kWglND = 16;            // step-done barriers (ring, power of two), >= LH + 2
 constexpr int kWglMaxNy = 8;           // bound of both dY rings (raw lines, expanded lines)
@@ -76,6 +89,8 @@ struct WgradLineParams {
     unsigned smem_x_off, smem_raw_off, smem_y_off, smem_bar_off;
     ActRef dy, x;
     float* partial;                   // [cta][48][144]
+    int pair;                         // 1: two dY lines per MMA (WglShape<.., PAIR = 1>); every band then has an even line count
+    int mirror;                       // ring slots mirrored behind the ring: 8, pair mode 11
     int debug;                        // B200_PROBES builds only: 1 no X copies, 2 no MMAs, 4 no shift copies, 8 no dY copies,
                                       // 256 cycle accounting of the MMA warp into g_wgl_prof
 };
@@ -105,10 +120,10 @@ __device__ __forceinline__ int wgl_segment(const WgradLineParams& p, long long u
     return (int)len;
 }
 
-template <int NCHY, int NCHX>
+template <int NCHY, int NCHX, int PAIR = 0>
 __global__ void __launch_bounds__(kWglThreads, 1)
 wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
-    using S = WglShape<NCHY, NCHX>;
+    using S = WglShape<NCHY, NCHX, PAIR>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -177,7 +192,7 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                         }
                     }
                     if (elect_one()) {
-                        const bool mirror = q < kWglMirror;
+                        const bool mirror = q < S::Mirror;
                         uint64_t* bar = &x_full[kx & (kWglNB - 1)];
                         if (WGL_DEBUG(1)) {
                             mbar_arrive(bar);
@@ -266,68 +281,120 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 // published the count of ready steps: one shared-memory poll here instead of two to four mbarrier waits
                 // (~100 cycles each even when complete).  The tcgen05 queue is shallow, so whatever this warp spends
                 // between two MMAs the tensor pipe idles: no fences, divisions or 64-bit arithmetic in this loop.
-                for (int l = 0; l < nl; l += 2) {
-                    const int n2 = min(2, nl - l);
-                    WGL_CLOCK(c0);
-                    while (*ready < t + n2) __nanosleep(20);      // not a hot spin: other kernels' warps share this SM
-                    WGL_CLOCK(c1);
-                    tc_fence_after();
-                    if (WGL_DEBUG(2)) {
-                        if (elect_one())
-                            for (int j = 0; j < n2; ++j) umma_commit(&step_done[(dslot + j) & (kWglND - 1)]);
-                    } else
-                    if (elect_one()) {
+                if constexpr (PAIR != 0) {
+                    // pair mode: one MMA per K step covers the lines l, l+1 (A: two adjacent expanded dY lines, B: the 12-slot
+                    // window of the input lines l .. l+3); two pairs per issue block.  nl is even (planner), the dY slot of a
+                    // pair's first line is even and Ny is even, so the two lines are always adjacent in the ring.  Both
+                    // lines' step_done barriers are committed behind the pair's last MMA: the producers' reuse rules (in
+                    // units of lines) hold unchanged - a ring slot's last reader is the pair that contains the line the
+                    // one-line rule names.
+                    for (int l = 0; l < nl; l += 4) {
+                        const int n4 = min(4, nl - l);
+                        WGL_CLOCK(c0);
+                        while (*ready < t + n4) __nanosleep(20);
+                        WGL_CLOCK(c1);
+                        tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            if (j < n2) {
-                                int q0 = qs + 3 * (l + j);
-                                if (q0 >= p.R) q0 -= p.R;
-                                int sl = slot + j;
-                                if (sl >= p.Ny) sl -= p.Ny;
-                                const uint32_t a16 = ybase16 + (uint32_t)sl * yline16 + 1u;     // row wp = 1 of the kw = 0 copy
-                                const uint32_t b16 = xbase16 + (uint32_t)q0 * slot16 + 1u;      // row wp = 1 of the window's first slot
-                                const uint32_t acc = (t + j) != 0;
-                                if (S::NM == 1) {
-                                    if (p.ksteps == 8) {                              // W = 128: the level-0 lines of the benchmark
+                            for (int j = 0; j < 2; ++j) {
+                                if (2 * j < n4) {
+                                    int q0 = qs + 3 * (l + 2 * j);
+                                    if (q0 >= p.R) q0 -= p.R;
+                                    int sl = slot + 2 * j;
+                                    if (sl >= p.Ny) sl -= p.Ny;
+                                    const uint32_t a16 = ybase16 + (uint32_t)sl * yline16 + 1u;
+                                    const uint32_t b16 = xbase16 + (uint32_t)q0 * slot16 + 1u;
+                                    const uint32_t acc = (t + 2 * j) != 0;
+                                    if (!WGL_DEBUG(2)) {
+                                        if (p.ksteps == 8) {
 #pragma unroll
-                                        for (int ks = 0; ks < 8; ++ks)
-                                            umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
-                                                      hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
-                                    } else {
-                                        for (int ks = 0; ks < p.ksteps; ++ks)             // 16 rows of 16 B per K step
-                                            umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
-                                                      hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                            for (int ks = 0; ks < 8; ++ks)
+                                                umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                          hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        } else {
+                                            for (int ks = 0; ks < p.ksteps; ++ks)
+                                                umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                          hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        }
                                     }
-                                } else {
-                                    // one MMA per kh: the three slots (kd 0..2) of window row kh, column block kh
-                                    const uint32_t kh16 = 3u * slot16;
-                                    if (p.ksteps == 4) {                              // W = 64: the level-1 lines of the benchmark
-#pragma unroll
-                                        for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-                                            for (int kh = 0; kh < S::NM; ++kh)
-                                                umma_bf16(tmem_base + (uint32_t)(kh * S::Nmma), hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
-                                                          hi | (uint64_t)((b16 + kh * kh16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
-                                    } else {
-                                        for (int ks = 0; ks < p.ksteps; ++ks)
-#pragma unroll
-                                            for (int kh = 0; kh < S::NM; ++kh)
-                                                umma_bf16(tmem_base + (uint32_t)(kh * S::Nmma), hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
-                                                          hi | (uint64_t)((b16 + kh * kh16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
-                                    }
+                                    umma_commit(&step_done[(dslot + 2 * j) & (kWglND - 1)]);
+                                    umma_commit(&step_done[(dslot + 2 * j + 1) & (kWglND - 1)]);
                                 }
-                                umma_commit(&step_done[(dslot + j) & (kWglND - 1)]);
                             }
                         }
-                    }
-                    __syncwarp();
-                    t += n2;
-                    slot += n2; if (slot >= p.Ny) slot -= p.Ny;
-                    dslot = (dslot + n2) & (kWglND - 1);
+                        __syncwarp();
+                        t += n4;
+                        slot += n4; if (slot >= p.Ny) slot -= p.Ny;
+                        dslot = (dslot + n4) & (kWglND - 1);
 #ifdef B200_PROBES
-                    WGL_CLOCK(c3);
-                    w_x += c1 - c0; t_issue += c3 - c1;
+                        WGL_CLOCK(c3);
+                        w_x += c1 - c0; t_issue += c3 - c1;
 #endif
+                    }
+                } else {
+                    for (int l = 0; l < nl; l += 2) {
+                        const int n2 = min(2, nl - l);
+                        WGL_CLOCK(c0);
+                        while (*ready < t + n2) __nanosleep(20);      // not a hot spin: other kernels' warps share this SM
+                        WGL_CLOCK(c1);
+                        tc_fence_after();
+                        if (WGL_DEBUG(2)) {
+                            if (elect_one())
+                                for (int j = 0; j < n2; ++j) umma_commit(&step_done[(dslot + j) & (kWglND - 1)]);
+                        } else
+                        if (elect_one()) {
+    #pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                if (j < n2) {
+                                    int q0 = qs + 3 * (l + j);
+                                    if (q0 >= p.R) q0 -= p.R;
+                                    int sl = slot + j;
+                                    if (sl >= p.Ny) sl -= p.Ny;
+                                    const uint32_t a16 = ybase16 + (uint32_t)sl * yline16 + 1u;     // row wp = 1 of the kw = 0 copy
+                                    const uint32_t b16 = xbase16 + (uint32_t)q0 * slot16 + 1u;      // row wp = 1 of the window's first slot
+                                    const uint32_t acc = (t + j) != 0;
+                                    if (S::NM == 1) {
+                                        if (p.ksteps == 8) {                              // W = 128: the level-0 lines of the benchmark
+    #pragma unroll
+                                            for (int ks = 0; ks < 8; ++ks)
+                                                umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                          hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        } else {
+                                            for (int ks = 0; ks < p.ksteps; ++ks)             // 16 rows of 16 B per K step
+                                                umma_bf16(tmem_base, hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                          hi | (uint64_t)((b16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        }
+                                    } else {
+                                        // one MMA per kh: the three slots (kd 0..2) of window row kh, column block kh
+                                        const uint32_t kh16 = 3u * slot16;
+                                        if (p.ksteps == 4) {                              // W = 64: the level-1 lines of the benchmark
+    #pragma unroll
+                                            for (int ks = 0; ks < 4; ++ks)
+    #pragma unroll
+                                                for (int kh = 0; kh < S::NM; ++kh)
+                                                    umma_bf16(tmem_base + (uint32_t)(kh * S::Nmma), hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                              hi | (uint64_t)((b16 + kh * kh16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        } else {
+                                            for (int ks = 0; ks < p.ksteps; ++ks)
+    #pragma unroll
+                                                for (int kh = 0; kh < S::NM; ++kh)
+                                                    umma_bf16(tmem_base + (uint32_t)(kh * S::Nmma), hi | (uint64_t)((a16 + 16 * ks) & 0x3FFF),
+                                                              hi | (uint64_t)((b16 + kh * kh16 + 16 * ks) & 0x3FFF), idesc, ks == 0 ? acc : 1u);
+                                        }
+                                    }
+                                    umma_commit(&step_done[(dslot + j) & (kWglND - 1)]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        t += n2;
+                        slot += n2; if (slot >= p.Ny) slot -= p.Ny;
+                        dslot = (dslot + n2) & (kWglND - 1);
+    #ifdef B200_PROBES
+                        WGL_CLOCK(c3);
+                        w_x += c1 - c0; t_issue += c3 - c1;
+    #endif
+                    }
                 }
                 if (++qs == p.R) qs = 0;
             }
@@ -372,17 +439,21 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
     } else if (warp >= 4) {
         // ============ epilogue: TMEM -> fp32 partial [Rows][Ntot] ============
         const int ew = warp - 4;
-        float* dst = p.partial + (size_t)cta * S::Rows * S::Ntot;
         // M = 64: rows 16*ew .. +15 live in lanes 0-15 of quadrant ew;  M = 128: row = TMEM lane
         const int row = S::M == 64 ? ew * 16 + lane : ew * 32 + lane;
-        const bool row_ok = (S::M == 64 ? lane < 16 : true) && row < S::Rows;
+        const bool row_ok = (S::M == 64 ? lane < 16 : true) && row < S::Lines * S::Rows;
+        // pair mode: row block jb = 1 (the second line of a pair) owns the accumulator columns of window lines 1..3, i.e.
+        // its partial's columns are the accumulator's shifted down by 3 CX; the two blocks are separate partials
+        const int jb = row >= S::Rows ? 1 : 0;
+        const int shift = jb * 3 * S::CX;
+        float* dst = p.partial + (((size_t)cta * S::Lines + jb) * S::Rows + (row - jb * S::Rows)) * S::Ntot;
         const bool any = u_end > u_begin;
         if (any) {
             while (!mbar_try_wait(done, 0)) __nanosleep(256);     // idle for the whole main loop: do not take issue slots
             tc_fence_after();
         }
 #pragma unroll
-        for (int c0 = 0; c0 < S::Ntot; c0 += 16) {
+        for (int c0 = 0; c0 < S::Nacc; c0 += 16) {
             float v[16];
             if (any) {
                 tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
@@ -391,12 +462,14 @@ wgrad_line_kernel(const __grid_constant__ WgradLineParams p) {
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
             if (row_ok) {
-                float4* o = reinterpret_cast<float4*>(dst + (size_t)row * S::Ntot + c0);
-                o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                o[1] = make_float4(v[4], v[5], v[6], v[7]);
-                if (c0 + 8 < S::Ntot) {                   // Ntot = 72: the last group carries 8 columns
-                    o[2] = make_float4(v[8], v[9], v[10], v[11]);
-                    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {                  // eight columns at a time (3 CX is a multiple of 8)
+                    const int oc = c0 + 8 * hf - shift;
+                    if (c0 + 8 * hf < S::Nacc && oc >= 0 && oc < S::Ntot) {
+                        float4* o = reinterpret_cast<float4*>(dst + oc);
+                        o[0] = make_float4(v[8 * hf + 0], v[8 * hf + 1], v[8 * hf + 2], v[8 * hf + 3]);
+                        o[1] = make_float4(v[8 * hf + 4], v[8 * hf + 5], v[8 * hf + 6], v[8 * hf + 7]);
+                    }
                 }
             }
         }

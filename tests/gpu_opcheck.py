@@ -409,6 +409,9 @@ def group_wgrad():
                                    (1, 8, 8, 16, 4, 16), (1, 16, 16, 64, 16, 16), (2, 5, 7, 32, 16, 16),
                                    (1, 3, 6, 128, 16, 16), (2, 12, 9, 48, 16, 16), (3, 1, 1, 16, 16, 16),
                                    (1, 20, 37, 128, 16, 16), (2, 7, 16, 144, 16, 16),
+                                   # pair form of the line kernel: band heights 8 / 6 / 4 / 2, partial last band, 3 and 4 real channels
+                                   (2, 9, 24, 128, 16, 16), (1, 7, 14, 128, 16, 16), (1, 5, 20, 64, 4, 16), (2, 6, 12, 128, 16, 3),
+                                   (1, 4, 2, 32, 16, 16), (2, 10, 22, 128, 4, 16),
                                    # 32 <-> 32 channels with W % 16 == 0: the line kernel's three-MMA form (and the linear one)
                                    (1, 8, 8, 16, 32, 32), (2, 5, 7, 32, 32, 32), (2, 9, 12, 64, 32, 32), (1, 3, 6, 48, 32, 32),
                                    (3, 1, 1, 16, 32, 32), (1, 11, 30, 64, 32, 32)):
@@ -417,22 +420,25 @@ def group_wgrad():
         w = torch.zeros(Cout, Cin, 3, 3, 3, device=dev, requires_grad=True)
         F.conv3d(x, w, padding=1).backward(dy)
         desc = ops.wgrad_desc(0, N, D, H, W, ops.pad16(Cout), ops.pad16(Cin))
-        forms = ("line", "march", "linear") if (ops.pad16(Cin) == 16 and ops.pad16(Cout) == 16 and W % 16 == 0) else \
+        # "line" = the default line kernel (one dY line per MMA), "line2" = its opt-in pair mode (two lines per MMA where H is even)
+        forms = ("line", "line2", "march", "linear") if (ops.pad16(Cin) == 16 and ops.pad16(Cout) == 16 and W % 16 == 0) else \
             ("line", "linear") if (Cin == 32 and Cout == 32 and W % 16 == 0) else ("linear",)
         for form in forms:
             os.environ["B200_WGRAD_MARCH"] = "1" if form == "march" else "0"
-            os.environ["B200_NO_WGRAD_LINE"] = "0" if form == "line" else "1"
+            os.environ["B200_NO_WGRAD_LINE"] = "0" if form in ("line", "line2") else "1"
+            os.environ["B200_WGL_PAIR"] = "7" if form == "line2" else "0"
             os.environ["B200_WGRAD_LINE32"] = "1" if form == "line" else "0"      # (the 32-channel line form is opt-in)
             g = torch.full((Cout, Cin, 3, 3, 3), 5.0, device=dev)
             ops.wgrad_run(desc, ops.act_from_ncdhw(dy), ops.act_from_ncdhw(x), g, ops.G_K3)
             report("wgrad3 %dx%d (%d,%d,%d,%d) %s" % (Cout, Cin, N, D, H, W, form), g, w.grad, tol_rel=1e-2)
-            if form in ("march", "line"):      # accumulate into an existing gradient
+            if form in ("march", "line", "line2"):      # accumulate into an existing gradient
                 g2 = g.clone()
                 ops.wgrad_run(desc, ops.act_from_ncdhw(dy), ops.act_from_ncdhw(x), g2, ops.G_K3, accumulate=True)
                 report("wgrad3 %dx%d (%d,%d,%d,%d) %s accumulate" % (Cout, Cin, N, D, H, W, form), g2, 2 * w.grad, tol_rel=1e-2)
         os.environ.pop("B200_WGRAD_MARCH", None)
         os.environ.pop("B200_NO_WGRAD_LINE", None)
         os.environ.pop("B200_WGRAD_LINE32", None)
+        os.environ.pop("B200_WGL_PAIR", None)
     N, D, H, W = 2, 6, 8, 12
     for Cin, Cout in ((32, 16), (128, 64), (16, 16), (64, 128)):
         x = bf(torch.randn(N, Cin, D, H, W, device=dev)); dy = bf(torch.randn(N, Cout, D, H, W, device=dev))

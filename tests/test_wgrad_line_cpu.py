@@ -23,14 +23,24 @@ import torch.nn.functional as F
 from brats2019_b200 import _lib
 from brats2019_b200._lib import WgradDesc
 
-FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off nchy nchx".split()
+FIELDS = "LH n_bands units ksteps R Ny Wp Lp smem_x_off smem_y_off smem_bar_off smem grid mirror NB ND NR smem_raw_off nchy nchx pair".split()
 
 
-def line_plan(N, D, H, W, Cc=16, real_out=0, real_in=0):
-    """real_out / real_in: PyTorch channel counts of the gradient (<= 8 on one side: that side's upper chunk is skipped)."""
+def line_plan(N, D, H, W, Cc=16, real_out=0, real_in=0, pair=False):
+    """real_out / real_in: PyTorch channel counts of the gradient (<= 8 on one side: that side's upper chunk is skipped).
+    pair: True = B200_WGL_PAIR=7 (opt-in: two dY lines per MMA wherever it applies), False = the default (one line per MMA)."""
+    import os
     d = WgradDesc(0, N, D, H, W, Cc, Cc)
     out = (C.c_int * 32)()
-    assert _lib.lib().b200_wgrad_line_plan_debug2(C.byref(d), real_out, real_in, out, 32) == 0, _lib.lib().b200_last_error()
+    old = os.environ.get("B200_WGL_PAIR")
+    os.environ["B200_WGL_PAIR"] = "7" if pair else "0"
+    try:
+        assert _lib.lib().b200_wgrad_line_plan_debug2(C.byref(d), real_out, real_in, out, 32) == 0, _lib.lib().b200_last_error()
+    finally:
+        if old is None:
+            del os.environ["B200_WGL_PAIR"]
+        else:
+            os.environ["B200_WGL_PAIR"] = old
     return {k: out[i] for i, k in enumerate(FIELDS)}
 
 
@@ -59,10 +69,13 @@ def replay_cta(p, segs, Y, X, W, rng):
     N = 96 MMAs, one per kh, into the column blocks kh * 96)."""
     R, Ny, NR, NB, ND, MIR, LH = p["R"], p["Ny"], p["NR"], p["NB"], p["ND"], p["mirror"], p["LH"]
     Cy, Cx = 8 * p["nchy"], 8 * p["nchx"]                 # channels of dY / X the kernel loads
-    Mm = 64 if 3 * Cy <= 64 else 128
+    PAIR = p["pair"]
+    LN, WIN = (2, 12) if PAIR else (1, 9)        # dY lines per MMA, ring slots per B operand
+    assert MIR == WIN - 1
+    Mm = 64 if LN * 3 * Cy <= 64 else 128
     ring = [None] * (R + MIR)                    # slot -> (seg index, slice s, line lam) currently stored
     yslot = [None] * Ny                          # slot -> step index whose expanded line it holds
-    acc = np.zeros((Mm, 9 * Cx))
+    acc = np.zeros((Mm, WIN * Cx))
     # ---- static schedules of the three actors (exactly the kernel's loops) ----
     xloads, steps = [], []                       # (seg, s, lam, wait_step or None) ; (seg, sd, l, k_need)
     t_base, seg_k0 = 0, 0
@@ -111,6 +124,41 @@ def replay_cta(p, segs, Y, X, W, rng):
                     assert t - 1 - (ky - Ny) < ND, "step_done phase ambiguity for the dY producer"
                 yslot[ky % Ny] = ky
                 ky += 1
+            elif who == 2 and t < nsteps and PAIR:
+                # pair mode: an issue block is up to four lines (two pairs) of one slice; the MMA warp polls `ready >= t + n4`
+                si, sd, l, _ = steps[t]
+                nl = segs[si]["nl"]
+                assert nl % 2 == 0 and l % 4 == 0 and Ny % 2 == 0
+                n4 = min(4, nl - l)
+                k_need = steps[t + n4 - 1][3]
+                if kx <= k_need or ky < t + n4:
+                    continue
+                max_ahead_x = max(max_ahead_x, kx - (k_need + 1))
+                sg = segs[si]
+                n, band, d0 = sg["n"], sg["band"], sg["d0"]
+                for j in range(0, n4, 2):
+                    tt, ll = t + j, l + j
+                    assert steps[tt][:3] == (si, sd, ll) and steps[tt + 1][:3] == (si, sd, ll + 1)
+                    sl = tt % Ny
+                    assert sl % 2 == 0 and yslot[sl] == tt and yslot[sl + 1] == tt + 1      # adjacent in the dY ring
+                    q0 = (3 * ll + sd - 1) % R
+                    assert q0 + 12 <= R + MIR                                               # the window never wraps
+                    for lr in range(4):
+                        for kd in range(3):
+                            assert ring[q0 + 3 * lr + kd] == (si, sd - 1 + kd, ll + lr), (tt, lr, kd, ring[q0 + 3 * lr + kd])
+                    dp = d0 + sd
+                    A = np.zeros((Mm, W))                        # rows line*3Cy + kw*Cy + co
+                    for jl in range(2):
+                        yl = Y[n, dp, band * LH + 1 + ll + jl][:, :Cy]
+                        for kw in range(3):
+                            A[jl * 3 * Cy + kw * Cy:jl * 3 * Cy + (kw + 1) * Cy] = yl[1 - kw + 1:1 - kw + 1 + W].T
+                    B = np.zeros((12 * Cx, W))                   # columns (window line, kd, ci)
+                    for lr in range(4):
+                        for kd in range(3):
+                            xl = X[n, d0 + sd - 1 + kd, band * LH + ll + lr][:, :Cx]
+                            B[(3 * lr + kd) * Cx:(3 * lr + kd + 1) * Cx] = xl[1:1 + W].T
+                    acc += A @ B.T
+                t += n4
             elif who == 2 and t < nsteps:
                 si, sd, l, k_need = steps[t]
                 if kx <= k_need or ky <= t:
@@ -143,6 +191,9 @@ def replay_cta(p, segs, Y, X, W, rng):
                         acc[:, kh * 3 * Cx:(kh + 1) * 3 * Cx] += A @ B[kh * 3 * Cx:(kh + 1) * 3 * Cx].T
                 t += 1
     assert max_ahead_x < NB
+    if PAIR:
+        # the epilogue's two partial blocks: line 0 of a pair owns the columns of window lines 0..2, line 1 those of 1..3
+        return acc[:3 * Cy, :9 * Cx] + acc[3 * Cy:6 * Cy, 3 * Cx:12 * Cx]
     return acc
 
 
@@ -153,7 +204,10 @@ def replay(dy, x, p, seed=0):
     nchy, nchx = p["nchy"], p["nchx"]
     Cy, Cx = 8 * nchy, 8 * nchx
     assert Cy <= dy.shape[1] and Cx <= x.shape[1]
-    slack = (64 if 3 * Cy <= 64 else 128) // 8 - 3 * nchy        # planes an A operand reads past the last expanded line
+    ln = 2 if p["pair"] else 1
+    slack = (64 if ln * 3 * Cy <= 64 else 128) // 8 - ln * 3 * nchy  # planes an A operand reads past the last expanded line
+    if p["pair"]:
+        assert p["LH"] % 2 == 0 and p["Ny"] % 2 == 0 and H % 2 == 0 and p["mirror"] == 11
     assert p["smem_raw_off"] >= (p["R"] + p["mirror"]) * nchx * p["Lp"] and p["smem_y_off"] >= p["smem_raw_off"] and p["NR"] == 0
     assert p["smem"] <= 227 * 1024 - 12 * 1024, "leave shared memory for the co-resident memory-bound kernels"
     assert p["smem_bar_off"] >= p["smem_y_off"] + (p["Ny"] * 3 * nchy + slack) * p["Lp"] and p["LH"] + 2 <= p["ND"]
@@ -173,12 +227,16 @@ def replay(dy, x, p, seed=0):
 # (padded channels, real output channels, real input channels): 16 <-> 16, 32 <-> 32 (three MMAs per K step), conv_input
 # (4 real input channels: X's upper chunk is skipped, N = 72), conv_output (3 real output channels: dY's upper chunk skipped)
 @pytest.mark.parametrize("chans", [(16, 16, 16), (32, 32, 32), (16, 16, 4), (16, 3, 16)])
-@pytest.mark.parametrize("shape", [(1, 3, 5, 16), (2, 9, 8, 16), (1, 5, 19, 32), (2, 2, 2, 16), (1, 1, 7, 48)])
-def test_replay_matches_autograd(shape, chans):
+@pytest.mark.parametrize("shape", [(1, 3, 5, 16), (2, 9, 8, 16), (1, 5, 19, 32), (2, 2, 2, 16), (1, 1, 7, 48),
+                                   (1, 3, 6, 16), (1, 4, 12, 32), (2, 3, 10, 16)])
+@pytest.mark.parametrize("pair", [True, False])
+def test_replay_matches_autograd(shape, chans, pair):
     N, D, H, W = shape
     Cc, ro, ri = chans
-    p = line_plan(N, D, H, W, Cc, ro, ri)
+    p = line_plan(N, D, H, W, Cc, ro, ri, pair=pair)
     assert (p["nchy"], p["nchx"]) == (1 if ro <= 8 else Cc // 8, 1 if ri <= 8 else Cc // 8)
+    # pair mode (two dY lines per MMA, opt-in) applies to 16-channel operands and even H
+    assert p["pair"] == int(pair and Cc == 16 and H % 2 == 0)
     g = torch.Generator().manual_seed(sum(shape))
     x = torch.randn(N, ri, D, H, W, generator=g, dtype=torch.float64)
     w = torch.randn(ro, ri, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
@@ -191,8 +249,17 @@ def test_replay_matches_autograd(shape, chans):
 
 def test_schedule_survives_many_interleavings_at_the_benchmark_shape():
     """Config-3 geometry (2 x 128^3): only the ring / barrier bookkeeping is replayed (operands skipped)."""
-    p = line_plan(2, 128, 128, 128)
-    assert p["LH"] == 8 and p["grid"] == 148 and p["Ny"] >= 4 and p["NR"] == 0
+    for pair in (True, False):
+        _schedule_at_benchmark_shape(pair)
+
+
+def _schedule_at_benchmark_shape(pair):
+    p = line_plan(2, 128, 128, 128, pair=pair)
+    if pair:
+        assert p["pair"] == 1 and p["LH"] % 2 == 0 and 128 % p["LH"] == 0 and p["Ny"] >= 4 and p["Ny"] % 2 == 0
+    else:
+        assert p["pair"] == 0 and p["LH"] == 8
+    assert p["grid"] == 148 and p["Ny"] >= 4 and p["NR"] == 0
     segs = segments(p, 17, 2, 128, 128) + segments(p, 18, 2, 128, 128)      # a CTA-sized run crossing a band boundary
 
     class NoData:                                                           # index-only stand-in for the activations

@@ -21,7 +21,12 @@ def main():
     ws = ops.wgrad_workspace(desc, dev)
     flops = 2.0 * B * S ** 3 * 27 * 16 * 16
     res = {}
-    sweeps = [("line", {"B200_NO_WGRAD_LINE": "0"}), ("linear", {"B200_NO_WGRAD_LINE": "1"})]
+    sweeps = [("line", {"B200_NO_WGRAD_LINE": "0", "B200_WGL_PAIR": "0"}), ("linear", {"B200_NO_WGRAD_LINE": "1"}),
+              ("line pair mode", {"B200_NO_WGRAD_LINE": "0", "B200_WGL_PAIR": "7"})]
+    if "--pair-sweep" in sys.argv:
+        sweeps += [("pair LH=%d Ny=%d" % (lh, ny), {"B200_NO_WGRAD_LINE": "0", "B200_WGL_PAIR": "7", "B200_WGL_LH": str(lh),
+                                                   "B200_WGL_NR": "0", "B200_WGL_NY": str(ny)})
+                   for lh, ny in ((4, 6), (4, 4), (6, 4), (2, 8), (4, 8))]
     if "--sweep" in sys.argv:
         sweeps += [("line LH=%d NR=%d Ny=%d" % (lh, nr, ny), {"B200_NO_WGRAD_LINE": "0", "B200_WGL_LH": str(lh), "B200_WGL_NR": str(nr),
                                                             "B200_WGL_NY": str(ny)})
@@ -68,8 +73,26 @@ def main():
             torch.cuda.synchronize()
             print("beside a device copy: %-8s %.4f ms per wgrad (20 launches), the 6 GiB of copies took %.3f ms (alone: ~%.3f ms)"
                   % (form, e0.elapsed_time(e1) / 20, c0.elapsed_time(c1), 6 * 2 * (1 << 30) / 6.5e9))
-    d = (res["line"] - res["linear"]).norm() / res["linear"].norm()
-    print("line vs linear rel-L2 %.2e" % d.item())
+    for k in ("B200_WGL_LH", "B200_WGL_NY", "B200_WGL_NR"):
+        os.environ.pop(k, None)
+    for name, r in res.items():
+        if name != "linear":
+            print("%s vs linear rel-L2 %.2e" % (name, ((r - res["linear"]).norm() / res["linear"].norm()).item()))
+    # the 4-input-channel (conv_input) and 3-output-channel (conv_output) variants
+    for (co, ci) in ((16, 4), (3, 16)):
+        for form, env in sweeps[:3]:
+            os.environ.update(env)
+            g = torch.zeros(co, ci, 3, 3, 3, device=dev)
+            for _ in range(3):
+                ops.wgrad_run(desc, dy, x, g, ops.G_K3, workspace=ws)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                ops.wgrad_run(desc, dy, x, g, ops.G_K3, workspace=ws)
+            e1.record()
+            torch.cuda.synchronize()
+            print("wgrad3 %dx%d %-22s %.4f ms" % (co, ci, form, e0.elapsed_time(e1) / 20))
 
 
 if __name__ == "__main__":
