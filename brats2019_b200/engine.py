@@ -122,6 +122,7 @@ class Engine:
         self._side_busy = False
         self._readers = {}        # id(buffer tensor) -> event recorded after the last side-stream read of it
         self._deferred = []       # side-stream weight-gradient jobs held back until the chain's next conv is enqueued
+        self.fwd_pack_mode = int(os.environ.get("B200_FWD_PACK", "1") or 1)   # A/B: 0 pack -> convert on one stream, 2 swapped
         self.sched = os.environ.get("B200_BWD_SCHED", "1") not in ("", "0")   # A/B: 0 = round-2a launch order
         self.last = None          # (plan, generation) of the most recent training forward
         self.tap = None           # tests only: callable(name, Act | tensor) invoked after every backward stage, while
@@ -278,7 +279,19 @@ class Engine:
         # everything the main stream held BEFORE the pack was enqueued (the last readers of x16, the producer of x).
         fwd_start = torch.cuda.Event()
         fwd_start.record(torch.cuda.current_stream())
-        repacked = self._refresh_packed() and self.overlap_wgrad
+        pack_done = None
+        if self.fwd_pack_mode == 2 and self.overlap_wgrad:
+            # A/B (B200_FWD_PACK=2): the weight re-pack on the side stream, the input conversion on the main one
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=P.device)
+            self._side_stream.wait_event(fwd_start)
+            with torch.cuda.stream(self._side_stream):
+                if self._refresh_packed():
+                    pack_done = torch.cuda.Event()
+                    pack_done.record(self._side_stream)
+            repacked = False
+        else:
+            repacked = self._refresh_packed() and self.overlap_wgrad and self.fwd_pack_mode == 1
         prm = self._params()
         ch = self.ch
         # cat([skip, up]) of model.py:424 is ONE 2C-channel buffer per level: the encoder writes the skip
@@ -302,6 +315,8 @@ class Engine:
             main.wait_event(done)        # (x stays alive: the main stream, which owns it, is ordered behind its last use)
         else:
             x16 = ops.pack_input(x, 16, out=P.act("x16", 0, 16))
+        if pack_done is not None:
+            torch.cuda.current_stream().wait_event(pack_done)
         c, m, r = self._conv3_gn(P, 0, "conv_input.weight", prm["conv_input.weight"], x16, "in.c", lrelu=False,
                                  **(dict(gamma=prm["norm_input.weight"], beta=prm["norm_input.bias"]) if training else {}))
         h = ops.gn_apply(c, m, r, prm["norm_input.weight"], prm["norm_input.bias"], P.act("in.a", 0, ch[0]),

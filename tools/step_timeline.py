@@ -1,7 +1,9 @@
 """Timeline of one steady-state training step (CUDA-graph replay): every kernel's start, duration and stream from
 CUPTI (torch.profiler), written as CSV for offline analysis of the main-stream / side-stream overlap.
 
-    python tools/step_timeline.py [B] [S] [out.csv]
+    python tools/step_timeline.py [B] [S] [out.csv] [--all]
+--all keeps both profiled replays and the memset / memcpy nodes too (what sits between two replays, what precedes the
+first kernel of a step).
 """
 import os
 import sys
@@ -31,17 +33,20 @@ with torch.cuda.stream(stream):
         g()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(2):
+        for _ in range(3 if "--all" in sys.argv else 2):
             g()
         torch.cuda.synchronize()
 path = out + ".trace.json"
 prof.export_chrome_trace(path)
 import json  # noqa: E402
-ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+ALL = "--all" in sys.argv
+cats = ("kernel", "gpu_memset", "gpu_memcpy") if ALL else ("kernel",)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in cats]
 ev.sort(key=lambda e: e["ts"])
-# keep the second replay only
-half = len(ev) // 2
-ev = ev[half:]
+if not ALL:
+    # keep the second replay only
+    half = len(ev) // 2
+    ev = ev[half:]
 t0 = ev[0]["ts"]
 with open(out, "w") as f:
     f.write("start_us,dur_us,stream,name\n")
