@@ -808,6 +808,10 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
     p.src_b = make_act(d->Cin_b > 0 ? src_b : src_a, vol);
     p.out = make_act(out, vol);
     p.residual = make_act(residual, vol);
+    {
+        const char* epf = getenv("B200_RES_PREFETCH");      // A/B: 0 = no L2 prefetch of the epilogue's residual operand
+        p.prefetch_residual = (epf && !atoi(epf)) ? 0 : 1;
+    }
     if (d->epi == EPI_D2S) {
         // the output and the residual are FINE tensors of Cout / 8 channels (conv_gemm.cuh ConvKParams::d2s)
         Vol fine{d->N, 2 * d->D, 2 * d->H, 2 * d->W};

@@ -159,6 +159,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------
+// One 128-bit read-only load.  Written as asm because nvcc turns `*reinterpret_cast<const uint4*>(ptr)` in the conv
+// epilogues into FOUR 32-bit LDG.E (cuobjdump: 64 scalar loads per 128-channel row, 0 vector loads): four times the L1
+// requests, and at the 32-byte row stride of the depth-to-space epilogue 32 sectors per request - ncu showed that kernel
+// bound by L1 sector throughput (profiles/r02c_ncu_d2s_summary.txt).  Not volatile: a pure function of the address (the
+// operand is never written by the kernel that reads it), so the compiler may schedule it early.
+__device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {
+    uint4 q;
+    asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(ptr));
+    return q;
+}
+
+// Request the 32-byte sector holding `ptr` from L2 (no register, no dependency: used to take DRAM latency off a chain of
+// dependent epilogue loads).
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

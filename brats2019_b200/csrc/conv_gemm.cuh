@@ -75,6 +75,7 @@ struct ConvKParams {
     // columns of coarse voxel (d, h, w) are the Cf channels of the eight fine voxels (2d+kd, 2h+kh, 2w+kw), column block
     // ((kd*2+kh)*2+kw) * Cf (elementwise.cuh s2d layout); `out` / `residual` are then FINE tensors (2D, 2H, 2W, Cf) and the
     // epilogue scatters its 16-byte vectors there (+ the skip gradient as residual) - no coarse tensor, no d2s pass.
+    int prefetch_residual; // 1 (default): request a row block's residual sectors from L2 one block ahead (B200_RES_PREFETCH=0: off)
     int d2s;               // 1: scatter
     int d2s_sh;            // log2(Cf / 8): coarse chunk q -> tap q >> sh, fine chunk q & ((1 << sh) - 1)
     float* stats_partial;            // optional [ctas][N][16] (sum[8], sumsq[8])
@@ -336,6 +337,57 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         };
 
+        // Residual operand (skip / residual-branch gradient of the data-gradient convs): the loads of a row sit behind
+        // the tcgen05.wait::ld of their column group (a memory clobber), so a row block used to be a chain of CO/16
+        // DRAM round trips - 8 x ~0.9 us per 128 rows in the depth-to-space data gradient, which ran at 2.9 TB/s with
+        // nothing else on the GPU.  The whole block's residual sectors are now requested from L2 one block ahead: for
+        // the first block of a tile BEFORE the wait for the tile's MMAs, for the next block before the current one is
+        // processed.  (Same address arithmetic as the row decode below.)
+        auto prefetch_residual = [&](int t, const TileCoord& tc, int r) {
+            const int dz = r / p.MB, mb = r - dz * p.MB;
+            bool valid;
+            long long orow, frow0 = 0;
+            if (MODE == MODE_K3) {
+                const int q = tc.q0 + mb * RB + m - (FOLD ? 1 : 0);
+                const int dpo = (p.whole ? 0 : tc.d0 + 1) + dz;
+                const int dq = p.by_SS.div(q);
+                const int r2 = q - dq * p.SS;
+                const int hp = p.by_Wp.div(r2);
+                const int wp = r2 - hp * p.Wp;
+                const int dp = dpo + dq;
+                valid = (q < p.Q0 + p.QN) && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
+                if (FOLD) valid = valid && m >= 1 && m <= RB;
+                orow = ((long long)tc.n * (p.D + 2) + dpo) * p.SS + q;
+            } else {
+                orow = (long long)t * p.TR + mb * 128 + m;
+                valid = orow < p.total_rows;
+                if (p.d2s) {
+                    const long long dpf = orow / p.SS;
+                    const int r2 = (int)(orow - dpf * p.SS);
+                    const int hp = p.by_Wp.div(r2), wp = r2 - hp * p.Wp;
+                    const int nn = (int)(dpf / (p.D + 2)), dp = (int)(dpf - (long long)nn * (p.D + 2));
+                    valid = valid && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
+                    frow0 = (((long long)nn * (2 * p.D + 2) + (2 * dp - 1)) * (2 * p.H + 2) + (2 * hp - 1)) * (2 * p.W + 2) +
+                            (2 * wp - 1);
+                }
+            }
+            if (!valid) return;
+#pragma unroll
+            for (int c0 = 0; c0 < CO; c0 += 16) {
+                int ch = (job * CO + c0) >> 3;
+                long long row = orow;
+                if (MODE == MODE_K1 && p.d2s) {
+                    const int tap8 = ch >> p.d2s_sh;
+                    ch &= (1 << p.d2s_sh) - 1;
+                    row = frow0 + (long long)(tap8 >> 2) * ((2 * p.H + 2) * (2 * p.W + 2)) +
+                          ((tap8 >> 1) & 1) * (2 * p.W + 2) + (tap8 & 1);
+                }
+                prefetch_l2(p.residual.at(ch, row));
+                prefetch_l2(p.residual.at(ch + 1, row));
+            }
+        };
+        const bool pf_res = (EPI == EPI_BF16) && p.residual.base != nullptr && p.prefetch_residual != 0;
+
         int it = 0;
         for (int t = cta; t < p.num_tiles; t += ctas, ++it) {
             const int as = it & 1;
@@ -344,9 +396,11 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 if (cur_n >= 0) flush_stats(cur_n);
                 cur_n = tc.n;
             }
+            if (pf_res && grp < R) prefetch_residual(t, tc, grp);
             mbar_wait(&t_full[as], (it >> 1) & 1);
             tc_fence_after();
             for (int r = grp; r < R; r += kEpiGroups) {
+                if (pf_res && r + kEpiGroups < R) prefetch_residual(t, tc, r + kEpiGroups);
                 const int dz = r / p.MB, mb = r - dz * p.MB;
                 // ---- which voxel is this row? ----
                 bool valid;
@@ -461,10 +515,10 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                             }
                             if (p.residual.base) {
                                 float f[8];
-                                unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch, orow)), f);
+                                unpack_bf16x8(ld_nc_v4(p.residual.at(ch, orow)), f);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] += f[i];
-                                unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch + 1, orow)), f);
+                                unpack_bf16x8(ld_nc_v4(p.residual.at(ch + 1, orow)), f);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
                             }

@@ -380,7 +380,7 @@ conv_march_kernel(const __grid_constant__ MarchParams p) {
 #pragma unroll
                             for (int c = 0; c < CO / 8; ++c) {
                                 float f[8];
-                                unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(c, orow)), f);
+                                unpack_bf16x8(ld_nc_v4(p.residual.at(c, orow)), f);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[c * 8 + i] += f[i];
                             }

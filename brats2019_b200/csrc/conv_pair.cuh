@@ -304,10 +304,10 @@ conv_pair_kernel(const __grid_constant__ ConvKParams p) {
                         const int ch = c0 >> 3;
                         if (p.residual.base) {
                             float f[8];
-                            unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch, orow)), f);
+                            unpack_bf16x8(ld_nc_v4(p.residual.at(ch, orow)), f);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] += f[i];
-                            unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual.at(ch + 1, orow)), f);
+                            unpack_bf16x8(ld_nc_v4(p.residual.at(ch + 1, orow)), f);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
                         }
