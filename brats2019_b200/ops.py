@@ -248,9 +248,16 @@ class PackTable:
         total = C.c_int(0)
         check(L.b200_pack_table_build(arr, n, host, nbytes, C.byref(total)), "b200_pack_table_build")
         dev = self.jobs[0][2].device
-        # pinned staging buffer (kept alive): the copy is legal even while a CUDA graph is being captured
-        self._host = torch.frombuffer(bytearray(host), dtype=torch.uint8).pin_memory()
-        self.table = self._host.to(dev, non_blocking=True)
+        if torch.cuda.is_current_stream_capturing():
+            # pinned staging buffer (kept alive): the copy is legal while a CUDA graph is being captured
+            self._host = torch.frombuffer(bytearray(host), dtype=torch.uint8).pin_memory()
+            self.table = self._host.to(dev, non_blocking=True)
+        else:
+            # A few KB, built once per model: a plain synchronous copy.  (Until round 2c this path pinned the buffer too;
+            # in a long process - the whole GPU test suite - torch's pinned-memory allocator then raised a one-shot
+            # "CUDA error: invalid argument" here while polling the events of earlier, already freed staging buffers.)
+            self._host = None
+            self.table = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(dev)
         self.total_blocks = total.value
         self.ptrs = [j[2].data_ptr() for j in self.jobs]
 

@@ -34,3 +34,19 @@ def golden():
         return np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
 
     return load
+
+
+@pytest.fixture(autouse=True)
+def _settle_gpu_between_tests(request):
+    """GPU tests build models, CUDA graphs and pinned staging buffers; what one test leaves behind (reference cycles
+    holding graphs, streams, pinned blocks) is collected and the device drained BEFORE the next test starts, not at
+    whatever point of its graph capture the garbage collector happens to run."""
+    yield
+    if "gpu" in request.keywords:
+        import gc
+
+        import torch
+
+        if torch.cuda.is_available():
+            gc.collect()
+            torch.cuda.synchronize()
