@@ -818,6 +818,14 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
         p.out = make_act(out, fine);
         p.residual = make_act(residual, fine);
         p.d2s = 1;
+        {
+            // 32-byte accesses (OPT-IN, B200_D2S_V8=1: bit-identical and measured SLOWER, 177 vs 101 us at 2 x 64^3 -> 128^3,
+            // profiles/r02c_ab_d2s.txt): even rows of every chunk plane must be 32-byte aligned - guard rows and plane
+            // rows are even for even W (common.cuh Vol), so it comes down to the base pointers
+            const char* e8 = getenv("B200_D2S_V8");
+            p.d2s_v8 = ((e8 && atoi(e8)) && d->W % 2 == 0 && ((uintptr_t)out & 31) == 0 && ((uintptr_t)residual & 31) == 0 &&
+                        p.out.plane_rows % 2 == 0 && p.out.guard % 2 == 0) ? 1 : 0;
+        }
         p.d2s_sh = 0;
         while ((8 << p.d2s_sh) < d->Cout / 8) ++p.d2s_sh;
         if (lrelu_out) return fail("conv: no activation with the depth-to-space epilogue");

@@ -170,6 +170,16 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* ptr) {
     return q;
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .ENL2.256): one full 32-byte sector per lane; `ptr` 32-byte aligned.
+__device__ __forceinline__ void ld_nc_v8(const void* ptr, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(ptr));
+}
+__device__ __forceinline__ void st_v8(void* ptr, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 // Request the 32-byte sector holding `ptr` from L2 (no register, no dependency: used to take DRAM latency off a chain of
 // dependent epilogue loads).
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }

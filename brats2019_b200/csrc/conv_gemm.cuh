@@ -76,6 +76,7 @@ struct ConvKParams {
     // ((kd*2+kh)*2+kw) * Cf (elementwise.cuh s2d layout); `out` / `residual` are then FINE tensors (2D, 2H, 2W, Cf) and the
     // epilogue scatters its 16-byte vectors there (+ the skip gradient as residual) - no coarse tensor, no d2s pass.
     int prefetch_residual; // 1 (default): request a row block's residual sectors from L2 one block ahead (B200_RES_PREFETCH=0: off)
+    int d2s_v8;            // d2s with 32-byte accesses (opt-in B200_D2S_V8=1; W even, 32-byte aligned tensors)
     int d2s;               // 1: scatter
     int d2s_sh;            // log2(Cf / 8): coarse chunk q -> tap q >> sh, fine chunk q & ((1 << sh) - 1)
     float* stats_partial;            // optional [ctas][N][16] (sum[8], sumsq[8])
@@ -434,6 +435,80 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                     }
                 }
                 const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((as * R + r) * NMMA);
+                if (MODE == MODE_K1 && EPI == EPI_BF16 && !FOLD && NMMA == 128 && p.d2s && p.d2s_v8 && !do_stats) {
+                    // ---- depth-to-space scatter with 32-byte accesses (round 2c; opt-in B200_D2S_V8=1: bit-identical to the
+                    //      16-byte form below and measured slower - 177 vs 101 us - so the default stays the 16-byte form) ----
+                    // A lane's two kw taps are the fine rows 2wp-1 and 2wp: 32 contiguous bytes that straddle a sector
+                    // boundary, and one 16-byte access per lane at a 32-byte lane stride touches 32 half-used sectors
+                    // per request (ncu: the kernel was bound by L1 sector throughput at 2.8 TB/s with the GPU to itself).
+                    // Sector-aligned pairs are (own kw = 1, NEXT lane's kw = 0) = fine rows 2wp, 2wp+1: the kw = 0
+                    // accumulators move one lane down by shuffle and every lane reads the skip gradient and writes its
+                    // result with one 256-bit access per chunk.  Lanes whose neighbour is missing (warp edge, line edge,
+                    // halo row) fall back to 16-byte accesses for the orphaned row.
+                    const int Cf = 8 << p.d2s_sh;                                   // fine channels = columns per tap
+                    const bool nvalid = (__shfl_down_sync(0xffffffffu, (int)valid, 1) != 0) && lane < 31;
+                    const bool pvalid = (__shfl_up_sync(0xffffffffu, (int)valid, 1) != 0) && lane > 0;
+                    const bool pair = valid && nvalid;                               // both valid <=> consecutive voxels of one line
+                    const bool solo1 = valid && !nvalid;                             // my kw = 1 row on its own
+                    const bool solo0 = valid && !pvalid;                             // my kw = 0 row: nobody above me takes it
+                    const bool has_res = p.residual.base != nullptr;
+                    const long long fslice = (long long)(2 * p.H + 2) * (2 * p.W + 2);
+#pragma unroll
+                    for (int c0 = 0; c0 < CO; c0 += 16) {
+                        const int chg = (job * CO + c0) >> 3;                        // global chunk index of this column group
+                        const int tap8 = chg >> p.d2s_sh;
+                        if (tap8 & 1) continue;                                      // kw = 1 groups are handled with their kw = 0 partner
+                        const int fch = chg & ((1 << p.d2s_sh) - 1);                 // first of the two fine chunks
+                        uint32_t r0[16], r1[16];
+                        tmem_ld16_nowait(trow + c0, r0);                             // kw = 0
+                        tmem_ld16_nowait(trow + c0 + Cf, r1);                        // kw = 1 (the next tap: Cf columns further)
+                        tmem_ld_wait();
+                        float v0[16], v1[16], n0[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v0[i] = __uint_as_float(r0[i]);
+                            v1[i] = __uint_as_float(r1[i]);
+                            n0[i] = __shfl_down_sync(0xffffffffu, v0[i], 1);         // the next voxel's kw = 0 values
+                        }
+                        const long long row0 = frow0 + (long long)(tap8 >> 2) * fslice + ((tap8 >> 1) & 1) * (2 * p.W + 2);
+                        const long long row1 = row0 + 1;                             // even row: 32-byte aligned in every plane
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            if (pair) {
+                                if (has_res) {
+                                    uint4 qa, qb;
+                                    ld_nc_v8(p.residual.at(fch + cc, row1), qa, qb);
+                                    float f[8];
+                                    unpack_bf16x8(qa, f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v1[8 * cc + i] += f[i];
+                                    unpack_bf16x8(qb, f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) n0[8 * cc + i] += f[i];
+                                }
+                                st_v8(p.out.at(fch + cc, row1), pack_bf16x8(v1 + 8 * cc), pack_bf16x8(n0 + 8 * cc));
+                            } else if (solo1) {
+                                if (has_res) {
+                                    float f[8];
+                                    unpack_bf16x8(ld_nc_v4(p.residual.at(fch + cc, row1)), f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v1[8 * cc + i] += f[i];
+                                }
+                                *reinterpret_cast<uint4*>(p.out.at(fch + cc, row1)) = pack_bf16x8(v1 + 8 * cc);
+                            }
+                            if (solo0) {
+                                if (has_res) {
+                                    float f[8];
+                                    unpack_bf16x8(ld_nc_v4(p.residual.at(fch + cc, row0)), f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v0[8 * cc + i] += f[i];
+                                }
+                                *reinterpret_cast<uint4*>(p.out.at(fch + cc, row0)) = pack_bf16x8(v0 + 8 * cc);
+                            }
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int c0 = 0; c0 < CO; c0 += 16) {
                     float v[16];

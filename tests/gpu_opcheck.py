@@ -373,6 +373,12 @@ def group_conv1():
         report("down k2s2 dgrad d2s-epilogue + skip %d<-%d" % (Cf, Cd), ops.act_to_ncdhw(fine3), ref + skip, tol_rel=1.5e-2)
         report("down k2s2 dgrad d2s-epilogue halo+guard stay zero %d" % Cf, ops.act_outside_absmax(fine3).view(1),
                torch.zeros(1, device=dev), tol_abs=0)
+        # the opt-in 32-byte form of the scatter (B200_D2S_V8=1) against the default 16-byte form: the same bits
+        os.environ["B200_D2S_V8"] = "1"
+        fine4 = ops.act_zeros(N, 2 * D, 2 * H, 2 * W, Cf, dev)
+        ops.conv_run(d2, ops.act_from_ncdhw(dy), pk2, fine4, residual=ops.act_from_ncdhw(skip))
+        os.environ.pop("B200_D2S_V8", None)
+        report("down k2s2 dgrad d2s-epilogue 32-byte == 16-byte form %d" % Cf, fine3.t, fine4.t, tol_abs=0)
 
 
 def group_dgrad():
