@@ -415,17 +415,19 @@ def run(args, rank, world, local_rank, dev):
     if rank == 0:
         if roof_all:
             top = roof_all[0]
-            traffic = None
+            traffic, traffic_src = None, None
             tp = os.path.join(REPO, "profiles", "dominant_kernel_traffic.json")
             if os.path.exists(tp):
                 try:
-                    traffic = json.load(open(tp)).get(top["kernel"], {}).get("dram_bytes_per_launch")
+                    ent = json.load(open(tp)).get(top["kernel"], {})
+                    traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
                 except Exception:
                     traffic = None
             roof = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                     "frac": top["frac"], "traffic": traffic, "kernel": top["kernel"], "launches_per_step": top["launches"],
                     "time_share": top["time_share"], "ms_per_launch": top["ms_per_step"] / max(1, top["launches"]),
                     "algorithmic_work_per_launch": top["work_per_step"] / max(1, top["launches"]),
+                    "traffic_source": traffic_src,
                     "peak_source": peaks["source"] + ", sustained (kernel timed inside the step)" if top["bound"] == "tensor"
                     else peaks["source"]}
 

@@ -128,7 +128,7 @@ def main():
         mean = torch.zeros(B * 8, device=dev); rstd = torch.ones(B * 8, device=dev)
         gamma = torch.ones(Cc, device=dev); beta = torch.zeros(Cc, device=dev)
         nb = vox * Cc * 2
-        line("gn_apply+lrelu+residual C=%d" % Cc, timeit(lambda: ops.gn_apply(x, mean, rstd, gamma, beta, y, residual=dy)), bytes_=4 * nb)
+        line("gn_apply+lrelu+residual C=%d" % Cc, timeit(lambda: ops.gn_apply(x, mean, rstd, gamma, beta, y, residual=dy)), bytes_=3 * nb)   # x + residual read, y written
         dx = ops.act_zeros(B, s, s, s, Cc, dev)
         dg = torch.empty(Cc, device=dev); db = torch.empty(Cc, device=dev)
         gws = ops.gn_backward_workspace(B, Cc, dev)
