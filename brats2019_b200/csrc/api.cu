@@ -109,6 +109,15 @@ static int pdl_level() {
 }
 static bool pdl_enabled() { return pdl_level() >= 2; }      // memory-bound kernels
 static bool pdl_conv() { return pdl_level() >= 1; }
+// Memory-bound kernels with FEW CTAs (the deep levels: 32 - 600 CTAs) as dependents: there are no thousands of parked CTAs
+// there, and each launch hides its ~2 us of launch latency under the predecessor's tail.  B200_PDL_EW_MAX = largest grid
+// (in CTAs) that is launched this way at level 1 (0 = none).
+static int pdl_ew_max() {
+    int n = 0;
+    if (const char* e = getenv("B200_PDL_EW_MAX")) n = atoi(e);
+    return n;
+}
+static bool pdl_ew(long long grid_ctas) { return pdl_level() >= 2 || (pdl_level() >= 1 && grid_ctas <= pdl_ew_max()); }
 // A conv launched as a programmatic dependent copies its weights BEFORE griddepcontrol.wait (they "were packed long
 // before").  That is false for the first conv enqueued on a stream right after a weight-packing kernel: it is launched
 // with full serialization instead.  (Host-side launch order per stream is what counts, also under stream capture.)
@@ -1272,12 +1281,12 @@ static int pack_input_t(const T* x, void* act_out, int N, int D, int H, int W, i
     Vol v{N, D, H, W};
     if (W % 4 == 0 && ((uintptr_t)x & (4 * sizeof(T) - 1)) == 0) {
         const int lpb = quad_lpb(N, D, H);
-        CUDA_OK(launch_ex(pack_input4_kernel<T>, dim3((N * D * H + lpb - 1) / lpb), dim3(256), 0, st, 0, pdl_enabled(), x, make_act(act_out, v), v, Creal, lpb,
+        CUDA_OK(launch_ex(pack_input4_kernel<T>, dim3((N * D * H + lpb - 1) / lpb), dim3(256), 0, st, 0, pdl_ew((long long)((N * D * H + lpb - 1) / lpb)), x, make_act(act_out, v), v, Creal, lpb,
                                                                           make_fastdiv((unsigned)(W / 4))));
         LAUNCH_OK("pack_input4_kernel");
         return 0;
     }
-    CUDA_OK(launch_ex(pack_input_kernel<T>, dim3(N * D * H), dim3(128), 0, st, 0, pdl_enabled(), x, make_act(act_out, v), v, Creal));
+    CUDA_OK(launch_ex(pack_input_kernel<T>, dim3(N * D * H), dim3(128), 0, st, 0, pdl_ew((long long)(N * D * H)), x, make_act(act_out, v), v, Creal));
     LAUNCH_OK("pack_input_kernel");
     return 0;
 }
@@ -1322,7 +1331,7 @@ extern "C" int b200_gn_apply(const void* x, const float* mean, const float* rstd
     if (check_act(N, D, H, W, C) || C > 256 || 256 % (C / 8)) return fail("gn_apply: C=%d unsupported", C);
     Vol v{N, D, H, W};
     const int lpb = lines_per_block(N, D, H);
-    CUDA_OK(launch_ex(gn_apply_kernel, dim3(N * D * H / lpb), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu,
+    CUDA_OK(launch_ex(gn_apply_kernel, dim3(N * D * H / lpb), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_ew((long long)(N * D * H / lpb)), make_act(x, v), mean, rstd, gamma, beta, make_act(residual, v), make_act(out, v), v, C, do_lrelu,
         make_line_geom(W, C, lpb)));
     LAUNCH_OK("gn_apply_kernel");
     return 0;
@@ -1543,7 +1552,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
         fin.tickets = reinterpret_cast<unsigned int*>(workspace);
         fin.m = m;
     }
-    CUDA_OK(launch_ex(gn_bwd_reduce2_kernel, dim3(blocks, N), dim3(256), 0, st, 0, pdl_enabled(), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+    CUDA_OK(launch_ex(gn_bwd_reduce2_kernel, dim3(blocks, N), dim3(256), 0, st, 0, pdl_ew((long long)(blocks) * (long long)(N)), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
                                                           partial, v, C, do_lrelu, by_W, rlpb, fin));
     LAUNCH_OK("gn_bwd_reduce2_kernel");
     if (fin.coef == nullptr) {
@@ -1553,7 +1562,7 @@ extern "C" int b200_gn_backward(const void* x, const void* dy, const float* mean
         LAUNCH_OK("gn_bwd_finalize2_kernel");
     }
     const int lpb = lines_per_block(N, D, H, W, C);
-    CUDA_OK(launch_ex(gn_bwd_apply2_kernel<false>, dim3(N * D * H / lpb), dim3(256), 0, st, 0, pdl_enabled(), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
+    CUDA_OK(launch_ex(gn_bwd_apply2_kernel<false>, dim3(N * D * H / lpb), dim3(256), 0, st, 0, pdl_ew((long long)(N * D * H / lpb)), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta,
                                                                 coef, make_act(dx, v), v, C, do_lrelu, by_W, lpb, nullptr));
     LAUNCH_OK("gn_bwd_apply2_kernel");
     return 0;
@@ -1584,7 +1593,7 @@ extern "C" int b200_gn_backward_folded(const void* x, const void* dy, const floa
     const FastDiv by_W = make_fastdiv((unsigned)W);
     const int lpb = lines_per_block(N, D, H, W, C);
     const int bps = D * H / lpb;
-    CUDA_OK(launch_ex(gn_bwd_apply2_kernel<true>, dim3(N * bps), dim3(256), 0, st, 0, pdl_enabled(), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
+    CUDA_OK(launch_ex(gn_bwd_apply2_kernel<true>, dim3(N * bps), dim3(256), 0, st, 0, pdl_ew((long long)(N * bps)), make_act(x, v), make_act(dy, v), mean, rstd, gamma, beta, coef,
                                                        make_act(dx, v), v, C, do_lrelu, by_W, lpb, aff));
     LAUNCH_OK("gn_bwd_apply2_kernel");
     const int fin_threads = std::min(1024, std::max(256, std::min(8, N) * (C / 8) * 2 * 32));
@@ -1598,7 +1607,7 @@ extern "C" int b200_upsample2x(const void* coarse, void* fine, int N, int D, int
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    CUDA_OK(launch_ex(upsample2x_fwd3_kernel, dim3(N * D * H), dim3(128), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(coarse, vc), make_act(fine, vf), vc, C,
+    CUDA_OK(launch_ex(upsample2x_fwd3_kernel, dim3(N * D * H), dim3(128), 0, (cudaStream_t)stream, 0, pdl_ew((long long)(N * D * H)), make_act(coarse, vc), make_act(fine, vf), vc, C,
                                                                        do_lrelu, make_fastdiv((unsigned)W)));
     LAUNCH_OK("upsample2x_fwd3_kernel");
     return 0;
@@ -1617,10 +1626,10 @@ extern "C" int b200_upsample2x_backward(const void* dfine, const void* fine_out,
     Vol vt{N, 2 * D, 2 * H, W};
     cudaStream_t st = (cudaStream_t)stream;
     const FastDiv by_W = make_fastdiv((unsigned)W);
-    CUDA_OK(launch_ex(upsample2x_bwd_w3_kernel, dim3(N * 2 * D * 2 * H), dim3(128), 0, st, 0, pdl_enabled(), make_act(dfine, vf), make_act(fine_out, vf),
+    CUDA_OK(launch_ex(upsample2x_bwd_w3_kernel, dim3(N * 2 * D * 2 * H), dim3(128), 0, st, 0, pdl_ew((long long)(N * 2 * D * 2 * H)), make_act(dfine, vf), make_act(fine_out, vf),
                                                                make_act(workspace, vt), vc, C, do_lrelu, by_W));
     LAUNCH_OK("upsample2x_bwd_w3_kernel");
-    CUDA_OK(launch_ex(upsample2x_bwd_dh3_kernel, dim3(N * D * H), dim3(128), 0, st, 0, pdl_enabled(), make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W));
+    CUDA_OK(launch_ex(upsample2x_bwd_dh3_kernel, dim3(N * D * H), dim3(128), 0, st, 0, pdl_ew((long long)(N * D * H)), make_act(workspace, vt), make_act(dcoarse, vc), vc, C, by_W));
     LAUNCH_OK("upsample2x_bwd_dh3_kernel");
     return 0;
 }
@@ -1629,7 +1638,7 @@ extern "C" int b200_space_to_depth(const void* fine, void* coarse, int N, int D,
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    CUDA_OK(launch_ex(s2d_kernel, dim3(N * D * H), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(fine, vf), make_act(coarse, vc), vc, C));
+    CUDA_OK(launch_ex(s2d_kernel, dim3(N * D * H), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_ew((long long)(N * D * H)), make_act(fine, vf), make_act(coarse, vc), vc, C));
     LAUNCH_OK("s2d_kernel");
     return 0;
 }
@@ -1638,7 +1647,7 @@ extern "C" int b200_depth_to_space(const void* coarse, const void* residual, voi
     if (check_act(N, D, H, W, C)) return 1;
     Vol vc{N, D, H, W};
     Vol vf{N, 2 * D, 2 * H, 2 * W};
-    CUDA_OK(launch_ex(d2s_kernel, dim3(N * D * H), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(coarse, vc), make_act(residual, vf),
+    CUDA_OK(launch_ex(d2s_kernel, dim3(N * D * H), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_ew((long long)(N * D * H)), make_act(coarse, vc), make_act(residual, vf),
                                                                   make_act(fine, vf), vc, C));
     LAUNCH_OK("d2s_kernel");
     return 0;
@@ -1647,7 +1656,7 @@ extern "C" int b200_add(const void* a, const void* b, void* out, int N, int D, i
     if (check_act(N, D, H, W, C)) return 1;
     Vol v{N, D, H, W};
     const int lpb = lines_per_block(N, D, H);
-    CUDA_OK(launch_ex(add_kernel, dim3(N * D * H / lpb), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_enabled(), make_act(a, v), make_act(b, v), make_act(out, v),
+    CUDA_OK(launch_ex(add_kernel, dim3(N * D * H / lpb), dim3(kEwThreads), 0, (cudaStream_t)stream, 0, pdl_ew((long long)(N * D * H / lpb)), make_act(a, v), make_act(b, v), make_act(out, v),
                                                                         v, C, make_line_geom(W, C, lpb)));
     LAUNCH_OK("add_kernel");
     return 0;
@@ -1669,11 +1678,11 @@ extern "C" int b200_sigmoid_backward(const float* grad_probs, const float* probs
     const int lpb = sigmoid_lpb(N, D, H);
     const int blocks = (N * D * H + lpb - 1) / lpb;
     if (W % 4 == 0 && (((uintptr_t)grad_probs | (uintptr_t)probs) & 15) == 0) {
-        CUDA_OK(launch_ex(sigmoid_bwd_pack4_kernel, dim3(blocks), dim3(256), 0, st, 0, pdl_enabled(), grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+        CUDA_OK(launch_ex(sigmoid_bwd_pack4_kernel, dim3(blocks), dim3(256), 0, st, 0, pdl_ew((long long)(blocks)), grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
                                                         make_fastdiv((unsigned)(W / 4))));
         LAUNCH_OK("sigmoid_bwd_pack4_kernel");
     } else {
-        CUDA_OK(launch_ex(sigmoid_bwd_pack2_kernel, dim3(blocks), dim3(256), 0, st, 0, pdl_enabled(), grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
+        CUDA_OK(launch_ex(sigmoid_bwd_pack2_kernel, dim3(blocks), dim3(256), 0, st, 0, pdl_ew((long long)(blocks)), grad_probs, probs, make_act(dlogit_act, v), workspace, v, Creal, lpb,
                                                         make_fastdiv((unsigned)W)));
         LAUNCH_OK("sigmoid_bwd_pack2_kernel");
     }

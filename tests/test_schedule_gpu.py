@@ -21,6 +21,7 @@ SETTINGS = [
     {"B200_PDL": "2"},                                      # every kernel a programmatic dependent
     {"B200_NO_WGRAD_OVERLAP": "1"},                         # one stream
     {"B200_PDL_WGRAD": "1"},
+    {"B200_PDL_EW_MAX": "600"},                             # memory-bound kernels of the deep levels (few CTAs) as dependents
 ]
 
 
