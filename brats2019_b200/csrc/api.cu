@@ -835,6 +835,10 @@ static int conv_run_impl(const b200_conv_desc* d, const void* src_a, const void*
             p.d2s_v8 = ((e8 && atoi(e8)) && d->W % 2 == 0 && ((uintptr_t)out & 31) == 0 && ((uintptr_t)residual & 31) == 0 &&
                         p.out.plane_rows % 2 == 0 && p.out.guard % 2 == 0) ? 1 : 0;
         }
+        {
+            const char* es = getenv("B200_D2S_SPREAD");
+            p.d2s_spread = (es && !atoi(es)) ? 0 : 1;
+        }
         p.d2s_sh = 0;
         while ((8 << p.d2s_sh) < d->Cout / 8) ++p.d2s_sh;
         if (lrelu_out) return fail("conv: no activation with the depth-to-space epilogue");

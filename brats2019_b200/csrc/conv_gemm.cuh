@@ -76,6 +76,7 @@ struct ConvKParams {
     // ((kd*2+kh)*2+kw) * Cf (elementwise.cuh s2d layout); `out` / `residual` are then FINE tensors (2D, 2H, 2W, Cf) and the
     // epilogue scatters its 16-byte vectors there (+ the skip gradient as residual) - no coarse tensor, no d2s pass.
     int prefetch_residual; // 1 (default): request a row block's residual sectors from L2 one block ahead (B200_RES_PREFETCH=0: off)
+    int d2s_spread;        // d2s: (row block, column group) items dealt to all epilogue groups (default; B200_D2S_SPREAD=0: one group per row block)
     int d2s_v8;            // d2s with 32-byte accesses (opt-in B200_D2S_V8=1; W even, 32-byte aligned tensors)
     int d2s;               // 1: scatter
     int d2s_sh;            // log2(Cf / 8): coarse chunk q -> tap q >> sh, fine chunk q & ((1 << sh) - 1)
@@ -396,6 +397,75 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
             if (do_stats && tc.n != cur_n) {
                 if (cur_n >= 0) flush_stats(cur_n);
                 cur_n = tc.n;
+            }
+            if (MODE == MODE_K1 && EPI == EPI_BF16 && !FOLD && NMMA == 128 && p.d2s && p.d2s_spread && !p.d2s_v8 && !do_stats && R <= 2) {
+                // ---- depth-to-space scatter, work spread over ALL epilogue groups (round 2c) ----
+                // A tile of this GEMM has R <= 2 row blocks (TMEM: 2 stages x R x 128 columns) but three epilogue groups, and a
+                // row block is a chain of CO/16 dependent (TMEM read -> skip gradient -> store) steps: with one group per row
+                // block a third of the epilogue warps idled and the kernel, which has the GPU to itself in the step, ran at
+                // 0.46 of the HBM peak.  The (row block, column group) items are dealt round-robin to the three groups instead;
+                // every group decodes both row blocks once and requests its own items' skip-gradient sectors from L2 before it
+                // waits for the accumulators.  (The same dealing for the 3x3x3 convs with R = 1 / 2 / 4 was measured too: no gain
+                // at 128 channels, 30 vs 26 us at 64 channels - profiles/r02c_ab_d2s.txt; not kept.)
+                constexpr int NCG = CO / 16;
+                bool val0 = false, val1 = false;
+                long long fr0 = 0, fr1 = 0;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (r < R) {
+                        const long long orow = (long long)t * p.TR + r * 128 + m;
+                        bool valid = orow < p.total_rows;
+                        const long long dpf = orow / p.SS;
+                        const int r2 = (int)(orow - dpf * p.SS);
+                        const int hp = p.by_Wp.div(r2), wp = r2 - hp * p.Wp;
+                        const int nn = (int)(dpf / (p.D + 2)), dp = (int)(dpf - (long long)nn * (p.D + 2));
+                        valid = valid && dp >= 1 && dp <= p.D && hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W;
+                        const long long f0 = (((long long)nn * (2 * p.D + 2) + (2 * dp - 1)) * (2 * p.H + 2) + (2 * hp - 1)) * (2 * p.W + 2) +
+                                             (2 * wp - 1);
+                        if (r == 0) { val0 = valid; fr0 = f0; } else { val1 = valid; fr1 = f0; }
+                    }
+                }
+                const long long fslice = (long long)(2 * p.H + 2) * (2 * p.W + 2);
+                const bool has_res = p.residual.base != nullptr;
+                auto item_row = [&](int item, int& r, int& c0, int& ch, long long& row) {
+                    r = item / NCG;
+                    c0 = (item - r * NCG) * 16;
+                    const int chg = (job * CO + c0) >> 3;
+                    const int tap8 = chg >> p.d2s_sh;
+                    ch = chg & ((1 << p.d2s_sh) - 1);
+                    row = (r ? fr1 : fr0) + (long long)(tap8 >> 2) * fslice + ((tap8 >> 1) & 1) * (2 * p.W + 2) + (tap8 & 1);
+                };
+                if (has_res && p.prefetch_residual) {
+                    for (int item = grp; item < R * NCG; item += kEpiGroups) {
+                        int r, c0, ch; long long row;
+                        item_row(item, r, c0, ch, row);
+                        if (r ? val1 : val0) { prefetch_l2(p.residual.at(ch, row)); prefetch_l2(p.residual.at(ch + 1, row)); }
+                    }
+                }
+                mbar_wait(&t_full[as], (it >> 1) & 1);
+                tc_fence_after();
+                for (int item = grp; item < R * NCG; item += kEpiGroups) {
+                    int r, c0, ch; long long row;
+                    item_row(item, r, c0, ch, row);
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((as * R + r) * NMMA) + (uint32_t)c0, v);
+                    if (r ? val1 : val0) {
+                        if (has_res) {
+                            float f[8];
+                            unpack_bf16x8(ld_nc_v4(p.residual.at(ch, row)), f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += f[i];
+                            unpack_bf16x8(ld_nc_v4(p.residual.at(ch + 1, row)), f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+                        }
+                        *reinterpret_cast<uint4*>(p.out.at(ch, row)) = pack_bf16x8(v);
+                        *reinterpret_cast<uint4*>(p.out.at(ch + 1, row)) = pack_bf16x8(v + 8);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&t_empty[as]);
+                continue;
             }
             if (pf_res && grp < R) prefetch_residual(t, tc, grp);
             mbar_wait(&t_full[as], (it >> 1) & 1);
