@@ -398,7 +398,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
                 if (cur_n >= 0) flush_stats(cur_n);
                 cur_n = tc.n;
             }
-            if (MODE == MODE_K1 && EPI == EPI_BF16 && !FOLD && NMMA == 128 && p.d2s && p.d2s_spread && !p.d2s_v8 && !do_stats && R <= 2) {
+            if (MODE == MODE_K1 && EPI == EPI_BF16 && !FOLD && (NMMA == 128 || NMMA == 256) && p.d2s && p.d2s_spread && !p.d2s_v8 && !do_stats && R <= 2) {
                 // ---- depth-to-space scatter, work spread over ALL epilogue groups (round 2c) ----
                 // A tile of this GEMM has R <= 2 row blocks (TMEM: 2 stages x R x 128 columns) but three epilogue groups, and a
                 // row block is a chain of CO/16 dependent (TMEM read -> skip gradient -> store) steps: with one group per row
