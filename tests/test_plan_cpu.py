@@ -261,3 +261,65 @@ def test_cpu_tensor_is_rejected_not_computed():
         m([torch.zeros(1, 4, 16, 16, 16)])
     with _pytest.raises(RuntimeError, match="CUDA only"):
         B.Dice_loss_joint()([torch.zeros(1, 3, 8, 8, 8)], [torch.zeros(1, 3, 8, 8, 8)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Depth-to-space epilogue of the k2 s2 data gradient (conv_gemm.cuh, EPI_D2S): the (row block, column group) items a
+# tile's accumulators are cut into are dealt round-robin to the three epilogue groups.  Replay of the item -> (fine
+# chunk, fine row) arithmetic against the definition of space-to-depth (elementwise.cuh: s2d channel
+# ((kd*2+kh)*2+kw)*Cf + c of coarse voxel (d,h,w) = fine[2d+kd][2h+kh][2w+kw][c]) - every fine (voxel, chunk) written
+# exactly once, by exactly one group, and only interior voxels.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Cf", [16, 32, 64])
+@pytest.mark.parametrize("dims", [(1, 2, 3, 4), (2, 3, 2, 6)])
+def test_d2s_epilogue_item_dealing_covers_the_fine_grid_once(Cf, dims):
+    N, D, H, W = dims                                   # coarse volume
+    groups = 3                                          # kEpiGroups
+    Cout = 8 * Cf                                       # GEMM N: (tap8, fine channel)
+    CO = 128 if Cout == 128 else 256                    # columns per CTA job (conv_nmma)
+    n_jobs = Cout // CO
+    R = 512 // (2 * CO)                                 # row blocks per tile: two accumulator stages in 512 TMEM columns
+    NCG = CO // 16
+    sh = (Cf // 8).bit_length() - 1                     # d2s_sh = log2(Cf / 8)
+    Wp, Hp, Dp = W + 2, H + 2, D + 2
+    SS = Hp * Wp
+    total_rows = N * Dp * SS
+    fWp, fHp, fDp = 2 * W + 2, 2 * H + 2, 2 * D + 2
+    fslice = fHp * fWp
+    TR = 128 * R
+    written = {}                                        # (fine chunk, fine padded row) -> (job, group)
+    for job in range(n_jobs):
+        for t in range((total_rows + TR - 1) // TR):
+            for grp in range(groups):
+                for item in range(grp, R * NCG, groups):
+                    r, c0 = item // NCG, (item % NCG) * 16
+                    for m in range(128):
+                        orow = t * TR + r * 128 + m
+                        if orow >= total_rows:
+                            continue
+                        dpf, r2 = divmod(orow, SS)
+                        hp, wp = divmod(r2, Wp)
+                        nn, dp = divmod(dpf, Dp)
+                        if not (1 <= dp <= D and 1 <= hp <= H and 1 <= wp <= W):
+                            continue                    # halo rows hold nothing
+                        frow0 = ((nn * fDp + (2 * dp - 1)) * fHp + (2 * hp - 1)) * fWp + (2 * wp - 1)
+                        chg = (job * CO + c0) >> 3
+                        tap8, ch = chg >> sh, chg & ((1 << sh) - 1)
+                        row = frow0 + (tap8 >> 2) * fslice + ((tap8 >> 1) & 1) * fWp + (tap8 & 1)
+                        for cc in (ch, ch + 1):         # a column group is two 8-channel chunks
+                            assert (cc, row) not in written, "fine element written twice"
+                            written[(cc, row)] = (job, grp)
+                        # definition: GEMM column n = tap8 * Cf + c  <->  fine voxel (2d+kd, 2h+kh, 2w+kw), channel c
+                        n0 = job * CO + c0
+                        kd, kh, kw = (n0 // Cf) >> 2, ((n0 // Cf) >> 1) & 1, (n0 // Cf) & 1
+                        d, h, w = dp - 1, hp - 1, wp - 1
+                        want = ((nn * fDp + (2 * d + kd + 1)) * fHp + (2 * h + kh + 1)) * fWp + (2 * w + kw + 1)
+                        assert row == want and ch == (n0 % Cf) // 8
+    # every interior fine voxel x every fine chunk, nothing else
+    assert len(written) == N * (2 * D) * (2 * H) * (2 * W) * (Cf // 8)
+    for (cc, row) in written:
+        nd, r2 = divmod(row, fslice)
+        fh, fw = divmod(r2, fWp)
+        fd = nd % fDp
+        assert 1 <= fd <= 2 * D and 1 <= fh <= 2 * H and 1 <= fw <= 2 * W and 0 <= cc < Cf // 8
+    assert len({g for (_, g) in written.values()}) == min(groups, R * NCG)      # all three groups take part
